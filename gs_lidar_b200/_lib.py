@@ -1,0 +1,116 @@
+"""ctypes binding of libgsl_b200.so (declared in include/gsl_b200.h).
+
+There is deliberately NO fallback here: if the CUDA library is missing the import of the
+rasterizer fails loudly with instructions to build it (python -m gs_lidar_b200.build).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgsl_b200.so")
+
+GSL_ABI_VERSION = 1
+GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
+GSL_FLAG_DEBUG_SYNC = 1
+GSL_MAX_FEATURES = 10
+
+vp = C.c_void_p
+
+
+class gsl_params(C.Structure):
+    _fields_ = [("P", C.c_int32), ("S", C.c_int32), ("D", C.c_int32), ("M", C.c_int32),
+                ("W", C.c_int32), ("H", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float),
+                ("scale_modifier", C.c_float), ("vfov_min", C.c_float), ("vfov_max", C.c_float),
+                ("hfov_min", C.c_float), ("hfov_max", C.c_float), ("scale_factor", C.c_float),
+                ("prefiltered", C.c_int32), ("flags", C.c_uint32)]
+
+
+class gsl_ws_sizes(C.Structure):
+    _fields_ = [("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t), ("image_bytes", C.c_size_t)]
+
+
+class gsl_workspace(C.Structure):
+    _fields_ = [("geom", vp), ("geom_bytes", C.c_size_t), ("binning", vp), ("binning_bytes", C.c_size_t),
+                ("image", vp), ("image_bytes", C.c_size_t), ("r_capacity", C.c_int64),
+                ("num_rendered_host", vp)]
+
+
+class gsl_fwd_inputs(C.Structure):
+    _fields_ = [(n, vp) for n in ("background", "means3D", "shs", "colors_precomp", "features", "opacities",
+                                  "scales", "rotations", "cov3D_precomp", "mask", "viewmatrix", "projmatrix",
+                                  "campos")]
+
+
+class gsl_fwd_outputs(C.Structure):
+    _fields_ = [(n, vp) for n in ("out_contrib", "out_color", "out_feature", "out_depth", "out_alpha", "radii")]
+
+
+class gsl_bwd_inputs(C.Structure):
+    _fields_ = [(n, vp) for n in ("dL_dout_color", "dL_dout_depth", "dL_dout_alpha", "dL_dout_feature")]
+
+
+class gsl_bwd_outputs(C.Structure):
+    _fields_ = [(n, vp) for n in ("dL_dmeans3D", "dL_dmeans2D", "dL_dsh", "dL_dcolors", "dL_dfeatures",
+                                  "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D")]
+
+
+class gsl_state_export(C.Structure):
+    _fields_ = [(n, vp) for n in ("depths", "means2D", "transMat", "normal_opacity", "rgb", "clamped",
+                                  "tiles_touched", "point_offsets", "point_list_keys", "point_list", "ranges",
+                                  "final_T", "pixbox")]
+
+
+# name -> (restype, argtypes); every symbol include/gsl_b200.h declares
+SYMBOLS = {
+    "gsl_abi_version": (C.c_int, []),
+    "gsl_last_error": (C.c_char_p, []),
+    "gsl_workspace_sizes": (C.c_int, [C.POINTER(gsl_params), C.c_int64, C.POINTER(gsl_ws_sizes)]),
+    "gsl_forward_preprocess": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs),
+                                         C.POINTER(gsl_fwd_outputs), C.POINTER(gsl_workspace), vp]),
+    "gsl_forward_render": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs),
+                                     C.POINTER(gsl_fwd_outputs), C.POINTER(gsl_workspace), vp]),
+    "gsl_forward": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
+                              C.POINTER(gsl_workspace), C.POINTER(C.c_int32), vp]),
+    "gsl_backward": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
+                               C.POINTER(gsl_bwd_inputs), C.POINTER(gsl_bwd_outputs),
+                               C.POINTER(gsl_workspace), vp]),
+    "gsl_mark_visible": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
+    "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
+                                   C.POINTER(gsl_state_export), vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and bind every symbol; raises if the extension is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "gs_lidar_b200: %s is missing. This package has no CPU or PyTorch fallback; build the sm_100a "
+            "library with `python -m gs_lidar_b200.build` (needs nvcc)." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    ver = lib.gsl_abi_version()
+    if ver != GSL_ABI_VERSION:
+        raise ImportError("libgsl_b200.so ABI version %d != expected %d; rebuild" % (ver, GSL_ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().gsl_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc > 0:
+        raise RuntimeError("%s failed with CUDA error %d: %s" % (what, rc, msg))
+    raise RuntimeError("%s: %s" % (what, msg))

@@ -1,0 +1,239 @@
+// gsl_api.cu -- extern "C" entry points declared in include/gsl_b200.h.
+// Validation, workspace carving and stage orchestration only; all arithmetic lives in the kernels.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "gsl_common.cuh"
+
+namespace gsl {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (int)e;
+}
+
+static int validate(const gsl_params* p) {
+  if (!p) return set_error(GSL_EINVAL, "params is NULL");
+  if (p->P < 0) return set_error(GSL_EINVAL, "P must be >= 0 (got %d)", p->P);
+  if (p->S < 0 || p->S > GSL_MAX_FEATURES)
+    return set_error(GSL_EINVAL, "features must have 0..%d channels (got %d): the compositor holds S+3 <= 13 "
+                     "feature accumulators like the reference", GSL_MAX_FEATURES, p->S);
+  if (p->D < 0 || p->D > 3) return set_error(GSL_EINVAL, "sh_degree must be 0..3 (got %d)", p->D);
+  if (p->M < 0 || (p->M > 0 && (p->D + 1) * (p->D + 1) > p->M))
+    return set_error(GSL_EINVAL, "sh has %d coefficients but degree %d needs %d", p->M, p->D, (p->D + 1) * (p->D + 1));
+  if (p->W <= 0 || p->H <= 0) return set_error(GSL_EINVAL, "image size must be positive (got %dx%d)", p->W, p->H);
+  if (p->W > 32767 || p->H > 32767) return set_error(GSL_EINVAL, "image side > 32767 not supported");
+  return 0;
+}
+
+static int validate_inputs(const gsl_params* p, const gsl_fwd_inputs* in) {
+  if (!in) return set_error(GSL_EINVAL, "inputs is NULL");
+  if (p->P == 0) return 0;
+  if (!in->means3D) return set_error(GSL_EINVAL, "means3D must have dimensions (num_points, 3)");
+  if (!in->scales || !in->rotations)
+    return set_error(GSL_EINVAL, "scales and rotations are required (the cov3D_precomp path is not computed, as in the reference)");
+  if (!in->opacities || !in->mask || !in->viewmatrix || !in->campos || !in->background)
+    return set_error(GSL_EINVAL, "opacities, mask, viewmatrix, campos and background are required");
+  if ((in->shs == nullptr) == (in->colors_precomp == nullptr))
+    return set_error(GSL_EINVAL, "Please provide exactly one of either SHs or precomputed colors!");
+  if (in->shs && p->M == 0) return set_error(GSL_EINVAL, "shs given but M == 0");
+  if (p->S > 0 && !in->features) return set_error(GSL_EINVAL, "features is NULL but S = %d", p->S);
+  return 0;
+}
+
+static int validate_ws(const gsl_params* p, const gsl_workspace* ws, bool need_binning) {
+  if (!ws) return set_error(GSL_EINVAL, "workspace is NULL");
+  gsl_ws_sizes sz;
+  GeomView g = geom_view(nullptr, p->P, p->S);
+  ImageView im = image_view(nullptr, p->W, p->H);
+  sz.geom_bytes = g.bytes;
+  sz.image_bytes = im.bytes;
+  if (!ws->geom || ws->geom_bytes < sz.geom_bytes)
+    return set_error(GSL_ENOSPACE, "geom chunk too small: %zu < %zu", ws->geom_bytes, sz.geom_bytes);
+  if (!ws->image || ws->image_bytes < sz.image_bytes)
+    return set_error(GSL_ENOSPACE, "image chunk too small: %zu < %zu", ws->image_bytes, sz.image_bytes);
+  if (need_binning) {
+    BinView b = bin_view(nullptr, ws->r_capacity);
+    if (!ws->binning || ws->binning_bytes < b.bytes)
+      return set_error(GSL_ENOSPACE, "binning chunk too small for capacity %lld: %zu < %zu",
+                       (long long)ws->r_capacity, ws->binning_bytes, b.bytes);
+  }
+  if (!ws->num_rendered_host) return set_error(GSL_EINVAL, "workspace.num_rendered_host (pinned int[2]) is NULL");
+  return 0;
+}
+
+static int debug_sync(const gsl_params* p, cudaStream_t st, const char* stage) {
+  if (!(p->flags & GSL_FLAG_DEBUG_SYNC)) return 0;
+  return check_cuda(cudaStreamSynchronize(st), stage);
+}
+
+}  // namespace gsl
+
+using namespace gsl;
+
+extern "C" {
+
+GSL_API int gsl_abi_version(void) { return GSL_ABI_VERSION; }
+
+GSL_API const char* gsl_last_error(void) { return g_err; }
+
+GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_sizes* out) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if (!out) return set_error(GSL_EINVAL, "out is NULL");
+  if (r_capacity < 0 || r_capacity > 0x7fffffffLL) return set_error(GSL_EINVAL, "r_capacity out of range");
+  out->geom_bytes = geom_view(nullptr, p->P, p->S).bytes;
+  out->image_bytes = image_view(nullptr, p->W, p->H).bytes;
+  out->binning_bytes = bin_view(nullptr, r_capacity).bytes;
+  return 0;
+}
+
+GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
+                           gsl_workspace* ws, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if ((rc = validate_inputs(p, in))) return rc;
+  if (!out || (p->P > 0 && !out->radii)) return set_error(GSL_EINVAL, "outputs / radii is NULL");
+  if ((rc = validate_ws(p, ws, false))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  GeomView g = geom_view(ws->geom, p->P, p->S);
+  if ((rc = launch_preprocess(*p, *in, *out, g, st))) return rc;
+  if ((rc = debug_sync(p, st, "preprocess"))) return rc;
+  if ((rc = launch_scan(*p, g, ws->num_rendered_host, st))) return rc;
+  return debug_sync(p, st, "scan");
+}
+
+GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
+                       gsl_workspace* ws, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if ((rc = validate_inputs(p, in))) return rc;
+  if (!out || !out->out_contrib || !out->out_color || !out->out_feature || !out->out_depth || !out->out_alpha)
+    return set_error(GSL_EINVAL, "an output image pointer is NULL");
+  if ((rc = validate_ws(p, ws, true))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  GeomView g = geom_view(ws->geom, p->P, p->S);
+  ImageView im = image_view(ws->image, p->W, p->H);
+  BinView b = bin_view(ws->binning, ws->r_capacity);
+  rc = launch_binning(*p, g, im, b, ws->r_capacity, ws->num_rendered_host, st);
+  if (rc == GSL_ENOSPACE)
+    return set_error(GSL_ENOSPACE, "binning capacity %lld < num_rendered %d", (long long)ws->r_capacity,
+                     ws->num_rendered_host[0]);
+  if (rc) return rc;
+  if ((rc = debug_sync(p, st, "binning"))) return rc;
+  if ((rc = launch_render_forward(*p, *in, *out, g, im, b, ws->r_capacity, st))) return rc;
+  return debug_sync(p, st, "render_forward");
+}
+
+GSL_API int gsl_forward(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out, gsl_workspace* ws,
+                int32_t* num_rendered, void* stream) {
+  int rc = gsl_forward_preprocess(p, in, out, ws, stream);
+  if (rc) return rc;
+  if ((rc = check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "forward: wait for instance count"))) return rc;
+  if (num_rendered) *num_rendered = ws->num_rendered_host[0];
+  return gsl_forward_render(p, in, out, ws, stream);
+}
+
+GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                 const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if ((rc = validate_inputs(p, in))) return rc;
+  if (!fwd || !gin || !gout) return set_error(GSL_EINVAL, "fwd / grad inputs / grad outputs is NULL");
+  if (p->P == 0) return 0;
+  if (!gin->dL_dout_color || !gin->dL_dout_depth || !gin->dL_dout_alpha || !gin->dL_dout_feature)
+    return set_error(GSL_EINVAL, "a cotangent pointer is NULL");
+  if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dcolors || !gout->dL_dopacity ||
+      !gout->dL_dscales || !gout->dL_drotations || (p->S > 0 && !gout->dL_dfeatures) ||
+      (in->shs && !gout->dL_dsh))
+    return set_error(GSL_EINVAL, "a gradient output pointer is NULL");
+  if (!fwd->radii || !fwd->out_contrib) return set_error(GSL_ESTATE, "forward outputs (radii, out_contrib) missing");
+  if ((rc = validate_ws(p, ws, true))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  GeomView g = geom_view(ws->geom, p->P, p->S);
+  ImageView im = image_view(ws->image, p->W, p->H);
+  BinView b = bin_view(ws->binning, ws->r_capacity);
+  if ((rc = launch_render_backward(*p, *in, *fwd, *gin, g, im, b, ws->r_capacity, st))) return rc;
+  if ((rc = debug_sync(p, st, "render_backward"))) return rc;
+  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, st))) return rc;
+  return debug_sync(p, st, "preprocess_backward");
+}
+
+GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  if (P < 0) return set_error(GSL_EINVAL, "P must be >= 0");
+  if (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present))
+    return set_error(GSL_EINVAL, "mark_visible: NULL pointer");
+  return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+}
+
+// ---- state export in the reference's layouts (tests only) ----------------------------------------
+__global__ void k_export_geom(int P, const float4* __restrict__ rec, const float4* __restrict__ rgb,
+                              const uint8_t* __restrict__ clamped, const short4* __restrict__ pixbox,
+                              gsl_state_export d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float4 a = rec[4 * (size_t)i], b = rec[4 * (size_t)i + 1], c = rec[4 * (size_t)i + 2], e = rec[4 * (size_t)i + 3];
+  if (d.depths) d.depths[i] = e.w;
+  if (d.means2D) { d.means2D[2 * i] = c.y; d.means2D[2 * i + 1] = c.z; }
+  if (d.transMat) {
+    float* t = d.transMat + 9 * (size_t)i;
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w; t[8] = c.x;
+  }
+  if (d.normal_opacity) {
+    float* t = d.normal_opacity + 4 * (size_t)i;
+    t[0] = e.x; t[1] = e.y; t[2] = e.z; t[3] = c.w;
+  }
+  if (d.rgb) reinterpret_cast<float4*>(d.rgb)[i] = rgb[i];
+  if (d.clamped) {
+    uint8_t cl = clamped[i];
+    for (int k = 0; k < 4; ++k) d.clamped[4 * (size_t)i + k] = (cl >> k) & 1;
+  }
+  if (d.pixbox) {
+    short4 pb = pixbox[i];
+    d.pixbox[4 * (size_t)i] = pb.x; d.pixbox[4 * (size_t)i + 1] = pb.y;
+    d.pixbox[4 * (size_t)i + 2] = pb.z; d.pixbox[4 * (size_t)i + 3] = pb.w;
+  }
+}
+
+GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64_t R, const gsl_state_export* dst,
+                     void* stream) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if (!ws || !dst) return set_error(GSL_EINVAL, "workspace / dst is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  GeomView g = geom_view(ws->geom, p->P, p->S);
+  ImageView im = image_view(ws->image, p->W, p->H);
+  if (p->P > 0) {
+    k_export_geom<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, g.rec, g.rgb, g.clamped, g.pixbox, *dst);
+    if (dst->tiles_touched)
+      cudaMemcpyAsync(dst->tiles_touched, g.tiles, (size_t)p->P * 4, cudaMemcpyDeviceToDevice, st);
+    if (dst->point_offsets)
+      cudaMemcpyAsync(dst->point_offsets, g.offs, (size_t)p->P * 4, cudaMemcpyDeviceToDevice, st);
+  }
+  if (R > 0 && ws->binning) {
+    if (R > ws->r_capacity) return set_error(GSL_EINVAL, "R exceeds the binning capacity");
+    BinView b = bin_view(ws->binning, ws->r_capacity);
+    if (dst->point_list_keys)
+      cudaMemcpyAsync(dst->point_list_keys, b.keys_b, (size_t)R * 8, cudaMemcpyDeviceToDevice, st);
+    if (dst->point_list) cudaMemcpyAsync(dst->point_list, b.vals_b, (size_t)R * 4, cudaMemcpyDeviceToDevice, st);
+  }
+  const size_t tiles = (size_t)((p->W + GSL_BLOCK_X - 1) / GSL_BLOCK_X) * ((p->H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y);
+  if (dst->ranges) cudaMemcpyAsync(dst->ranges, im.ranges, tiles * 8, cudaMemcpyDeviceToDevice, st);
+  if (dst->final_T)
+    cudaMemcpyAsync(dst->final_T, im.final_T, (size_t)3 * p->W * p->H * 4, cudaMemcpyDeviceToDevice, st);
+  return check_cuda(cudaGetLastError(), "export_state");
+}
+
+}  // extern "C"

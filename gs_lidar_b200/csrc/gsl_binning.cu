@@ -1,0 +1,251 @@
+// gsl_binning.cu -- tile binning: scan of tile counts, key duplication, tile|depth sort, tile ranges.
+// Semantics of rasterizer_impl.cu:68-142 and :310-354 (K2-K7 in SURVEY.md):
+//   offsets = inclusive_scan(tiles_touched); R = offsets[P-1]
+//   key = (tile_id << 32) | float_bits(depth), value = surfel id, emitted y-major/x-minor per surfel
+//   stable sort over key bits [0, 32 + bits(tiles));  ranges[tile] = [first, last+1)
+// All of it is integer work and must be bit-exact.
+#include <cub/cub.cuh>
+#include "gsl_common.cuh"
+
+namespace gsl {
+
+// ------------------------------------------------------------------------------------------------
+// scan: 1024 elements per block, three small kernels (reduce, scan of block sums, downsweep)
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += n;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total in *total
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem, uint32_t* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan(v);
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = (lane < (blockDim.x >> 5)) ? smem[lane] : 0;
+    uint32_t wi = warp_incl_scan(w);
+    smem[lane] = wi - w;
+    if (lane == 31) smem[32] = wi;
+  }
+  __syncthreads();
+  uint32_t res = inc - v + smem[wid];
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, int P,
+                                                              uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t sm[33];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+  if (base + SCAN_ITEMS <= P) {
+    uint4 v = *reinterpret_cast<const uint4*>(in + base);
+    s = v.x + v.y + v.z + v.w;
+  } else {
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+      if (base + i < P) s += in[base + i];
+  }
+  uint32_t total;
+  block_excl_scan(s, sm, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ block_sums, int nblocks,
+                                                    uint32_t* __restrict__ ctrl, int32_t* r_host_unused) {
+  __shared__ uint32_t sm[33];
+  uint32_t carry = 0;
+  for (int base = 0; base < nblocks; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = (i < nblocks) ? block_sums[i] : 0;
+    uint32_t total;
+    uint32_t ex = block_excl_scan(v, sm, &total);
+    if (i < nblocks) block_sums[i] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    ctrl[0] = carry;  // R
+    ctrl[1] = 0;      // overflow flag
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const uint32_t* __restrict__ in, int P,
+                                                            const uint32_t* __restrict__ block_sums,
+                                                            uint32_t* __restrict__ out) {
+  __shared__ uint32_t sm[33];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS] = {0, 0, 0, 0};
+  if (base + SCAN_ITEMS <= P) {
+    uint4 q = *reinterpret_cast<const uint4*>(in + base);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+      if (base + i < P) v[i] = in[base + i];
+  }
+  uint32_t s = v[0] + v[1] + v[2] + v[3];
+  uint32_t total;
+  uint32_t ex = block_excl_scan(s, sm, &total) + block_sums[blockIdx.x];
+  uint32_t o0 = ex + v[0], o1 = o0 + v[1], o2 = o1 + v[2], o3 = o2 + v[3];
+  if (base + SCAN_ITEMS <= P) {
+    *reinterpret_cast<uint4*>(out + base) = make_uint4(o0, o1, o2, o3);
+  } else {
+    uint32_t o[4] = {o0, o1, o2, o3};
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+      if (base + i < P) out[base + i] = o[i];
+  }
+}
+
+int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st) {
+  if (p.P == 0) {
+    cudaMemsetAsync(g.ctrl, 0, 8, st);
+  } else {
+    int nblocks = (p.P + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<nblocks, SCAN_THREADS, 0, st>>>(g.tiles, p.P, g.scan_state);
+    k_scan_sums<<<1, 1024, 0, st>>>(g.scan_state, nblocks, g.ctrl, nullptr);
+    k_scan_down<<<nblocks, SCAN_THREADS, 0, st>>>(g.tiles, p.P, g.scan_state, g.offs);
+  }
+  if (r_host) cudaMemcpyAsync(r_host, g.ctrl, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  return check_cuda(cudaGetLastError(), "scan launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// key duplication (rasterizer_impl.cu:68-111).  One WARP per 32 surfels: lanes first take their own
+// surfel, then surfels whose rect spans many tiles (azimuth-seam surfels span whole tile rows) are
+// emitted cooperatively by the whole warp so no lane serialises a long loop.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_duplicate(int P, const float4* __restrict__ rec,
+                                                   const ushort4* __restrict__ rect,
+                                                   const uint32_t* __restrict__ tiles,
+                                                   const uint32_t* __restrict__ offs, int gx,
+                                                   const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
+                                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  if (ctrl[0] > r_capacity) return;  // binning chunk too small: host re-runs after growing it
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t n = 0, off = 0, depth_bits = 0;
+  ushort4 rc = make_ushort4(0, 0, 0, 0);
+  if (idx < P) {
+    n = tiles[idx];
+    if (n > 0) {
+      off = offs[idx] - n;  // exclusive offset
+      rc = rect[idx];
+      depth_bits = __float_as_uint(rec[4 * (size_t)idx + 3].w);
+    }
+  }
+  constexpr uint32_t COOP = 16;
+  // small rects: each lane emits its own
+  if (n > 0 && n <= COOP) {
+    const uint32_t w = rc.z - rc.x;
+    for (uint32_t k = 0; k < n; ++k) {
+      uint32_t y = rc.y + k / w, x = rc.x + k % w;
+      uint64_t key = ((uint64_t)(y * gx + x) << 32) | depth_bits;
+      keys[off + k] = key;
+      vals[off + k] = (uint32_t)idx;
+    }
+  }
+  // large rects: whole warp
+  uint32_t big = __ballot_sync(0xffffffffu, n > COOP);
+  while (big) {
+    int src = __ffs(big) - 1;
+    big &= big - 1;
+    uint32_t bn = __shfl_sync(0xffffffffu, n, src);
+    uint32_t boff = __shfl_sync(0xffffffffu, off, src);
+    uint32_t bdepth = __shfl_sync(0xffffffffu, depth_bits, src);
+    uint32_t bx = __shfl_sync(0xffffffffu, (uint32_t)rc.x, src);
+    uint32_t by = __shfl_sync(0xffffffffu, (uint32_t)rc.y, src);
+    uint32_t bz = __shfl_sync(0xffffffffu, (uint32_t)rc.z, src);
+    uint32_t bidx = (uint32_t)(idx - lane + src);
+    uint32_t w = bz - bx;
+    for (uint32_t k = lane; k < bn; k += 32) {
+      uint32_t y = by + k / w, x = bx + k % w;
+      keys[boff + k] = ((uint64_t)(y * gx + x) << 32) | bdepth;
+      vals[boff + k] = bidx;
+    }
+  }
+}
+
+// identifyTileRanges (rasterizer_impl.cu:116-142), grid-stride over the device-side R.
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint64_t* __restrict__ keys,
+                                                     const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
+                                                     uint2* __restrict__ ranges) {
+  const uint32_t R = ctrl[0];
+  if (R > r_capacity) return;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+    uint32_t cur = (uint32_t)(keys[i] >> 32);
+    if (i == 0) {
+      ranges[cur].x = 0;
+    } else {
+      uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+      if (cur != prev) {
+        ranges[prev].y = i;
+        ranges[cur].x = i;
+      }
+    }
+    if (i == R - 1) ranges[cur].y = R;
+  }
+}
+
+__global__ void k_flag_overflow(uint32_t* ctrl, uint32_t r_capacity) {
+  if (ctrl[0] > r_capacity) ctrl[1] = 1;
+}
+
+static uint32_t higher_msb(uint32_t n) {  // rasterizer_impl.cu:32-47
+  uint32_t msb = sizeof(n) * 4;
+  uint32_t step = msb;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb) msb += step; else msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+
+size_t sort_temp_bytes(int64_t Rcap) {
+  static thread_local int64_t cached_cap = -1;
+  static thread_local size_t cached_bytes = 0;
+  if (Rcap == cached_cap) return cached_bytes;
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)Rcap);
+  cached_cap = Rcap;
+  cached_bytes = bytes + 256;
+  return cached_bytes;
+}
+
+// r_host[0] must already hold R (the caller synchronised on the scan) -- cub needs the count on
+// the host.  TODO(round 2): device-count sort to drop this dependency.
+int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,
+                   int64_t r_capacity, int32_t* r_host, cudaStream_t st) {
+  const int gx = (p.W + GSL_BLOCK_X - 1) / GSL_BLOCK_X, gy = (p.H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
+  const int tiles = gx * gy;
+  cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
+  const int64_t R = r_host[0];
+  if (p.P == 0 || R == 0) return check_cuda(cudaGetLastError(), "binning (empty)");
+  if (R > r_capacity) {
+    k_flag_overflow<<<1, 1, 0, st>>>(g.ctrl, (uint32_t)r_capacity);
+    return GSL_ENOSPACE;
+  }
+  k_duplicate<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, g.rec, g.rect, g.tiles, g.offs, gx, g.ctrl,
+                                                 (uint32_t)r_capacity, b.keys_a, b.vals_a);
+  int bit = (int)higher_msb((uint32_t)tiles);
+  size_t tmp = b.sort_tmp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.keys_a, b.keys_b, b.vals_a, b.vals_b,
+                                                  (int)R, 0, 32 + bit, st);
+  if (e != cudaSuccess) return check_cuda(e, "cub::DeviceRadixSort::SortPairs");
+  int blocks = (int)((R + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_tile_ranges<<<blocks, 256, 0, st>>>(b.keys_b, g.ctrl, (uint32_t)r_capacity, im.ranges);
+  return check_cuda(cudaGetLastError(), "binning launch");
+}
+
+}  // namespace gsl

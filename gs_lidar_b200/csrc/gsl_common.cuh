@@ -1,0 +1,166 @@
+// gsl_common.cuh -- shared definitions for the sm_100a surfel rasterizer kernels.
+//
+// HBM layout of the three scratch chunks (all offsets 256-B aligned), replacing the reference's
+// GeometryState / ImageState / BinningState (cuda_rasterizer/rasterizer_impl.h:26-63):
+//
+//   geom chunk (per surfel i):
+//     rec[4*i .. 4*i+3]  float4 x4 = one 64-B record gathered by the compositors:
+//         rec0 = (Tu.x, Tu.y, Tu.z, Tv.x)      Tu,Tv,Tw = rows of the reference's transMat
+//         rec1 = (Tv.y, Tv.z, Tw.x, Tw.y)      (forward.cu:238-241)
+//         rec2 = (Tw.z, xy.x, xy.y, opacity)   xy = means2D (forward.cu:252-253)
+//         rec3 = (n.x, n.y, n.z, depth)        normal_opacity.xyz + depths (forward.cu:282-285)
+//     rgb[i]      float4   SH colour (forward.cu:275-278); unused with colors_precomp
+//     rect[i]     ushort4  tile rect (min.x, min.y, max.x, max.y) of getRect (auxiliary.h:47-55)
+//     pixbox[i]   short4   conservative pixel box of the surfel's support (this design)
+//     tiles[i]    u32      tiles_touched;  offs[i] u32 inclusive scan
+//     clamped[i]  u8       bit c set when SH channel c was clamped (forward.cu:64-67)
+//     grad[i]     float[GS] packed gradient accumulators, kept all-zero between steps:
+//         [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity,
+//         [12..15] dL_dcolor, [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature
+//     ctrl        u32[64]  [0]=R, [1]=overflow, [2]=scan ticket, ...
+//   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2)
+//   binning chunk (capacity Rcap): keys_a u64, keys_b u64, vals_a u32, vals_b u32, sort temp
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gsl_b200.h"
+
+#define GSL_BLOCK_X 16
+#define GSL_BLOCK_Y 16
+#define GSL_MY_PI 3.14159265  // auxiliary.h:17 (a double literal, NOT M_PI)
+
+namespace gsl {
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline __host__ __device__ int grad_stride(int S) { return 20 + ((S + 3) / 4) * 4; }
+
+struct GeomView {
+  float4* rec;
+  float4* rgb;
+  ushort4* rect;
+  short4* pixbox;
+  uint32_t* tiles;
+  uint32_t* offs;
+  uint8_t* clamped;
+  float* grad;
+  uint32_t* ctrl;
+  uint32_t* scan_state;  // decoupled look-back tile descriptors
+  size_t bytes;
+};
+
+struct ImageView {
+  float* final_T;   // 3N
+  uint2* ranges;    // tiles
+  size_t bytes;
+};
+
+struct BinView {
+  uint64_t* keys_a;
+  uint64_t* keys_b;
+  uint32_t* vals_a;
+  uint32_t* vals_b;
+  void* sort_tmp;
+  size_t sort_tmp_bytes;
+  size_t bytes;
+};
+
+template <typename T>
+inline void carve(char*& p, T*& out, size_t count) {
+  size_t a = align_up((size_t)(uintptr_t)p, 256);
+  out = (T*)a;
+  p = (char*)(a + count * sizeof(T));
+}
+
+inline GeomView geom_view(void* base, int P, int S) {
+  GeomView g;
+  char* p = (char*)base;
+  size_t Pp = (size_t)(P > 0 ? P : 1);
+  carve(p, g.rec, 4 * Pp);
+  carve(p, g.rgb, Pp);
+  carve(p, g.rect, Pp);
+  carve(p, g.pixbox, Pp);
+  carve(p, g.tiles, Pp);
+  carve(p, g.offs, Pp);
+  carve(p, g.clamped, Pp);
+  carve(p, g.grad, Pp * grad_stride(S));
+  carve(p, g.ctrl, 64);
+  carve(p, g.scan_state, 2 * ((Pp + 1023) / 1024 + 1));
+  g.bytes = (size_t)(p - (char*)base) + 256;
+  return g;
+}
+
+inline ImageView image_view(void* base, int W, int H) {
+  ImageView v;
+  char* p = (char*)base;
+  size_t N = (size_t)W * H;
+  size_t tiles = (size_t)((W + GSL_BLOCK_X - 1) / GSL_BLOCK_X) * ((H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y);
+  carve(p, v.final_T, 3 * N);
+  carve(p, v.ranges, tiles + 1);
+  v.bytes = (size_t)(p - (char*)base) + 256;
+  return v;
+}
+
+size_t sort_temp_bytes(int64_t Rcap);
+
+inline BinView bin_view(void* base, int64_t Rcap) {
+  BinView b;
+  char* p = (char*)base;
+  size_t R = (size_t)(Rcap > 0 ? Rcap : 1);
+  carve(p, b.keys_a, R);
+  carve(p, b.keys_b, R);
+  carve(p, b.vals_a, R);
+  carve(p, b.vals_b, R);
+  b.sort_tmp_bytes = sort_temp_bytes((int64_t)R);
+  char* tmp;
+  carve(p, tmp, b.sort_tmp_bytes);
+  b.sort_tmp = tmp;
+  b.bytes = (size_t)(p - (char*)base) + 256;
+  return b;
+}
+
+// FOV constants, evaluated in double then rounded exactly as forward.cu:221-226 does per thread.
+struct Fov {
+  float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
+};
+inline Fov make_fov(const gsl_params& p) {
+  Fov f;
+  f.VFOV_max = (float)(GSL_MY_PI / 2 - p.vfov_min * GSL_MY_PI / 180);
+  f.VFOV_min = (float)(GSL_MY_PI / 2 - p.vfov_max * GSL_MY_PI / 180);
+  f.HFOV_max = (float)(p.hfov_max * GSL_MY_PI / 180);
+  f.HFOV_min = (float)(p.hfov_min * GSL_MY_PI / 180);
+  return f;
+}
+
+// Launch constants of the two compositing kernels.
+struct RenderParams {
+  int W, H, gx, gy, S;
+  float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
+  float near_, far_, far_over_range;  // 2*sf, 300*sf, far/(far-near) (forward.cu:366-367,453)
+  uint32_t r_capacity;
+};
+RenderParams make_render_params(const gsl_params& p, int64_t r_capacity);
+
+// error plumbing (gsl_api.cu)
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// stage launchers (one per .cu file)
+int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
+                      const GeomView& g, cudaStream_t st);
+int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st);
+int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,
+                   int64_t r_capacity, int32_t* r_host, cudaStream_t st);
+int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
+                          const GeomView& g, const ImageView& im, const BinView& b,
+                          int64_t r_capacity, cudaStream_t st);
+int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
+                           const gsl_bwd_inputs& gin, const GeomView& g, const ImageView& im,
+                           const BinView& b, int64_t r_capacity, cudaStream_t st);
+int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
+                               const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
+                               cudaStream_t st);
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                        const float* projmatrix, uint8_t* present, cudaStream_t st);
+
+}  // namespace gsl

@@ -1,0 +1,583 @@
+// gsl_preprocess.cu -- per-surfel stages of the panoramic surfel rasterizer:
+//   k_preprocess_fwd  : equirectangular projection, ray-splat transform T, 12-sample AABB, tile
+//                       rect, conservative pixel box, SH -> 4-channel colour
+//                       (semantics of forward.cu:173-287 incl. helpers :17-171, auxiliary.h:47-55,
+//                        182-228, 276-283)
+//   k_preprocess_bwd  : VJP of the above from the packed gradient accumulators to the dense
+//                       per-parameter gradients (semantics of backward.cu:517-712, :17-134)
+//   k_mark_visible    : pinhole frustum test (rasterizer_impl.cu:51-64, auxiliary.h:157-180)
+// One thread per surfel, 256-thread blocks; every load of the per-surfel record is a float4.
+#include <math.h>
+#include "gsl_common.cuh"
+#include "gsl_math.cuh"
+
+namespace gsl {
+
+__device__ __constant__ float kSH_C0 = 0.28209479177387814f;
+__device__ __constant__ float kSH_C1 = 0.4886025119029199f;
+__device__ __constant__ float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                          -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                          0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                          -0.5900435899266435f};
+
+struct PreParams {
+  int P, D, M, W, H, gx, gy;
+  float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
+  float scale_factor;
+  float samp[12];  // (float)(2*MY_PI*i/12), forward.cu:155
+};
+
+struct Rot3 {  // columns c0,c1,c2 of the rotation matrix
+  float r00, r01, r02, r10, r11, r12, r20, r21, r22;  // rCR : column C, row R
+};
+
+// quat_to_rotmat (auxiliary.h:206-228); q = (q0,q1,q2,q3) as stored, w = q0.
+__device__ __forceinline__ Rot3 quat_to_rot(float q0, float q1, float q2, float q3) {
+  float n = GSL_FF(q2, q2, GSL_FF(q1, q1, GSL_FF(q0, q0, GSL_FM(q3, q3))));
+  float s = rsqrtf(n);
+  float w = GSL_FM(q0, s), x = GSL_FM(q1, s), y = GSL_FM(q2, s), z = GSL_FM(q3, s);
+  float wz = GSL_FM(w, z), wx = GSL_FM(w, x), wy = GSL_FM(w, y);
+  float yy = GSL_FM(y, y), zz = GSL_FM(z, z);
+  float xy_p = GSL_FF(x, y, wz), xy_m = GSL_FF(x, y, -wz);
+  float yz_p = GSL_FF(y, z, wx), yz_m = GSL_FF(y, z, -wx);
+  float xz_m = GSL_FF(x, z, -wy), xz_p = GSL_FF(x, z, wy);
+  float yyzz = GSL_FA(yy, zz);
+  float xxzz = GSL_FF(x, x, zz);
+  float xxyy = GSL_FF(x, x, yy);
+  Rot3 R;
+  R.r00 = GSL_FS(1.f, GSL_FA(yyzz, yyzz));
+  R.r01 = GSL_FA(xy_p, xy_p);
+  R.r02 = GSL_FA(xz_m, xz_m);
+  R.r10 = GSL_FA(xy_m, xy_m);
+  R.r11 = GSL_FS(1.f, GSL_FA(xxzz, xxzz));
+  R.r12 = GSL_FA(yz_p, yz_p);
+  R.r20 = GSL_FA(xz_p, xz_p);
+  R.r21 = GSL_FA(yz_m, yz_m);
+  R.r22 = GSL_FS(1.f, GSL_FA(xxyy, xxyy));
+  return R;
+}
+
+// SH -> 4 channels (forward.cu:17-69).  sh points at this surfel's M float4 coefficients.
+__device__ __forceinline__ float4 eval_sh(int deg, const float4* __restrict__ sh, float x, float y, float z) {
+  float4 c0 = sh[0];
+  float r[4] = {kSH_C0 * c0.x, kSH_C0 * c0.y, kSH_C0 * c0.z, kSH_C0 * c0.w};
+#define GSL_ACC(coef, idx, sign)                         \
+  {                                                      \
+    float4 c = sh[idx];                                  \
+    float k = (coef);                                    \
+    r[0] = r[0] sign k * c.x;                            \
+    r[1] = r[1] sign k * c.y;                            \
+    r[2] = r[2] sign k * c.z;                            \
+    r[3] = r[3] sign k * c.w;                            \
+  }
+  if (deg > 0) {
+    GSL_ACC(kSH_C1 * y, 1, -)
+    GSL_ACC(kSH_C1 * z, 2, +)
+    GSL_ACC(kSH_C1 * x, 3, -)
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      GSL_ACC(kSH_C2[0] * xy, 4, +)
+      GSL_ACC(kSH_C2[1] * yz, 5, +)
+      GSL_ACC(kSH_C2[2] * (2.0f * zz - xx - yy), 6, +)
+      GSL_ACC(kSH_C2[3] * xz, 7, +)
+      GSL_ACC(kSH_C2[4] * (xx - yy), 8, +)
+      if (deg > 2) {
+        GSL_ACC(kSH_C3[0] * y * (3.0f * xx - yy), 9, +)
+        GSL_ACC(kSH_C3[1] * xy * z, 10, +)
+        GSL_ACC(kSH_C3[2] * y * (4.0f * zz - xx - yy), 11, +)
+        GSL_ACC(kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy), 12, +)
+        GSL_ACC(kSH_C3[4] * x * (4.0f * zz - xx - yy), 13, +)
+        GSL_ACC(kSH_C3[5] * z * (xx - yy), 14, +)
+        GSL_ACC(kSH_C3[6] * x * (xx - 3.0f * yy), 15, +)
+      }
+    }
+  }
+#undef GSL_ACC
+  return make_float4(r[0] + 0.5f, r[1] + 0.5f, r[2] + 0.5f, r[3] + 0.5f);
+}
+
+__global__ void __launch_bounds__(256) k_preprocess_fwd(
+    PreParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
+    const float* __restrict__ rotations, const float* __restrict__ opacities,
+    const float* __restrict__ shs, const float* __restrict__ colors_precomp,
+    const uint8_t* __restrict__ mask, const float* __restrict__ viewmatrix,
+    const float* __restrict__ campos, int* __restrict__ radii, float4* __restrict__ rec,
+    float4* __restrict__ rgb, ushort4* __restrict__ rect, short4* __restrict__ pixbox,
+    uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped) {
+  __shared__ float s_sin[12], s_cos[12];
+  if (threadIdx.x < 12) {
+    s_sin[threadIdx.x] = sinf(pp.samp[threadIdx.x]);
+    s_cos[threadIdx.x] = cosf(pp.samp[threadIdx.x]);
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pp.P) return;
+
+  // Invisible unless proven otherwise (forward.cu:214-215).
+  int out_radius = 0;
+  uint32_t out_tiles = 0;
+  ushort4 out_rect = make_ushort4(0, 0, 0, 0);
+  short4 out_box = make_short4(0, 1, 0, 0);  // y0 > y1 : empty
+
+  const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
+  const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
+  const float vm8 = viewmatrix[8], vm9 = viewmatrix[9], vm10 = viewmatrix[10];
+  const float vm12 = viewmatrix[12], vm13 = viewmatrix[13], vm14 = viewmatrix[14];
+
+  const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+  const float opacity = opacities[idx];
+
+  // view-space centre, polar coordinates (forward.cu:116-125, auxiliary.h:77-85)
+  const float tx = GSL_FA(vm12, dot3_ref(px, vm0, py, vm4, pz, vm8));
+  const float ty = GSL_FA(vm13, dot3_ref(px, vm1, py, vm5, pz, vm9));
+  const float tz = GSL_FA(vm14, dot3_ref(px, vm2, py, vm6, pz, vm10));
+  const float phi = atan2f(tx, tz);
+  const float tx2 = GSL_FM(tx, tx), tz2 = GSL_FM(tz, tz);
+  const float rxz = sqrtf(GSL_FA(tx2, tz2));
+  const float theta = atan2f(rxz, -ty);
+  const float r = sqrtf(GSL_FA(GSL_FF(ty, ty, tx2), tz2));
+
+  bool visible = mask[idx] != 0;
+  const float dV = GSL_FS(pp.VFOV_max, pp.VFOV_min);
+  const float dH = GSL_FS(pp.HFOV_max, pp.HFOV_min);
+  if (visible) {
+    // in_frustum_panorama (auxiliary.h:182-204); the 1.3 compares are in double.
+    float center_v = GSL_FM(GSL_FA(pp.VFOV_max, pp.VFOV_min), 0.5f);
+    float ratio_v = fabsf(GSL_FD(GSL_FS(theta, center_v), GSL_FM(dV, 0.5f)));
+    float center_h = GSL_FM(GSL_FA(pp.HFOV_min, pp.HFOV_max), 0.5f);
+    float ratio_h = fabsf(GSL_FD(GSL_FS(phi, center_h), GSL_FM(dH, 0.5f)));
+    float near_ = GSL_FA(pp.scale_factor, pp.scale_factor);
+    if (r <= near_ || (double)ratio_v > 1.3 || (double)ratio_h > 1.3) visible = false;
+  }
+
+  if (visible) {
+    const float sx = scales[3 * idx], sy = scales[3 * idx + 1];
+    const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+    const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
+    // L = R * diag(sx, sy, 1)  (scale.z and scale_modifier are ignored: auxiliary.h:276-283)
+    const float l0x = GSL_FM(sx, R.r00), l0y = GSL_FM(sx, R.r01), l0z = GSL_FM(sx, R.r02);
+    const float l1x = GSL_FM(sy, R.r10), l1y = GSL_FM(sy, R.r11), l1z = GSL_FM(sy, R.r12);
+    // T rows (forward.cu:84-105): Tu = x-coefficients, Tv = y, Tw = z over splat coords (u,v,1)
+    Splat s;
+    s.Tux = dot3_ref(l0x, vm0, l0y, vm4, l0z, vm8);
+    s.Tuy = dot3_ref(l1x, vm0, l1y, vm4, l1z, vm8);
+    s.Tuz = tx;
+    s.Tvx = dot3_ref(l0x, vm1, l0y, vm5, l0z, vm9);
+    s.Tvy = dot3_ref(l1x, vm1, l1y, vm5, l1z, vm9);
+    s.Tvz = ty;
+    s.Twx = dot3_ref(l0x, vm2, l0y, vm6, l0z, vm10);
+    s.Twy = dot3_ref(l1x, vm2, l1y, vm6, l1z, vm10);
+    s.Twz = tz;
+    // view-space normal, flipped towards the sensor (forward.cu:106-112)
+    float nx = dot3_ref(vm0, R.r20, vm4, R.r21, vm8, R.r22);
+    float ny = dot3_ref(vm1, R.r20, vm5, R.r21, vm9, R.r22);
+    float nz = dot3_ref(vm2, R.r20, vm6, R.r21, vm10, R.r22);
+    float ndot = dot3_ref(nx, tx, ny, ty, nz, tz);
+    float mult = ndot < 0.f ? 1.f : -1.f;
+    nx = GSL_FM(nx, mult); ny = GSL_FM(ny, mult); nz = GSL_FM(nz, mult);
+
+    // The reference stores T before any further culling (forward.cu:238-241).
+    float4* my = rec + 4 * (size_t)idx;
+    my[0] = make_float4(s.Tux, s.Tuy, s.Tuz, s.Tvx);
+    my[1] = make_float4(s.Tvy, s.Tvz, s.Twx, s.Twy);
+
+    const float cutoff = sqrtf((float)fmax((double)GSL_FF(logf(opacity), 2.f, 9.f), 0.000001));
+    float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+    const float Wf = (float)pp.W, Hf = (float)pp.H;
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i) {
+      float vx = GSL_FM(s_sin[i], cutoff), vy = GSL_FM(s_cos[i], cutoff);
+      float X = GSL_FA(s.Tuz, GSL_FF(s.Tux, vx, GSL_FM(s.Tuy, vy)));
+      float Y = GSL_FA(s.Tvz, GSL_FF(s.Tvx, vx, GSL_FM(s.Tvy, vy)));
+      float Z = GSL_FA(s.Twz, GSL_FF(s.Twx, vx, GSL_FM(s.Twy, vy)));
+      float ph = atan2f(X, Z);
+      float th = atan2f(sqrtf(GSL_FF(X, X, GSL_FM(Z, Z))), -Y);
+      float ppx = GSL_FD(GSL_FM(GSL_FS(ph, pp.HFOV_min), Wf), dH);
+      float ppy = GSL_FD(GSL_FM(GSL_FS(th, pp.VFOV_min), Hf), dV);
+      minx = fminf(minx, ppx); maxx = fmaxf(maxx, ppx);
+      miny = fminf(miny, ppy); maxy = fmaxf(maxy, ppy);
+    }
+    const float cx = GSL_FD(GSL_FM(GSL_FS(phi, pp.HFOV_min), Wf), dH);
+    const float cy = GSL_FD(GSL_FM(GSL_FS(theta, pp.VFOV_min), Hf), dV);
+    const float rad = fmaxf(fmaxf(GSL_FS(maxx, cx), GSL_FS(cx, minx)), fmaxf(GSL_FS(maxy, cy), GSL_FS(cy, miny)));
+    if (!((double)rad < 0.3)) {
+      const int my_radius = (int)ceilf(rad);
+      const float rf = (float)my_radius;
+      // getRect (auxiliary.h:47-55)
+      int rminx = min(pp.gx, max(0, (int)(GSL_FM(GSL_FS(cx, rf), 0.0625f))));
+      int rminy = min(pp.gy, max(0, (int)(GSL_FM(GSL_FS(cy, rf), 0.0625f))));
+      int rmaxx = min(pp.gx, max(0, (int)(GSL_FM(GSL_FS(GSL_FA(GSL_FA(cx, rf), 16.f), 1.f), 0.0625f))));
+      int rmaxy = min(pp.gy, max(0, (int)(GSL_FM(GSL_FS(GSL_FA(GSL_FA(cy, rf), 16.f), 1.f), 0.0625f))));
+      const int area = (rmaxx - rminx) * (rmaxy - rminy);
+      if (area != 0) {
+        // colour: SH or precomputed (forward.cu:269-279)
+        if (colors_precomp == nullptr) {
+          float dx = px - campos[0], dy = py - campos[1], dz = pz - campos[2];
+          float len = sqrtf(dx * dx + dy * dy + dz * dz);
+          dx = dx / len; dy = dy / len; dz = dz / len;
+          float4 c = eval_sh(pp.D, reinterpret_cast<const float4*>(shs) + (size_t)idx * pp.M, dx, dy, dz);
+          uint8_t cl = (uint8_t)((c.x < 0.f ? 1 : 0) | (c.y < 0.f ? 2 : 0) | (c.z < 0.f ? 4 : 0) | (c.w < 0.f ? 8 : 0));
+          clamped[idx] = cl;
+          rgb[idx] = make_float4(fmaxf(c.x, 0.f), fmaxf(c.y, 0.f), fmaxf(c.z, 0.f), fmaxf(c.w, 0.f));
+        }
+        my[2] = make_float4(s.Twz, cx, cy, opacity);
+        my[3] = make_float4(nx, ny, nz, r);
+        out_radius = my_radius;
+        out_tiles = (uint32_t)area;
+        out_rect = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx,
+                                (unsigned short)rmaxy);
+
+        // ---- conservative pixel box of the pair-level support (this design, not in the reference).
+        // A pair can only contribute if alpha >= 1/255  <=>  min(rho3d, rho2d) <= tau := 2 ln(255 o).
+        //  * rho2d <= tau : |pixel - means2D| <= sqrt(tau/2) (plain pixel distance, no wrap);
+        //  * rho3d <= tau with a positive in-range depth: the ray hits the splat plane inside the
+        //    ellipse |(u,v)|^2 <= tau in front of the sensor, so its direction lies in the spherical
+        //    cap of angular radius asin(D/r) around the centre direction, D = sqrt(tau*lambda_max).
+        // Both are inflated by safety margins; anything unusual falls back to the full image.
+        int bx0 = 0, bx1 = pp.W - 1, by0 = 0, by1 = pp.H - 1;
+        float tau = 2.f * logf(255.f * opacity);
+        float tauc = tau + 1e-3f * fabsf(tau) + 1e-3f;
+        if (tauc == tauc && fabsf(tauc) < 1e30f) {
+          if (tauc <= 0.f) {
+            by0 = 1; by1 = 0;  // can never reach alpha >= 1/255
+          } else {
+            float A = s.Tux * s.Tux + s.Tvx * s.Tvx + s.Twx * s.Twx;
+            float B = s.Tuy * s.Tuy + s.Tvy * s.Tvy + s.Twy * s.Twy;
+            float C = s.Tux * s.Tuy + s.Tvx * s.Tvy + s.Twx * s.Twy;
+            float hd = 0.5f * (A - B);
+            float lam = 0.5f * (A + B) + sqrtf(hd * hd + C * C);
+            float Dm = sqrtf(tauc * lam) * 1.001f;
+            float rd = sqrtf(0.5f * tauc) * 1.001f;
+            float sd = Dm / r;
+            float hx = -1.f, hy = -1.f;  // negative: unbounded
+            if (sd == sd && sd < 0.9f) {
+              float delta = asinf(sd) * 1.001f + 1e-6f;
+              hy = fmaxf(delta * Hf / dV, rd) + 0.02f;
+              float sth = rxz / r;  // sin of the polar angle of the centre
+              if (sd < 0.9f * sth) {
+                float dphi = asinf(sd / sth) * 1.001f + 1e-6f;
+                hx = fmaxf(dphi * Wf / dH, rd) + 0.02f;
+              }
+            }
+            if (hy >= 0.f && hy < 30000.f) {
+              by0 = max(0, (int)floorf(cy - hy));
+              by1 = min(pp.H - 1, (int)ceilf(cy + hy));
+              if (by0 > by1) { by0 = 1; by1 = 0; }
+            }
+            if (hx >= 0.f && hx < 30000.f && !(by0 > by1)) {
+              // azimuth is periodic with Wp pixels; collect the images that intersect the picture
+              float Wp = 6.2831853071795864f * Wf / dH;
+              int lo[3], hi[3], n = 0;
+#pragma unroll
+              for (int k = -1; k <= 1; ++k) {
+                float c = cx + (float)k * Wp;
+                int a = max(0, (int)floorf(c - hx)), b = min(pp.W - 1, (int)ceilf(c + hx));
+                if (a <= b) { lo[n] = a; hi[n] = b; ++n; }
+              }
+              if (n == 0) { by0 = 1; by1 = 0; }
+              else if (n == 1) { bx0 = lo[0]; bx1 = hi[0]; }
+              else if (n == 2 && lo[0] == 0 && hi[1] == pp.W - 1 && hi[0] + 1 < lo[1]) {
+                bx0 = lo[1]; bx1 = hi[0];  // wrapped: x >= bx0 || x <= bx1
+              }
+            }
+          }
+        }
+        out_box = make_short4((short)bx0, (short)by0, (short)bx1, (short)by1);
+      }
+    }
+  }
+  radii[idx] = out_radius;
+  tiles[idx] = out_tiles;
+  rect[idx] = out_rect;
+  pixbox[idx] = out_box;
+}
+
+int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
+                      const GeomView& g, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  PreParams pp;
+  pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.W = p.W; pp.H = p.H;
+  pp.gx = (p.W + GSL_BLOCK_X - 1) / GSL_BLOCK_X;
+  pp.gy = (p.H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
+  Fov f = make_fov(p);
+  pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
+  pp.scale_factor = p.scale_factor;
+  for (int i = 0; i < 12; ++i) pp.samp[i] = (float)(2 * GSL_MY_PI * i / 12);
+  int blocks = (p.P + 255) / 256;
+  k_preprocess_fwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.opacities, in.shs,
+                                          in.colors_precomp, in.mask, in.viewmatrix, in.campos, out.radii,
+                                          g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped);
+  return check_cuda(cudaGetLastError(), "k_preprocess_fwd launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward preprocess
+// ------------------------------------------------------------------------------------------------
+
+struct PreBwdParams {
+  int P, D, M, S, W, H, gstride;
+  float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
+};
+
+__device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {  // auxiliary.h:128-139
+  float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+  float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+  float3 o;
+  o.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+  o.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+  o.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+  return o;
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 operator*(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ void operator+=(float4& a, float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// SH VJP (backward.cu:17-134).  Writes dL_dsh[0..(D+1)^2) and returns the gradient w.r.t. the
+// mean through the view direction.
+__device__ __forceinline__ float3 sh_backward(int deg, int M, const float4* __restrict__ sh, float4 dL_dRGB,
+                                              float3 dir_orig, float4* __restrict__ dL_dsh) {
+  float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+  float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+  float4 dRGBdx = make_float4(0, 0, 0, 0), dRGBdy = dRGBdx, dRGBdz = dRGBdx;
+  dL_dsh[0] = kSH_C0 * dL_dRGB;
+  if (deg > 0) {
+    dL_dsh[1] = (-kSH_C1 * y) * dL_dRGB;
+    dL_dsh[2] = (kSH_C1 * z) * dL_dRGB;
+    dL_dsh[3] = (-kSH_C1 * x) * dL_dRGB;
+    dRGBdx = (-kSH_C1) * sh[3];
+    dRGBdy = (-kSH_C1) * sh[1];
+    dRGBdz = kSH_C1 * sh[2];
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      dL_dsh[4] = (kSH_C2[0] * xy) * dL_dRGB;
+      dL_dsh[5] = (kSH_C2[1] * yz) * dL_dRGB;
+      dL_dsh[6] = (kSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB;
+      dL_dsh[7] = (kSH_C2[3] * xz) * dL_dRGB;
+      dL_dsh[8] = (kSH_C2[4] * (xx - yy)) * dL_dRGB;
+      float4 s4 = sh[4], s5 = sh[5], s6 = sh[6], s7 = sh[7], s8 = sh[8];
+      dRGBdx += (kSH_C2[0] * y) * s4 + (kSH_C2[2] * 2.f * -x) * s6 + (kSH_C2[3] * z) * s7 + (kSH_C2[4] * 2.f * x) * s8;
+      dRGBdy += (kSH_C2[0] * x) * s4 + (kSH_C2[1] * z) * s5 + (kSH_C2[2] * 2.f * -y) * s6 + (kSH_C2[4] * 2.f * -y) * s8;
+      dRGBdz += (kSH_C2[1] * y) * s5 + (kSH_C2[2] * 2.f * 2.f * z) * s6 + (kSH_C2[3] * x) * s7;
+      if (deg > 2) {
+        dL_dsh[9] = (kSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB;
+        dL_dsh[10] = (kSH_C3[1] * xy * z) * dL_dRGB;
+        dL_dsh[11] = (kSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB;
+        dL_dsh[12] = (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB;
+        dL_dsh[13] = (kSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB;
+        dL_dsh[14] = (kSH_C3[5] * z * (xx - yy)) * dL_dRGB;
+        dL_dsh[15] = (kSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB;
+        float4 s9 = sh[9], s10 = sh[10], s11 = sh[11], s12 = sh[12], s13 = sh[13], s14 = sh[14], s15 = sh[15];
+        dRGBdx += (kSH_C3[0] * 3.f * 2.f * xy) * s9 + (kSH_C3[1] * yz) * s10 + (kSH_C3[2] * -2.f * xy) * s11 +
+                  (kSH_C3[3] * -3.f * 2.f * xz) * s12 + (kSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
+                  (kSH_C3[5] * 2.f * xz) * s14 + (kSH_C3[6] * 3.f * (xx - yy)) * s15;
+        dRGBdy += (kSH_C3[0] * 3.f * (xx - yy)) * s9 + (kSH_C3[1] * xz) * s10 +
+                  (kSH_C3[2] * (-3.f * yy + 4.f * zz - xx)) * s11 + (kSH_C3[3] * -3.f * 2.f * yz) * s12 +
+                  (kSH_C3[4] * -2.f * xy) * s13 + (kSH_C3[5] * -2.f * yz) * s14 + (kSH_C3[6] * -3.f * 2.f * xy) * s15;
+        dRGBdz += (kSH_C3[1] * xy) * s10 + (kSH_C3[2] * 4.f * 2.f * yz) * s11 +
+                  (kSH_C3[3] * 3.f * (2.f * zz - xx - yy)) * s12 + (kSH_C3[4] * 4.f * 2.f * xz) * s13 +
+                  (kSH_C3[5] * (xx - yy)) * s14;
+      }
+    }
+  }
+  float3 dL_ddir = make_float3(dot4(dRGBdx, dL_dRGB), dot4(dRGBdy, dL_dRGB), dot4(dRGBdz, dL_dRGB));
+  return dnormvdv3(dir_orig, dL_ddir);
+}
+
+// One thread per surfel.  Reads the packed accumulators, re-zeroes them (they must be all-zero when
+// the next backward starts), and writes EVERY element of every dense output.
+__global__ void __launch_bounds__(256) k_preprocess_bwd(
+    PreBwdParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
+    const float* __restrict__ rotations, const float* __restrict__ shs,
+    const float* __restrict__ viewmatrix, const float* __restrict__ campos,
+    const int* __restrict__ radii, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
+    float* __restrict__ grad, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
+    float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors, float* __restrict__ dL_dfeatures,
+    float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
+    float* __restrict__ dL_dcov3D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pp.P) return;
+  const int S = pp.S;
+  float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
+  float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
+             (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f) | (g2.z != 0.f) | (g2.w != 0.f) |
+             (gc.x != 0.f) | (gc.y != 0.f) | (gc.z != 0.f) | (gc.w != 0.f) | (gn.x != 0.f) | (gn.y != 0.f) |
+             (gn.z != 0.f);
+  // features: copy through and clean
+  const int nf4 = (S + 3) / 4;
+  for (int k = 0; k < nf4; ++k) {
+    float4 f = gq[5 + k];
+    float fv[4] = {f.x, f.y, f.z, f.w};
+    bool fany = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ch = 4 * k + j;
+      if (ch < S) { dL_dfeatures[(size_t)idx * S + ch] = fv[j]; fany |= (fv[j] != 0.f); }
+    }
+    if (fany) gq[5 + k] = zero4;
+  }
+  if (any) { gq[0] = zero4; gq[1] = zero4; gq[2] = zero4; gq[3] = zero4; gq[4] = zero4; }
+
+  // direct copies
+  dL_dopacity[idx] = g2.w;
+  if (dL_dcov3D) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) dL_dcov3D[(size_t)idx * 6 + j] = 0.f;
+  }
+  float4 dcol = gc;
+
+  float3 dmean = make_float3(0.f, 0.f, 0.f);
+  float3 dscale = make_float3(0.f, 0.f, 0.f);
+  float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 dm2 = make_float2(0.f, 0.f);
+  const bool vis = radii[idx] > 0;
+  const int ncoef = (pp.D + 1) * (pp.D + 1);
+
+  if (vis) {
+    const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
+    const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
+    const float vm8 = viewmatrix[8], vm9 = viewmatrix[9], vm10 = viewmatrix[10];
+    const float sx = scales[3 * idx], sy = scales[3 * idx + 1];
+    const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+    const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
+    const float4 r0 = rec[4 * (size_t)idx], r1 = rec[4 * (size_t)idx + 1], r2 = rec[4 * (size_t)idx + 2];
+    // view-space centre = z column of T (backward.cu:584-586, :684-686)
+    const float u = r0.z, v = r1.y, w = r2.x;
+    // raw accumulated dL_dT rows
+    float dTu_x = g0.x, dTu_y = g0.y, dTu_z = g0.z;
+    float dTv_x = g0.w, dTv_y = g1.x, dTv_z = g1.y;
+    float dTw_x = g1.z, dTw_y = g1.w, dTw_z = g2.x;
+    const float raw_du = dTu_z, raw_dv = dTv_z, raw_dw = dTw_z;
+    const float gm_x = g2.y, gm_y = g2.z;
+    const float dHr = pp.HFOV_max - pp.HFOV_min, dVr = pp.VFOV_max - pp.VFOV_min;
+    if (gm_x != 0.f || gm_y != 0.f) {  // backward.cu:579-595
+      const float Wrange = pp.W / dHr;
+      const float Hrange = pp.H / dVr;
+      const float r2_uw = u * u + w * w;
+      const float r_uw = sqrtf(u * u + w * w);
+      const float r2 = u * u + v * v + w * w;
+      dTu_z += gm_x * Wrange * w / r2_uw - gm_y * Hrange * u * v / (r_uw * r2);
+      dTv_z += gm_y * Hrange * r_uw / r2;
+      dTw_z += -gm_x * Wrange * u / r2_uw - gm_y * Hrange * v * w / (r_uw * r2);
+    }
+    // dL_dM = P * dL_dT^T, P = rotation part of the view matrix as used in T = M^T P
+    // (backward.cu:598): world-space gradients of L0, L1 and the mean.
+    // dL_dM[j] (j = 0: L0, 1: L1, 2: mean) = V^T-rotation applied to column j of dL_dT rows.
+    float3 dL0 = make_float3(vm0 * dTu_x + vm1 * dTv_x + vm2 * dTw_x, vm4 * dTu_x + vm5 * dTv_x + vm6 * dTw_x,
+                             vm8 * dTu_x + vm9 * dTv_x + vm10 * dTw_x);
+    float3 dL1 = make_float3(vm0 * dTu_y + vm1 * dTv_y + vm2 * dTw_y, vm4 * dTu_y + vm5 * dTv_y + vm6 * dTw_y,
+                             vm8 * dTu_y + vm9 * dTv_y + vm10 * dTw_y);
+    dmean = make_float3(vm0 * dTu_z + vm1 * dTv_z + vm2 * dTw_z, vm4 * dTu_z + vm5 * dTv_z + vm6 * dTw_z,
+                        vm8 * dTu_z + vm9 * dTv_z + vm10 * dTw_z);
+    // normal gradient back to world, sign by the UNFLIPPED view normal's z (backward.cu:599-603)
+    float3 dtn = make_float3(vm0 * gn.x + vm1 * gn.y + vm2 * gn.z, vm4 * gn.x + vm5 * gn.y + vm6 * gn.z,
+                             vm8 * gn.x + vm9 * gn.y + vm10 * gn.z);
+    const float nz_view = vm2 * R.r20 + vm6 * R.r21 + vm10 * R.r22;
+    const float mult = nz_view < 0.f ? 1.f : -1.f;
+    dtn.x *= mult; dtn.y *= mult; dtn.z *= mult;
+    // dL_dscale, dL_dR (backward.cu:604-619)
+    dscale.x = dL0.x * R.r00 + dL0.y * R.r01 + dL0.z * R.r02;
+    dscale.y = dL1.x * R.r10 + dL1.y * R.r11 + dL1.z * R.r12;
+    dscale.z = 0.f;
+    // v_R columns: c0 = dL0*sx, c1 = dL1*sy, c2 = dtn ; vR[c][r]
+    const float v00 = dL0.x * sx, v01 = dL0.y * sx, v02 = dL0.z * sx;
+    const float v10 = dL1.x * sy, v11 = dL1.y * sy, v12 = dL1.z * sy;
+    const float v20 = dtn.x, v21 = dtn.y, v22 = dtn.z;
+    {  // quat_to_rotmat_vjp (auxiliary.h:230-274)
+      float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+      float qw = q.x * s, qx = q.y * s, qy = q.z * s, qz = q.w * s;
+      drot.x = 2.f * (qx * (v12 - v21) + qy * (v20 - v02) + qz * (v01 - v10));
+      drot.y = 2.f * (-2.f * qx * (v11 + v22) + qy * (v01 + v10) + qz * (v02 + v20) + qw * (v12 - v21));
+      drot.z = 2.f * (qx * (v01 + v10) - 2.f * qy * (v00 + v22) + qz * (v12 + v21) + qw * (v20 - v02));
+      drot.w = 2.f * (qx * (v02 + v20) + qy * (v12 + v21) - 2.f * qz * (v00 + v11) + qw * (v01 - v10));
+    }
+    // SH (backward.cu:676-677)
+    if (shs != nullptr) {
+      const uint8_t cl = clamped[idx];
+      float4 dRGB = make_float4((cl & 1) ? 0.f : dcol.x, (cl & 2) ? 0.f : dcol.y, (cl & 4) ? 0.f : dcol.z,
+                                (cl & 8) ? 0.f : dcol.w);
+      // the reference masks dL_dcolors only in a local copy; the returned tensor is discarded on the SH
+      // path by the Python wrapper semantics (colors_precomp is empty), so dcol stays as accumulated.
+      float3 dir = make_float3(means3D[3 * idx] - campos[0], means3D[3 * idx + 1] - campos[1],
+                               means3D[3 * idx + 2] - campos[2]);
+      float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)idx * pp.M;
+      float3 dm = sh_backward(pp.D, pp.M, reinterpret_cast<const float4*>(shs) + (size_t)idx * pp.M, dRGB, dir,
+                              out_sh);
+      for (int k = ncoef; k < pp.M; ++k) out_sh[k] = zero4;
+      dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
+    }
+    // densification proxy (backward.cu:684-711), from the RAW accumulated dT z-column
+    const float phi = atan2f(u, w);
+    dm2.x = (float)((raw_du * w + raw_dw * (-u)) * 0.5 * dHr);
+    const float du_dth = -v * sinf(phi), dv_dth = sqrtf(u * u + w * w), dw_dth = -v * cosf(phi);
+    dm2.y = (float)((raw_du * du_dth + raw_dv * dv_dth + raw_dw * dw_dth) * 0.5 * dVr * pp.W / pp.H);
+  } else if (shs != nullptr) {
+    float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)idx * pp.M;
+    for (int k = 0; k < pp.M; ++k) out_sh[k] = zero4;
+  }
+  dL_dmeans3D[3 * (size_t)idx] = dmean.x; dL_dmeans3D[3 * (size_t)idx + 1] = dmean.y; dL_dmeans3D[3 * (size_t)idx + 2] = dmean.z;
+  dL_dscales[3 * (size_t)idx] = dscale.x; dL_dscales[3 * (size_t)idx + 1] = dscale.y; dL_dscales[3 * (size_t)idx + 2] = dscale.z;
+  reinterpret_cast<float4*>(dL_drot)[idx] = drot;
+  reinterpret_cast<float4*>(dL_dmeans2D)[idx] = make_float4(dm2.x, dm2.y, 0.f, 0.f);
+  reinterpret_cast<float4*>(dL_dcolors)[idx] = dcol;
+}
+
+int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
+                               gsl_bwd_outputs& gout, const GeomView& g, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  PreBwdParams pp;
+  pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.S = p.S;
+  {
+    // The reference re-derives W,H from focal*tan*2 in float (rasterizer_impl.cu:440-441,
+    // backward.cu:658-659); reproduce the truncation instead of assuming it round-trips.
+    volatile float fy = p.H / (2.0f * p.tanfovy), fx = p.W / (2.0f * p.tanfovx);
+    volatile float wf = fx * p.tanfovx, hf = fy * p.tanfovy;
+    volatile float w2 = wf * 2, h2 = hf * 2;
+    pp.W = (int)w2; pp.H = (int)h2;
+    if (!(p.tanfovx == p.tanfovx) || p.tanfovx == 0.f) pp.W = p.W;
+    if (!(p.tanfovy == p.tanfovy) || p.tanfovy == 0.f) pp.H = p.H;
+  }
+  pp.gstride = grad_stride(p.S);
+  Fov f = make_fov(p);
+  pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
+  int blocks = (p.P + 255) / 256;
+  k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.viewmatrix,
+                                          in.campos, fwd.radii, g.rec, g.clamped, g.grad, gout.dL_dmeans3D,
+                                          gout.dL_dmeans2D, gout.dL_dsh, gout.dL_dcolors, gout.dL_dfeatures,
+                                          gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D);
+  return check_cuda(cudaGetLastError(), "k_preprocess_bwd launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// markVisible (pinhole test kept for API parity; never on the training path)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mark_visible(int P, const float* __restrict__ pts, const float* __restrict__ vm,
+                               const float* __restrict__ pm, uint8_t* __restrict__ present) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  float x = pts[3 * idx], y = pts[3 * idx + 1], z = pts[3 * idx + 2];
+  float hx = pm[0] * x + pm[4] * y + pm[8] * z + pm[12];
+  float hy = pm[1] * x + pm[5] * y + pm[9] * z + pm[13];
+  float hw = pm[3] * x + pm[7] * y + pm[11] * z + pm[15];
+  float pw = 1.0f / (hw + 0.0000001f);
+  float projx = hx * pw, projy = hy * pw;
+  float vz = vm[2] * x + vm[6] * y + vm[10] * z + vm[14];
+  bool out = vz <= 0.2f || (projx < -1.3 || projx > 1.3 || projy < -1.3 || projy > 1.3);
+  present[idx] = out ? 0 : 1;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                        uint8_t* present, cudaStream_t st) {
+  if (P == 0) return 0;
+  k_mark_visible<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, viewmatrix, projmatrix, present);
+  return check_cuda(cudaGetLastError(), "k_mark_visible launch");
+}
+
+}  // namespace gsl

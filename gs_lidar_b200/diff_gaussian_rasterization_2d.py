@@ -1,0 +1,392 @@
+"""Drop-in replacement for GS-LiDAR's gaussian_renderer/diff_gaussian_rasterization_2d.py.
+
+Same public names, keyword arguments, return tuple, dtypes, shapes and autograd contract as the
+reference module (reference: gaussian_renderer/diff_gaussian_rasterization_2d.py:28-267), so that
+`gaussian_renderer/__init__.py:10` can switch with one import line:
+
+    from gs_lidar_b200.diff_gaussian_rasterization_2d import GaussianRasterizationSettings, GaussianRasterizer
+
+Host side only: argument marshalling, a grow-only workspace pool (replaces the reference's
+per-call geomBuffer/binningBuffer/imgBuffer tensors, rasterize_points.cu:84-91) and the
+torch.autograd.Function.  All computation happens in libgsl_b200.so (hand-written sm_100a CUDA);
+there is no PyTorch or CPU fallback.
+"""
+import ctypes as C
+import threading
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_lib = L.load()
+
+NUM_CHANNELS = 4  # cuda_rasterizer/config.h:12
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    copied_tensors = [item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple]
+    return tuple(copied_tensors)
+
+
+# --------------------------------------------------------------------------------------------------
+# workspace pool
+# --------------------------------------------------------------------------------------------------
+class _Workspace:
+    """Three device scratch chunks + a pinned int32[2] for the instance count."""
+
+    def __init__(self, device):
+        self.device = device
+        self.geom = torch.zeros(0, dtype=torch.uint8, device=device)
+        self.binning = torch.empty(0, dtype=torch.uint8, device=device)
+        self.image = torch.empty(0, dtype=torch.uint8, device=device)
+        self.r_capacity = 0
+        self.host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.key = None  # (P, S) the geom chunk was last laid out for
+
+    def ensure(self, params, r_capacity):
+        sz = L.gsl_ws_sizes()
+        L.check(_lib.gsl_workspace_sizes(C.byref(params), int(r_capacity), C.byref(sz)), "gsl_workspace_sizes")
+        key = (params.P, params.S)
+        if self.geom.numel() < sz.geom_bytes or self.key != key:
+            # the packed gradient accumulators inside the geom chunk must start all-zero and the
+            # layout depends on (P, S): re-zero on any relayout.
+            n = max(int(sz.geom_bytes), self.geom.numel())
+            if self.geom.numel() < n:
+                self.geom = torch.zeros(n + n // 8, dtype=torch.uint8, device=self.device)
+            else:
+                self.geom.zero_()
+            self.key = key
+        if self.image.numel() < sz.image_bytes:
+            self.image = torch.empty(int(sz.image_bytes), dtype=torch.uint8, device=self.device)
+        if self.binning.numel() < sz.binning_bytes or self.r_capacity < r_capacity:
+            self.binning = torch.empty(int(sz.binning_bytes), dtype=torch.uint8, device=self.device)
+        self.r_capacity = int(r_capacity)
+
+    def as_struct(self):
+        ws = L.gsl_workspace()
+        ws.geom = self.geom.data_ptr()
+        ws.geom_bytes = self.geom.numel()
+        ws.binning = self.binning.data_ptr() if self.binning.numel() else None
+        ws.binning_bytes = self.binning.numel()
+        ws.image = self.image.data_ptr()
+        ws.image_bytes = self.image.numel()
+        ws.r_capacity = self.r_capacity
+        ws.num_rendered_host = self.host.data_ptr()
+        return ws
+
+
+class _Pool:
+    def __init__(self):
+        self.free = {}
+        self.lock = threading.Lock()
+        self.r_hint = {}
+
+    def acquire(self, device):
+        with self.lock:
+            lst = self.free.setdefault(device, [])
+            if lst:
+                return lst.pop()
+        return _Workspace(device)
+
+    def release(self, ws):
+        with self.lock:
+            self.free.setdefault(ws.device, []).append(ws)
+
+
+_pool = _Pool()
+
+
+class _Holder:
+    """Keeps a workspace attached to one forward call until its backward ran (or it is dropped)."""
+
+    def __init__(self, ws):
+        self.ws = ws
+
+    def release(self):
+        if self.ws is not None:
+            _pool.release(self.ws)
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def _ptr(t):
+    return t.data_ptr() if (t is not None and t.numel() > 0) else None
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _make_params(settings, P, S, M):
+    p = L.gsl_params()
+    p.P, p.S, p.D, p.M = int(P), int(S), int(settings.sh_degree), int(M)
+    p.W, p.H = int(settings.image_width), int(settings.image_height)
+    p.tanfovx, p.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
+    p.scale_modifier = float(settings.scale_modifier)
+    p.vfov_min, p.vfov_max = float(settings.vfov[0]), float(settings.vfov[1])
+    p.hfov_min, p.hfov_max = float(settings.hfov[0]), float(settings.hfov[1])
+    p.scale_factor = float(settings.scale_factor)
+    p.prefiltered = int(bool(settings.prefiltered))
+    p.flags = L.GSL_FLAG_DEBUG_SYNC if settings.debug else 0
+    return p
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
+                        cov3Ds_precomp, mask, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, features, opacities, scales,
+                                     rotations, cov3Ds_precomp, mask, raster_settings)
+
+
+def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rotations, mask, settings):
+    """Runs the forward pass; returns (outputs..., holder, params, keepalive inputs)."""
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("gs_lidar_b200 runs on CUDA tensors only (no CPU fallback)")
+    dev = means3D.device
+    P = means3D.shape[0]
+    S = features.shape[1] if features.dim() == 2 else 0
+    M = sh.shape[1] if (sh.numel() != 0 and sh.dim() == 3) else 0
+    H, W = int(settings.image_height), int(settings.image_width)
+    if scales.numel() == 0 or rotations.numel() == 0:
+        if P > 0:
+            raise RuntimeError("scales and rotations are required: like the reference kernels "
+                               "(forward.cu:237) the cov3D_precomp path is not computed")
+
+    inputs = dict(
+        background=_f32c(settings.bg), means3D=_f32c(means3D), shs=_f32c(sh), colors_precomp=_f32c(colors_precomp),
+        features=_f32c(features), opacities=_f32c(opacities), scales=_f32c(scales), rotations=_f32c(rotations),
+        mask=mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous(),
+        viewmatrix=_f32c(settings.viewmatrix), projmatrix=_f32c(settings.projmatrix), campos=_f32c(settings.campos))
+    params = _make_params(settings, P, S, M)
+
+    with torch.cuda.device(dev):
+        out_contrib = torch.empty((2, H, W), dtype=torch.int32, device=dev)
+        out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        out_feature = torch.empty((S + 3, H, W), dtype=torch.float32, device=dev)
+        out_depth = torch.empty((4, H, W), dtype=torch.float32, device=dev)
+        out_alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+
+        fin = L.gsl_fwd_inputs()
+        for k, t in inputs.items():
+            setattr(fin, k, _ptr(t))
+        fin.cov3D_precomp = None
+        fout = L.gsl_fwd_outputs()
+        fout.out_contrib, fout.out_color, fout.out_feature = out_contrib.data_ptr(), out_color.data_ptr(), out_feature.data_ptr()
+        fout.out_depth, fout.out_alpha, fout.radii = out_depth.data_ptr(), out_alpha.data_ptr(), _ptr(radii)
+
+        ws = _pool.acquire(dev)
+        holder = _Holder(ws)
+        hint = _pool.r_hint.get((dev, P, W, H), max(4 * P, 1024))
+        ws.ensure(params, max(ws.r_capacity, hint))
+        wss = ws.as_struct()
+        st = _stream_ptr(dev)
+        L.check(_lib.gsl_forward_preprocess(C.byref(params), C.byref(fin), C.byref(fout), C.byref(wss), st),
+                "gsl_forward_preprocess")
+        ws.event.record(torch.cuda.current_stream(dev))
+        ws.event.synchronize()
+        R = int(ws.host[0])
+        if R > ws.r_capacity:
+            ws.ensure(params, R + R // 4)
+            wss = ws.as_struct()
+        _pool.r_hint[(dev, P, W, H)] = max(R + R // 4, 1024)
+        L.check(_lib.gsl_forward_render(C.byref(params), C.byref(fin), C.byref(fout), C.byref(wss), st),
+                "gsl_forward_render")
+    outs = (out_contrib, out_color, out_feature, out_depth, out_alpha, radii)
+    return outs, holder, params, inputs, R
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
+                cov3Ds_precomp, mask, raster_settings):
+        args = (means3D, sh, colors_precomp, features, opacities, scales, rotations, mask, raster_settings)
+        if raster_settings.debug:
+            cpu_args = cpu_deep_copy_tuple(args[:-1])  # copy them before they can be corrupted
+            try:
+                outs, holder, params, inputs, R = _forward_impl(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            outs, holder, params, inputs, R = _forward_impl(*args)
+        contrib, color, feature, depth, alpha, radii = outs
+
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = R
+        ctx.gsl_params = params
+        ctx.means2D_shape = tuple(means2D.shape)
+        ctx.cov_shape = tuple(cov3Ds_precomp.shape)
+        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        if needs_grad:
+            ctx.holder = holder
+            ctx.inputs = inputs  # contiguous fp32 views the kernels read again in backward
+            ctx.save_for_backward(contrib, radii)
+        else:
+            holder.release()
+            ctx.holder = None
+        ctx.mark_non_differentiable(contrib, radii)
+        return contrib, color, feature, depth, alpha, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_contrib, grad_out_color, grad_out_feature, grad_depth, grad_alpha, _):
+        holder = ctx.holder
+        if holder is None or holder.ws is None:
+            raise RuntimeError("gs_lidar_b200: the workspace of this forward call was already released "
+                               "(backward called twice, or forward ran without grad)")
+        params, inputs, settings = ctx.gsl_params, ctx.inputs, ctx.raster_settings
+        contrib, radii = ctx.saved_tensors
+        dev = contrib.device
+        P, S, M = params.P, params.S, params.M
+        H, W = params.H, params.W
+
+        def cot(g, shape):
+            if g is None:
+                return torch.zeros(shape, dtype=torch.float32, device=dev)
+            return _f32c(g)
+
+        g_color = cot(grad_out_color, (NUM_CHANNELS, H, W))
+        g_feature = cot(grad_out_feature, (S + 3, H, W))
+        g_depth = cot(grad_depth, (4, H, W))
+        g_alpha = cot(grad_alpha, (1, H, W))
+
+        with torch.cuda.device(dev):
+            e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+            d_means3D, d_means2D = e(P, 3), e(P, 4)
+            d_colors, d_features, d_opacity = e(P, NUM_CHANNELS), e(P, S), e(P, 1)
+            d_cov3D = e(P, 6)
+            d_sh = e(P, M, NUM_CHANNELS)
+            d_scales, d_rot = e(P, 3), e(P, 4)
+
+            fin = L.gsl_fwd_inputs()
+            for k, t in inputs.items():
+                setattr(fin, k, _ptr(t))
+            fin.cov3D_precomp = None
+            ffwd = L.gsl_fwd_outputs()
+            ffwd.out_contrib, ffwd.radii = contrib.data_ptr(), _ptr(radii)
+            gin = L.gsl_bwd_inputs()
+            gin.dL_dout_color, gin.dL_dout_depth = g_color.data_ptr(), g_depth.data_ptr()
+            gin.dL_dout_alpha, gin.dL_dout_feature = g_alpha.data_ptr(), g_feature.data_ptr()
+            gout = L.gsl_bwd_outputs()
+            gout.dL_dmeans3D, gout.dL_dmeans2D, gout.dL_dsh = _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh)
+            gout.dL_dcolors, gout.dL_dfeatures, gout.dL_dopacity = _ptr(d_colors), _ptr(d_features), _ptr(d_opacity)
+            gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D = _ptr(d_scales), _ptr(d_rot), _ptr(d_cov3D)
+            wss = holder.ws.as_struct()
+
+            def run():
+                L.check(_lib.gsl_backward(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gin), C.byref(gout),
+                                          C.byref(wss), _stream_ptr(dev)), "gsl_backward")
+
+            if settings.debug:
+                cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) + tuple(inputs.values()))
+                try:
+                    run()
+                except Exception as ex:
+                    torch.save(cpu_args, "snapshot_bw.dump")
+                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                    raise ex
+            else:
+                run()
+        if not _KEEP_WORKSPACE_AFTER_BACKWARD:
+            holder.release()
+
+        grad_cov = d_cov3D if tuple(d_cov3D.shape) == ctx.cov_shape else None
+        grads = (d_means3D, d_means2D, d_sh if M > 0 else None, d_colors if inputs["colors_precomp"].numel() else None,
+                 d_features, d_opacity, d_scales, d_rot, grad_cov, None, None)
+        return grads
+
+
+# Set True to allow a second backward through the same graph (retain_graph=True); the workspace is
+# then only returned to the pool when the autograd node is freed.
+_KEEP_WORKSPACE_AFTER_BACKWARD = False
+
+
+def set_keep_workspace_after_backward(flag: bool):
+    global _KEEP_WORKSPACE_AFTER_BACKWARD
+    _KEEP_WORKSPACE_AFTER_BACKWARD = bool(flag)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    vfov: tuple
+    hfov: tuple
+    scale_factor: float
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = _f32c(positions)
+            P = pos.shape[0]
+            present = torch.zeros((P,), dtype=torch.bool, device=pos.device)
+            if P > 0:
+                vm, pm = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
+                with torch.cuda.device(pos.device):
+                    L.check(_lib.gsl_mark_visible(P, pos.data_ptr(), vm.data_ptr(), pm.data_ptr(),
+                                                  present.data_ptr(), _stream_ptr(pos.device)), "gsl_mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, features=None, scales=None,
+                rotations=None, cov3D_precomp=None, mask=None):
+        raster_settings = self.raster_settings
+
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+        dev = means3D.device
+        empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+        if shs is None:
+            shs = empty()
+        if colors_precomp is None:
+            colors_precomp = empty()
+        if features is None:
+            features = torch.empty_like(means3D[..., :0])
+        if scales is None:
+            scales = empty()
+        if rotations is None:
+            rotations = empty()
+        if cov3D_precomp is None:
+            cov3D_precomp = empty()
+        if mask is None:
+            mask = torch.ones_like(means3D[:, :1], dtype=torch.bool)
+
+        # Invoke the CUDA rasterization routine
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, features, opacities, scales, rotations,
+                                   cov3D_precomp, mask, raster_settings)

@@ -1,0 +1,185 @@
+/*
+ * gsl_b200.h -- C-ABI of the B200-native panoramic 2D-Gaussian-surfel rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path of GS-LiDAR
+ * (diff-gaussian-rasterization-2d).  Every entry point cites the reference interface it
+ * replaces (paths relative to /root/reference):
+ *
+ *   gsl_forward*      <- RasterizeGaussiansCUDA            rasterize_points.cu:35-139
+ *                        CudaRasterizer::Rasterizer::forward  cuda_rasterizer/rasterizer.h:28-63
+ *   gsl_backward      <- RasterizeGaussiansBackwardCUDA    rasterize_points.cu:141-247
+ *                        CudaRasterizer::Rasterizer::backward cuda_rasterizer/rasterizer.h:65-103
+ *   gsl_mark_visible  <- markVisible                       rasterize_points.cu:249-267
+ *                        CudaRasterizer::Rasterizer::markVisible cuda_rasterizer/rasterizer.h:22-27
+ *   gsl_workspace_*   <- GeometryState/ImageState/BinningState::fromChunk + required<T>()
+ *                        cuda_rasterizer/rasterizer_impl.h:26-70, rasterizer_impl.cu:159-208
+ *
+ * Plain pointers and sizes only: no torch / pybind / C++ types cross this boundary.  All data
+ * pointers are DEVICE pointers (float32 contiguous, same layouts as the reference tensors)
+ * unless a parameter name ends in _host.  `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success, a negative GSL_E* code on a validation error, or a
+ * positive cudaError_t; gsl_last_error() returns a thread-local message for the last failure.
+ * Nothing here falls back to a CPU path.
+ */
+#ifndef GSL_B200_H_
+#define GSL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSL_API __attribute__((visibility("default")))
+#else
+#define GSL_API
+#endif
+
+#define GSL_ABI_VERSION 1
+#define GSL_NUM_CHANNELS 4 /* cuda_rasterizer/config.h:12 */
+#define GSL_TILE 16        /* cuda_rasterizer/config.h:13-14 */
+#define GSL_MAX_FEATURES 10 /* forward.cu:348: F[13] holds S features + 3 normal channels */
+
+#define GSL_EINVAL -1   /* bad argument (shape, null pointer, S > 10, ...) */
+#define GSL_ENOSPACE -2 /* a workspace buffer is smaller than gsl_workspace_sizes() demands */
+#define GSL_ESTATE -3   /* backward called without a matching forward */
+
+/* flags */
+#define GSL_FLAG_DEBUG_SYNC 1u /* raster_settings.debug: sync + check after every stage */
+
+/* Mirrors the scalar arguments of Rasterizer::forward / ::backward
+ * (rasterizer.h:31-63) plus GaussianRasterizationSettings (diff_gaussian_rasterization_2d.py:194-209). */
+typedef struct gsl_params {
+  int32_t P;          /* surfels */
+  int32_t S;          /* extra feature channels (features.shape[1]), 0..10 */
+  int32_t D;          /* active SH degree 0..3 */
+  int32_t M;          /* stored SH coefficients per surfel (0 when colors_precomp is used) */
+  int32_t W, H;       /* image_width, image_height */
+  float tanfovx, tanfovy; /* carried for API parity; unused by the math like in the reference */
+  float scale_modifier;   /* carried for API parity; the reference ignores it (forward.cu:85) */
+  float vfov_min, vfov_max, hfov_min, hfov_max; /* degrees */
+  float scale_factor;
+  int32_t prefiltered;
+  uint32_t flags;
+} gsl_params;
+
+/* Byte sizes of the three scratch chunks (the reference's geomBuffer / binningBuffer / imgBuffer). */
+typedef struct gsl_ws_sizes {
+  size_t geom_bytes;    /* function of P */
+  size_t binning_bytes; /* function of the instance capacity R_cap */
+  size_t image_bytes;   /* function of W*H */
+} gsl_ws_sizes;
+
+/* Caller-owned scratch.  The wrapper keeps these alive from forward to backward exactly as the
+ * reference keeps geomBuffer/binningBuffer/imgBuffer in ctx (diff_gaussian_rasterization_2d.py:122). */
+typedef struct gsl_workspace {
+  void* geom;    size_t geom_bytes;
+  void* binning; size_t binning_bytes;
+  void* image;   size_t image_bytes;
+  int64_t r_capacity;     /* instance capacity the binning chunk was sized for */
+  int32_t* num_rendered_host; /* PINNED host int[2]: [0]=R (tile instances), [1]=overflow flag */
+} gsl_workspace;
+
+typedef struct gsl_fwd_inputs {
+  const float* background;     /* (4) */
+  const float* means3D;        /* (P,3) */
+  const float* shs;            /* (P,M,4) or NULL */
+  const float* colors_precomp; /* (P,4) or NULL */
+  const float* features;       /* (P,S) or NULL when S==0 */
+  const float* opacities;      /* (P,1) */
+  const float* scales;         /* (P,3) */
+  const float* rotations;      /* (P,4) */
+  const float* cov3D_precomp;  /* ignored, like the reference */
+  const uint8_t* mask;         /* (P,1) bool */
+  const float* viewmatrix;     /* (4,4) transposed world->camera, as scene/cameras.py:62 */
+  const float* projmatrix;     /* (4,4), only used by gsl_mark_visible */
+  const float* campos;         /* (3) */
+} gsl_fwd_inputs;
+
+typedef struct gsl_fwd_outputs {
+  int32_t* out_contrib; /* (2,H,W): last contributor, median contributor */
+  float* out_color;     /* (4,H,W) */
+  float* out_feature;   /* (S+3,H,W) */
+  float* out_depth;     /* (4,H,W): mean, median, distortion, mean of squares */
+  float* out_alpha;     /* (1,H,W) = 1 - T  (the reference returns T and Python does 1-T) */
+  int32_t* radii;       /* (P) */
+} gsl_fwd_outputs;
+
+typedef struct gsl_bwd_inputs {
+  const float* dL_dout_color;   /* (4,H,W) */
+  const float* dL_dout_depth;   /* (4,H,W) */
+  const float* dL_dout_alpha;   /* (1,H,W)  (fed as dL_dout_mask in the reference) */
+  const float* dL_dout_feature; /* (S+3,H,W) */
+} gsl_bwd_inputs;
+
+typedef struct gsl_bwd_outputs {
+  float* dL_dmeans3D;  /* (P,3) */
+  float* dL_dmeans2D;  /* (P,4): densification proxy in .xy, zeros in .zw (backward.cu:700-711) */
+  float* dL_dsh;       /* (P,M,4) or NULL */
+  float* dL_dcolors;   /* (P,4) */
+  float* dL_dfeatures; /* (P,S) or NULL */
+  float* dL_dopacity;  /* (P,1) */
+  float* dL_dscales;   /* (P,3) */
+  float* dL_drotations;/* (P,4) */
+  float* dL_dcov3D;    /* (P,6) all zero, like the reference; may be NULL */
+} gsl_bwd_outputs;
+
+GSL_API int gsl_abi_version(void);
+GSL_API const char* gsl_last_error(void);
+
+/* Sizes of the scratch chunks for P surfels, r_capacity tile instances and W*H pixels. */
+GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_sizes* out);
+
+/* Stage 1 of the forward pass: preprocess + tile-count scan.  Enqueues an async copy of the
+ * instance count R into ws->num_rendered_host[0]; never blocks the host. */
+GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
+                           gsl_workspace* ws, void* stream);
+
+/* Stage 2: key duplication, tile|depth sort, tile ranges and per-tile compositing.  Safe to
+ * enqueue speculatively: if the device-side R exceeds ws->r_capacity the kernels do nothing and
+ * num_rendered_host[1] is set to 1 (after the stream reaches that point); the caller then grows
+ * the binning chunk and calls this function again. */
+GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
+                       gsl_workspace* ws, void* stream);
+
+/* Blocking convenience with the semantics of Rasterizer::forward: runs both stages, waits for
+ * R, returns it in *num_rendered.  Returns GSL_ENOSPACE (with *num_rendered set) if the
+ * binning chunk is too small for R. */
+GSL_API int gsl_forward(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
+                gsl_workspace* ws, int32_t* num_rendered, void* stream);
+
+/* Backward pass for the forward that last used `ws`.  Writes every element of every output
+ * (no pre-zeroing needed by the caller). */
+GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                 const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream);
+
+/* Pinhole frustum test, present[i] = in_frustum(means3D[i]) (auxiliary.h:157-180). */
+GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* Test/diagnostic export of the internal state in the REFERENCE's layouts so parity tests can
+ * compare bit-for-bit (rasterizer_impl.h:26-63).  Any pointer may be NULL. */
+typedef struct gsl_state_export {
+  float* depths;          /* (P) */
+  float* means2D;         /* (P,2) */
+  float* transMat;        /* (P,9) */
+  float* normal_opacity;  /* (P,4) */
+  float* rgb;             /* (P,4) */
+  uint8_t* clamped;       /* (P,4) */
+  uint32_t* tiles_touched;/* (P) */
+  uint32_t* point_offsets;/* (P) inclusive scan */
+  uint64_t* point_list_keys; /* (R) sorted keys */
+  uint32_t* point_list;      /* (R) sorted surfel ids */
+  uint32_t* ranges;          /* (tiles,2) */
+  float* final_T;            /* (3,H,W): T, M1, M2 */
+  int16_t* pixbox;           /* (P,4) conservative pixel box x0,y0,x1,y1 (this design only) */
+} gsl_state_export;
+GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64_t R,
+                     const gsl_state_export* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSL_B200_H_ */
