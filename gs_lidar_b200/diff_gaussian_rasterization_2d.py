@@ -233,7 +233,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.gsl_params = params
         ctx.means2D_shape = tuple(means2D.shape)
         ctx.cov_shape = tuple(cov3Ds_precomp.shape)
-        needs_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        needs_grad = any(ctx.needs_input_grad)  # all False under torch.no_grad()
         if needs_grad:
             ctx.holder = holder
             ctx.inputs = inputs  # contiguous fp32 views the kernels read again in backward

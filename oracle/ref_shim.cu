@@ -185,4 +185,9 @@ int gslref_state(void* h, void** ptrs) {
 
 int gslref_num_channels() { return NUM_CHANNELS; }
 
+// device-to-device copy helper so the Python side needs no cudart binding of its own
+int gslref_copy(void* dst, const void* src, size_t nbytes) {
+  return (int)cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToDevice);
+}
+
 }  // extern "C"
