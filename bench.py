@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- panoramas/s, forward+backward, 1M synthetic surfels on a 66x1030 KITTI-360-shaped
+panorama (BASELINE.json metric; workload = configs[2], the config the metric is quoted on).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One process per GPU.  For N > 1 launch with torchrun (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* from the
+env): every rank renders its own LiDAR frame (camera pose) of the replicated surfel set, and the
+per-surfel gradients are summed with one NCCL all-reduce inside the timed step ("weak" scaling:
+per-GPU work is fixed, value = frames of all ranks / max-over-ranks time).
+
+A "step" is one forward+backward pass of the rasterizer op for one frame through the public
+GaussianRasterizer API.  Rank 0 prints ONE JSON line (see the module-level keys at the end).
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "panoramas/sec fwd+bwd at 1M surfels 66x1030"
+UNIT = "panoramas/s"
+WORKLOAD = "KITTI-360 seq 1908-shaped static training step: 1M synthetic surfels, fwd+bwd 66x1030 (hfov +-180, SH deg 3, S=4)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--surfels", type=int, default=1000000)
+    ap.add_argument("--height", type=int, default=66)
+    ap.add_argument("--width", type=int, default=1030)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-surfels", type=int, default=0, help="0 = pick from a quick calibration")
+    return ap.parse_args()
+
+
+def init_dist(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for nme, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def algorithmic_bytes(P, V, R, N, S, K, M):
+    """algorithmic bytes of one fwd+bwd panorama."""
+    fwd = 45 * P + V * (16 * K + 4 * S) + 4 * P + N * (8 + 16 + 4 * (S + 3) + 16 + 4)
+    bwd = N * (16 + 4 * (S + 3) + 16 + 4) + V * (44 + 16 * K + 4 * S) + P * (12 + 16 + 16 + 4 * S + 4 + 24 + 16 * M + 12 + 16)
+    binning = 40 * R
+    return fwd, bwd, binning
+
+
+def render_bwd_algorithmic_bytes(V, N, S):
+    """Dominant kernel (k_render_bwd), DESIGN.md 'kernels': cotangents + forward state per pixel,
+    one 64-B record + 16-B colour read and one packed gradient record written per visible surfel."""
+    per_px = 4 * (4 + (S + 3) + 4 + 1) + 12 + 8
+    per_surfel = 64 + 16 + 4 * (20 + ((S + 3) // 4) * 4)
+    return N * per_px + V * per_surfel
+
+
+def make_frame_pose(rank):
+    # frame k of a drive: yaw N(0, 0.5 deg)-like fixed offsets and +0.1*sf*k along x
+    yaw = [0.0, 0.4, -0.3, 0.7, -0.6, 0.2, -0.1, 0.5][rank % 8]
+    return dict(view_yaw_deg=yaw, view_shift=(0.01 * rank, 0.0, 0.0))
+
+
+def run_ours(args, rank, world, local):
+    from gs_lidar_b200 import synth, parallel
+    from gs_lidar_b200 import _lib as L
+    import gs_lidar_b200.diff_gaussian_rasterization_2d as G
+    dev = torch.device("cuda", local)
+    P, H, W, S = args.surfels, args.height, args.width, 4
+    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(rank)).to(dev)
+    cot_cpu = synth.make_cotangents(H, W, S, seed=1)
+    cot = {k: v.to(dev) for k, v in cot_cpu.items()}
+    settings = synth.settings_for(scene)
+    rast = G.GaussianRasterizer(settings)
+    names = ["means3D", "means2D", "opacities", "shs", "features", "scales", "rotations"]
+    leaves = dict(means3D=scene.means3D.clone(), means2D=torch.zeros((P, 4), device=dev), opacities=scene.opacities.clone(),
+                  shs=scene.shs.clone(), features=scene.features.clone(), scales=scene.scales.clone(),
+                  rotations=scene.rotations.clone())
+    for v in leaves.values():
+        v.requires_grad_(True)
+    bucket = parallel.GradBucket(parallel.surfel_grad_shapes(P, S, scene.shs.shape[1]), dev) if world > 1 else None
+    last = {}
+
+    def step(rasterizer=rast, cots=cot):
+        for v in leaves.values():
+            v.grad = None
+        contrib, color, feature, depth, alpha, radii = rasterizer(
+            means3D=leaves["means3D"], means2D=leaves["means2D"], opacities=leaves["opacities"], shs=leaves["shs"],
+            features=leaves["features"], scales=leaves["scales"], rotations=leaves["rotations"], mask=scene.mask)
+        torch.autograd.backward([color, feature, depth, alpha],
+                                [cots["color"], cots["feature"], cots["depth"], cots["alpha"]])
+        if bucket is not None:
+            bucket.load({k: leaves[k].grad for k in names})
+            bucket.all_reduce()
+        last.update(color=color, feature=feature, depth=depth, alpha=alpha, radii=radii, contrib=contrib)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # realised V and R (for the roofline arithmetic)
+    V = int((last["radii"] > 0).sum())
+    R = int(last["color"].grad_fn.num_rendered) if last["color"].grad_fn is not None else 0
+
+    # ---- timed region: device-resident inputs --------------------------------------------------
+    L.load().gsl_profile_read(None, None, 1)
+    L.load().gsl_profile_enable(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else {}
+    L.load().gsl_profile_enable(0)
+    kms = (C.c_double * L.GSL_K_COUNT)()
+    kn = (C.c_int64 * L.GSL_K_COUNT)()
+    L.load().gsl_profile_read(kms, kn, 1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- e2e: per-step host->device copy of the frame's inputs, device->host read of the result --
+    # Per-step inputs of the op are the camera (view matrix, camera centre) and the cotangent maps the
+    # loss produced from the host-side ground-truth panoramas; the surfel parameters are resident model
+    # state, exactly as scene/gaussian_model.py keeps them on the GPU in the reference's training loop.
+    pin = lambda x: x.clone().pin_memory()
+    h_cam = dict(viewmatrix=pin(scene.viewmatrix.cpu()), campos=pin(scene.campos.cpu()))
+    h_cot = {k: pin(v) for k, v in cot_cpu.items()}
+    d_cam = {k: torch.empty_like(v, device=dev) for k, v in h_cam.items()}
+    d_cot = {k: torch.empty_like(v, device=dev) for k, v in h_cot.items()}
+    h_out = dict(color=torch.empty((4, H, W)).pin_memory(), feature=torch.empty((S + 3, H, W)).pin_memory(),
+                 depth=torch.empty((4, H, W)).pin_memory(), alpha=torch.empty((1, H, W)).pin_memory(),
+                 gradsum=torch.empty((3,)).pin_memory())
+    h2d = sum(v.numel() * 4 for v in h_cam.values()) + sum(v.numel() * 4 for v in h_cot.values())
+    d2h = sum(v.numel() * 4 for v in h_out.values())
+
+    def e2e_step():
+        for k in h_cam:
+            d_cam[k].copy_(h_cam[k], non_blocking=True)
+        for k in h_cot:
+            d_cot[k].copy_(h_cot[k], non_blocking=True)
+        st = settings._replace(viewmatrix=d_cam["viewmatrix"], campos=d_cam["campos"])
+        step(G.GaussianRasterizer(st), d_cot)
+        for k in ("color", "feature", "depth", "alpha"):
+            h_out[k].copy_(last[k].detach(), non_blocking=True)
+        h_out["gradsum"].copy_(leaves["means3D"].grad.sum(0), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(5, args.steps // 2)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(e2e_ms, e2e_wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if rank != 0:
+        return None
+    N = H * W
+    K = (scene.sh_degree + 1) ** 2
+    M = scene.shs.shape[1]
+    fwd_b, bwd_b, bin_b = algorithmic_bytes(P, V, R, N, S, K, M)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    per_kernel = {}
+    for i in range(L.GSL_K_COUNT):
+        if kn[i] > 0:
+            per_kernel[L.load().gsl_kernel_name(i).decode()] = dict(ms_per_launch=kms[i] / kn[i], launches=int(kn[i]))
+    dom_id = max(range(L.GSL_K_COUNT), key=lambda i: kms[i] if i != 3 else -1.0)
+    dom_ms = kms[dom_id] / max(kn[dom_id], 1)
+    dom_name = L.load().gsl_kernel_name(dom_id).decode()
+    if dom_id == 6:
+        dom_bytes = render_bwd_algorithmic_bytes(V, N, S)
+    elif dom_id == 5:
+        dom_bytes = N * (8 + 16 + 4 * (S + 3) + 16 + 4 + 12) + V * (64 + 16 + 4 * S)
+    else:
+        dom_bytes = fwd_b if dom_id < 5 else bwd_b
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = {6: 156.6e6, 5: 102.7e6}.get(dom_id)  # ncu --set full, profiles/r01_render_kernels.md
+    step_bytes = fwd_b + bwd_b + bin_b
+    step_ms = ms / args.steps
+    value = world * args.steps / (ms * 1e-3)
+    res = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "visible_surfels": V, "tile_instances": R,
+                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, ", fp32 gradient all-reduce (NCCL) in the step" if world > 1 else ""),
+                   "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6),
+                   "grad_bucket_bytes": bucket.nbytes if bucket is not None else 0},
+        "clocks": clocks,
+        "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "note": "per-step camera + cotangent maps from pinned host memory, rendered maps + a gradient checksum read back; surfel parameters stay resident like model weights"},
+        "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                     "note": "compositing is FP32/latency-bound at 325 tiles, not HBM-bound; see profiles/"},
+        "step_roofline": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak},
+        "kernels": per_kernel,
+    }
+    return res
+
+
+def cpu_baseline(args, full=True):
+    """CPU oracle (plain-C port of the reference algorithm) timed on the host cores on a bounded sample."""
+    import numpy as np
+    import oracle
+    from gs_lidar_b200 import synth
+    o = oracle.CpuOracle()
+    H, W, S = args.height, args.width, 4
+
+    def run(P):
+        s = synth.make_scene(P, H=H, W=W, S=S, seed=0)
+        cot = {k: v.numpy() for k, v in synth.make_cotangents(H, W, S, seed=1).items()}
+        p = o.params(P, S, s.sh_degree, s.shs.shape[1], W, H, s.vfov, s.hfov, s.scale_factor, math.tan(-0.5), math.tan(-0.5))
+        a = [s.means3D.numpy(), s.scales.numpy(), s.rotations.numpy(), s.opacities.numpy(), s.shs.numpy()]
+        t0 = time.perf_counter()
+        st = o.forward(p, a[0], a[1], a[2], a[3], a[4], None, s.features.numpy(), s.mask.numpy(), s.viewmatrix.numpy(),
+                       s.campos.numpy(), s.bg.numpy())
+        o.backward(p, st, a[0], a[1], a[2], a[4], s.features.numpy(), s.viewmatrix.numpy(), s.campos.numpy(), s.bg.numpy(),
+                   cot["color"], cot["depth"], cot["alpha"], cot["feature"])
+        return time.perf_counter() - t0
+
+    t_small = run(50000)
+    P = args.cpu_sample_surfels
+    if P <= 0:
+        # CPU time grows ~linearly in surfels until pixels saturate; keep the sample within ~25 s
+        P = args.surfels if t_small * (args.surfels / 50000.0) < 25.0 else int(50000 * 25.0 / max(t_small, 1e-3))
+        P = max(50000, min(P, args.surfels))
+    t = run(P)
+    sample = "1 panorama fwd+bwd, %d of %d surfels, %dx%d" % (P, args.surfels, H, W)
+    if P < args.surfels:
+        sample += " (value = 1/time of this reduced sample; the full workload is slower)"
+    return {"value": 1.0 / t, "unit": UNIT, "cores": o.threads, "kind": "port", "sample": sample, "seconds": t}
+
+
+def run_reference(args, rank, world, local):
+    """Reference arm: the UNMODIFIED reference CUDA rasterizer (oracle/_ref) on the same GPU, same scene,
+    same cotangents; falls back to the CPU oracle port when the compiled reference is absent."""
+    if rank != 0:
+        return None
+    import oracle
+    from gs_lidar_b200 import synth
+    if not os.path.exists(oracle.REF_SO):
+        cb = cpu_baseline(args)
+        return {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 1, "steps": 1, "warmup": 0,
+                "ms_per_step": cb["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "compiled reference (oracle/_ref) missing: CPU port of the reference algorithm timed instead"}
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    dev = torch.device("cuda", local)
+    P, H, W, S = args.surfels, args.height, args.width, 4
+    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(0)).to(dev)
+    cot = {k: v.to(dev) for k, v in synth.make_cotangents(H, W, S, seed=1).items()}
+    ref = oracle.RefCuda()
+    a = common.ref_args(scene)
+    bufs = {}
+
+    def step():
+        f = ref.forward(a, zero_fill=True, outs=bufs.get("o"))
+        bufs["o"] = {k: v for k, v in f.items() if k != "R"}
+        bufs["g"] = ref.backward(a, f, cot, zero_fill=True, grads=bufs.get("g"))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), 0.0)
+    wall = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    value = args.steps / (ms * 1e-3)
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W,
+                       "what": "unmodified reference CUDA rasterizer (diff-gaussian-rasterization-2d) compiled for sm_100a by oracle/build_ref.sh, "
+                               "buffers pre-allocated, outputs/gradients zero-filled per step like its torch binding"},
+            "clocks": clocks,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                             "sample": "full workload on the GPU (the reference path is CUDA; it has no CPU implementation)"},
+            "e2e": {"value": args.steps / (max(ms, wall) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse_args()
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
+        sys.exit(1)
+    rank, world, local = init_dist(args)
+    if args.impl == "reference":
+        res = run_reference(args, rank, world, local)
+    else:
+        res = run_ours(args, rank, world, local)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                res["cpu_baseline"] = cpu_baseline(args)
+            except Exception as ex:  # the baseline must never take the measurement down
+                res["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and res is not None:
+        print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

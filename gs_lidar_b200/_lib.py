@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgsl_b200.so")
+LIB_PATH = os.environ.get("GSL_B200_LIB", os.path.join(HERE, "libgsl_b200.so"))  # override: dev builds only
 
 GSL_ABI_VERSION = 1
 GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
@@ -77,7 +77,15 @@ SYMBOLS = {
     "gsl_mark_visible": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
                                    C.POINTER(gsl_state_export), vp]),
+    "gsl_profile_enable": (C.c_int, [C.c_int]),
+    "gsl_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "gsl_kernel_name": (C.c_char_p, [C.c_int]),
 }
+GSL_K_COUNT = 8
+# kernels of THIS repo launched per forward / backward call (k_scan is three launches; the cub sort is
+# library code and not counted): used by bench.py for "gpu_launches".
+OWN_LAUNCHES_FWD = 1 + 3 + 1 + 1 + 1   # preprocess, scan x3, duplicate, tile_ranges, render_fwd
+OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
 
 _lib = None
 

@@ -3,9 +3,43 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
+#include <vector>
 #include "gsl_common.cuh"
 
 namespace gsl {
+
+// ---- per-kernel profiling ----------------------------------------------------------------------
+struct ProfRec { int id; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_pending;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_free;
+static double g_prof_ms[GSL_K_COUNT] = {0};
+static int64_t g_prof_n[GSL_K_COUNT] = {0};
+
+ProfScope::ProfScope(int id_, cudaStream_t st_) : id(id_), st(st_), slot(nullptr) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec* r = new ProfRec();
+  r->id = id;
+  if (!g_prof_free.empty()) {
+    r->e0 = g_prof_free.back().first; r->e1 = g_prof_free.back().second;
+    g_prof_free.pop_back();
+  } else {
+    cudaEventCreate(&r->e0); cudaEventCreate(&r->e1);
+  }
+  cudaEventRecord(r->e0, st);
+  slot = r;
+}
+ProfScope::~ProfScope() {
+  if (!slot) return;
+  ProfRec* r = (ProfRec*)slot;
+  cudaEventRecord(r->e1, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_pending.push_back(*r);
+  delete r;
+}
 
 static thread_local char g_err[512] = "";
 
@@ -176,6 +210,32 @@ GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewm
   if (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present))
     return set_error(GSL_EINVAL, "mark_visible: NULL pointer");
   return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_profile_enable(int on) { g_prof_on = on != 0; return 0; }
+
+GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_pending) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { g_prof_ms[r.id] += ms; g_prof_n[r.id] += 1; }
+    g_prof_free.push_back({r.e0, r.e1});
+  }
+  g_prof_pending.clear();
+  for (int i = 0; i < GSL_K_COUNT; ++i) {
+    if (total_ms) total_ms[i] = g_prof_ms[i];
+    if (launches) launches[i] = g_prof_n[i];
+    if (reset) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
+  }
+  return 0;
+}
+
+GSL_API const char* gsl_kernel_name(int id) {
+  static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_scan_(reduce|sums|down)", "k_duplicate",
+                                           "cub::DeviceRadixSort (library)", "k_tile_ranges", "k_render_fwd",
+                                           "k_render_bwd", "k_preprocess_bwd"};
+  return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
 }
 
 // ---- state export in the reference's layouts (tests only) ----------------------------------------

@@ -110,6 +110,7 @@ int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStr
     cudaMemsetAsync(g.ctrl, 0, 8, st);
   } else {
     int nblocks = (p.P + SCAN_TILE - 1) / SCAN_TILE;
+    ProfScope prof(GSL_K_SCAN, st);
     k_scan_reduce<<<nblocks, SCAN_THREADS, 0, st>>>(g.tiles, p.P, g.scan_state);
     k_scan_sums<<<1, 1024, 0, st>>>(g.scan_state, nblocks, g.ctrl, nullptr);
     k_scan_down<<<nblocks, SCAN_THREADS, 0, st>>>(g.tiles, p.P, g.scan_state, g.offs);
@@ -235,15 +236,22 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
     k_flag_overflow<<<1, 1, 0, st>>>(g.ctrl, (uint32_t)r_capacity);
     return GSL_ENOSPACE;
   }
-  k_duplicate<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, g.rec, g.rect, g.tiles, g.offs, gx, g.ctrl,
-                                                 (uint32_t)r_capacity, b.keys_a, b.vals_a);
+  {
+    ProfScope prof(GSL_K_DUPLICATE, st);
+    k_duplicate<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, g.rec, g.rect, g.tiles, g.offs, gx, g.ctrl,
+                                                   (uint32_t)r_capacity, b.keys_a, b.vals_a);
+  }
   int bit = (int)higher_msb((uint32_t)tiles);
   size_t tmp = b.sort_tmp_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.keys_a, b.keys_b, b.vals_a, b.vals_b,
-                                                  (int)R, 0, 32 + bit, st);
-  if (e != cudaSuccess) return check_cuda(e, "cub::DeviceRadixSort::SortPairs");
+  {
+    ProfScope prof(GSL_K_SORT, st);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.keys_a, b.keys_b, b.vals_a, b.vals_b,
+                                                    (int)R, 0, 32 + bit, st);
+    if (e != cudaSuccess) return check_cuda(e, "cub::DeviceRadixSort::SortPairs");
+  }
   int blocks = (int)((R + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope prof(GSL_K_RANGES, st);
   k_tile_ranges<<<blocks, 256, 0, st>>>(b.keys_b, g.ctrl, (uint32_t)r_capacity, im.ranges);
   return check_cuda(cudaGetLastError(), "binning launch");
 }

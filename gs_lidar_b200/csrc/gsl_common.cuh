@@ -141,6 +141,15 @@ struct RenderParams {
 };
 RenderParams make_render_params(const gsl_params& p, int64_t r_capacity);
 
+// Optional per-kernel event timing (gsl_api.cu); a no-op unless gsl_profile_enable(1) was called.
+struct ProfScope {
+  int id;
+  cudaStream_t st;
+  void* slot;
+  ProfScope(int id, cudaStream_t st);
+  ~ProfScope();
+};
+
 // error plumbing (gsl_api.cu)
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);

@@ -306,6 +306,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
   pp.scale_factor = p.scale_factor;
   for (int i = 0; i < 12; ++i) pp.samp[i] = (float)(2 * GSL_MY_PI * i / 12);
   int blocks = (p.P + 255) / 256;
+  ProfScope prof(GSL_K_PREPROCESS_FWD, st);
   k_preprocess_fwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.opacities, in.shs,
                                           in.colors_precomp, in.mask, in.viewmatrix, in.campos, out.radii,
                                           g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped);
@@ -548,6 +549,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   Fov f = make_fov(p);
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
   int blocks = (p.P + 255) / 256;
+  ProfScope prof(GSL_K_PREPROCESS_BWD, st);
   k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.viewmatrix,
                                           in.campos, fwd.radii, g.rec, g.clamped, g.grad, gout.dL_dmeans3D,
                                           gout.dL_dmeans2D, gout.dL_dsh, gout.dL_dcolors, gout.dL_dfeatures,

@@ -16,6 +16,16 @@ namespace gsl {
 
 constexpr int BWD_BATCH = 128;
 
+#ifdef GSL_STATS
+__device__ unsigned long long g_stats_bwd[16];
+#define STATB_ADD(i, v) do { unsigned long long _s = __reduce_add_sync(0xffffffffu, (unsigned)(v)); if ((threadIdx.x & 31) == 0) atomicAdd(&g_stats_bwd[i], _s); } while (0)
+extern "C" __attribute__((visibility("default"))) void gsl_stats_read_bwd(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_stats_bwd, sizeof(g_stats_bwd));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_stats_bwd, z, sizeof(z)); }
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -101,6 +111,9 @@ __global__ void __launch_bounds__(256) k_render_bwd(
   __syncthreads();
   const int total = min(s_max, (int)(range.y - range.x));
 
+#ifdef GSL_STATS
+  unsigned st_scan = 0, st_box = 0, st_any = 0, st_valid = 0, st_multi = 0;
+#endif
   const float far_near = rp.far_ * rp.near_;
   const float range_fn = rp.far_ - rp.near_;
 
@@ -124,11 +137,17 @@ __global__ void __launch_bounds__(256) k_render_bwd(
     for (int j = nb - 1; j >= 0; --j) {
       const int pos0 = lo + j;  // 0-based list position == the reference's `contributor` after --
       if (pos0 >= warp_max) continue;  // warp-uniform
+#ifdef GSL_STATS
+      if (lane == 0) st_scan++;
+#endif
       const short4 bb = s_box[j];
       const bool ovy = (int)bb.y <= wby1 && (int)bb.w >= by0;
       const bool ovx = (bb.x <= bb.z) ? ((int)bb.x <= wbx1 && (int)bb.z >= bx0)
                                       : ((int)bb.x <= wbx1 || (int)bb.z >= bx0);
       if (!(ovx && ovy)) continue;  // warp-uniform
+#ifdef GSL_STATS
+      if (lane == 0) st_box++;
+#endif
 
       bool valid = pos0 < last_contributor;
       Splat s;
@@ -145,6 +164,10 @@ __global__ void __launch_bounds__(256) k_render_bwd(
       valid = valid && e.valid;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       if (vmask == 0) continue;
+#ifdef GSL_STATS
+      if (lane == 0) { st_any++; if (__popc(vmask) > 1) st_multi++; }
+      if (valid) st_valid++;
+#endif
 
       float g_dT[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float g_m2x = 0.f, g_m2y = 0.f, g_op = 0.f;
@@ -263,6 +286,9 @@ __global__ void __launch_bounds__(256) k_render_bwd(
       }
     }
   }
+#ifdef GSL_STATS
+  STATB_ADD(0, st_scan); STATB_ADD(1, st_box); STATB_ADD(2, st_any); STATB_ADD(3, st_valid); STATB_ADD(4, st_multi);
+#endif
 }
 
 int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
@@ -273,6 +299,7 @@ int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const 
   if (tiles == 0 || p.P == 0) return 0;
   const float4* colors = in.colors_precomp ? reinterpret_cast<const float4*>(in.colors_precomp) : g.rgb;
   const int gs = grad_stride(p.S);
+  ProfScope prof(GSL_K_RENDER_BWD, st);
 #define GSL_LAUNCH_BWD(ST)                                                                                \
   k_render_bwd<ST><<<tiles, 256, 0, st>>>(rp, im.ranges, b.vals_b, g.rec, g.pixbox, colors, in.features,   \
                                           in.background, g.ctrl, im.final_T, fwd.out_contrib,              \

@@ -13,6 +13,13 @@ namespace gsl {
 
 constexpr int FWD_BATCH = 256;
 
+#ifdef GSL_STATS
+__device__ unsigned long long g_stats[16];
+#define STAT_ADD(i, v) do { unsigned long long _s = __reduce_add_sync(0xffffffffu, (unsigned)(v)); if ((threadIdx.x & 31) == 0) atomicAdd(&g_stats[i], _s); } while (0)
+#else
+#define STAT_ADD(i, v)
+#endif
+
 template <int S_T>
 __global__ void __launch_bounds__(256) k_render_fwd(
     RenderParams rp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
@@ -51,6 +58,9 @@ __global__ void __launch_bounds__(256) k_render_fwd(
   for (int i = 0; i < GSL_MAX_FEATURES; ++i) F[i] = 0.f;
   float Nn[3] = {0.f, 0.f, 0.f};
   float D = 0.f, D2 = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f, median_depth = 0.f;
+#ifdef GSL_STATS
+  unsigned st_scan = 0, st_box = 0, st_any = 0, st_valid = 0, st_eval_lanes = 0;
+#endif
 
   for (int base = 0; base < total; base += FWD_BATCH) {
     if (__syncthreads_count(done) == 256) break;
@@ -69,12 +79,19 @@ __global__ void __launch_bounds__(256) k_render_fwd(
     // The warp leaves the batch loop as a unit; done lanes are masked by the branch below.
     for (int j = 0; j < nb; ++j) {
       if (__all_sync(0xffffffffu, done)) break;
+#ifdef GSL_STATS
+      if (lane == 0) st_scan++;
+#endif
       // warp-uniform cull: does the surfel's conservative pixel box touch this warp's 8x4 block?
       const short4 bb = s_box[j];
       const bool ovy = (int)bb.y <= wby1 && (int)bb.w >= by0;
       const bool ovx = (bb.x <= bb.z) ? ((int)bb.x <= wbx1 && (int)bb.z >= bx0)
                                       : ((int)bb.x <= wbx1 || (int)bb.z >= bx0);
       if (!(ovx && ovy)) continue;  // no pixel of this warp can get alpha >= 1/255 from it
+#ifdef GSL_STATS
+      if (lane == 0) st_box++;
+      if (!done) st_eval_lanes++;
+#endif
       if (done) continue;
       Splat s;
       {
@@ -85,6 +102,10 @@ __global__ void __launch_bounds__(256) k_render_fwd(
         s.nx = d.x; s.ny = d.y; s.nz = d.z; s.depth = d.w;
       }
       const PairEval e = eval_pair<false>(s, ray, rp.near_, rp.far_);
+#ifdef GSL_STATS
+      if (e.valid) st_valid++;
+      { unsigned m = __ballot_sync(__activemask(), e.valid); if (m && (lane == (__ffs(__activemask()) - 1))) st_any++; }
+#endif
       if (!e.valid) continue;
       const float alpha = e.alpha;
       const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
@@ -133,6 +154,9 @@ __global__ void __launch_bounds__(256) k_render_fwd(
     (void)contributor;
   }
 
+#ifdef GSL_STATS
+  STAT_ADD(0, st_scan); STAT_ADD(1, st_box); STAT_ADD(2, st_any); STAT_ADD(3, st_valid); STAT_ADD(4, st_eval_lanes);
+#endif
   if (inside) {
     final_T[pix_id] = T;
     final_T[pix_id + N] = M1;
@@ -173,6 +197,14 @@ RenderParams make_render_params(const gsl_params& p, int64_t r_capacity) {
   return rp;
 }
 
+#ifdef GSL_STATS
+extern "C" __attribute__((visibility("default"))) void gsl_stats_read(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_stats, sizeof(g_stats));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
+}
+#endif
+
 int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
                           const GeomView& g, const ImageView& im, const BinView& b, int64_t r_capacity,
                           cudaStream_t st) {
@@ -180,6 +212,7 @@ int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd
   const int tiles = rp.gx * rp.gy;
   if (tiles == 0) return 0;
   const float4* colors = in.colors_precomp ? reinterpret_cast<const float4*>(in.colors_precomp) : g.rgb;
+  ProfScope prof(GSL_K_RENDER_FWD, st);
 #define GSL_LAUNCH_FWD(ST)                                                                              \
   k_render_fwd<ST><<<tiles, 256, 0, st>>>(rp, im.ranges, b.vals_b, g.rec, g.pixbox, colors, in.features, \
                                           in.background, g.ctrl, im.final_T, out.out_contrib,            \

@@ -85,6 +85,18 @@ def make_cotangents(H, W, S, seed=1):
     return dict(color=n(4, H, W), feature=n(S + 3, H, W), depth=n(4, H, W), alpha=n(1, H, W))
 
 
+def pattern_cotangents(H, W, S):
+    """Deterministic cotangents made of exactly representable values (integer arithmetic / 8), so
+    golden fixtures need not store them."""
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+
+    def chan(c, mul):
+        return (((xs * 7 + ys * 13 + c * 5 + mul) % 17) - 8).float() / 8.0
+
+    mk = lambda n, mul: torch.stack([chan(c, mul) for c in range(n)], 0)
+    return dict(color=mk(4, 0), feature=mk(S + 3, 3), depth=mk(4, 6), alpha=mk(1, 9))
+
+
 def settings_for(scene, debug=False):
     from .diff_gaussian_rasterization_2d import GaussianRasterizationSettings
     return GaussianRasterizationSettings(

@@ -179,6 +179,24 @@ typedef struct gsl_state_export {
 GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64_t R,
                      const gsl_state_export* dst, void* stream);
 
+/* Per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline block.
+ * Kernel ids index the arrays of gsl_profile_read. */
+enum {
+  GSL_K_PREPROCESS_FWD = 0,
+  GSL_K_SCAN = 1,
+  GSL_K_DUPLICATE = 2,
+  GSL_K_SORT = 3,      /* library radix sort (cub) -- not one of this repo's kernels */
+  GSL_K_RANGES = 4,
+  GSL_K_RENDER_FWD = 5,
+  GSL_K_RENDER_BWD = 6,
+  GSL_K_PREPROCESS_BWD = 7,
+  GSL_K_COUNT = 8
+};
+GSL_API int gsl_profile_enable(int on);
+/* Waits for all recorded events, then returns accumulated milliseconds and launch counts per id. */
+GSL_API int gsl_profile_read(double* total_ms /*[GSL_K_COUNT]*/, int64_t* launches /*[GSL_K_COUNT]*/, int reset);
+GSL_API const char* gsl_kernel_name(int id);
+
 #ifdef __cplusplus
 }
 #endif

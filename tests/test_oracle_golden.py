@@ -1,0 +1,123 @@
+"""CPU: pins the oracle (oracle/gsl_oracle.c) against the golden outputs of the reference's own CUDA
+kernels (tests/golden/*.npz, see tests/golden/README.md).
+
+Stage by stage, each stage is fed the REFERENCE's inputs for that stage so errors do not compound:
+integer stages (scan, keys, stable sort, ranges) must be bit-exact; float stages are compared with
+tolerances that allow for libm-vs-libdevice last-ulp differences (which can flip a threshold for an
+isolated surfel or pixel)."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gs_lidar_b200 import synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+TANFOV = math.tan(-0.5)
+
+
+def load(path):
+    g = dict(np.load(path))
+    H, W, D, S = [int(x) for x in g["in_meta"]]
+    fov = [float(x) for x in g["in_fov"]]
+    precomp = "in_colors_precomp" in g
+    P = g["in_means3D"].shape[0]
+    M = 0 if precomp else g["in_shs"].shape[1]
+    o = oracle.CpuOracle()
+    p = o.params(P, S, D, M, W, H, (fov[0], fov[1]), (fov[2], fov[3]), fov[4], TANFOV, TANFOV)
+    cot = {k: v.numpy() for k, v in synth.pattern_cotangents(H, W, S).items()}
+    return g, o, p, cot, precomp
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) / (np.abs(b) + 1e-3 * (np.abs(b).max() + 1e-30))
+
+
+def test_fixtures_present():
+    assert len(GOLDEN) >= 4
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_preprocess_matches_reference(path):
+    g, o, p, cot, precomp = load(path)
+    pre = o.preprocess(p, g["in_means3D"], g["in_scales"], g["in_rotations"], g["in_opacities"],
+                       None if precomp else g["in_shs"], g["in_colors_precomp"] if precomp else None, g["in_mask"],
+                       g["in_viewmatrix"], g["in_campos"])
+    ref_radii = g["out_radii"]
+    vis = ref_radii > 0
+    # integer outcomes: at most one surfel in a few hundred may flip on a last-ulp difference
+    assert (pre["radii"] != ref_radii).mean() <= 0.01
+    assert (pre["tiles_touched"] != g["st_tiles_touched"].astype(np.uint32)).mean() <= 0.01
+    both = vis & (pre["radii"] > 0)
+    assert both.sum() >= 0.99 * vis.sum()
+    # the GPU normalises quaternions with the approximate rsqrtf intrinsic (auxiliary.h:208), the oracle with 1/sqrtf
+    for k, tol in (("depths", 1e-6), ("means2D", 1e-4), ("transMat", 1e-4), ("normal_opacity", 1e-4)):
+        assert relerr(pre[k][both], g["st_" + k][both]).max() < tol, k
+    if not precomp:
+        assert relerr(pre["rgb"][both], g["st_rgb"][both]).max() < 1e-4  # cancellation in the SH sum, fma vs mul+add
+        assert (pre["clamped"][both] != g["st_clamped"][both]).mean() < 0.005
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_binning_bit_exact(path):
+    g, o, p, cot, precomp = load(path)
+    b = o.binning(p, g["out_radii"], g["st_means2D"], g["st_depths"], g["st_tiles_touched"])
+    assert b["R"] == g["st_point_list"].shape[0]
+    assert np.array_equal(b["point_offsets"], g["st_point_offsets"].astype(np.uint32))
+    assert np.array_equal(b["point_list_keys"], g["st_point_list_keys"].astype(np.uint64))
+    assert np.array_equal(b["point_list"], g["st_point_list"].astype(np.uint32))
+    assert np.array_equal(b["ranges"], g["st_ranges"].astype(np.uint32))
+    keys = b["point_list_keys"]
+    assert np.all(keys[1:] >= keys[:-1])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_render_forward_matches_reference(path):
+    g, o, p, cot, precomp = load(path)
+    colors = g["in_colors_precomp"] if precomp else g["st_rgb"]
+    r = o.render_forward(p, g["st_ranges"], g["st_point_list"], g["st_means2D"], colors, g["in_features"], g["st_transMat"],
+                         g["st_depths"], g["st_normal_opacity"], g["in_bg"])
+    for k, rk in (("out_color", "out_color"), ("out_feature", "out_feature"), ("out_depth", "out_depth")):
+        e = relerr(r[k], g[rk])
+        assert np.median(e) < 1e-6 and np.quantile(e, 0.995) < 1e-3, (k, np.median(e), e.max())
+    e = relerr(1.0 - r["final_T"][0:1], g["out_alpha"])
+    assert np.quantile(e, 0.995) < 1e-3
+    assert (r["n_contrib"] != g["out_contrib"]).mean() < 0.005
+    assert relerr(r["final_T"], g["st_accum_alpha"]).max() < 5e-2
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_backward_matches_reference(path):
+    g, o, p, cot, precomp = load(path)
+    colors = g["in_colors_precomp"] if precomp else g["st_rgb"]
+    rb = o.render_backward(p, g["st_ranges"], g["st_point_list"], g["in_bg"], g["st_means2D"], g["st_normal_opacity"],
+                           g["st_transMat"], colors, g["st_depths"], g["in_features"], g["st_accum_alpha"],
+                           g["out_contrib"], cot["color"], cot["depth"], cot["alpha"], cot["feature"])
+
+    def close(a, b, tol, name):
+        a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+        rel = np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+        assert rel < tol, (name, rel)
+
+    close(rb["dL_dtransMat"], g["st_dL_dtransMat"], 2e-3, "dL_dtransMat")
+    close(rb["dL_dnormals"], g["st_dL_dnormals"], 2e-3, "dL_dnormals")
+    close(rb["dL_dcolors"], g["grad_dL_dcolors"], 2e-3, "dL_dcolors")
+    close(rb["dL_dopacity"], g["grad_dL_dopacity"], 2e-3, "dL_dopacity")
+    if p.S > 0:
+        close(rb["dL_dfeatures"], g["grad_dL_dfeatures"][:, :p.S], 2e-3, "dL_dfeatures")
+    # K11 fed with the reference's accumulated per-surfel gradients.  The low-pass dL_dmean2D accumulations are
+    # overwritten by the densification proxy inside the reference, so take them from the oracle's own K10.
+    pb = o.preprocess_backward(p, g["in_means3D"], g["in_scales"], g["in_rotations"], None if precomp else g["in_shs"],
+                               g["st_clamped"], g["in_viewmatrix"], g["in_campos"], g["out_radii"], g["st_transMat"],
+                               g["st_dL_dtransMat"], g["st_dL_dnormals"], g["grad_dL_dcolors"], rb["dL_dmean2D"])
+    close(pb["dL_dmeans3D"], g["grad_dL_dmeans3D"], 2e-3, "dL_dmeans3D")
+    close(pb["dL_dscales"], g["grad_dL_dscales"], 2e-3, "dL_dscales")
+    close(pb["dL_drotations"], g["grad_dL_drotations"], 2e-3, "dL_drotations")
+    close(pb["dL_dmeans2D"], g["grad_dL_dmeans2D"], 2e-3, "dL_dmeans2D")
+    if not precomp:
+        close(pb["dL_dsh"], g["grad_dL_dsh"][:, :p.M], 2e-3, "dL_dsh")
+    assert np.all(g["grad_dL_dcov3D"] == 0)
