@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?"
+tail -15 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err
+echo "bench exit $?"; cat gpurun_out/bench_ours.json; tail -3 gpurun_out/bench_ours.err
+timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+echo "bench ref exit $?"; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err

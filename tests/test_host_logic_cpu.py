@@ -1,0 +1,118 @@
+"""CPU: host-side logic -- synthetic scene generator, settings tuple, frame sharding, gradient bucket,
+and the world_size-2 gloo path of the data-parallel gradient exchange."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gs_lidar_b200 import parallel, synth
+from gs_lidar_b200 import GaussianRasterizationSettings
+
+
+def test_settings_tuple_matches_reference_fields():
+    # gaussian_renderer/diff_gaussian_rasterization_2d.py:194-209
+    assert GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug", "vfov", "hfov", "scale_factor")
+
+
+def test_scene_is_deterministic_and_shaped_like_render_inputs():
+    a, b = synth.make_scene(500, seed=7), synth.make_scene(500, seed=7)
+    for x, y in zip(a, b):
+        if isinstance(x, torch.Tensor):
+            assert torch.equal(x, y)
+    assert a.means3D.shape == (500, 3) and a.shs.shape == (500, 16, 4) and a.features.shape == (500, 4)
+    assert a.opacities.shape == (500, 1) and a.mask.dtype == torch.bool and a.mask.shape == (500, 1)
+    assert a.viewmatrix.shape == (4, 4) and a.bg.tolist() == [0.0, 0.0, 0.0, 1.0]
+    c = synth.make_scene(500, seed=8)
+    assert not torch.equal(a.means3D, c.means3D)
+
+
+def test_scene_pose_places_surfels_in_the_panorama():
+    s = synth.make_scene(2000, view_yaw_deg=30.0, view_shift=(0.2, 0.0, -0.1))
+    V = s.viewmatrix.t()
+    pv = s.means3D @ V[:3, :3].t() + V[:3, 3]
+    r = pv.norm(dim=1)
+    theta = torch.atan2(torch.sqrt(pv[:, 0] ** 2 + pv[:, 2] ** 2), -pv[:, 1])
+    lo = math.pi / 2 - math.radians(2.0)
+    hi = math.pi / 2 + math.radians(24.9)
+    d = hi - lo
+    assert float(r.min()) > 0.29 and float(r.max()) < 8.1
+    assert float(theta.min()) > lo - 0.06 * d and float(theta.max()) < hi + 0.06 * d
+    cam = torch.linalg.inv(V)[:3, 3]
+    assert torch.allclose(cam, s.campos, atol=1e-6)
+
+
+def test_pattern_cotangents_are_exact():
+    c = synth.pattern_cotangents(18, 258, 4)
+    assert c["color"].shape == (4, 18, 258) and c["feature"].shape == (7, 18, 258)
+    assert torch.equal(c["color"] * 8, (c["color"] * 8).round())
+    assert float(c["depth"].abs().max()) <= 1.0
+
+
+def test_shard_frames_partitions_round_robin():
+    frames = 51  # KITTI-360 10750-10800
+    seen = []
+    for r in range(8):
+        mine = parallel.shard_frames(frames, r, 8)
+        assert all(f % 8 == r for f in mine)
+        seen += mine
+    assert sorted(seen) == list(range(frames))
+    with pytest.raises(ValueError):
+        parallel.shard_frames(10, 8, 8)
+
+
+def test_grad_bucket_layout():
+    shapes = parallel.surfel_grad_shapes(100, 4, 16)
+    b = parallel.GradBucket(shapes, "cpu")
+    assert b.nbytes == 4 * 100 * (3 + 4 + 1 + 3 + 4 + 4 + 64)
+    g = {k: torch.randn(v) for k, v in shapes.items()}
+    b.load(g)
+    for k in shapes:
+        assert torch.equal(b.views[k], g[k])
+    b.accumulate(g)
+    assert torch.allclose(b.views["shs"], 2 * g["shs"])
+    assert b.all_reduce() is None  # not initialised -> no-op
+
+
+def _dp_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, S, M = 64, 4, 16
+        shapes = parallel.surfel_grad_shapes(P, S, M)
+        bucket = parallel.GradBucket(shapes, "cpu")
+        # every rank "renders" its own frames: the per-frame gradient is a deterministic function of the frame id
+        total = torch.zeros_like(bucket.flat)
+        frames = parallel.shard_frames(5, rank, world)
+        for f in frames:
+            g = {k: torch.full(v, float(f + 1)) for k, v in shapes.items()}
+            bucket.accumulate(g)
+        bucket.all_reduce()
+        expect = float(sum(f + 1 for f in range(5)))
+        ok = bool(torch.all(bucket.flat == expect))
+        ret[rank] = (ok, frames)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_sum_gloo_world2():
+    world = 2
+    port = 29600 + (os.getpid() % 200)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] and ret[1][0]
+    assert ret[0][1] == [0, 2, 4] and ret[1][1] == [1, 3]
+
+
+def test_bench_byte_model_matches_survey():
+    import bench
+    # P=V=1M, R=2M, N=67,980, S=4, K=M=16 -> ~326 + ~692 + 80 MB
+    f, b, r = bench.algorithmic_bytes(10**6, 10**6, 2 * 10**6, 66 * 1030, 4, 16, 16)
+    assert abs(f / 1e6 - 326) < 3 and abs(b / 1e6 - 692) < 3 and r == 80 * 10**6

@@ -1,0 +1,350 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the public
+GaussianRasterizer API -> C-ABI -> sm_100a kernels and is checked against
+
+  * the committed golden outputs of the reference's own CUDA kernels (tests/golden/*.npz),
+  * the reference CUDA rasterizer itself when oracle/_ref/libgslidar_ref.so travelled with the repo,
+  * the CPU oracle (oracle/gsl_oracle.c) at sizes it finishes in seconds,
+  * size-independent properties at BASELINE.json's full size (1M surfels, 66x1030).
+
+Contract (BASELINE.json north_star): bit-exact tile keys / sorted ids / tile ranges; <= 1e-5 relative
+on rendered maps; <= 1e-4 relative on gradients.  For maps "relative" = |a-b| / max(|b|, 1e-3 * max|b|)
+(in practice the maps are bit-identical); for gradients see common.grad_err (elementwise with a floor
+of 1% of the tensor's scale -- the reference's own atomics are not reproducible below that -- and
+norm-wise).
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+import oracle
+from gs_lidar_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+HAVE_REF = os.path.exists(oracle.REF_SO)
+TOL_MAP, TOL_GRAD = 1e-5, 1e-4
+GRAD_KEYS = dict(means3D="dL_dmeans3D", means2D="dL_dmeans2D", shs="dL_dsh", colors_precomp="dL_dcolors",
+                 features="dL_dfeatures", opacities="dL_dopacity", scales="dL_dscales", rotations="dL_drotations")
+
+
+def test_extension_is_the_cuda_library():
+    """The product path must be the in-tree CUDA .so; there is no fallback to fall back to."""
+    from gs_lidar_b200 import _lib as L
+    assert os.path.basename(L.LIB_PATH).startswith("libgsl_b200") and os.path.exists(L.LIB_PATH)
+    with open("/proc/self/maps") as f:
+        assert "libgsl_b200" in f.read()
+
+
+def scene_from_golden(g):
+    H, W, D, S = [int(x) for x in g["in_meta"]]
+    fov = [float(x) for x in g["in_fov"]]
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    sc = synth.Scene(t("in_means3D"), t("in_opacities"), t("in_scales"), t("in_rotations"), t("in_shs"), t("in_features"),
+                     t("in_mask"), t("in_viewmatrix"), t("in_projmatrix"), t("in_campos"), t("in_bg"), H, W,
+                     (fov[0], fov[1]), (fov[2], fov[3]), fov[4], D)
+    cp = t("in_colors_precomp") if "in_colors_precomp" in g else None
+    cot = {k: v.cuda() for k, v in synth.pattern_cotangents(H, W, S).items()}
+    return sc, cp, cot
+
+
+def check_against(out, state, grads, r_out, r_state, r_grads, precomp):
+    """Shared assertions: `r_*` are the reference's outputs as torch tensors (any device)."""
+    dev = out["radii"].device
+    to = lambda x: x.to(dev)
+    # --- integer state: bit exact
+    assert torch.equal(out["radii"], to(r_out["radii"]).int())
+    assert torch.equal(state["tiles_touched"], to(r_state["tiles_touched"]).int())
+    assert torch.equal(state["point_offsets"], to(r_state["point_offsets"]).int())
+    assert state["R"] == r_state["point_list"].numel()
+    assert torch.equal(state["point_list_keys"], to(r_state["point_list_keys"]).long())
+    assert torch.equal(state["point_list"], to(r_state["point_list"]).int())
+    assert torch.equal(state["ranges"], to(r_state["ranges"]).int())
+    vis = out["radii"] > 0
+    # --- per-surfel float state: the design goal is bit-exactness (keys embed depth bits)
+    for k in ("depths", "means2D", "transMat", "normal_opacity"):
+        assert common.bits_equal(state[k][vis], to(r_state[k])[vis]), k
+    if not precomp:
+        assert common.rel_err(state["rgb"][vis], to(r_state["rgb"])[vis]) < TOL_MAP
+        assert torch.equal(state["clamped"][vis], to(r_state["clamped"])[vis])
+    # --- rendered maps
+    for k in ("out_color", "out_feature", "out_depth", "out_alpha"):
+        assert common.rel_err(out[k], to(r_out[k])) < TOL_MAP, k
+    assert torch.equal(out["out_contrib"], to(r_out["out_contrib"]).int())
+    # --- gradients
+    if grads is not None:
+        for k, rk in GRAD_KEYS.items():
+            if grads.get(k) is None or rk not in r_grads:
+                continue
+            elem, norm = common.grad_err(grads[k], to(r_grads[rk]).reshape(grads[k].shape))
+            assert elem < TOL_GRAD and norm < TOL_GRAD, (k, elem, norm)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_matches_golden_reference_outputs(path):
+    g = dict(np.load(path))
+    scene, cp, cot = scene_from_golden(g)
+    out, state, grads = common.run_ours(scene, cot, colors_precomp=cp)
+    t = lambda k: torch.from_numpy(g[k])
+    r_out = dict(radii=t("out_radii"), out_color=t("out_color"), out_feature=t("out_feature"), out_depth=t("out_depth"),
+                 out_alpha=t("out_alpha"), out_contrib=t("out_contrib"))
+    r_state = {k[3:]: t(k) for k in g if k.startswith("st_")}
+    r_grads = {k[5:]: t(k) for k in g if k.startswith("grad_")}
+    S = scene.features.shape[1]
+    if S == 0:
+        r_grads.pop("dL_dfeatures", None)
+    else:
+        r_grads["dL_dfeatures"] = r_grads["dL_dfeatures"][:, :S]
+    if cp is not None:
+        r_grads.pop("dL_dsh", None)
+    check_against(out, state, grads, r_out, r_state, r_grads, cp is not None)
+
+
+CASES = [
+    dict(P=30000, H=66, W=1030, hfov=(-180.0, 180.0), seed=1),
+    dict(P=30000, H=66, W=515, hfov=(-90.0, 90.0), seed=2, view_yaw_deg=-35.0, view_shift=(0.3, 0.1, -0.2)),
+    dict(P=20000, H=128, W=2048, vfov=synth.OPV2V_VFOV, hfov=(-180.0, 180.0), seed=3),
+    dict(P=5000, H=66, W=1030, hfov=(-180.0, 180.0), seed=4, footprint_px=12.0),      # big splats, many tiles each
+    dict(P=5000, H=50, W=70, vfov=(-60.0, 60.0), hfov=(-100.0, 100.0), seed=5, footprint_px=3.0, S=0, sh_degree=0),
+    dict(P=8000, H=66, W=515, hfov=(-90.0, 90.0), seed=6, S=10, sh_degree=2),          # S at the cap, generic-S kernels
+    dict(P=8000, H=33, W=1030, vfov=(-85.0, 85.0), hfov=(-180.0, 180.0), seed=7, footprint_px=4.0),  # near the poles
+]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libgslidar_ref.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_matches_reference_cuda(kw):
+    kw = dict(kw)
+    P = kw.pop("P")
+    scene = synth.make_scene(P, **kw).to("cuda")
+    S = scene.features.shape[1]
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, S, seed=99).items()}
+    out, state, grads = common.run_ours(scene, cot)
+    r_out, r_state, r_grads, _ = common.run_ref(scene, cot)
+    if S > 0:
+        r_grads["dL_dfeatures"] = r_grads["dL_dfeatures"][:, :S]
+    else:
+        r_grads.pop("dL_dfeatures", None)
+    check_against(out, state, grads, r_out, r_state, r_grads, False)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
+def test_matches_reference_cuda_colors_precomp_and_close_range():
+    scene = synth.make_scene(6000, seed=21, footprint_px=6.0).to("cuda")
+    # pull a few surfels very close / very far to exercise near (2*sf) and far (300*sf) clipping and huge footprints
+    m = scene.means3D.clone()
+    m[:50] *= 0.05
+    m[50:100] *= 40.0
+    scene = scene._replace(means3D=m)
+    cp = torch.rand(6000, 4, generator=torch.Generator().manual_seed(5)).cuda()
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=98).items()}
+    out, state, grads = common.run_ours(scene, cot, colors_precomp=cp)
+    r_out, r_state, r_grads, _ = common.run_ref(scene, cot, colors_precomp=cp)
+    r_grads.pop("dL_dsh", None)
+    check_against(out, state, grads, r_out, r_state, r_grads, True)
+
+
+def test_matches_cpu_oracle_small():
+    scene = synth.make_scene(3000, seed=31, footprint_px=1.5).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=32).items()}
+    out, state, grads = common.run_ours(scene, cot)
+    st, og = common.run_oracle(scene, cot)
+    assert st["R"] == state["R"] or abs(st["R"] - state["R"]) <= 0.002 * state["R"]
+    assert (torch.from_numpy(st["radii"]) != out["radii"].cpu()).double().mean() < 2e-3
+    for k in ("out_color", "out_depth", "out_alpha", "out_feature"):
+        a, b = out[k].detach().cpu().double(), torch.from_numpy(st[k]).double()
+        err = (a - b).abs() / (b.abs() + 1e-3 * b.abs().max() + 1e-12)
+        assert float(err.median()) < 1e-5 and float(err.quantile(0.995)) < 1e-2, (k, float(err.max()))
+    for k, ok in dict(means3D="dL_dmeans3D", opacities="dL_dopacity", scales="dL_dscales", rotations="dL_drotations",
+                      shs="dL_dsh", features="dL_dfeatures").items():
+        a = grads[k].cpu().double().flatten()
+        b = torch.from_numpy(np.ascontiguousarray(og[ok])).double().flatten()
+        assert float((a - b).norm() / (b.norm() + 1e-30)) < 1e-2, k
+
+
+# ----------------------------------------------------------------------------------------------
+# edge cases
+# ----------------------------------------------------------------------------------------------
+def _call(scene, **over):
+    from gs_lidar_b200 import GaussianRasterizer
+    rast = GaussianRasterizer(synth.settings_for(scene))
+    P = scene.means3D.shape[0]
+    kw = dict(means3D=scene.means3D, means2D=torch.zeros((P, 4), device="cuda"), opacities=scene.opacities, shs=scene.shs,
+              features=scene.features, scales=scene.scales, rotations=scene.rotations, mask=scene.mask)
+    kw.update(over)
+    return rast(**kw)
+
+
+def test_empty_scene_renders_background():
+    scene = synth.make_scene(0).to("cuda")
+    contrib, color, feature, depth, alpha, radii = _call(scene)
+    assert radii.numel() == 0 and int(contrib.abs().sum()) == 0
+    assert torch.equal(color, scene.bg.view(4, 1, 1).expand_as(color).contiguous())
+    assert float(feature.abs().sum()) == 0 and float(depth.abs().sum()) == 0 and float(alpha.abs().sum()) == 0
+
+
+def test_all_masked_or_culled():
+    scene = synth.make_scene(500).to("cuda")
+    contrib, color, feature, depth, alpha, radii = _call(scene, mask=torch.zeros_like(scene.mask))
+    assert int(radii.abs().sum()) == 0 and float(alpha.abs().sum()) == 0
+    # everything nearer than near = 2 * scale_factor is culled (auxiliary.h:199)
+    near = scene._replace(means3D=scene.means3D * (0.15 / scene.means3D.norm(dim=1, keepdim=True)))
+    contrib, color, feature, depth, alpha, radii = _call(near)
+    assert int(radii.abs().sum()) == 0
+
+
+def test_default_mask_and_features_like_reference():
+    scene = synth.make_scene(2000, seed=41).to("cuda")
+    a = _call(scene, mask=None, features=None)
+    b = _call(scene, mask=torch.ones_like(scene.mask), features=torch.empty((2000, 0), device="cuda"))
+    assert a[2].shape[0] == 3  # S=0 -> only the 3 normal channels
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_non_contiguous_and_fp64_inputs_are_normalised():
+    scene = synth.make_scene(2000, seed=42).to("cuda")
+    ref = _call(scene)
+    big = torch.zeros((2000, 6), device="cuda")
+    big[:, ::2] = scene.means3D
+    out = _call(scene, means3D=big[:, ::2], scales=scene.scales.double())
+    for x, y in zip(ref, out):
+        assert torch.equal(x, y)
+
+
+def test_forward_is_deterministic_and_no_grad_releases_workspace():
+    import gs_lidar_b200.diff_gaussian_rasterization_2d as G
+    scene = synth.make_scene(50000, seed=43).to("cuda")
+    with torch.no_grad():
+        a = _call(scene)
+        n_free = sum(len(v) for v in G._pool.free.values())
+        b = _call(scene)
+        assert sum(len(v) for v in G._pool.free.values()) == n_free  # same workspace reused, none leaked
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_second_backward_raises_clear_error():
+    scene = synth.make_scene(1000, seed=44).to("cuda")
+    m = scene.means3D.clone().requires_grad_(True)
+    out = _call(scene, means3D=m)
+    out[1].sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already released"):
+        out[1].sum().backward()
+
+
+def test_backward_is_linear_in_cotangents_and_accumulators_self_clean():
+    scene = synth.make_scene(20000, seed=45).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=46).items()}
+    _, _, g1 = common.run_ours(scene, cot, export=False)
+    _, _, g1b = common.run_ours(scene, cot, export=False)  # reuses the workspace: accumulators must be zero again
+    _, _, g2 = common.run_ours(scene, {k: 2 * v for k, v in cot.items()}, export=False)
+    for k in ("means3D", "shs", "opacities", "scales", "rotations", "features", "means2D"):
+        assert max(common.grad_err(g1b[k], g1[k])) < TOL_GRAD, k
+        assert max(common.grad_err(g2[k], 2 * g1[k])) < TOL_GRAD, k
+
+
+def test_unused_arguments_are_ignored_like_the_reference():
+    # scale_modifier, scales.z, projmatrix, tanfov are not used by the math (SURVEY.md 8a parity trap 1)
+    scene = synth.make_scene(3000, seed=47).to("cuda")
+    a = _call(scene)
+    sc = scene.scales.clone()
+    sc[:, 2] *= 7.0
+    b = _call(scene._replace(scales=sc, projmatrix=torch.randn(4, 4, device="cuda")))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_mark_visible_matches_oracle():
+    from gs_lidar_b200 import GaussianRasterizer
+    scene = synth.make_scene(5000, seed=48).to("cuda")
+    proj = torch.tensor([[1.2, 0, 0, 0], [0, 1.2, 0, 0], [0, 0, 1.0, 1.0], [0, 0, -0.1, 0]], device="cuda")
+    st = synth.settings_for(scene)._replace(projmatrix=proj)
+    vis = GaussianRasterizer(st).markVisible(scene.means3D)
+    exp = oracle.CpuOracle().mark_visible(scene.means3D.cpu().numpy(), scene.viewmatrix.cpu().numpy(), proj.cpu().numpy())
+    assert vis.dtype == torch.bool and float((vis.cpu() != torch.from_numpy(exp)).double().mean()) < 1e-3
+
+
+def test_debug_mode_runs_synchronously():
+    scene = synth.make_scene(2000, seed=49).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=50).items()}
+    a, _, ga = common.run_ours(scene, cot, export=False, debug=True)
+    b, _, gb = common.run_ours(scene, cot, export=False, debug=False)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+
+
+# ----------------------------------------------------------------------------------------------
+# full size (BASELINE.json configs[2]): size-independent properties
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_run():
+    scene = synth.make_scene(1000000, seed=0).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=1).items()}
+    out, state, grads = common.run_ours(scene, cot)
+    return scene, cot, out, state, grads
+
+
+def test_full_size_binning_invariants(full_run):
+    scene, cot, out, state, grads = full_run
+    keys, lst, ranges = state["point_list_keys"], state["point_list"].long(), state["ranges"].long()
+    R = state["R"]
+    assert R == int(state["tiles_touched"].long().sum()) == int(state["point_offsets"][-1])
+    assert bool((keys[1:] >= keys[:-1]).all())                       # sorted by tile | depth
+    tile = keys >> 32
+    depth_bits = (keys & 0xffffffff).int()
+    assert torch.equal(depth_bits, state["depths"][lst].view(torch.int32))  # key low word = depth bits of its surfel
+    # stable: equal keys keep ascending surfel id
+    same = keys[1:] == keys[:-1]
+    assert bool((lst[1:][same] > lst[:-1][same]).all())
+    # ranges partition [0, R) in tile order and agree with the keys
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    counts = torch.bincount(tile, minlength=ranges.shape[0])
+    assert torch.equal(counts, lens)
+    nz = lens > 0
+    assert bool((tile[ranges[nz, 0]] == torch.nonzero(nz).flatten()).all())
+    # every surfel appears exactly tiles_touched times
+    assert torch.equal(torch.bincount(lst, minlength=scene.means3D.shape[0]), state["tiles_touched"].long())
+
+
+def test_full_size_render_invariants(full_run):
+    scene, cot, out, state, grads = full_run
+    alpha = out["out_alpha"]
+    alpha = alpha.detach()
+    assert float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0
+    assert torch.equal(alpha, 1.0 - state["final_T"][0:1])
+    lens = (state["ranges"][:, 1] - state["ranges"][:, 0]).long()
+    H, W = scene.H, scene.W
+    gx = (W + 15) // 16
+    ys, xs = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+    tl = lens[(ys // 16) * gx + xs // 16]
+    assert bool((out["out_contrib"][0].long() <= tl).all()) and bool((out["out_contrib"][1] <= out["out_contrib"][0]).all())
+    for k in ("out_color", "out_feature", "out_depth"):
+        assert bool(torch.isfinite(out[k]).all()), k
+    # depth mean <= far * alpha, distortion >= 0 up to rounding
+    far = 300.0 * scene.scale_factor
+    assert bool((out["out_depth"][0] <= far * alpha[0] + 1e-3).all())
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
+def test_full_size_matches_reference_cuda(full_run):
+    scene, cot, out, state, grads = full_run
+    r_out, r_state, r_grads, _ = common.run_ref(scene, cot)
+    check_against(out, state, grads, r_out, r_state, r_grads, False)
+
+
+def test_full_size_gradients_are_finite_and_sparse(full_run):
+    scene, cot, out, state, grads = full_run
+    culled = out["radii"] == 0
+    for k in ("means3D", "shs", "opacities", "scales", "rotations", "features", "means2D"):
+        g = grads[k]
+        assert bool(torch.isfinite(g).all()), k
+        assert float(g[culled].abs().sum()) == 0.0, k   # culled surfels get exactly zero gradient
+    assert float(grads["scales"][:, 2].abs().sum()) == 0.0  # dL_dscale.z is always 0 (backward.cu:618)
+    assert float(grads["means2D"][:, 2:].abs().sum()) == 0.0
