@@ -35,19 +35,23 @@ def _stamp():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    stamp_file = os.path.join(HERE, ".build_stamp")
-    stamp = _stamp()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: developer builds (e.g. variant="stats", defines=["-DGSL_STATS"]) written to
+    libgsl_b200_<variant>.so and selected at run time with GSL_B200_LIB; the product is the default build."""
+    lib = LIB if not variant else os.path.join(HERE, "libgsl_b200_%s.so" % variant)
+    stamp_file = os.path.join(HERE, ".build_stamp" + ("_" + variant if variant else ""))
+    stamp = _stamp() + "|" + " ".join(defines)
+    if not force and os.path.exists(lib) and os.path.exists(stamp_file):
         with open(stamp_file) as f:
             if f.read().strip() == stamp:
-                return LIB
-    objdir = os.path.join(HERE, "build")
+                return lib
+    objdir = os.path.join(HERE, "build" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -57,14 +61,20 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(stamp_file, "w") as f:
         f.write(stamp)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    variant, defines = None, []
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            variant = a.split("=", 1)[1]
+        elif a.startswith("-D"):
+            defines.append(a)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant, defines=defines))

@@ -175,10 +175,15 @@ __global__ void __launch_bounds__(256) k_duplicate(int P, const float4* __restri
   }
 }
 
-// identifyTileRanges (rasterizer_impl.cu:116-142), grid-stride over the device-side R.
+// identifyTileRanges (rasterizer_impl.cu:116-142), grid-stride over the device-side R, fused with the
+// per-position block mask: bit b of bmask[i] says whether the conservative pixel box of surfel vals[i]
+// overlaps 8x4 pixel block b of tile (key >> 32).
 __global__ void __launch_bounds__(256) k_tile_ranges(const uint64_t* __restrict__ keys,
+                                                     const uint32_t* __restrict__ vals,
+                                                     const short4* __restrict__ pixbox,
                                                      const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
-                                                     uint2* __restrict__ ranges) {
+                                                     int gx, int W, int H, uint2* __restrict__ ranges,
+                                                     uint8_t* __restrict__ bmask) {
   const uint32_t R = ctrl[0];
   if (R > r_capacity) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
@@ -193,6 +198,26 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint64_t* __restrict_
       }
     }
     if (i == R - 1) ranges[cur].y = R;
+    const short4 bb = pixbox[vals[i]];
+    const int tx0 = (int)(cur % (uint32_t)gx) * GSL_BLOCK_X, ty0 = (int)(cur / (uint32_t)gx) * GSL_BLOCK_Y;
+    uint32_t colm = 0, rowm = 0;
+#pragma unroll
+    for (int bc = 0; bc < 2; ++bc) {
+      const int x0 = tx0 + bc * 8, x1 = min(x0 + 7, W - 1);
+      const bool ov = (bb.x <= bb.z) ? ((int)bb.x <= x1 && (int)bb.z >= x0) : ((int)bb.x <= x1 || (int)bb.z >= x0);
+      colm |= (ov && x0 < W) ? (1u << bc) : 0u;
+    }
+#pragma unroll
+    for (int br = 0; br < 4; ++br) {
+      const int y0 = ty0 + br * 4, y1 = min(y0 + 3, H - 1);
+      const bool ov = (int)bb.y <= y1 && (int)bb.w >= y0;
+      rowm |= (ov && y0 < H) ? (1u << br) : 0u;
+    }
+    uint32_t m = 0;
+#pragma unroll
+    for (int br = 0; br < 4; ++br)
+      if (rowm & (1u << br)) m |= colm << (2 * br);
+    bmask[i] = (uint8_t)m;
   }
 }
 
@@ -230,6 +255,7 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
   const int gx = (p.W + GSL_BLOCK_X - 1) / GSL_BLOCK_X, gy = (p.H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
   const int tiles = gx * gy;
   cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
+  cudaMemsetAsync(b.used, 0, 8 * b.used_words * sizeof(uint32_t), st);
   const int64_t R = r_host[0];
   if (p.P == 0 || R == 0) return check_cuda(cudaGetLastError(), "binning (empty)");
   if (R > r_capacity) {
@@ -252,7 +278,8 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
   int blocks = (int)((R + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof(GSL_K_RANGES, st);
-  k_tile_ranges<<<blocks, 256, 0, st>>>(b.keys_b, g.ctrl, (uint32_t)r_capacity, im.ranges);
+  k_tile_ranges<<<blocks, 256, 0, st>>>(b.keys_b, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W, p.H,
+                                        im.ranges, b.bmask);
   return check_cuda(cudaGetLastError(), "binning launch");
 }
 

@@ -14,12 +14,16 @@
 //     pixbox[i]   short4   conservative pixel box of the surfel's support (this design)
 //     tiles[i]    u32      tiles_touched;  offs[i] u32 inclusive scan
 //     clamped[i]  u8       bit c set when SH channel c was clamped (forward.cu:64-67)
-//     grad[i]     float[GS] packed gradient accumulators, kept all-zero between steps:
+//     grad[i]     float[32] packed gradient accumulators, kept all-zero between steps:
 //         [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity,
-//         [12..15] dL_dcolor, [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature
+//         [12..15] dL_dcolor, [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature, pad to 32
 //     ctrl        u32[64]  [0]=R, [1]=overflow, [2]=scan ticket, ...
 //   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2)
-//   binning chunk (capacity Rcap): keys_a u64, keys_b u64, vals_a u32, vals_b u32, sort temp
+//   binning chunk (capacity Rcap): keys_a u64, keys_b u64, vals_a u32, vals_b u32, sort temp,
+//     bmask u8[Rcap]  per sorted list position: bit b set when the surfel's pixel box overlaps 8x4 pixel
+//                     block b = (row/4)*2 + col/8 of its 16x16 tile (written with the tile ranges)
+//     used  u32[8][ceil(Rcap/32)+2]  bit-plane per block: list positions that contributed to >= 1 pixel of
+//                     that block in the forward pass (the backward pass walks only these)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,7 +37,9 @@ namespace gsl {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-inline __host__ __device__ int grad_stride(int S) { return 20 + ((S + 3) / 4) * 4; }
+// 32 floats (128 B) per surfel whatever S is: the backward compositor's warp reduction leaves component c of
+// the record in lane c, so one 32-lane reduction instruction flushes a whole record.
+inline __host__ __device__ int grad_stride(int /*S*/) { return 32; }
 
 struct GeomView {
   float4* rec;
@@ -62,6 +68,9 @@ struct BinView {
   uint32_t* vals_b;
   void* sort_tmp;
   size_t sort_tmp_bytes;
+  uint8_t* bmask;
+  uint32_t* used;
+  size_t used_words;  // words per bit-plane
   size_t bytes;
 };
 
@@ -115,6 +124,9 @@ inline BinView bin_view(void* base, int64_t Rcap) {
   char* tmp;
   carve(p, tmp, b.sort_tmp_bytes);
   b.sort_tmp = tmp;
+  carve(p, b.bmask, R + 128);
+  b.used_words = (R + 31) / 32 + 2;
+  carve(p, b.used, 8 * b.used_words);
   b.bytes = (size_t)(p - (char*)base) + 256;
   return b;
 }

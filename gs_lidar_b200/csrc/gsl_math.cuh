@@ -83,11 +83,12 @@ struct PairEval {
 
 // Ray-splat intersection, low-pass filter, depth and alpha for one pair, with the skip tests of
 // forward.cu:410-441 (identical in backward.cu:308-339).  `near`/`far` are 2*sf and 300*sf.
-// The rounding sequence is the reference forward kernel's.
+// The rounding sequence is the reference forward kernel's.  Written branch-free (the skip tests only
+// feed `valid`) so that the compiler can interleave the evaluation of consecutive candidates; values
+// computed past a failed test are never used.
 template <bool KEEP_KL>
 __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r, float near_, float far_) {
   PairEval e;
-  e.valid = false;
   // k = cos(phi)*Tu - sin(phi)*Tw            (x,y,z components over Tu/Tv... columns)
   float kx = GSL_FF(s.Tux, r.cphi, -GSL_FM(s.Twx, r.sphi));
   float ky = GSL_FF(s.Tuy, r.cphi, -GSL_FM(s.Twy, r.sphi));
@@ -102,7 +103,7 @@ __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r,
   float pz = GSL_FF(kx, ly, -GSL_FM(ky, lx));
   if (KEEP_KL) { e.kx = kx; e.ky = ky; e.kz = kz; e.lx = lx; e.ly = ly; e.lz = lz; }
   e.pz = pz;
-  if (pz == 0.0f) return e;
+  bool ok = pz != 0.0f;
   float sx = GSL_FD(px, pz);
   float sy = GSL_FD(py, pz);
   float rho3d = GSL_FF(sx, sx, GSL_FM(sy, sy));
@@ -118,15 +119,14 @@ __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r,
   d3 = GSL_FF(GSL_FM(sTw, r.sth), r.cphi, d3);
   float depth = (rho3d <= rho2d) ? d3 : s.depth;
   e.sx = sx; e.sy = sy; e.rho3d = rho3d; e.rho2d = rho2d; e.dx = dx; e.dy = dy; e.depth = depth;
-  if (depth < near_ || depth > far_) return e;
+  ok = ok && !(depth < near_ || depth > far_);
   float power = GSL_FM(fminf(rho3d, rho2d), -0.5f);
-  if (power > 0.0f) return e;
+  ok = ok && !(power > 0.0f);
   float G = expf(power);
   float alpha = fminf(GSL_FM(s.opacity, G), 0.99f);
   e.G = G;
   e.alpha = alpha;
-  if (alpha < 1.0f / 255.0f) return e;
-  e.valid = true;
+  e.valid = ok && !(alpha < 1.0f / 255.0f);
   return e;
 }
 

@@ -1,57 +1,48 @@
-// gsl_render_fwd.cu -- per-tile front-to-back alpha compositing (semantics of forward.cu:292-505).
+// gsl_render_fwd.cu -- front-to-back alpha compositing (semantics of forward.cu:292-505).
 //
-// One CTA per 16x16 tile, one thread per pixel; each warp owns an 8x4 pixel block so that the
-// conservative pixel boxes computed by the preprocess cull whole warps.  Surfel records are staged
-// through shared memory as float4 (one 64-B record per list entry, coalesced 16-B loads).  The
-// per-pair arithmetic is gsl::eval_pair (bit-identical to the reference), the blend recursion below
-// follows the reference's rounding sequence too, so the rendered maps match bit-for-bit in
-// practice; the contract tested is 1e-5 relative.
-#include "gsl_common.cuh"
-#include "gsl_math.cuh"
+// One warp per 8x4 pixel block (see gsl_render.cuh for the decomposition and the pipeline).  Per-pair
+// arithmetic is gsl::eval_pair and the blend recursion follows the reference's rounding sequence, so the
+// maps match the reference bit-for-bit in practice (contract: 1e-5 relative).  Two consecutive candidates
+// are evaluated together (their ray-splat intersections are independent; only the short blend is serial).
+// The forward also records, per block and list position, whether the entry contributed to any pixel of
+// the block (bit-planes `used`); the backward pass walks only those.
+#include "gsl_render.cuh"
 
 namespace gsl {
-
-constexpr int FWD_BATCH = 256;
 
 #ifdef GSL_STATS
 __device__ unsigned long long g_stats[16];
 #define STAT_ADD(i, v) do { unsigned long long _s = __reduce_add_sync(0xffffffffu, (unsigned)(v)); if ((threadIdx.x & 31) == 0) atomicAdd(&g_stats[i], _s); } while (0)
-#else
-#define STAT_ADD(i, v)
 #endif
 
 template <int S_T>
-__global__ void __launch_bounds__(256) k_render_fwd(
+__global__ void __launch_bounds__(32) k_render_fwd(
     RenderParams rp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-    const float4* __restrict__ rec, const short4* __restrict__ pixbox, const float4* __restrict__ colors,
+    const uint8_t* __restrict__ bmask, const float4* __restrict__ rec, const float4* __restrict__ colors,
     const float* __restrict__ features, const float* __restrict__ bg, const uint32_t* __restrict__ ctrl,
-    float* __restrict__ final_T, int32_t* __restrict__ out_contrib, float* __restrict__ out_color,
-    float* __restrict__ out_feature, float* __restrict__ out_depth, float* __restrict__ out_alpha) {
+    uint32_t* __restrict__ used, size_t used_words, float* __restrict__ final_T, int32_t* __restrict__ out_contrib,
+    float* __restrict__ out_color, float* __restrict__ out_feature, float* __restrict__ out_depth,
+    float* __restrict__ out_alpha) {
+  constexpr bool FEAT4 = (S_T == 4);
   const int S = (S_T >= 0) ? S_T : rp.S;
-  __shared__ float4 s_rec[4][FWD_BATCH];
-  __shared__ uint32_t s_id[FWD_BATCH];
-  __shared__ short4 s_box[FWD_BATCH];
+  __shared__ WarpStage stg[2];
 
-  const int tile = blockIdx.x;
-  const int tx = tile % rp.gx, ty = tile / rp.gx;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bx0 = tx * GSL_BLOCK_X + (warp & 1) * 8, by0 = ty * GSL_BLOCK_Y + (warp >> 1) * 4;
-  const int pxi = bx0 + (lane & 7), pyi = by0 + (lane >> 3);
-  const bool inside = pxi < rp.W && pyi < rp.H;
+  const int lane = threadIdx.x;
+  const BlockGeom bg_ = block_geom(rp, blockIdx.x, lane);
+  const int bbit = bg_.bbit;
+  const bool inside = bg_.inside;
   const int N = rp.W * rp.H;
-  const int pix_id = rp.W * pyi + pxi;
-  // warp block extents clipped to the image (for the box test)
-  const int wbx1 = min(bx0 + 7, rp.W - 1), wby1 = min(by0 + 3, rp.H - 1);
+  const int pix_id = bg_.pix_id;
 
-  uint2 range = ranges[tile];
+  uint2 range = ranges[bg_.tile];
   if (ctrl[0] > rp.r_capacity) range = make_uint2(0, 0);
-  const int total = (int)(range.y - range.x);
+  const uint32_t r0 = range.x, r1 = range.y;
 
-  const PixelRay ray = make_pixel_ray((float)pxi, (float)pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min,
+  const PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min,
                                       rp.VFOV_max, rp.W, rp.H);
   bool done = !inside;
   float T = 1.0f;
-  int contributor = 0, last_contributor = 0, median_contributor = 0;
+  int last_contributor = 0, median_contributor = 0;
   float C[4] = {0.f, 0.f, 0.f, 0.f};
   float F[GSL_MAX_FEATURES];
 #pragma unroll
@@ -62,101 +53,138 @@ __global__ void __launch_bounds__(256) k_render_fwd(
   unsigned st_scan = 0, st_box = 0, st_any = 0, st_valid = 0, st_eval_lanes = 0;
 #endif
 
-  for (int base = 0; base < total; base += FWD_BATCH) {
-    if (__syncthreads_count(done) == 256) break;
-    const int nb = min(FWD_BATCH, total - base);
-    if ((int)threadIdx.x < nb) {
-      uint32_t id = point_list[range.x + base + threadIdx.x];
-      s_id[threadIdx.x] = id;
-      s_box[threadIdx.x] = pixbox[id];
-      const float4* r4 = rec + 4 * (size_t)id;
-      s_rec[0][threadIdx.x] = r4[0];
-      s_rec[1][threadIdx.x] = r4[1];
-      s_rec[2][threadIdx.x] = r4[2];
-      s_rec[3][threadIdx.x] = r4[3];
+  // blend of one evaluated candidate into this lane's pixel; returns whether it contributed
+  auto blend = [&](const WarpStage& sb, int s, const Splat& sp, const PairEval& e, uint32_t wbase) -> bool {
+    if (done || !e.valid) return false;
+    const float alpha = e.alpha;
+    const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
+    if (test_T < 0.0001f) {
+      done = true;
+      return false;
     }
-    __syncthreads();
-    // The warp leaves the batch loop as a unit; done lanes are masked by the branch below.
-    for (int j = 0; j < nb; ++j) {
-      if (__all_sync(0xffffffffu, done)) break;
-#ifdef GSL_STATS
-      if (lane == 0) st_scan++;
-#endif
-      // warp-uniform cull: does the surfel's conservative pixel box touch this warp's 8x4 block?
-      const short4 bb = s_box[j];
-      const bool ovy = (int)bb.y <= wby1 && (int)bb.w >= by0;
-      const bool ovx = (bb.x <= bb.z) ? ((int)bb.x <= wbx1 && (int)bb.z >= bx0)
-                                      : ((int)bb.x <= wbx1 || (int)bb.z >= bx0);
-      if (!(ovx && ovy)) continue;  // no pixel of this warp can get alpha >= 1/255 from it
-#ifdef GSL_STATS
-      if (lane == 0) st_box++;
-      if (!done) st_eval_lanes++;
-#endif
-      if (done) continue;
-      Splat s;
-      {
-        float4 a = s_rec[0][j], b = s_rec[1][j], c = s_rec[2][j], d = s_rec[3][j];
-        s.Tux = a.x; s.Tuy = a.y; s.Tuz = a.z; s.Tvx = a.w;
-        s.Tvy = b.x; s.Tvz = b.y; s.Twx = b.z; s.Twy = b.w;
-        s.Twz = c.x; s.mx = c.y; s.my = c.z; s.opacity = c.w;
-        s.nx = d.x; s.ny = d.y; s.nz = d.z; s.depth = d.w;
-      }
-      const PairEval e = eval_pair<false>(s, ray, rp.near_, rp.far_);
-#ifdef GSL_STATS
-      if (e.valid) st_valid++;
-      { unsigned m = __ballot_sync(__activemask(), e.valid); if (m && (lane == (__ffs(__activemask()) - 1))) st_any++; }
-#endif
-      if (!e.valid) continue;
-      const float alpha = e.alpha;
-      const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
-      if (test_T < 0.0001f) {
-        done = true;
-        continue;
-      }
-      const int pos = base + j + 1;  // 1-based list position == the reference's `contributor`
-      const float w = GSL_FM(T, alpha);
-      const float A = GSL_FS(1.f, T);
-      const float m = GSL_FM(rp.far_over_range, GSL_FS(1.f, GSL_FD(rp.near_, e.depth)));
-      const float mm = GSL_FM(m, m);
-      const float t0 = GSL_FF(-M1, GSL_FA(m, m), GSL_FF(A, mm, M2));
-      distortion = GSL_FF(w, t0, distortion);
-      M1 = GSL_FF(w, m, M1);
-      M2 = GSL_FF(w, mm, M2);
-      if (T > 0.5f) {
-        median_depth = e.depth;
-        median_contributor = pos;
-      }
-      const uint32_t id = s_id[j];
-      const float4 col = colors[id];
-      C[0] = GSL_FF(T, GSL_FM(alpha, col.x), C[0]);
-      C[1] = GSL_FF(T, GSL_FM(alpha, col.y), C[1]);
-      C[2] = GSL_FF(T, GSL_FM(alpha, col.z), C[2]);
-      C[3] = GSL_FF(T, GSL_FM(alpha, col.w), C[3]);
-      if (S_T == 4) {
-        const float4 f = *reinterpret_cast<const float4*>(features + 4 * (size_t)id);
-        F[0] = GSL_FF(T, GSL_FM(alpha, f.x), F[0]);
-        F[1] = GSL_FF(T, GSL_FM(alpha, f.y), F[1]);
-        F[2] = GSL_FF(T, GSL_FM(alpha, f.z), F[2]);
-        F[3] = GSL_FF(T, GSL_FM(alpha, f.w), F[3]);
-      } else {
+    const int pos = (int)(wbase + sb.lanepos[s] - r0) + 1;  // 1-based list position (the reference's `contributor`)
+    const float wgt = GSL_FM(T, alpha);
+    const float A = GSL_FS(1.f, T);
+    const float mm1 = GSL_FM(rp.far_over_range, GSL_FS(1.f, GSL_FD(rp.near_, e.depth)));
+    const float mm = GSL_FM(mm1, mm1);
+    const float t0 = GSL_FF(-M1, GSL_FA(mm1, mm1), GSL_FF(A, mm, M2));
+    distortion = GSL_FF(wgt, t0, distortion);
+    M1 = GSL_FF(wgt, mm1, M1);
+    M2 = GSL_FF(wgt, mm, M2);
+    if (T > 0.5f) {
+      median_depth = e.depth;
+      median_contributor = pos;
+    }
+    const float4 col = sb.v[4][s];
+    C[0] = GSL_FF(T, GSL_FM(alpha, col.x), C[0]);
+    C[1] = GSL_FF(T, GSL_FM(alpha, col.y), C[1]);
+    C[2] = GSL_FF(T, GSL_FM(alpha, col.z), C[2]);
+    C[3] = GSL_FF(T, GSL_FM(alpha, col.w), C[3]);
+    if (FEAT4) {
+      const float4 f = sb.v[5][s];
+      F[0] = GSL_FF(T, GSL_FM(alpha, f.x), F[0]);
+      F[1] = GSL_FF(T, GSL_FM(alpha, f.y), F[1]);
+      F[2] = GSL_FF(T, GSL_FM(alpha, f.z), F[2]);
+      F[3] = GSL_FF(T, GSL_FM(alpha, f.w), F[3]);
+    } else if (S > 0) {
+      const float* fp = features + (size_t)sb.id[s] * S;
 #pragma unroll
-        for (int ch = 0; ch < GSL_MAX_FEATURES; ++ch)
-          if (ch < S) F[ch] = GSL_FF(T, GSL_FM(alpha, features[(size_t)id * S + ch]), F[ch]);
-      }
-      Nn[0] = GSL_FF(T, GSL_FM(alpha, s.nx), Nn[0]);
-      Nn[1] = GSL_FF(T, GSL_FM(alpha, s.ny), Nn[1]);
-      Nn[2] = GSL_FF(T, GSL_FM(alpha, s.nz), Nn[2]);
-      D = GSL_FF(T, GSL_FM(alpha, e.depth), D);
-      D2 = GSL_FF(T, GSL_FM(alpha, GSL_FM(e.depth, e.depth)), D2);
-      T = test_T;
-      last_contributor = pos;
+      for (int ch = 0; ch < GSL_MAX_FEATURES; ++ch)
+        if (ch < S) F[ch] = GSL_FF(T, GSL_FM(alpha, __ldg(fp + ch)), F[ch]);
     }
-    (void)contributor;
-  }
+    Nn[0] = GSL_FF(T, GSL_FM(alpha, sp.nx), Nn[0]);
+    Nn[1] = GSL_FF(T, GSL_FM(alpha, sp.ny), Nn[1]);
+    Nn[2] = GSL_FF(T, GSL_FM(alpha, sp.nz), Nn[2]);
+    D = GSL_FF(T, GSL_FM(alpha, e.depth), D);
+    D2 = GSL_FF(T, GSL_FM(alpha, GSL_FM(e.depth, e.depth)), D2);
+    T = test_T;
+    last_contributor = pos;
+    return true;
+  };
 
+  if (r1 > r0) {
+    const uint32_t w0 = r0 >> 5, w1 = (r1 - 1) >> 5;
+    uint32_t* __restrict__ used_plane = used + (size_t)bbit * used_words;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    auto load_mi = [&](uint32_t w, bool& cand, uint32_t& id) {
+      const uint32_t p = (w << 5) + lane;
+      const bool in = (w <= w1) && p >= r0 && p < r1;
+      cand = in && ((__ldg(bmask + p) >> bbit) & 1u);
+      id = cand ? __ldg(point_list + p) : 0u;
+    };
+
+    // prologue: word w0 staged in buffer 0, ids of word w0+1 in flight
+    bool candN, candNN;
+    uint32_t idN, idNN;
+    CandRegs rg;
+    int cur = 0;
+    uint32_t mCur;
+    {
+      bool c0;
+      uint32_t id0;
+      load_mi(w0, c0, id0);
+      gather_cand<FEAT4>(c0, id0, rec, colors, features, rg);
+      load_mi(w0 + 1, candN, idN);
+      mCur = __ballot_sync(0xffffffffu, c0);
+      if (c0) stage_cand<FEAT4>(stg[0], __popc(mCur & lt_mask), rg, id0, (uint32_t)lane);
+      __syncwarp();
+    }
+    for (uint32_t w = w0; w <= w1; ++w) {
+      // ---- later pipeline stages: records of word w+1, mask + ids of word w+2
+      gather_cand<FEAT4>(candN, idN, rec, colors, features, rg);
+      load_mi(w + 2, candNN, idNN);
+      // ---- composite the staged candidates of word w
+      const WarpStage& sb = stg[cur];
+      const int cnt = __popc(mCur);
+      const uint32_t wbase = w << 5;
+#ifdef GSL_STATS
+      if (lane == 0) { st_scan += min(32u, r1 - max(r0, wbase)); st_box += cnt; }
+#endif
+      uint32_t slotmask = 0;
+      for (int s = 0; s < cnt; s += 2) {
+        if (__all_sync(0xffffffffu, done)) break;
+        const bool two = s + 1 < cnt;  // warp-uniform
+        const int s1 = two ? s + 1 : s;
+        const Splat spa = staged_splat(sb, s);
+        const Splat spb = staged_splat(sb, s1);
+        const PairEval ea = eval_pair<false>(spa, ray, rp.near_, rp.far_);
+        PairEval eb = eval_pair<false>(spb, ray, rp.near_, rp.far_);
+        eb.valid = eb.valid && two;
+#ifdef GSL_STATS
+        if (!done) { st_eval_lanes += two ? 2 : 1; st_valid += (ea.valid ? 1 : 0) + (eb.valid ? 1 : 0); }
+#endif
+        const bool ca = blend(sb, s, spa, ea, wbase);
+        const bool cb = blend(sb, s1, spb, eb, wbase);
+        if (__any_sync(0xffffffffu, ca)) slotmask |= 1u << s;
+        if (__any_sync(0xffffffffu, cb)) slotmask |= 1u << s1;
+      }
+      if (slotmask != 0u) {
+        // slot mask -> list-position mask of this word
+        const bool mine = ((mCur >> lane) & 1u) && ((slotmask >> __popc(mCur & lt_mask)) & 1u);
+        const uint32_t usedbits = __ballot_sync(0xffffffffu, mine);
+#ifdef GSL_STATS
+        if (lane == 0) st_any += __popc(usedbits);
+#endif
+        if (lane == 0) {
+          if (w == w0 || w == w1) atomicOr(&used_plane[w], usedbits);  // word shared with the neighbouring tile
+          else used_plane[w] = usedbits;
+        }
+      }
+      if (__all_sync(0xffffffffu, done)) break;
+      // ---- stage word w+1 into the other buffer, rotate
+      cur ^= 1;
+      mCur = __ballot_sync(0xffffffffu, candN);
+      if (candN) stage_cand<FEAT4>(stg[cur], __popc(mCur & lt_mask), rg, idN, (uint32_t)lane);
+      __syncwarp();
+      candN = candNN;
+      idN = idNN;
+    }
+  }
 #ifdef GSL_STATS
   STAT_ADD(0, st_scan); STAT_ADD(1, st_box); STAT_ADD(2, st_any); STAT_ADD(3, st_valid); STAT_ADD(4, st_eval_lanes);
 #endif
+
   if (inside) {
     final_T[pix_id] = T;
     final_T[pix_id + N] = M1;
@@ -209,14 +237,15 @@ int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd
                           const GeomView& g, const ImageView& im, const BinView& b, int64_t r_capacity,
                           cudaStream_t st) {
   RenderParams rp = make_render_params(p, r_capacity);
-  const int tiles = rp.gx * rp.gy;
-  if (tiles == 0) return 0;
+  const int nblocks = ((p.W + 7) / 8) * ((p.H + 3) / 4);
+  if (nblocks == 0) return 0;
   const float4* colors = in.colors_precomp ? reinterpret_cast<const float4*>(in.colors_precomp) : g.rgb;
   ProfScope prof(GSL_K_RENDER_FWD, st);
-#define GSL_LAUNCH_FWD(ST)                                                                              \
-  k_render_fwd<ST><<<tiles, 256, 0, st>>>(rp, im.ranges, b.vals_b, g.rec, g.pixbox, colors, in.features, \
-                                          in.background, g.ctrl, im.final_T, out.out_contrib,            \
-                                          out.out_color, out.out_feature, out.out_depth, out.out_alpha)
+#define GSL_LAUNCH_FWD(ST)                                                                                  \
+  k_render_fwd<ST><<<nblocks, 32, 0, st>>>(rp, im.ranges, b.vals_b, b.bmask, g.rec, colors, in.features,     \
+                                           in.background, g.ctrl, b.used, b.used_words, im.final_T,          \
+                                           out.out_contrib, out.out_color, out.out_feature, out.out_depth,  \
+                                           out.out_alpha)
   if (p.S == 4) GSL_LAUNCH_FWD(4);
   else if (p.S == 0) GSL_LAUNCH_FWD(0);
   else GSL_LAUNCH_FWD(-1);
