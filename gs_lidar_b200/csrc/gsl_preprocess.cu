@@ -232,10 +232,16 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
         // ---- conservative pixel box of the pair-level support (this design, not in the reference).
         // A pair can only contribute if alpha >= 1/255  <=>  min(rho3d, rho2d) <= tau := 2 ln(255 o).
         //  * rho2d <= tau : |pixel - means2D| <= sqrt(tau/2) (plain pixel distance, no wrap);
-        //  * rho3d <= tau with a positive in-range depth: the ray hits the splat plane inside the
-        //    ellipse |(u,v)|^2 <= tau in front of the sensor, so its direction lies in the spherical
-        //    cap of angular radius asin(D/r) around the centre direction, D = sqrt(tau*lambda_max).
-        // Both are inflated by safety margins; anything unusual falls back to the full image.
+        //  * rho3d <= tau with a positive in-range depth: the pixel's ray meets the splat plane at a point
+        //    p = t + u a + v b of the ellipse E = {u^2 + v^2 <= tau} in front of the sensor, so the pixel's
+        //    (phi, theta) is the direction of some p in E.  With q = p - t written in the local spherical
+        //    frame (r^, phi^, theta^) at t and the extents E_x = sqrt(tau ((a.x^)^2 + (b.x^)^2)) of E
+        //    along each frame axis:
+        //       dphi   = atan2(q_phi, (r + q_r) sin th + q_th cos th)            (exact)
+        //       dtheta = atan2(q_th, r + q_r) + xi,  |xi| <= (q_phi / |(r + q_r, q_th)|)^2 / (2 sin(th + .))
+        //    which gives the half-widths below.  Where the local bound degenerates (huge or very close
+        //    splats, poles) the spherical-cap bound asin(D / r), D = sqrt(tau lambda_max), is used, and
+        //    failing that the whole image.  All bounds are inflated by safety margins.
         int bx0 = 0, bx1 = pp.W - 1, by0 = 0, by1 = pp.H - 1;
         float tau = 2.f * logf(255.f * opacity);
         float tauc = tau + 1e-3f * fabsf(tau) + 1e-3f;
@@ -251,19 +257,51 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
             float Dm = sqrtf(tauc * lam) * 1.001f;
             float rd = sqrtf(0.5f * tauc) * 1.001f;
             float sd = Dm / r;
+            float sth = rxz / r;  // sin of the polar angle of the centre
             float hx = -1.f, hy = -1.f;  // negative: unbounded
+            // spherical-cap bound
             if (sd == sd && sd < 0.9f) {
               float delta = asinf(sd) * 1.001f + 1e-6f;
-              hy = fmaxf(delta * Hf / dV, rd) + 0.02f;
-              float sth = rxz / r;  // sin of the polar angle of the centre
+              hy = delta * Hf / dV;
               if (sd < 0.9f * sth) {
                 float dphi = asinf(sd / sth) * 1.001f + 1e-6f;
-                hx = fmaxf(dphi * Wf / dH, rd) + 0.02f;
+                hx = dphi * Wf / dH;
               }
             }
+            // local-frame bound (tighter for anisotropic / foreshortened splats)
+            {
+              const float inv_r = 1.f / r, inv_rxz = 1.f / rxz;
+              const float cth = -ty * inv_r;
+              const float phx = tz * inv_rxz, phz = -tx * inv_rxz;                      // phi^
+              const float thx = cth * tx * inv_rxz, thy = sth, thz = cth * tz * inv_rxz;  // theta^
+              const float rhx = tx * inv_r, rhy = ty * inv_r, rhz = tz * inv_r;          // r^
+              const float ap = s.Tux * phx + s.Twx * phz, bp = s.Tuy * phx + s.Twy * phz;
+              const float at = s.Tux * thx + s.Tvx * thy + s.Twx * thz, bt = s.Tuy * thx + s.Tvy * thy + s.Twy * thz;
+              const float ar = s.Tux * rhx + s.Tvx * rhy + s.Twx * rhz, br = s.Tuy * rhx + s.Tvy * rhy + s.Twy * rhz;
+              const float sq = sqrtf(tauc) * 1.002f;
+              const float Eph = sq * sqrtf(ap * ap + bp * bp), Eth = sq * sqrtf(at * at + bt * bt);
+              const float Er = sq * sqrtf(ar * ar + br * br);
+              const float rr = r - Er;
+              if (rr > 0.25f * r) {
+                const float rho_min = r * sth - (Er * sth + Eth * fabsf(cth));
+                if (rho_min > 0.1f * rxz) {
+                  const float t_hx = (atanf(Eph / rho_min) * 1.001f + 1e-6f) * Wf / dH;
+                  if (t_hx >= 0.f && (hx < 0.f || t_hx < hx)) hx = t_hx;
+                }
+                const float d1 = Eth / rr, smin = sth - d1;
+                if (smin > 0.1f) {
+                  const float ep = Eph / rr;
+                  const float t_hy = ((d1 + 0.5f * ep * ep / smin) * 1.001f + 1e-6f) * Hf / dV;
+                  if (t_hy >= 0.f && (hy < 0.f || t_hy < hy)) hy = t_hy;
+                }
+              }
+            }
+            if (hx >= 0.f) hx = fmaxf(hx, rd) + 0.02f;
+            if (hy >= 0.f) hy = fmaxf(hy, rd) + 0.02f;
+            // pixel centres sit at integer coordinates: pixel x is reachable iff |x - cx| <= hx
             if (hy >= 0.f && hy < 30000.f) {
-              by0 = max(0, (int)floorf(cy - hy));
-              by1 = min(pp.H - 1, (int)ceilf(cy + hy));
+              by0 = max(0, (int)ceilf(cy - hy));
+              by1 = min(pp.H - 1, (int)floorf(cy + hy));
               if (by0 > by1) { by0 = 1; by1 = 0; }
             }
             if (hx >= 0.f && hx < 30000.f && !(by0 > by1)) {
@@ -273,7 +311,7 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
 #pragma unroll
               for (int k = -1; k <= 1; ++k) {
                 float c = cx + (float)k * Wp;
-                int a = max(0, (int)floorf(c - hx)), b = min(pp.W - 1, (int)ceilf(c + hx));
+                int a = max(0, (int)ceilf(c - hx)), b = min(pp.W - 1, (int)floorf(c + hx));
                 if (a <= b) { lo[n] = a; hi[n] = b; ++n; }
               }
               if (n == 0) { by0 = 1; by1 = 0; }

@@ -279,6 +279,69 @@ def test_debug_mode_runs_synchronously():
         assert torch.equal(a[k], b[k])
 
 
+@pytest.mark.parametrize("kw", [dict(P=4000, seed=61), dict(P=3000, seed=62, footprint_px=6.0),
+                                dict(P=3000, seed=63, H=33, W=1030, vfov=(-85.0, 85.0), footprint_px=3.0),
+                                dict(P=3000, seed=64, H=66, W=515, hfov=(-90.0, 90.0), view_yaw_deg=20.0)],
+                         ids=["kitti", "big", "poles", "half"])
+def test_pixel_box_is_conservative(kw):
+    """The per-surfel pixel box that culls (block, surfel) candidates (this design; not in the reference) must
+    contain every pixel that can pass the reference's alpha >= 1/255 test, for EVERY pixel of the image --
+    brute force over all (surfel, pixel) pairs with the pair formula of forward.cu:397-441."""
+    kw = dict(kw)
+    scene = synth.make_scene(kw.pop("P"), **kw).to("cuda")
+    # stretch a few surfels to exercise the fallbacks (very close, very large, strongly anisotropic)
+    sc = scene.scales.clone()
+    sc[:40, 0] *= 30.0
+    sc[40:80] *= 15.0
+    m = scene.means3D.clone()
+    m[80:120] *= 0.08
+    scene = scene._replace(scales=sc, means3D=m)
+    out, state, _ = common.run_ours(scene, None)
+    H, W = scene.H, scene.W
+    vis = torch.nonzero(out["radii"] > 0).flatten()
+    T = state["transMat"][vis].double()
+    m2 = state["means2D"][vis].double()
+    op = state["normal_opacity"][vis, 3].double()
+    box = state["pixbox"][vis].long()
+    pi = 3.14159265
+    hmin, hmax = scene.hfov[0] * pi / 180, scene.hfov[1] * pi / 180
+    vmax, vmin = pi / 2 - scene.vfov[0] * pi / 180, pi / 2 - scene.vfov[1] * pi / 180
+    ys, xs = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+    xs, ys = xs.flatten(), ys.flatten()
+    phi = xs.double() * (hmax - hmin) / W + hmin
+    th = ys.double() * (vmax - vmin) / H + vmin
+    sp, cp, st, ct = phi.sin(), phi.cos(), th.sin(), th.cos()
+    near, far = 2 * scene.scale_factor, 300 * scene.scale_factor
+    bad = 0
+    for i0 in range(0, vis.numel(), 128):
+        t = T[i0:i0 + 128]
+        Tu, Tv, Tw = t[:, None, 0:3], t[:, None, 3:6], t[:, None, 6:9]
+        k = cp[None, :, None] * Tu - sp[None, :, None] * Tw
+        l = (sp * ct)[None, :, None] * Tu + st[None, :, None] * Tv + (cp * ct)[None, :, None] * Tw
+        p = torch.cross(k, l, dim=2)
+        s = p[..., :2] / p[..., 2:3]
+        rho3d = (s * s).sum(-1)
+        d = m2[i0:i0 + 128, None, :] - torch.stack([xs, ys], 1).double()[None]
+        rho2d = 2 * (d * d).sum(-1)
+        hom = torch.cat([s, torch.ones_like(s[..., :1])], -1)
+        depth3 = (hom * Tu).sum(-1) * (st * sp)[None] - (hom * Tv).sum(-1) * ct[None] + (hom * Tw).sum(-1) * (st * cp)[None]
+        depth = torch.where(rho3d <= rho2d, depth3, state["depths"][vis][i0:i0 + 128, None].double())
+        rho = torch.minimum(rho3d, rho2d)
+        alpha = op[i0:i0 + 128, None] * torch.exp(-0.5 * rho)
+        valid = (p[..., 2] != 0) & (depth >= near) & (depth <= far) & (alpha >= (1.0 / 255.0) * (1 + 1e-6))
+        b = box[i0:i0 + 128]
+        iny = (ys[None] >= b[:, None, 1]) & (ys[None] <= b[:, None, 3])
+        x0, x1 = b[:, None, 0], b[:, None, 2]
+        inx = torch.where(x0 <= x1, (xs[None] >= x0) & (xs[None] <= x1), (xs[None] >= x0) | (xs[None] <= x1))
+        bad += int((valid & ~(inx & iny)).sum())
+    assert bad == 0, "%d valid (surfel, pixel) pairs fall outside the conservative pixel box" % bad
+    # and the box must actually cull: mean area well below a 16x16 tile for the KITTI-like scene
+    if kw.get("footprint_px", 0.8) <= 1.0 and H == 66:
+        wdt = torch.where(box[:, 0] <= box[:, 2], box[:, 2] - box[:, 0] + 1, W - box[:, 0] + box[:, 2] + 1)
+        area = (wdt * (box[:, 3] - box[:, 1] + 1).clamp_min(0)).double()
+        assert float(area[120:].median()) < 60.0
+
+
 # ----------------------------------------------------------------------------------------------
 # full size (BASELINE.json configs[2]): size-independent properties
 # ----------------------------------------------------------------------------------------------
