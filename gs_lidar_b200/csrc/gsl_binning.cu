@@ -175,49 +175,166 @@ __global__ void __launch_bounds__(256) k_duplicate(int P, const float4* __restri
   }
 }
 
-// identifyTileRanges (rasterizer_impl.cu:116-142), grid-stride over the device-side R, fused with the
-// per-position block mask: bit b of bmask[i] says whether the conservative pixel box of surfel vals[i]
-// overlaps 8x4 pixel block b of tile (key >> 32).
-__global__ void __launch_bounds__(256) k_tile_ranges(const uint64_t* __restrict__ keys,
-                                                     const uint32_t* __restrict__ vals,
-                                                     const short4* __restrict__ pixbox,
-                                                     const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
-                                                     int gx, int W, int H, uint2* __restrict__ ranges,
-                                                     uint8_t* __restrict__ bmask) {
+// ------------------------------------------------------------------------------------------------
+// identifyTileRanges (rasterizer_impl.cu:116-142) + second-level binning into 8x4-pixel BLOCK LISTS.
+// Three small kernels over the sorted list, GSL_BL_CHUNK positions per CTA (thread t takes positions
+// base + k*256 + t, so every warp handles 32 consecutive positions per round and ballots give ranks):
+//   k_ranges_bmask   ranges[tile] = [first, last+1); bmask[i] = which of the tile's 8 blocks the surfel's
+//                    conservative pixel box overlaps; per-CTA count of set bits per plane
+//   k_blist_scan     exclusive scan of the per-CTA counts, per plane
+//   k_blist_scatter  blist[b][prefix_b(i)] = (surfel id, i) for every set bit; block descriptors
+// ------------------------------------------------------------------------------------------------
+constexpr int BL_THREADS = 256;
+constexpr int BL_ROUNDS = GSL_BL_CHUNK / BL_THREADS;
+
+__device__ __forceinline__ uint32_t block_mask_of(const short4 bb, uint32_t tile, int gx, int W, int H) {
+  const int tx0 = (int)(tile % (uint32_t)gx) * GSL_BLOCK_X, ty0 = (int)(tile / (uint32_t)gx) * GSL_BLOCK_Y;
+  uint32_t colm = 0, rowm = 0;
+#pragma unroll
+  for (int bc = 0; bc < 2; ++bc) {
+    const int x0 = tx0 + bc * 8, x1 = min(x0 + 7, W - 1);
+    const bool ov = (bb.x <= bb.z) ? ((int)bb.x <= x1 && (int)bb.z >= x0) : ((int)bb.x <= x1 || (int)bb.z >= x0);
+    colm |= (ov && x0 < W) ? (1u << bc) : 0u;
+  }
+#pragma unroll
+  for (int br = 0; br < 4; ++br) {
+    const int y0 = ty0 + br * 4, y1 = min(y0 + 3, H - 1);
+    const bool ov = (int)bb.y <= y1 && (int)bb.w >= y0;
+    rowm |= (ov && y0 < H) ? (1u << br) : 0u;
+  }
+  uint32_t m = 0;
+#pragma unroll
+  for (int br = 0; br < 4; ++br)
+    if (rowm & (1u << br)) m |= colm << (2 * br);
+  return m;
+}
+
+__global__ void __launch_bounds__(BL_THREADS) k_ranges_bmask(
+    const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const short4* __restrict__ pixbox,
+    const uint32_t* __restrict__ ctrl, uint32_t r_capacity, int gx, int W, int H, uint2* __restrict__ ranges,
+    uint8_t* __restrict__ bmask, uint32_t* __restrict__ cta_counts) {
   const uint32_t R = ctrl[0];
   if (R > r_capacity) return;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
-    uint32_t cur = (uint32_t)(keys[i] >> 32);
-    if (i == 0) {
-      ranges[cur].x = 0;
-    } else {
-      uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+  __shared__ uint32_t s_cnt[8];
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * GSL_BL_CHUNK;
+  uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < BL_ROUNDS; ++k) {
+    const uint32_t i = base + k * BL_THREADS + threadIdx.x;
+    uint32_t m = 0;
+    if (i < R) {
+      const uint32_t cur = (uint32_t)(keys[i] >> 32);
+      if (i == 0) {
+        ranges[cur].x = 0;
+      } else {
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        if (cur != prev) {
+          ranges[prev].y = i;
+          ranges[cur].x = i;
+        }
+      }
+      if (i == R - 1) ranges[cur].y = R;
+      m = block_mask_of(pixbox[vals[i]], cur, gx, W, H);
+      bmask[i] = (uint8_t)m;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) cnt[b] += __popc(__ballot_sync(0xffffffffu, (m >> b) & 1u));
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) atomicAdd(&s_cnt[b], cnt[b]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) cta_counts[blockIdx.x * 8 + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// one CTA; thread group b (128 threads) scans plane b
+__global__ void __launch_bounds__(1024) k_blist_scan(uint32_t* __restrict__ cta_counts, int nctas,
+                                                     const uint32_t* __restrict__ ctrl, uint32_t r_capacity) {
+  if (ctrl[0] > r_capacity) return;
+  __shared__ uint32_t s_w[8][4];
+  const int b = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, wv = t >> 5;
+  uint32_t carry = 0;
+  for (int base = 0; base < nctas; base += 128) {
+    const int i = base + t;
+    const uint32_t v = (i < nctas) ? cta_counts[i * 8 + b] : 0u;
+    const uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) s_w[b][wv] = inc;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t x = s_w[b][k];
+      if (k < wv) off += x;
+      tot += x;
+    }
+    if (i < nctas) cta_counts[i * 8 + b] = carry + off + inc - v;
+    carry += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(BL_THREADS) k_blist_scatter(
+    const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint8_t* __restrict__ bmask,
+    const uint32_t* __restrict__ cta_prefix, const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
+    size_t plane_stride, uint2* __restrict__ blist, uint4* __restrict__ bdesc) {
+  const uint32_t R = ctrl[0];
+  if (R > r_capacity) return;
+  constexpr int SEGS = BL_ROUNDS * (BL_THREADS / 32);
+  __shared__ uint32_t s_seg[SEGS][8];
+  const uint32_t base = blockIdx.x * GSL_BL_CHUNK;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t mk[BL_ROUNDS];
+#pragma unroll
+  for (int k = 0; k < BL_ROUNDS; ++k) {
+    const uint32_t i = base + k * BL_THREADS + threadIdx.x;
+    mk[k] = (i < R) ? (uint32_t)bmask[i] : 0u;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (mk[k] >> b) & 1u);
+      if (lane == b) s_seg[k * (BL_THREADS / 32) + wv][b] = __popc(bal);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {  // exclusive scan over the segments of plane threadIdx.x, seeded with the CTA prefix
+    uint32_t run = cta_prefix[blockIdx.x * 8 + threadIdx.x];
+    for (int sgm = 0; sgm < SEGS; ++sgm) {
+      const uint32_t c = s_seg[sgm][threadIdx.x];
+      s_seg[sgm][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < BL_ROUNDS; ++k) {
+    const uint32_t i = base + k * BL_THREADS + threadIdx.x;
+    const int sgm = k * (BL_THREADS / 32) + wv;
+    uint32_t pre[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      pre[b] = s_seg[sgm][b] + __popc(__ballot_sync(0xffffffffu, (mk[k] >> b) & 1u) & lt);
+    if (i < R) {
+      const uint32_t id = vals[i];
+      const uint32_t cur = (uint32_t)(keys[i] >> 32);
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        if ((mk[k] >> b) & 1u) blist[(size_t)b * plane_stride + pre[b]] = make_uint2(id, i);
+      const uint32_t prev = (i == 0) ? 0xffffffffu : (uint32_t)(keys[i - 1] >> 32);
       if (cur != prev) {
-        ranges[prev].y = i;
-        ranges[cur].x = i;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          bdesc[cur * 8 + b].x = pre[b];
+          if (i != 0) bdesc[prev * 8 + b].y = pre[b];
+        }
+      }
+      if (i == R - 1) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) bdesc[cur * 8 + b].y = pre[b] + ((mk[k] >> b) & 1u);
       }
     }
-    if (i == R - 1) ranges[cur].y = R;
-    const short4 bb = pixbox[vals[i]];
-    const int tx0 = (int)(cur % (uint32_t)gx) * GSL_BLOCK_X, ty0 = (int)(cur / (uint32_t)gx) * GSL_BLOCK_Y;
-    uint32_t colm = 0, rowm = 0;
-#pragma unroll
-    for (int bc = 0; bc < 2; ++bc) {
-      const int x0 = tx0 + bc * 8, x1 = min(x0 + 7, W - 1);
-      const bool ov = (bb.x <= bb.z) ? ((int)bb.x <= x1 && (int)bb.z >= x0) : ((int)bb.x <= x1 || (int)bb.z >= x0);
-      colm |= (ov && x0 < W) ? (1u << bc) : 0u;
-    }
-#pragma unroll
-    for (int br = 0; br < 4; ++br) {
-      const int y0 = ty0 + br * 4, y1 = min(y0 + 3, H - 1);
-      const bool ov = (int)bb.y <= y1 && (int)bb.w >= y0;
-      rowm |= (ov && y0 < H) ? (1u << br) : 0u;
-    }
-    uint32_t m = 0;
-#pragma unroll
-    for (int br = 0; br < 4; ++br)
-      if (rowm & (1u << br)) m |= colm << (2 * br);
-    bmask[i] = (uint8_t)m;
   }
 }
 
@@ -255,7 +372,7 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
   const int gx = (p.W + GSL_BLOCK_X - 1) / GSL_BLOCK_X, gy = (p.H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
   const int tiles = gx * gy;
   cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
-  cudaMemsetAsync(b.used, 0, 8 * b.used_words * sizeof(uint32_t), st);
+  cudaMemsetAsync(im.bdesc, 0, (size_t)tiles * 8 * sizeof(uint4), st);
   const int64_t R = r_host[0];
   if (p.P == 0 || R == 0) return check_cuda(cudaGetLastError(), "binning (empty)");
   if (R > r_capacity) {
@@ -275,11 +392,13 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
                                                     (int)R, 0, 32 + bit, st);
     if (e != cudaSuccess) return check_cuda(e, "cub::DeviceRadixSort::SortPairs");
   }
-  int blocks = (int)((R + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int nctas = (int)((R + GSL_BL_CHUNK - 1) / GSL_BL_CHUNK);
   ProfScope prof(GSL_K_RANGES, st);
-  k_tile_ranges<<<blocks, 256, 0, st>>>(b.keys_b, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W, p.H,
-                                        im.ranges, b.bmask);
+  k_ranges_bmask<<<nctas, BL_THREADS, 0, st>>>(b.keys_b, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W,
+                                               p.H, im.ranges, b.bmask, b.cta_counts);
+  k_blist_scan<<<1, 1024, 0, st>>>(b.cta_counts, nctas, g.ctrl, (uint32_t)r_capacity);
+  k_blist_scatter<<<nctas, BL_THREADS, 0, st>>>(b.keys_b, b.vals_b, b.bmask, b.cta_counts, g.ctrl,
+                                                (uint32_t)r_capacity, b.plane_stride, b.blist, im.bdesc);
   return check_cuda(cudaGetLastError(), "binning launch");
 }
 

@@ -4,15 +4,17 @@
 // with thousands of surfels per tile list, so "one CTA per tile" leaves the machine idle and latency-bound):
 //   * one WARP per 8x4 pixel block, one thread per pixel, one warp per CTA -> ~2200 independent warps over
 //     the SMs, no __syncthreads anywhere, a warp retires the moment its 32 pixels are finished;
-//   * the tile|depth sorted list is exactly the reference's (16x16 tiles, bit-exact keys), but every list
-//     position carries an 8-bit block mask (gsl_binning.cu) built from the surfel's conservative pixel
-//     box, so a warp only evaluates the entries that can reach one of its pixels;
-//   * the forward records per block which list positions contributed to at least one of its pixels (`used`
-//     bit-planes); the backward walks just those, back to front.
-//   * per-warp software pipeline over 32-position words of the list:
-//        [mask/used bits + surfel ids of word w+2] -> [record gathers of word w+1] -> [composite word w]
-//     candidates are compacted with ballot/popc into a double-buffered shared-memory stage and read back
-//     with broadcast LDS.128.
+//   * the tile|depth sorted list is exactly the reference's (16x16 tiles, bit-exact keys and positions); a
+//     second-level binning (gsl_binning.cu) splits every tile list into the lists of its eight 8x4 blocks
+//     using the surfels' conservative pixel boxes, so a warp only sees entries that can reach its pixels;
+//   * a warp stages 32 block-list entries at a time in shared memory (cp.async gathers of the 64-B records,
+//     double buffered: the gathers of chunk c+1 and the entry loads of chunk c+2 fly while chunk c is
+//     composited), then every LANE walks -- in list order, at its own pace -- only the staged entries
+//     whose pixel box contains its own pixel.  The lanes of a warp therefore work on different surfels in
+//     the same instruction; a chunk costs max-over-lanes(entries relevant to that pixel) evaluations
+//     instead of 32, and the per-pixel recursion never waits for pixels the surfel cannot reach;
+//   * the forward stores, per block-list entry, the 32-bit mask of pixels it contributed to (`pairmask`);
+//     the backward walks the block list back to front and evaluates exactly those (pixel, surfel) pairs.
 #pragma once
 #include "gsl_common.cuh"
 #include "gsl_math.cuh"
@@ -44,47 +46,59 @@ __device__ __forceinline__ BlockGeom block_geom(const RenderParams& rp, int bloc
   return g;
 }
 
-// One staged candidate: the 64-B record + colour + (S == 4) features, gathered by one lane.
-struct CandRegs {
-  float4 r0, r1, r2, r3, col, feat;
+// ---- per-warp candidate stage (double-buffered, filled with cp.async, component-major) --------------
+struct ChunkStage {
+  float4 v[6][32];  // 64-B record (4), colour, features (S == 4)
+  uint2 ent[32];    // (surfel id, list position)
+  short4 box[32];   // conservative pixel box (forward only)
 };
 
-// Double-buffered per-warp stage (component-major so that the compaction store is conflict-free and the
-// broadcast read of one candidate is six LDS.128 of the same address in every lane).
-struct WarpStage {
-  float4 v[6][32];
-  uint32_t id[32];
-  uint32_t lanepos[32];
-};
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool WITH_FEAT4>
-__device__ __forceinline__ void gather_cand(bool c, uint32_t id, const float4* __restrict__ rec,
-                                            const float4* __restrict__ colors, const float* __restrict__ features,
-                                            CandRegs& o) {
-  if (c) {
-    const float4* r4 = rec + 4 * (size_t)id;
-    o.r0 = __ldg(r4);
-    o.r1 = __ldg(r4 + 1);
-    o.r2 = __ldg(r4 + 2);
-    o.r3 = __ldg(r4 + 3);
-    o.col = __ldg(colors + id);
-    if (WITH_FEAT4) o.feat = __ldg(reinterpret_cast<const float4*>(features) + id);
+// 32x32 bit-matrix transpose across the warp: bit i of the result in lane j = bit j of `m` in lane i.
+__device__ __forceinline__ uint32_t transpose32(uint32_t m, int lane) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+    if (lane == j) out = b;
   }
+  return out;
 }
 
-template <bool WITH_FEAT4>
-__device__ __forceinline__ void stage_cand(WarpStage& sb, int slot, const CandRegs& r, uint32_t id, uint32_t lanepos) {
-  sb.v[0][slot] = r.r0;
-  sb.v[1][slot] = r.r1;
-  sb.v[2][slot] = r.r2;
-  sb.v[3][slot] = r.r3;
-  sb.v[4][slot] = r.col;
-  if (WITH_FEAT4) sb.v[5][slot] = r.feat;
-  sb.id[slot] = id;
-  sb.lanepos[slot] = lanepos;
+// Which of the 32 pixels of the 8x4 block at (bx0, by0) lie inside the (possibly azimuth-wrapped) pixel box;
+// bit = row * 8 + column, i.e. the lane that owns the pixel.
+__device__ __forceinline__ uint32_t box_pixel_mask(const short4 bb, int bx0, int by0) {
+  const int r_lo = max((int)bb.y - by0, 0), r_hi = min((int)bb.w - by0, 3);
+  if (r_lo > r_hi) return 0u;
+  const int c0 = (int)bb.x - bx0, c1 = (int)bb.z - bx0;
+  uint32_t colbits;
+  if (bb.x <= bb.z) {
+    const int lo = max(c0, 0), hi = min(c1, 7);
+    colbits = (lo <= hi) ? ((0xffu >> (7 - hi)) & (0xffu << lo)) : 0u;
+  } else {  // wrapped: x >= bb.x || x <= bb.z
+    const uint32_t up = (c0 <= 7) ? (0xffu << max(c0, 0)) : 0u;
+    const uint32_t dn = (c1 >= 0) ? (0xffu >> (7 - min(c1, 7))) : 0u;
+    colbits = up | dn;
+  }
+  colbits &= 0xffu;
+  uint32_t m = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (r >= r_lo && r <= r_hi) m |= colbits << (8 * r);
+  return m;
 }
 
-__device__ __forceinline__ Splat staged_splat(const WarpStage& sb, int s) {
+__device__ __forceinline__ Splat staged_splat(const ChunkStage& sb, int s) {
   const float4 a = sb.v[0][s], b = sb.v[1][s], c = sb.v[2][s], d = sb.v[3][s];
   Splat sp;
   sp.Tux = a.x; sp.Tuy = a.y; sp.Tuz = a.z; sp.Tvx = a.w;

@@ -1,14 +1,13 @@
 // gsl_render_bwd.cu -- reverse-order backward compositing (semantics of backward.cu:137-515).
 //
-// One warp per 8x4 pixel block, walking back to front ONLY the list positions the forward pass marked as
-// having contributed to this block (`used` bit-planes, gsl_render_fwd.cu); see gsl_render.cuh for the
-// decomposition and the pipeline.  Differences from the reference's schedule (same sums):
-//   * traversal starts at the block's largest last_contributor instead of the end of the tile list;
-//   * the per-pair gradient contributions (20 + S floats) of the warp's 32 pixels are combined with a
-//     transposing butterfly (K shuffles for K components instead of 5K) that leaves component c in one
-//     lane, and the whole packed 128-B per-surfel accumulator record is updated by ONE coalesced
-//     red.global.add.f32 instruction -- instead of ~21 scalar atomics per (pixel, surfel) pair;
-//   * a candidate that only one pixel of the block uses skips the butterfly (vector reductions from that lane).
+// One warp per 8x4 pixel block walking that block's list back to front (see gsl_render.cuh): 32 entries are
+// staged at a time and every lane runs the reference's per-pixel recursion over exactly the staged entries
+// its pixel contributed to in the forward pass (`pairmask`), at its own pace.  Differences from the
+// reference's schedule (same sums):
+//   * traversal starts at the last entry that contributed to the block instead of the end of the tile list,
+//     and never evaluates a (pixel, surfel) pair that did not contribute;
+//   * each contributing pair adds its 20 + S gradient components to the surfel's packed 128-B accumulator
+//     record with 16-byte vector reductions (red.global.add.v4.f32) instead of ~21 scalar atomics.
 // Summation order differs from the reference's atomics (which are unordered anyway): the contract
 // is 1e-4 relative on the final gradients.
 #include "gsl_render.cuh"
@@ -29,63 +28,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
-__device__ __forceinline__ void red_add_f32(float* addr, float a) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
-}
-
-// Transposing butterfly: on entry every lane holds K partial sums v[0..K); on exit v[0] of lane L holds the
-// warp-wide total of component butterfly_component<K>(L) (>= K means "padding, ignore").  Stage `off` halves
-// the number of live values: lanes with bit `off` clear keep the lower half and receive the partner's lower
-// half, the others keep/receive the upper half.  Shuffles: ceil(K/2) + ceil(K/4) + ... (24 for K = 24).
-template <int K, int OFF>
-struct Butterfly {
-  static constexpr int H = (K + 1) / 2;
-  __device__ __forceinline__ static void run(float (&v)[32], bool (&up)[5]) {
-    const bool upper = up[OFF == 16 ? 0 : OFF == 8 ? 1 : OFF == 4 ? 2 : OFF == 2 ? 3 : 4];
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-      const float a = v[i];
-      const float b = (i + H < K) ? v[i + H] : 0.f;
-      const float send = upper ? a : b;
-      const float keep = upper ? b : a;
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-    }
-    Butterfly<H, OFF / 2>::run(v, up);
-  }
-};
-template <int K>
-struct Butterfly<K, 0> {
-  __device__ __forceinline__ static void run(float (&)[32], bool (&)[5]) {}
-};
-// Component whose total ends up in v[0] of `lane` (-1: structural padding).  Traces the slot kept at each
-// stage back from the last stage to the first.
-__device__ __forceinline__ int butterfly_component(int K0, int lane) {
-  int Ks[5], Hs[5];
-  int k = K0;
-#pragma unroll
-  for (int t = 0; t < 5; ++t) { Ks[t] = k; Hs[t] = (k + 1) / 2; k = Hs[t]; }
-  int i = 0;
-  bool pad = false;
-#pragma unroll
-  for (int t = 4; t >= 0; --t) {
-    if (lane & (16 >> t)) i += Hs[t];
-    pad = pad || (i >= Ks[t]);
-  }
-  return pad ? -1 : i;
-}
 
 template <int S_T>
 __global__ void __launch_bounds__(32) k_render_bwd(
-    RenderParams rp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-    const float4* __restrict__ rec, const float4* __restrict__ colors, const float* __restrict__ features,
-    const float* __restrict__ bg, const uint32_t* __restrict__ ctrl, const uint32_t* __restrict__ used,
-    size_t used_words, const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
+    RenderParams rp, const uint2* __restrict__ ranges, const uint4* __restrict__ bdesc,
+    const uint2* __restrict__ blist, const uint32_t* __restrict__ pairmask, size_t plane_stride,
+    const float4* __restrict__ rec, const float4* __restrict__ colors, const float* __restrict__ bg,
+    const uint32_t* __restrict__ ctrl, const float* __restrict__ final_T, const int32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dmask,
     const float* __restrict__ dL_dfeat, float* __restrict__ grad) {
   constexpr int KS = (S_T >= 0) ? S_T : GSL_MAX_FEATURES;  // feature slots held in registers
-  constexpr int K = 20 + KS;                               // live components of the packed record
   const int S = (S_T >= 0) ? S_T : rp.S;
-  __shared__ WarpStage stg[2];
+  __shared__ ChunkStage stg[2];
 
   const int lane = threadIdx.x;
   const BlockGeom bg_ = block_geom(rp, blockIdx.x, lane);
@@ -93,13 +47,13 @@ __global__ void __launch_bounds__(32) k_render_bwd(
   const int N = rp.W * rp.H;
   const int pix_id = bg_.pix_id;
 
-  uint2 range = ranges[bg_.tile];
-  if (ctrl[0] > rp.r_capacity) range = make_uint2(0, 0);
-  const uint32_t r0 = range.x;
-
-  const int last_contributor = inside ? n_contrib[pix_id] : 0;
-  const int warp_max = min(__reduce_max_sync(0xffffffffu, last_contributor), (int)(range.y - range.x));
-  if (warp_max <= 0) return;
+  uint4 bd = bdesc[bg_.tile * 8 + bg_.bbit];
+  if (ctrl[0] > rp.r_capacity) bd = make_uint4(0, 0, 0, 0);
+  const uint32_t bs = bd.x, nwalk = min(bd.z, bd.y - bd.x);
+  if (nwalk == 0) return;
+  const uint32_t r0 = ranges[bg_.tile].x;
+  const uint2* __restrict__ bl = blist + (size_t)bg_.bbit * plane_stride;
+  const uint32_t* __restrict__ pmk = pairmask + (size_t)bg_.bbit * plane_stride;
 
   const PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min,
                                       rp.VFOV_max, rp.W, rp.H);
@@ -140,88 +94,90 @@ __global__ void __launch_bounds__(32) k_render_bwd(
 
   const float far_near = rp.far_ * rp.near_;
   const float range_fn = rp.far_ - rp.near_;
-  bool up[5];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) up[i] = (lane >> (4 - i)) & 1;
-  int my_comp = butterfly_component(K, lane);
-  if (my_comp == 19 || my_comp >= 20 + S) my_comp = -1;  // padding slots of the packed record
-  const uint32_t gt_mask = (lane == 31) ? 0u : (0xffffffffu << (lane + 1));
-
 #ifdef GSL_STATS
-  unsigned st_scan = 0, st_any = 0, st_valid = 0, st_multi = 0;
+  unsigned st_cand = 0, st_iter = 0, st_valid = 0;
 #endif
 
-  // absolute list positions [r0, top] may hold contributors of this block
-  const uint32_t top = r0 + (uint32_t)warp_max - 1u;
-  const int w_hi = (int)(top >> 5), w_lo = (int)(r0 >> 5);
-  const uint32_t* __restrict__ used_plane = used + (size_t)bg_.bbit * used_words;
-
-  auto word_bits = [&](int w) -> uint32_t {
-    if (w < w_lo) return 0u;
-    uint32_t b = __ldg(used_plane + w);
-    if (w == w_lo) b &= 0xffffffffu << (r0 & 31u);
-    if (w == w_hi) b &= 0xffffffffu >> (31u - (top & 31u));
-    return b;
+  // slot j of a chunk ending at entry index c1 (exclusive) holds entry c1 - 1 - j: ascending slots go back to front
+  auto issue = [&](ChunkStage& sb, const uint2 ent, bool act) {
+    if (act) {
+      const float4* r4 = rec + 4 * (size_t)ent.x;
+      cp_async16(&sb.v[0][lane], r4);
+      cp_async16(&sb.v[1][lane], r4 + 1);
+      cp_async16(&sb.v[2][lane], r4 + 2);
+      cp_async16(&sb.v[3][lane], r4 + 3);
+      cp_async16(&sb.v[4][lane], colors + ent.x);
+      sb.ent[lane] = ent;
+    }
+    cp_async_commit();
   };
-  auto load_id = [&](int w, uint32_t bits, bool& cand, uint32_t& id) {
-    cand = (bits >> lane) & 1u;
-    id = cand ? __ldg(point_list + ((uint32_t)w << 5) + lane) : 0u;
+  auto load_entry = [&](int64_t c1, uint32_t& pm, uint2& ent) {
+    const int64_t e = c1 - 1 - lane;
+    pm = 0u;
+    ent = make_uint2(0, 0);
+    if (e >= (int64_t)bs) {
+      pm = __ldg(pmk + e);
+      if (pm != 0u) ent = __ldg(bl + e);
+    }
   };
 
-  // prologue
-  uint32_t bitsCur = word_bits(w_hi), bitsN = word_bits(w_hi - 1), bitsNN;
-  bool candN;
-  uint32_t idN;
-  CandRegs rg;
+  const int64_t hi = (int64_t)bs + nwalk;
   int cur = 0;
+  uint32_t pmCur, pmN;
+  uint2 entN;
   {
-    bool c0;
-    uint32_t id0;
-    load_id(w_hi, bitsCur, c0, id0);
-    gather_cand<false>(c0, id0, rec, colors, features, rg);
-    load_id(w_hi - 1, bitsN, candN, idN);
-    if (c0) stage_cand<false>(stg[0], __popc(bitsCur & gt_mask), rg, id0, (uint32_t)lane);
-    __syncwarp();
+    uint2 ent0;
+    load_entry(hi, pmCur, ent0);
+    load_entry(hi - 32, pmN, entN);
+    issue(stg[0], ent0, pmCur != 0u);
   }
-  for (int w = w_hi; w >= w_lo; --w) {
-    gather_cand<false>(candN, idN, rec, colors, features, rg);  // records of word w-1
-    bitsNN = word_bits(w - 2);
-    const WarpStage& sb = stg[cur];
-    const int cnt = __popc(bitsCur);
-    const int wbase = (int)(((uint32_t)w << 5) - r0);  // relative position of bit 0 (may be negative in w_lo)
-    for (int sidx = 0; sidx < cnt; ++sidx) {
-      const int pos0 = wbase + (int)sb.lanepos[sidx];  // 0-based list position == the reference's `contributor` after --
-#ifdef GSL_STATS
-      if (lane == 0) st_scan++;
-#endif
-      const Splat s = staged_splat(sb, sidx);
-      const PairEval e = eval_pair<true>(s, ray, rp.near_, rp.far_);
-      const bool valid = (pos0 < last_contributor) && e.valid;
-      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      if (vmask == 0) continue;
-#ifdef GSL_STATS
-      if (lane == 0) { st_any++; if (__popc(vmask) > 1) st_multi++; }
-      if (valid) st_valid++;
-#endif
-      // packed record: [0..8] dL_dT, [9..10] dL_dmean2D, [11] dL_dopacity, [12..15] dL_dcolor,
-      // [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature
-      float g[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) g[i] = 0.f;
+  for (int64_t c1 = hi; c1 > (int64_t)bs; c1 -= 32) {
+    cp_async_wait_all();
+    __syncwarp();
+    issue(stg[cur ^ 1], entN, pmN != 0u);
+    uint32_t pmNN;
+    uint2 entNN;
+    load_entry(c1 - 64, pmNN, entNN);
 
-      if (valid) {
+    const ChunkStage& sb = stg[cur];
+    uint32_t mine = transpose32(pmCur, lane);  // bit j: my pixel contributed to the entry staged in slot j
+#ifdef GSL_STATS
+    if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pmCur != 0u));
+    else __ballot_sync(0xffffffffu, pmCur != 0u);
+#endif
+    while (__any_sync(0xffffffffu, mine != 0)) {
+#ifdef GSL_STATS
+      if (lane == 0) st_iter++;
+#endif
+      if (mine != 0) {
+        const int j = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const Splat s = staged_splat(sb, j);
+        const PairEval e = eval_pair<true>(s, ray, rp.near_, rp.far_);
+#ifdef GSL_STATS
+        st_valid++;
+#endif
+        const uint2 ent = sb.ent[j];
+        const int pos0 = (int)(ent.y - r0);  // 0-based list position == the reference's `contributor` after --
+        // packed record: [0..8] dL_dT, [9..10] dL_dmean2D, [11] dL_dopacity, [12..15] dL_dcolor,
+        // [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature
+        float g[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) g[i] = 0.f;
+        float gcol[4], gnrm[3];
+
         const float alpha = e.alpha, G = e.G, depth = e.depth;
         T = T / (1.f - alpha);
         const float wgt = alpha * T;
         float dL_dalpha = 0.f;
-        const float4 c4 = sb.v[4][sidx];
+        const float4 c4 = sb.v[4][j];
         const float col[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
           last_color[ch] = col[ch];
           dL_dalpha += (col[ch] - accum_rec[ch]) * dpix[ch];
-          g[12 + ch] = wgt * dpix[ch];
+          gcol[ch] = wgt * dpix[ch];
         }
         float dL_dr = 0.f;
         dL_dr += alpha * T * dL_depth;
@@ -236,16 +192,13 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_ddist;
         dL_dr += dL_dmd * dmd_dd;
 
-#pragma unroll
-        for (int ch = 0; ch < KS; ++ch)
-          if (ch < S) g[20 + ch] = wgt * dfeat[ch];  // features do not feed dL_dalpha (backward.cu:395)
         const float nrm[3] = {s.nx, s.ny, s.nz};
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           accum_n[ch] = last_alpha * last_n[ch] + (1.f - last_alpha) * accum_n[ch];
           last_n[ch] = nrm[ch];
           dL_dalpha += (nrm[ch] - accum_n[ch]) * dnorm[ch];
-          g[16 + ch] = wgt * dnorm[ch];
+          gnrm[ch] = wgt * dnorm[ch];
         }
         accum_depth = last_alpha * last_depth + (1.f - last_alpha) * accum_depth;
         last_depth = depth;
@@ -284,34 +237,30 @@ __global__ void __launch_bounds__(32) k_render_bwd(
           g[8] = dL_dr * s.Twz / depth;
         }
         g[11] = G * dL_dalpha;
-      }
 
-      // ---- combine the block's 32 pixels and update the packed accumulator record
-      float* gdst = grad + (size_t)sb.id[sidx] * 32;
-      if (__popc(vmask) > 1) {
-        Butterfly<K, 16>::run(g, up);
-        if (my_comp >= 0) red_add_f32(gdst + my_comp, g[0]);
-      } else if (valid) {
+        float* gdst = grad + (size_t)ent.x * 32;
         red_add_v4(gdst + 0, g[0], g[1], g[2], g[3]);
         red_add_v4(gdst + 4, g[4], g[5], g[6], g[7]);
         red_add_v4(gdst + 8, g[8], g[9], g[10], g[11]);
-        red_add_v4(gdst + 12, g[12], g[13], g[14], g[15]);
-        red_add_v4(gdst + 16, g[16], g[17], g[18], 0.f);
-        if (KS > 0) red_add_v4(gdst + 20, g[20], g[21], g[22], g[23]);
-        if (KS > 4) red_add_v4(gdst + 24, g[24], g[25], g[26], g[27]);
-        if (KS > 8) red_add_v4(gdst + 28, g[28], g[29], 0.f, 0.f);
+        red_add_v4(gdst + 12, gcol[0], gcol[1], gcol[2], gcol[3]);
+        red_add_v4(gdst + 16, gnrm[0], gnrm[1], gnrm[2], 0.f);
+        // features do not feed dL_dalpha (backward.cu:395)
+        if (KS > 0) red_add_v4(gdst + 20, wgt * dfeat[0], KS > 1 ? wgt * dfeat[1 % (KS > 0 ? KS : 1)] : 0.f,
+                               KS > 2 ? wgt * dfeat[2 % (KS > 0 ? KS : 1)] : 0.f,
+                               KS > 3 ? wgt * dfeat[3 % (KS > 0 ? KS : 1)] : 0.f);
+        if (KS > 4) red_add_v4(gdst + 24, wgt * dfeat[4 % (KS > 0 ? KS : 1)], wgt * dfeat[5 % (KS > 0 ? KS : 1)],
+                               wgt * dfeat[6 % (KS > 0 ? KS : 1)], wgt * dfeat[7 % (KS > 0 ? KS : 1)]);
+        if (KS > 8) red_add_v4(gdst + 28, wgt * dfeat[8 % (KS > 0 ? KS : 1)], wgt * dfeat[9 % (KS > 0 ? KS : 1)], 0.f, 0.f);
       }
     }
-    // ---- stage word w-1 into the other buffer, rotate
     cur ^= 1;
-    bitsCur = bitsN;
-    if (candN) stage_cand<false>(stg[cur], __popc(bitsCur & gt_mask), rg, idN, (uint32_t)lane);
-    __syncwarp();
-    bitsN = bitsNN;
-    load_id(w - 2, bitsN, candN, idN);
+    pmCur = pmN;
+    pmN = pmNN;
+    entN = entNN;
   }
+  cp_async_wait_all();
 #ifdef GSL_STATS
-  STATB_ADD(0, st_scan); STATB_ADD(2, st_any); STATB_ADD(3, st_valid); STATB_ADD(4, st_multi);
+  STATB_ADD(0, st_cand); STATB_ADD(1, st_iter); STATB_ADD(3, st_valid);
 #endif
 }
 
@@ -325,9 +274,9 @@ int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const 
   static_assert(sizeof(float) * 32 == 128, "packed accumulator record is one 128-B line");
   ProfScope prof(GSL_K_RENDER_BWD, st);
 #define GSL_LAUNCH_BWD(ST)                                                                                \
-  k_render_bwd<ST><<<nblocks, 32, 0, st>>>(rp, im.ranges, b.vals_b, g.rec, colors, in.features, in.background, \
-                                           g.ctrl, b.used, b.used_words, im.final_T, fwd.out_contrib,          \
-                                           gin.dL_dout_color, gin.dL_dout_depth, gin.dL_dout_alpha,             \
+  k_render_bwd<ST><<<nblocks, 32, 0, st>>>(rp, im.ranges, im.bdesc, b.blist, b.pairmask, b.plane_stride, g.rec, \
+                                           colors, in.background, g.ctrl, im.final_T, fwd.out_contrib,        \
+                                           gin.dL_dout_color, gin.dL_dout_depth, gin.dL_dout_alpha,            \
                                            gin.dL_dout_feature, g.grad)
   if (p.S == 4) GSL_LAUNCH_BWD(4);
   else if (p.S == 0) GSL_LAUNCH_BWD(0);

@@ -1,11 +1,12 @@
 // gsl_render_fwd.cu -- front-to-back alpha compositing (semantics of forward.cu:292-505).
 //
-// One warp per 8x4 pixel block (see gsl_render.cuh for the decomposition and the pipeline).  Per-pair
-// arithmetic is gsl::eval_pair and the blend recursion follows the reference's rounding sequence, so the
-// maps match the reference bit-for-bit in practice (contract: 1e-5 relative).  Two consecutive candidates
-// are evaluated together (their ray-splat intersections are independent; only the short blend is serial).
-// The forward also records, per block and list position, whether the entry contributed to any pixel of
-// the block (bit-planes `used`); the backward pass walks only those.
+// One warp per 8x4 pixel block walking that block's list (see gsl_render.cuh for the decomposition and
+// the pipeline): 32 entries are staged at a time and every lane composites, in list order, the staged
+// entries whose pixel box contains its pixel.  Per-pair arithmetic is gsl::eval_pair and the blend
+// recursion follows the reference's rounding sequence, so the maps match the reference bit-for-bit in
+// practice (contract: 1e-5 relative); `contributor` numbers are the reference's 16x16-tile list positions.
+// The forward also stores, per block-list entry, the mask of pixels it contributed to (`pairmask`) and,
+// per block, how many leading entries the backward pass has to walk.
 #include "gsl_render.cuh"
 
 namespace gsl {
@@ -17,26 +18,29 @@ __device__ unsigned long long g_stats[16];
 
 template <int S_T>
 __global__ void __launch_bounds__(32) k_render_fwd(
-    RenderParams rp, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-    const uint8_t* __restrict__ bmask, const float4* __restrict__ rec, const float4* __restrict__ colors,
-    const float* __restrict__ features, const float* __restrict__ bg, const uint32_t* __restrict__ ctrl,
-    uint32_t* __restrict__ used, size_t used_words, float* __restrict__ final_T, int32_t* __restrict__ out_contrib,
-    float* __restrict__ out_color, float* __restrict__ out_feature, float* __restrict__ out_depth,
-    float* __restrict__ out_alpha) {
+    RenderParams rp, const uint2* __restrict__ ranges, uint4* __restrict__ bdesc, const uint2* __restrict__ blist,
+    uint32_t* __restrict__ pairmask, size_t plane_stride, const float4* __restrict__ rec,
+    const float4* __restrict__ colors, const float* __restrict__ features, const short4* __restrict__ pixbox,
+    const float* __restrict__ bg, const uint32_t* __restrict__ ctrl, float* __restrict__ final_T,
+    int32_t* __restrict__ out_contrib, float* __restrict__ out_color, float* __restrict__ out_feature,
+    float* __restrict__ out_depth, float* __restrict__ out_alpha) {
   constexpr bool FEAT4 = (S_T == 4);
   const int S = (S_T >= 0) ? S_T : rp.S;
-  __shared__ WarpStage stg[2];
+  __shared__ ChunkStage stg[2];
 
   const int lane = threadIdx.x;
   const BlockGeom bg_ = block_geom(rp, blockIdx.x, lane);
-  const int bbit = bg_.bbit;
   const bool inside = bg_.inside;
   const int N = rp.W * rp.H;
   const int pix_id = bg_.pix_id;
+  const int bidx = bg_.tile * 8 + bg_.bbit;
 
-  uint2 range = ranges[bg_.tile];
-  if (ctrl[0] > rp.r_capacity) range = make_uint2(0, 0);
-  const uint32_t r0 = range.x, r1 = range.y;
+  uint4 bd = bdesc[bidx];
+  if (ctrl[0] > rp.r_capacity) bd = make_uint4(0, 0, 0, 0);
+  const uint32_t bs = bd.x, be = bd.y;
+  const uint32_t r0 = ranges[bg_.tile].x;
+  const uint2* __restrict__ bl = blist + (size_t)bg_.bbit * plane_stride;
+  uint32_t* __restrict__ pmk = pairmask + (size_t)bg_.bbit * plane_stride;
 
   const PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min,
                                       rp.VFOV_max, rp.W, rp.H);
@@ -50,139 +54,132 @@ __global__ void __launch_bounds__(32) k_render_fwd(
   float Nn[3] = {0.f, 0.f, 0.f};
   float D = 0.f, D2 = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f, median_depth = 0.f;
 #ifdef GSL_STATS
-  unsigned st_scan = 0, st_box = 0, st_any = 0, st_valid = 0, st_eval_lanes = 0;
+  unsigned st_cand = 0, st_iter = 0, st_any = 0, st_valid = 0, st_eval = 0;
 #endif
 
-  // blend of one evaluated candidate into this lane's pixel; returns whether it contributed
-  auto blend = [&](const WarpStage& sb, int s, const Splat& sp, const PairEval& e, uint32_t wbase) -> bool {
-    if (done || !e.valid) return false;
-    const float alpha = e.alpha;
-    const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
-    if (test_T < 0.0001f) {
-      done = true;
-      return false;
+  // gathers of one staged candidate (lane = slot), straight into shared memory
+  auto issue = [&](ChunkStage& sb, const uint2 ent, bool act) {
+    if (act) {
+      const float4* r4 = rec + 4 * (size_t)ent.x;
+      cp_async16(&sb.v[0][lane], r4);
+      cp_async16(&sb.v[1][lane], r4 + 1);
+      cp_async16(&sb.v[2][lane], r4 + 2);
+      cp_async16(&sb.v[3][lane], r4 + 3);
+      cp_async16(&sb.v[4][lane], colors + ent.x);
+      if (FEAT4) cp_async16(&sb.v[5][lane], reinterpret_cast<const float4*>(features) + ent.x);
+      cp_async8(&sb.box[lane], pixbox + ent.x);
+      sb.ent[lane] = ent;
     }
-    const int pos = (int)(wbase + sb.lanepos[s] - r0) + 1;  // 1-based list position (the reference's `contributor`)
-    const float wgt = GSL_FM(T, alpha);
-    const float A = GSL_FS(1.f, T);
-    const float mm1 = GSL_FM(rp.far_over_range, GSL_FS(1.f, GSL_FD(rp.near_, e.depth)));
-    const float mm = GSL_FM(mm1, mm1);
-    const float t0 = GSL_FF(-M1, GSL_FA(mm1, mm1), GSL_FF(A, mm, M2));
-    distortion = GSL_FF(wgt, t0, distortion);
-    M1 = GSL_FF(wgt, mm1, M1);
-    M2 = GSL_FF(wgt, mm, M2);
-    if (T > 0.5f) {
-      median_depth = e.depth;
-      median_contributor = pos;
-    }
-    const float4 col = sb.v[4][s];
-    C[0] = GSL_FF(T, GSL_FM(alpha, col.x), C[0]);
-    C[1] = GSL_FF(T, GSL_FM(alpha, col.y), C[1]);
-    C[2] = GSL_FF(T, GSL_FM(alpha, col.z), C[2]);
-    C[3] = GSL_FF(T, GSL_FM(alpha, col.w), C[3]);
-    if (FEAT4) {
-      const float4 f = sb.v[5][s];
-      F[0] = GSL_FF(T, GSL_FM(alpha, f.x), F[0]);
-      F[1] = GSL_FF(T, GSL_FM(alpha, f.y), F[1]);
-      F[2] = GSL_FF(T, GSL_FM(alpha, f.z), F[2]);
-      F[3] = GSL_FF(T, GSL_FM(alpha, f.w), F[3]);
-    } else if (S > 0) {
-      const float* fp = features + (size_t)sb.id[s] * S;
-#pragma unroll
-      for (int ch = 0; ch < GSL_MAX_FEATURES; ++ch)
-        if (ch < S) F[ch] = GSL_FF(T, GSL_FM(alpha, __ldg(fp + ch)), F[ch]);
-    }
-    Nn[0] = GSL_FF(T, GSL_FM(alpha, sp.nx), Nn[0]);
-    Nn[1] = GSL_FF(T, GSL_FM(alpha, sp.ny), Nn[1]);
-    Nn[2] = GSL_FF(T, GSL_FM(alpha, sp.nz), Nn[2]);
-    D = GSL_FF(T, GSL_FM(alpha, e.depth), D);
-    D2 = GSL_FF(T, GSL_FM(alpha, GSL_FM(e.depth, e.depth)), D2);
-    T = test_T;
-    last_contributor = pos;
-    return true;
+    cp_async_commit();
   };
 
-  if (r1 > r0) {
-    const uint32_t w0 = r0 >> 5, w1 = (r1 - 1) >> 5;
-    uint32_t* __restrict__ used_plane = used + (size_t)bbit * used_words;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-
-    auto load_mi = [&](uint32_t w, bool& cand, uint32_t& id) {
-      const uint32_t p = (w << 5) + lane;
-      const bool in = (w <= w1) && p >= r0 && p < r1;
-      cand = in && ((__ldg(bmask + p) >> bbit) & 1u);
-      id = cand ? __ldg(point_list + p) : 0u;
-    };
-
-    // prologue: word w0 staged in buffer 0, ids of word w0+1 in flight
-    bool candN, candNN;
-    uint32_t idN, idNN;
-    CandRegs rg;
+  uint32_t walk = 0;  // entries (from the start of the block list) up to the last one that contributed
+  if (be > bs) {
     int cur = 0;
-    uint32_t mCur;
+    uint2 entN = make_uint2(0, 0);
     {
-      bool c0;
-      uint32_t id0;
-      load_mi(w0, c0, id0);
-      gather_cand<FEAT4>(c0, id0, rec, colors, features, rg);
-      load_mi(w0 + 1, candN, idN);
-      mCur = __ballot_sync(0xffffffffu, c0);
-      if (c0) stage_cand<FEAT4>(stg[0], __popc(mCur & lt_mask), rg, id0, (uint32_t)lane);
-      __syncwarp();
+      uint2 ent0 = make_uint2(0, 0);
+      if (bs + lane < be) ent0 = __ldg(bl + bs + lane);
+      if (bs + 32 + lane < be) entN = __ldg(bl + bs + 32 + lane);
+      issue(stg[0], ent0, bs + lane < be);
     }
-    for (uint32_t w = w0; w <= w1; ++w) {
-      // ---- later pipeline stages: records of word w+1, mask + ids of word w+2
-      gather_cand<FEAT4>(candN, idN, rec, colors, features, rg);
-      load_mi(w + 2, candNN, idNN);
-      // ---- composite the staged candidates of word w
-      const WarpStage& sb = stg[cur];
-      const int cnt = __popc(mCur);
-      const uint32_t wbase = w << 5;
+    for (uint32_t c0 = bs; c0 < be; c0 += 32) {
+      const int n = (int)min(32u, be - c0);
+      cp_async_wait_all();
+      __syncwarp();
+      // ---- later pipeline stages: gathers of chunk c0+32, entries of chunk c0+64
+      issue(stg[cur ^ 1], entN, c0 + 32 + lane < be);
+      uint2 entNN = make_uint2(0, 0);
+      if (c0 + 64 + lane < be) entNN = __ldg(bl + c0 + 64 + lane);
+      // ---- which staged entries can reach my pixel
+      const ChunkStage& sb = stg[cur];
+      uint32_t bm = 0;
+      if (lane < n) bm = box_pixel_mask(sb.box[lane], bg_.bx0, bg_.by0);
+      uint32_t mine = transpose32(bm, lane);
+      if (done) mine = 0;
+      uint32_t contributed = 0;
 #ifdef GSL_STATS
-      if (lane == 0) { st_scan += min(32u, r1 - max(r0, wbase)); st_box += cnt; }
+      if (lane == 0) st_cand += n;
 #endif
-      uint32_t slotmask = 0;
-      for (int s = 0; s < cnt; s += 2) {
-        if (__all_sync(0xffffffffu, done)) break;
-        const bool two = s + 1 < cnt;  // warp-uniform
-        const int s1 = two ? s + 1 : s;
-        const Splat spa = staged_splat(sb, s);
-        const Splat spb = staged_splat(sb, s1);
-        const PairEval ea = eval_pair<false>(spa, ray, rp.near_, rp.far_);
-        PairEval eb = eval_pair<false>(spb, ray, rp.near_, rp.far_);
-        eb.valid = eb.valid && two;
+      while (__any_sync(0xffffffffu, mine != 0)) {
 #ifdef GSL_STATS
-        if (!done) { st_eval_lanes += two ? 2 : 1; st_valid += (ea.valid ? 1 : 0) + (eb.valid ? 1 : 0); }
+        if (lane == 0) st_iter++;
 #endif
-        const bool ca = blend(sb, s, spa, ea, wbase);
-        const bool cb = blend(sb, s1, spb, eb, wbase);
-        if (__any_sync(0xffffffffu, ca)) slotmask |= 1u << s;
-        if (__any_sync(0xffffffffu, cb)) slotmask |= 1u << s1;
-      }
-      if (slotmask != 0u) {
-        // slot mask -> list-position mask of this word
-        const bool mine = ((mCur >> lane) & 1u) && ((slotmask >> __popc(mCur & lt_mask)) & 1u);
-        const uint32_t usedbits = __ballot_sync(0xffffffffu, mine);
+        if (mine != 0) {
+          const int j = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const Splat sp = staged_splat(sb, j);
+          const PairEval e = eval_pair<false>(sp, ray, rp.near_, rp.far_);
 #ifdef GSL_STATS
-        if (lane == 0) st_any += __popc(usedbits);
+          st_eval++;
+          if (e.valid) st_valid++;
 #endif
-        if (lane == 0) {
-          if (w == w0 || w == w1) atomicOr(&used_plane[w], usedbits);  // word shared with the neighbouring tile
-          else used_plane[w] = usedbits;
+          if (e.valid) {
+            const float alpha = e.alpha;
+            const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
+            if (test_T < 0.0001f) {
+              done = true;
+              mine = 0;
+            } else {
+              const int pos = (int)(sb.ent[j].y - r0) + 1;  // 1-based list position (the reference's `contributor`)
+              const float wgt = GSL_FM(T, alpha);
+              const float A = GSL_FS(1.f, T);
+              const float mm1 = GSL_FM(rp.far_over_range, GSL_FS(1.f, GSL_FD(rp.near_, e.depth)));
+              const float mm = GSL_FM(mm1, mm1);
+              const float t0 = GSL_FF(-M1, GSL_FA(mm1, mm1), GSL_FF(A, mm, M2));
+              distortion = GSL_FF(wgt, t0, distortion);
+              M1 = GSL_FF(wgt, mm1, M1);
+              M2 = GSL_FF(wgt, mm, M2);
+              if (T > 0.5f) {
+                median_depth = e.depth;
+                median_contributor = pos;
+              }
+              const float4 col = sb.v[4][j];
+              C[0] = GSL_FF(T, GSL_FM(alpha, col.x), C[0]);
+              C[1] = GSL_FF(T, GSL_FM(alpha, col.y), C[1]);
+              C[2] = GSL_FF(T, GSL_FM(alpha, col.z), C[2]);
+              C[3] = GSL_FF(T, GSL_FM(alpha, col.w), C[3]);
+              if (FEAT4) {
+                const float4 f = sb.v[5][j];
+                F[0] = GSL_FF(T, GSL_FM(alpha, f.x), F[0]);
+                F[1] = GSL_FF(T, GSL_FM(alpha, f.y), F[1]);
+                F[2] = GSL_FF(T, GSL_FM(alpha, f.z), F[2]);
+                F[3] = GSL_FF(T, GSL_FM(alpha, f.w), F[3]);
+              } else if (S > 0) {
+                const float* fp = features + (size_t)sb.ent[j].x * S;
+#pragma unroll
+                for (int ch = 0; ch < GSL_MAX_FEATURES; ++ch)
+                  if (ch < S) F[ch] = GSL_FF(T, GSL_FM(alpha, __ldg(fp + ch)), F[ch]);
+              }
+              Nn[0] = GSL_FF(T, GSL_FM(alpha, sp.nx), Nn[0]);
+              Nn[1] = GSL_FF(T, GSL_FM(alpha, sp.ny), Nn[1]);
+              Nn[2] = GSL_FF(T, GSL_FM(alpha, sp.nz), Nn[2]);
+              D = GSL_FF(T, GSL_FM(alpha, e.depth), D);
+              D2 = GSL_FF(T, GSL_FM(alpha, GSL_FM(e.depth, e.depth)), D2);
+              T = test_T;
+              last_contributor = pos;
+              contributed |= 1u << j;
+            }
+          }
         }
       }
-      if (__all_sync(0xffffffffu, done)) break;
-      // ---- stage word w+1 into the other buffer, rotate
-      cur ^= 1;
-      mCur = __ballot_sync(0xffffffffu, candN);
-      if (candN) stage_cand<FEAT4>(stg[cur], __popc(mCur & lt_mask), rg, idN, (uint32_t)lane);
-      __syncwarp();
-      candN = candNN;
-      idN = idNN;
-    }
-  }
+      // ---- per-entry masks of the pixels it contributed to
+      const uint32_t pm = transpose32(contributed, lane);
+      if (lane < n) pmk[c0 + lane] = pm;
+      const uint32_t nz = __ballot_sync(0xffffffffu, pm != 0u);
+      if (nz) walk = (c0 - bs) + (32u - (uint32_t)__clz(nz));
 #ifdef GSL_STATS
-  STAT_ADD(0, st_scan); STAT_ADD(1, st_box); STAT_ADD(2, st_any); STAT_ADD(3, st_valid); STAT_ADD(4, st_eval_lanes);
+      if (lane == 0) st_any += __popc(nz);
+#endif
+      if (__all_sync(0xffffffffu, done)) break;
+      cur ^= 1;
+      entN = entNN;
+    }
+    cp_async_wait_all();
+  }
+  if (lane == 0) bdesc[bidx].z = walk;
+#ifdef GSL_STATS
+  STAT_ADD(0, st_cand); STAT_ADD(1, st_iter); STAT_ADD(2, st_any); STAT_ADD(3, st_valid); STAT_ADD(4, st_eval);
 #endif
 
   if (inside) {
@@ -242,9 +239,9 @@ int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd
   const float4* colors = in.colors_precomp ? reinterpret_cast<const float4*>(in.colors_precomp) : g.rgb;
   ProfScope prof(GSL_K_RENDER_FWD, st);
 #define GSL_LAUNCH_FWD(ST)                                                                                  \
-  k_render_fwd<ST><<<nblocks, 32, 0, st>>>(rp, im.ranges, b.vals_b, b.bmask, g.rec, colors, in.features,     \
-                                           in.background, g.ctrl, b.used, b.used_words, im.final_T,          \
-                                           out.out_contrib, out.out_color, out.out_feature, out.out_depth,  \
+  k_render_fwd<ST><<<nblocks, 32, 0, st>>>(rp, im.ranges, im.bdesc, b.blist, b.pairmask, b.plane_stride, g.rec, \
+                                           colors, in.features, g.pixbox, in.background, g.ctrl, im.final_T,  \
+                                           out.out_contrib, out.out_color, out.out_feature, out.out_depth,   \
                                            out.out_alpha)
   if (p.S == 4) GSL_LAUNCH_FWD(4);
   else if (p.S == 0) GSL_LAUNCH_FWD(0);

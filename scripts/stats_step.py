@@ -24,5 +24,6 @@ G._lib.gsl_stats_read(buf, 1)
 f = list(buf)[:5]
 G._lib.gsl_stats_read_bwd(buf, 1)
 b = list(buf)[:5]
-print(json.dumps(dict(P=P, fwd=dict(scan=f[0], box=f[1], any=f[2], valid_pairs=f[3], eval_lanes=f[4]),
-                      bwd=dict(scan=b[0], box=b[1], any=b[2], valid_pairs=b[3], multi=b[4]))))
+print(json.dumps(dict(P=P, fwd=dict(staged_entries=f[0], warp_iterations=f[1], contributing_entries=f[2],
+                                    valid_pairs=f[3], evaluated_pairs=f[4]),
+                      bwd=dict(staged_entries=b[0], warp_iterations=b[1], evaluated_pairs=b[3]))))
