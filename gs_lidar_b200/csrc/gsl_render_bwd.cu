@@ -29,6 +29,51 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+// Transposing butterfly: on entry every lane holds K partial sums v[0..K); on exit v[0] of lane L holds the
+// warp-wide total of component butterfly_component(K, L).  Stage `off` halves the number of live values:
+// lanes with bit `off` clear keep the lower half and receive the partner's lower half, the others keep and
+// receive the upper half.  Shuffles: ceil(K/2) + ceil(K/4) + ... (24 for K = 24) instead of 5 K.
+template <int K, int OFF>
+struct Butterfly {
+  static constexpr int H = (K + 1) / 2;
+  __device__ __forceinline__ static void run(float (&v)[32], int lane) {
+    const bool upper = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float a = v[i];
+      const float b = (i + H < K) ? v[i + H] : 0.f;
+      const float send = upper ? a : b;
+      const float keep = upper ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+    Butterfly<H, OFF / 2>::run(v, lane);
+  }
+};
+template <int K>
+struct Butterfly<K, 0> {
+  __device__ __forceinline__ static void run(float (&)[32], int) {}
+};
+// Component whose total ends up in v[0] of `lane` (-1: structural padding).  Traces the slot kept at each
+// stage back from the last stage to the first.
+__device__ __forceinline__ int butterfly_component(int K0, int lane) {
+  int Ks[5], Hs[5];
+  int k = K0;
+#pragma unroll
+  for (int t = 0; t < 5; ++t) { Ks[t] = k; Hs[t] = (k + 1) / 2; k = Hs[t]; }
+  int i = 0;
+  bool pad = false;
+#pragma unroll
+  for (int t = 4; t >= 0; --t) {
+    if (lane & (16 >> t)) i += Hs[t];
+    pad = pad || (i >= Ks[t]);
+  }
+  return pad ? -1 : i;
+}
+
 template <int S_T>
 __global__ void __launch_bounds__(32) k_render_bwd(
     RenderParams rp, const uint2* __restrict__ ranges, const uint4* __restrict__ bdesc,
@@ -38,6 +83,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
     const float* __restrict__ dL_dpix, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_dmask,
     const float* __restrict__ dL_dfeat, float* __restrict__ grad) {
   constexpr int KS = (S_T >= 0) ? S_T : GSL_MAX_FEATURES;  // feature slots held in registers
+  constexpr int K = 20 + KS;                               // live components of the packed record
   const int S = (S_T >= 0) ? S_T : rp.S;
   __shared__ ChunkStage stg[2];
 
@@ -94,8 +140,10 @@ __global__ void __launch_bounds__(32) k_render_bwd(
 
   const float far_near = rp.far_ * rp.near_;
   const float range_fn = rp.far_ - rp.near_;
+  int my_comp = butterfly_component(K, lane);
+  if (my_comp == 19 || my_comp >= 20 + S) my_comp = -1;  // padding slots of the packed record
 #ifdef GSL_STATS
-  unsigned st_cand = 0, st_iter = 0, st_valid = 0;
+  unsigned st_cand = 0, st_iter = 0, st_valid = 0, st_uni = 0;
 #endif
 
   // slot j of a chunk ending at entry index c1 (exclusive) holds entry c1 - 1 - j: ascending slots go back to front
@@ -145,12 +193,26 @@ __global__ void __launch_bounds__(32) k_render_bwd(
     if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pmCur != 0u));
     else __ballot_sync(0xffffffffu, pmCur != 0u);
 #endif
-    while (__any_sync(0xffffffffu, mine != 0)) {
+    for (;;) {
+      // Lanes normally sit on different entries.  When (almost) every pixel of the block is on the SAME entry --
+      // splats much larger than the block -- the pairs are summed by a transposing butterfly and the record is
+      // updated by one coalesced reduction instead of 32 colliding ones (also a more accurate sum).
+      const bool active = mine != 0;
+      const uint32_t amask = __ballot_sync(0xffffffffu, active);
+      if (amask == 0u) break;
+      const int j = active ? (__ffs(mine) - 1) : -1;
+      const int j0 = __shfl_sync(0xffffffffu, j, __ffs(amask) - 1);
+      const bool uniform = __popc(amask) >= 8 && __all_sync(0xffffffffu, !active || j == j0);
 #ifdef GSL_STATS
-      if (lane == 0) st_iter++;
+      if (lane == 0) { st_iter++; if (uniform) st_uni++; }
 #endif
-      if (mine != 0) {
-        const int j = __ffs(mine) - 1;
+      // packed record: [0..8] dL_dT, [9..10] dL_dmean2D, [11] dL_dopacity, [12..15] dL_dcolor,
+      // [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature
+      float g[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[i] = 0.f;
+      uint32_t sid = 0;
+      if (active) {
         mine &= mine - 1;
         const Splat s = staged_splat(sb, j);
         const PairEval e = eval_pair<true>(s, ray, rp.near_, rp.far_);
@@ -158,13 +220,8 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         st_valid++;
 #endif
         const uint2 ent = sb.ent[j];
+        sid = ent.x;
         const int pos0 = (int)(ent.y - r0);  // 0-based list position == the reference's `contributor` after --
-        // packed record: [0..8] dL_dT, [9..10] dL_dmean2D, [11] dL_dopacity, [12..15] dL_dcolor,
-        // [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature
-        float g[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) g[i] = 0.f;
-        float gcol[4], gnrm[3];
 
         const float alpha = e.alpha, G = e.G, depth = e.depth;
         T = T / (1.f - alpha);
@@ -177,7 +234,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
           accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
           last_color[ch] = col[ch];
           dL_dalpha += (col[ch] - accum_rec[ch]) * dpix[ch];
-          gcol[ch] = wgt * dpix[ch];
+          g[12 + ch] = wgt * dpix[ch];
         }
         float dL_dr = 0.f;
         dL_dr += alpha * T * dL_depth;
@@ -192,13 +249,16 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_ddist;
         dL_dr += dL_dmd * dmd_dd;
 
+#pragma unroll
+        for (int ch = 0; ch < KS; ++ch)
+          if (ch < S) g[20 + ch] = wgt * dfeat[ch];  // features do not feed dL_dalpha (backward.cu:395)
         const float nrm[3] = {s.nx, s.ny, s.nz};
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           accum_n[ch] = last_alpha * last_n[ch] + (1.f - last_alpha) * accum_n[ch];
           last_n[ch] = nrm[ch];
           dL_dalpha += (nrm[ch] - accum_n[ch]) * dnorm[ch];
-          gnrm[ch] = wgt * dnorm[ch];
+          g[16 + ch] = wgt * dnorm[ch];
         }
         accum_depth = last_alpha * last_depth + (1.f - last_alpha) * accum_depth;
         last_depth = depth;
@@ -238,19 +298,22 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         }
         g[11] = G * dL_dalpha;
 
-        float* gdst = grad + (size_t)ent.x * 32;
-        red_add_v4(gdst + 0, g[0], g[1], g[2], g[3]);
-        red_add_v4(gdst + 4, g[4], g[5], g[6], g[7]);
-        red_add_v4(gdst + 8, g[8], g[9], g[10], g[11]);
-        red_add_v4(gdst + 12, gcol[0], gcol[1], gcol[2], gcol[3]);
-        red_add_v4(gdst + 16, gnrm[0], gnrm[1], gnrm[2], 0.f);
-        // features do not feed dL_dalpha (backward.cu:395)
-        if (KS > 0) red_add_v4(gdst + 20, wgt * dfeat[0], KS > 1 ? wgt * dfeat[1 % (KS > 0 ? KS : 1)] : 0.f,
-                               KS > 2 ? wgt * dfeat[2 % (KS > 0 ? KS : 1)] : 0.f,
-                               KS > 3 ? wgt * dfeat[3 % (KS > 0 ? KS : 1)] : 0.f);
-        if (KS > 4) red_add_v4(gdst + 24, wgt * dfeat[4 % (KS > 0 ? KS : 1)], wgt * dfeat[5 % (KS > 0 ? KS : 1)],
-                               wgt * dfeat[6 % (KS > 0 ? KS : 1)], wgt * dfeat[7 % (KS > 0 ? KS : 1)]);
-        if (KS > 8) red_add_v4(gdst + 28, wgt * dfeat[8 % (KS > 0 ? KS : 1)], wgt * dfeat[9 % (KS > 0 ? KS : 1)], 0.f, 0.f);
+        if (!uniform) {
+          float* gdst = grad + (size_t)sid * 32;
+          red_add_v4(gdst + 0, g[0], g[1], g[2], g[3]);
+          red_add_v4(gdst + 4, g[4], g[5], g[6], g[7]);
+          red_add_v4(gdst + 8, g[8], g[9], g[10], g[11]);
+          red_add_v4(gdst + 12, g[12], g[13], g[14], g[15]);
+          red_add_v4(gdst + 16, g[16], g[17], g[18], 0.f);
+          if (KS > 0) red_add_v4(gdst + 20, g[20], g[21], g[22], g[23]);
+          if (KS > 4) red_add_v4(gdst + 24, g[24], g[25], g[26], g[27]);
+          if (KS > 8) red_add_v4(gdst + 28, g[28], g[29], 0.f, 0.f);
+        }
+      }
+      if (uniform) {
+        const uint32_t sid0 = __shfl_sync(0xffffffffu, sid, __ffs(amask) - 1);
+        Butterfly<K, 16>::run(g, lane);
+        if (my_comp >= 0) red_add_f32(grad + (size_t)sid0 * 32 + my_comp, g[0]);
       }
     }
     cur ^= 1;
@@ -260,7 +323,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
   }
   cp_async_wait_all();
 #ifdef GSL_STATS
-  STATB_ADD(0, st_cand); STATB_ADD(1, st_iter); STATB_ADD(3, st_valid);
+  STATB_ADD(0, st_cand); STATB_ADD(1, st_iter); STATB_ADD(3, st_valid); STATB_ADD(4, st_uni);
 #endif
 }
 

@@ -26,4 +26,4 @@ G._lib.gsl_stats_read_bwd(buf, 1)
 b = list(buf)[:5]
 print(json.dumps(dict(P=P, fwd=dict(staged_entries=f[0], warp_iterations=f[1], contributing_entries=f[2],
                                     valid_pairs=f[3], evaluated_pairs=f[4]),
-                      bwd=dict(staged_entries=b[0], warp_iterations=b[1], evaluated_pairs=b[3]))))
+                      bwd=dict(staged_entries=b[0], warp_iterations=b[1], evaluated_pairs=b[3], uniform_iterations=b[4]))))
