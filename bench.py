@@ -225,17 +225,41 @@ def run_ours(args, rank, world, local):
     h2d = sum(v.numel() * 4 for v in h_cam.values()) + sum(v.numel() * 4 for v in h_cot.values())
     d2h = sum(v.numel() * 4 for v in h_out.values())
 
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in, ev_fwd = torch.cuda.Event(), torch.cuda.Event()
+
     def e2e_step():
+        # within ONE step: the cotangent upload rides a copy stream under the forward pass (the backward waits for
+        # it), the rendered maps are read back on a second copy stream under the backward pass; nothing overlaps
+        # across steps (the step ends with a full synchronisation of all three streams).
+        main = torch.cuda.current_stream(dev)
         for k in h_cam:
             d_cam[k].copy_(h_cam[k], non_blocking=True)
-        for k in h_cot:
-            d_cot[k].copy_(h_cot[k], non_blocking=True)
+        s_in.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            for k in h_cot:
+                d_cot[k].copy_(h_cot[k], non_blocking=True)
+            ev_in.record(s_in)
         st = settings._replace(viewmatrix=d_cam["viewmatrix"], campos=d_cam["campos"])
-        step(G.GaussianRasterizer(st), d_cot)
-        for k in ("color", "feature", "depth", "alpha"):
-            h_out[k].copy_(last[k].detach(), non_blocking=True)
+        for v in leaves.values():
+            v.grad = None
+        contrib, color, feature, depth, alpha, radii = G.GaussianRasterizer(st)(
+            means3D=leaves["means3D"], means2D=leaves["means2D"], opacities=leaves["opacities"], shs=leaves["shs"],
+            features=leaves["features"], scales=leaves["scales"], rotations=leaves["rotations"], mask=scene.mask)
+        ev_fwd.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_fwd)
+            for k, t in (("color", color), ("feature", feature), ("depth", depth), ("alpha", alpha)):
+                h_out[k].copy_(t.detach(), non_blocking=True)
+        main.wait_event(ev_in)
+        torch.autograd.backward([color, feature, depth, alpha],
+                                [d_cot["color"], d_cot["feature"], d_cot["depth"], d_cot["alpha"]])
+        if bucket is not None:
+            bucket.load({k: leaves[k].grad for k in names})
+            bucket.all_reduce()
         h_out["gradsum"].copy_(leaves["means3D"].grad.sum(0), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        s_out.synchronize()
+        main.synchronize()
 
     for _ in range(3):
         e2e_step()

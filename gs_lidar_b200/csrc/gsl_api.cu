@@ -233,7 +233,7 @@ GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
 
 GSL_API const char* gsl_kernel_name(int id) {
   static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_scan_(reduce|sums|down)", "k_duplicate",
-                                           "cub::DeviceRadixSort (library)", "k_ranges_bmask+k_blist_(scan|scatter)", "k_render_fwd",
+                                           "cub::DeviceRadixSort (library)", "k_tile_blists", "k_render_fwd",
                                            "k_render_bwd", "k_preprocess_bwd"};
   return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
 }

@@ -176,16 +176,16 @@ __global__ void __launch_bounds__(256) k_duplicate(int P, const float4* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// identifyTileRanges (rasterizer_impl.cu:116-142) + second-level binning into 8x4-pixel BLOCK LISTS.
-// Three small kernels over the sorted list, GSL_BL_CHUNK positions per CTA (thread t takes positions
-// base + k*256 + t, so every warp handles 32 consecutive positions per round and ballots give ranks):
-//   k_ranges_bmask   ranges[tile] = [first, last+1); bmask[i] = which of the tile's 8 blocks the surfel's
-//                    conservative pixel box overlaps; per-CTA count of set bits per plane
-//   k_blist_scan     exclusive scan of the per-CTA counts, per plane
-//   k_blist_scatter  blist[b][prefix_b(i)] = (surfel id, i) for every set bit; block descriptors
+// identifyTileRanges (rasterizer_impl.cu:116-142) + second-level binning into 8x4-pixel BLOCK LISTS,
+// one CTA per 16x16 tile:
+//   * two warps find the tile's [first, last+1) in the sorted keys with a 32-ary search (5 probes rounds for
+//     millions of instances) -> ranges[tile] (empty tiles get (0,0) like the reference's memset);
+//   * the CTA then streams the tile's list; every position computes which of the tile's eight 8x4 blocks
+//     the surfel's conservative pixel box overlaps, and an order-preserving compaction per block (ballot
+//     ranks + running counters) appends (surfel id, list position) to blist[b][first + k].  The region of
+//     block (tile, b) starts at the tile's own `first` inside plane b, so no global scan is needed.
 // ------------------------------------------------------------------------------------------------
-constexpr int BL_THREADS = 256;
-constexpr int BL_ROUNDS = GSL_BL_CHUNK / BL_THREADS;
+constexpr int TB_THREADS = 512;
 
 __device__ __forceinline__ uint32_t block_mask_of(const short4 bb, uint32_t tile, int gx, int W, int H) {
   const int tx0 = (int)(tile % (uint32_t)gx) * GSL_BLOCK_X, ty0 = (int)(tile / (uint32_t)gx) * GSL_BLOCK_Y;
@@ -209,133 +209,103 @@ __device__ __forceinline__ uint32_t block_mask_of(const short4 bb, uint32_t tile
   return m;
 }
 
-__global__ void __launch_bounds__(BL_THREADS) k_ranges_bmask(
+// first index in [0, R) whose tile id (key >> 32) is >= t; executed by one full warp
+__device__ __forceinline__ uint32_t warp_lower_bound_tile(const uint64_t* __restrict__ keys, uint32_t R, uint32_t t) {
+  const int lane = threadIdx.x & 31;
+  uint32_t lo = 0, hi = R;  // answer in [lo, hi]
+  while (hi > lo) {
+    const uint32_t span = hi - lo;
+    if (span <= 32u) {
+      const uint32_t p = lo + lane;
+      const bool ge = (p < hi) ? ((uint32_t)(keys[p] >> 32) >= t) : true;
+      const uint32_t bal = __ballot_sync(0xffffffffu, ge);
+      return lo + (uint32_t)(__ffs(bal) - 1);
+    }
+    // 32 interior probes split [lo, hi) into 33 pieces
+    const uint32_t p = lo + (uint32_t)(((uint64_t)span * (uint32_t)(lane + 1)) / 33u);
+    const bool ge = (uint32_t)(keys[p] >> 32) >= t;
+    const uint32_t bal = __ballot_sync(0xffffffffu, ge);
+    const int f = bal ? (__ffs(bal) - 1) : 32;  // first probe that is >= t
+    const uint32_t p_f = __shfl_sync(0xffffffffu, p, f & 31);
+    const uint32_t p_prev = __shfl_sync(0xffffffffu, p, (f - 1) & 31);
+    const uint32_t new_hi = (f < 32) ? p_f : hi;
+    const uint32_t new_lo = (f > 0) ? p_prev + 1 : lo;
+    lo = new_lo;
+    hi = new_hi;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
     const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const short4* __restrict__ pixbox,
-    const uint32_t* __restrict__ ctrl, uint32_t r_capacity, int gx, int W, int H, uint2* __restrict__ ranges,
-    uint8_t* __restrict__ bmask, uint32_t* __restrict__ cta_counts) {
+    const uint32_t* __restrict__ ctrl, uint32_t r_capacity, int gx, int W, int H, size_t plane_stride,
+    uint2* __restrict__ ranges, uint2* __restrict__ blist, uint4* __restrict__ bdesc) {
   const uint32_t R = ctrl[0];
-  if (R > r_capacity) return;
-  __shared__ uint32_t s_cnt[8];
-  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t base = blockIdx.x * GSL_BL_CHUNK;
-  uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int k = 0; k < BL_ROUNDS; ++k) {
-    const uint32_t i = base + k * BL_THREADS + threadIdx.x;
-    uint32_t m = 0;
-    if (i < R) {
-      const uint32_t cur = (uint32_t)(keys[i] >> 32);
-      if (i == 0) {
-        ranges[cur].x = 0;
-      } else {
-        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-        if (cur != prev) {
-          ranges[prev].y = i;
-          ranges[cur].x = i;
-        }
-      }
-      if (i == R - 1) ranges[cur].y = R;
-      m = block_mask_of(pixbox[vals[i]], cur, gx, W, H);
-      bmask[i] = (uint8_t)m;
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) cnt[b] += __popc(__ballot_sync(0xffffffffu, (m >> b) & 1u));
-  }
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int b = 0; b < 8; ++b) atomicAdd(&s_cnt[b], cnt[b]);
-  }
-  __syncthreads();
-  if (threadIdx.x < 8) cta_counts[blockIdx.x * 8 + threadIdx.x] = s_cnt[threadIdx.x];
-}
-
-// one CTA; thread group b (128 threads) scans plane b
-__global__ void __launch_bounds__(1024) k_blist_scan(uint32_t* __restrict__ cta_counts, int nctas,
-                                                     const uint32_t* __restrict__ ctrl, uint32_t r_capacity) {
-  if (ctrl[0] > r_capacity) return;
-  __shared__ uint32_t s_w[8][4];
-  const int b = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, wv = t >> 5;
-  uint32_t carry = 0;
-  for (int base = 0; base < nctas; base += 128) {
-    const int i = base + t;
-    const uint32_t v = (i < nctas) ? cta_counts[i * 8 + b] : 0u;
-    const uint32_t inc = warp_incl_scan(v);
-    if (lane == 31) s_w[b][wv] = inc;
-    __syncthreads();
-    uint32_t off = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t x = s_w[b][k];
-      if (k < wv) off += x;
-      tot += x;
-    }
-    if (i < nctas) cta_counts[i * 8 + b] = carry + off + inc - v;
-    carry += tot;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(BL_THREADS) k_blist_scatter(
-    const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const uint8_t* __restrict__ bmask,
-    const uint32_t* __restrict__ cta_prefix, const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
-    size_t plane_stride, uint2* __restrict__ blist, uint4* __restrict__ bdesc) {
-  const uint32_t R = ctrl[0];
-  if (R > r_capacity) return;
-  constexpr int SEGS = BL_ROUNDS * (BL_THREADS / 32);
-  __shared__ uint32_t s_seg[SEGS][8];
-  const uint32_t base = blockIdx.x * GSL_BL_CHUNK;
+  const uint32_t tile = blockIdx.x;
+  constexpr int NW = TB_THREADS / 32;
+  constexpr int ITEMS = 4;             // list positions per thread and round (round k: base + k*TB_THREADS + tid)
+  constexpr int SEGS = ITEMS * NW;     // warp-sized segments of one round, in list order
+  __shared__ uint32_t s_bounds[2];
+  __shared__ uint32_t s_seg[SEGS][8];  // per segment and plane: count, then exclusive prefix (incl. running total)
+  __shared__ uint32_t s_run[8];
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  if (R == 0 || R > r_capacity) {
+    if (threadIdx.x == 0) ranges[tile] = make_uint2(0, 0);
+    if (threadIdx.x < 8) bdesc[tile * 8 + threadIdx.x] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  if (wv < 2) {
+    const uint32_t v = warp_lower_bound_tile(keys, R, tile + wv);
+    if (lane == 0) s_bounds[wv] = v;
+  }
+  if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lo = s_bounds[0], hi = s_bounds[1];
+  if (threadIdx.x == 0) ranges[tile] = (hi > lo) ? make_uint2(lo, hi) : make_uint2(0, 0);
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t mk[BL_ROUNDS];
+  for (uint32_t base = lo; base < hi; base += ITEMS * TB_THREADS) {
+    uint32_t id[ITEMS], m[ITEMS];
 #pragma unroll
-  for (int k = 0; k < BL_ROUNDS; ++k) {
-    const uint32_t i = base + k * BL_THREADS + threadIdx.x;
-    mk[k] = (i < R) ? (uint32_t)bmask[i] : 0u;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (mk[k] >> b) & 1u);
-      if (lane == b) s_seg[k * (BL_THREADS / 32) + wv][b] = __popc(bal);
+    for (int k = 0; k < ITEMS; ++k) {
+      const uint32_t i = base + k * TB_THREADS + threadIdx.x;
+      id[k] = (i < hi) ? vals[i] : 0u;
     }
-  }
-  __syncthreads();
-  if (threadIdx.x < 8) {  // exclusive scan over the segments of plane threadIdx.x, seeded with the CTA prefix
-    uint32_t run = cta_prefix[blockIdx.x * 8 + threadIdx.x];
-    for (int sgm = 0; sgm < SEGS; ++sgm) {
-      const uint32_t c = s_seg[sgm][threadIdx.x];
-      s_seg[sgm][threadIdx.x] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < BL_ROUNDS; ++k) {
-    const uint32_t i = base + k * BL_THREADS + threadIdx.x;
-    const int sgm = k * (BL_THREADS / 32) + wv;
-    uint32_t pre[8];
+    for (int k = 0; k < ITEMS; ++k) {
+      const uint32_t i = base + k * TB_THREADS + threadIdx.x;
+      m[k] = (i < hi) ? block_mask_of(pixbox[id[k]], tile, gx, W, H) : 0u;
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
-      pre[b] = s_seg[sgm][b] + __popc(__ballot_sync(0xffffffffu, (mk[k] >> b) & 1u) & lt);
-    if (i < R) {
-      const uint32_t id = vals[i];
-      const uint32_t cur = (uint32_t)(keys[i] >> 32);
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if ((mk[k] >> b) & 1u) blist[(size_t)b * plane_stride + pre[b]] = make_uint2(id, i);
-      const uint32_t prev = (i == 0) ? 0xffffffffu : (uint32_t)(keys[i - 1] >> 32);
-      if (cur != prev) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          bdesc[cur * 8 + b].x = pre[b];
-          if (i != 0) bdesc[prev * 8 + b].y = pre[b];
-        }
-      }
-      if (i == R - 1) {
-#pragma unroll
-        for (int b = 0; b < 8; ++b) bdesc[cur * 8 + b].y = pre[b] + ((mk[k] >> b) & 1u);
+      for (int b = 0; b < 8; ++b) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (m[k] >> b) & 1u);
+        if (lane == b) s_seg[k * NW + wv][b] = __popc(bal);
       }
     }
+    __syncthreads();
+    if (threadIdx.x < 8) {  // exclusive prefix over the segments of this plane, seeded with the running total
+      uint32_t run = s_run[threadIdx.x];
+#pragma unroll 8
+      for (int sg = 0; sg < SEGS; ++sg) {
+        const uint32_t c = s_seg[sg][threadIdx.x];
+        s_seg[sg][threadIdx.x] = run;
+        run += c;
+      }
+      s_run[threadIdx.x] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const uint32_t i = base + k * TB_THREADS + threadIdx.x;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (m[k] >> b) & 1u);
+        if ((m[k] >> b) & 1u)
+          blist[(size_t)b * plane_stride + lo + s_seg[k * NW + wv][b] + __popc(bal & lt)] = make_uint2(id[k], i);
+      }
+    }
+    __syncthreads();  // s_seg is rewritten by the next round
   }
+  __syncthreads();
+  if (threadIdx.x < 8) bdesc[tile * 8 + threadIdx.x] = make_uint4(lo, lo + s_run[threadIdx.x], 0, 0);
 }
 
 __global__ void k_flag_overflow(uint32_t* ctrl, uint32_t r_capacity) {
@@ -371,10 +341,12 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
                    int64_t r_capacity, int32_t* r_host, cudaStream_t st) {
   const int gx = (p.W + GSL_BLOCK_X - 1) / GSL_BLOCK_X, gy = (p.H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
   const int tiles = gx * gy;
-  cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
-  cudaMemsetAsync(im.bdesc, 0, (size_t)tiles * 8 * sizeof(uint4), st);
   const int64_t R = r_host[0];
-  if (p.P == 0 || R == 0) return check_cuda(cudaGetLastError(), "binning (empty)");
+  if (p.P == 0 || R == 0) {
+    cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
+    cudaMemsetAsync(im.bdesc, 0, (size_t)tiles * 8 * sizeof(uint4), st);
+    return check_cuda(cudaGetLastError(), "binning (empty)");
+  }
   if (R > r_capacity) {
     k_flag_overflow<<<1, 1, 0, st>>>(g.ctrl, (uint32_t)r_capacity);
     return GSL_ENOSPACE;
@@ -392,13 +364,9 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
                                                     (int)R, 0, 32 + bit, st);
     if (e != cudaSuccess) return check_cuda(e, "cub::DeviceRadixSort::SortPairs");
   }
-  const int nctas = (int)((R + GSL_BL_CHUNK - 1) / GSL_BL_CHUNK);
   ProfScope prof(GSL_K_RANGES, st);
-  k_ranges_bmask<<<nctas, BL_THREADS, 0, st>>>(b.keys_b, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W,
-                                               p.H, im.ranges, b.bmask, b.cta_counts);
-  k_blist_scan<<<1, 1024, 0, st>>>(b.cta_counts, nctas, g.ctrl, (uint32_t)r_capacity);
-  k_blist_scatter<<<nctas, BL_THREADS, 0, st>>>(b.keys_b, b.vals_b, b.bmask, b.cta_counts, g.ctrl,
-                                                (uint32_t)r_capacity, b.plane_stride, b.blist, im.bdesc);
+  k_tile_blists<<<tiles, TB_THREADS, 0, st>>>(b.keys_b, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W, p.H,
+                                             b.plane_stride, im.ranges, b.blist, im.bdesc);
   return check_cuda(cudaGetLastError(), "binning launch");
 }
 

@@ -17,18 +17,16 @@
 //     grad[i]     float[32] packed gradient accumulators, kept all-zero between steps:
 //         [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity,
 //         [12..15] dL_dcolor, [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature, pad to 32
-//     ctrl        u32[64]  [0]=R, [1]=overflow, [2]=scan ticket, ...
+//     ctrl        u32[64]  [0]=R, [1]=overflow
 //   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2),
 //     bdesc uint4[tiles*8]  per 8x4 pixel block (tile, b): (start, end) of its block list inside plane b,
 //                     .z = number of leading entries the backward pass has to walk (written by the forward)
 //   binning chunk (capacity Rcap): keys_a u64, keys_b u64, vals_a u32, vals_b u32, sort temp,
-//     bmask u8[Rcap]  per sorted list position: bit b set when the surfel's pixel box overlaps 8x4 pixel
-//                     block b = (row/4)*2 + col/8 of its 16x16 tile (written with the tile ranges)
-//     blist uint2[8][Rcap]  BLOCK LISTS: plane b holds, in list order, (surfel id, list position) of every
-//                     position whose bmask has bit b -- the entries of tile t form the list of block (t, b)
+//     blist uint2[8][Rcap]  BLOCK LISTS: plane b holds, for tile t at [ranges[t].x, ...), in list order, the
+//                     (surfel id, list position) of every entry of t whose conservative pixel box overlaps
+//                     8x4 pixel block b = (row/4)*2 + col/8 of the tile -- the list of block (t, b)
 //     pairmask u32[8][Rcap] per block-list entry: which of the block's 32 pixels the entry contributed to
 //                     in the forward pass (the backward pass evaluates exactly those pairs)
-//     cta_counts u32[ceil(Rcap/2048)+1][8]  per-CTA plane counts / prefixes of the block-list build
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -37,7 +35,6 @@
 #define GSL_BLOCK_X 16
 #define GSL_BLOCK_Y 16
 #define GSL_MY_PI 3.14159265  // auxiliary.h:17 (a double literal, NOT M_PI)
-#define GSL_BL_CHUNK 2048     // list positions per CTA of the block-list build
 
 namespace gsl {
 
@@ -75,10 +72,8 @@ struct BinView {
   uint32_t* vals_b;
   void* sort_tmp;
   size_t sort_tmp_bytes;
-  uint8_t* bmask;
   uint2* blist;
   uint32_t* pairmask;
-  uint32_t* cta_counts;
   size_t plane_stride;  // entries per plane of blist / pairmask
   size_t bytes;
 };
@@ -134,11 +129,9 @@ inline BinView bin_view(void* base, int64_t Rcap) {
   char* tmp;
   carve(p, tmp, b.sort_tmp_bytes);
   b.sort_tmp = tmp;
-  carve(p, b.bmask, R + 128);
   b.plane_stride = align_up(R, 64) + 64;
   carve(p, b.blist, 8 * b.plane_stride);
   carve(p, b.pairmask, 8 * b.plane_stride);
-  carve(p, b.cta_counts, 8 * (R / GSL_BL_CHUNK + 2));
   b.bytes = (size_t)(p - (char*)base) + 256;
   return b;
 }

@@ -428,65 +428,23 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float4* __re
   return dnormvdv3(dir_orig, dL_ddir);
 }
 
-// One thread per surfel.  Reads the packed accumulators, re-zeroes them (they must be all-zero when
-// the next backward starts), and writes EVERY element of every dense output.
-__global__ void __launch_bounds__(256) k_preprocess_bwd(
-    PreBwdParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
-    const float* __restrict__ rotations, const float* __restrict__ shs,
-    const float* __restrict__ viewmatrix, const float* __restrict__ campos,
-    const int* __restrict__ radii, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
-    float* __restrict__ grad, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
-    float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors, float* __restrict__ dL_dfeatures,
-    float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
-    float* __restrict__ dL_dcov3D) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= pp.P) return;
-  const int S = pp.S;
-  float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
-  float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
-             (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f) | (g2.z != 0.f) | (g2.w != 0.f) |
-             (gc.x != 0.f) | (gc.y != 0.f) | (gc.z != 0.f) | (gc.w != 0.f) | (gn.x != 0.f) | (gn.y != 0.f) |
-             (gn.z != 0.f);
-  // features: copy through and clean
-  const int nf4 = (S + 3) / 4;
-  for (int k = 0; k < nf4; ++k) {
-    float4 f = gq[5 + k];
-    float fv[4] = {f.x, f.y, f.z, f.w};
-    bool fany = false;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int ch = 4 * k + j;
-      if (ch < S) { dL_dfeatures[(size_t)idx * S + ch] = fv[j]; fany |= (fv[j] != 0.f); }
-    }
-    if (fany) gq[5 + k] = zero4;
-  }
-  if (any) { gq[0] = zero4; gq[1] = zero4; gq[2] = zero4; gq[3] = zero4; gq[4] = zero4; }
-
-  // direct copies
-  dL_dopacity[idx] = g2.w;
-  if (dL_dcov3D) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) dL_dcov3D[(size_t)idx * 6 + j] = 0.f;
-  }
-  float4 dcol = gc;
-
-  float3 dmean = make_float3(0.f, 0.f, 0.f);
-  float3 dscale = make_float3(0.f, 0.f, 0.f);
-  float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 dm2 = make_float2(0.f, 0.f);
-  const bool vis = radii[idx] > 0;
-  const int ncoef = (pp.D + 1) * (pp.D + 1);
-
-  if (vis) {
+// (k_preprocess_bwd is defined after preprocess_vjp_one)
+// VJP of k_preprocess_fwd and of the SH evaluation for one surfel with accumulator record (g0, g1, g2, dcol, gn).
+__device__ __forceinline__ void preprocess_vjp_one(
+    const PreBwdParams& pp, int i, float4 g0, float4 g1, float4 g2, float4 dcol, float4 gn,
+    const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rotations,
+    const float* __restrict__ shs, const float* __restrict__ viewmatrix, const float* __restrict__ campos,
+    const float4* __restrict__ rec, const uint8_t* __restrict__ clamped, float* __restrict__ dL_dmeans3D,
+    float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
+    float* __restrict__ dL_drot) {
+  {
     const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
     const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
     const float vm8 = viewmatrix[8], vm9 = viewmatrix[9], vm10 = viewmatrix[10];
-    const float sx = scales[3 * idx], sy = scales[3 * idx + 1];
-    const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
+    const float sx = scales[3 * (size_t)i], sy = scales[3 * (size_t)i + 1];
+    const float4 q = reinterpret_cast<const float4*>(rotations)[i];
     const Rot3 R = quat_to_rot(q.x, q.y, q.z, q.w);
-    const float4 r0 = rec[4 * (size_t)idx], r1 = rec[4 * (size_t)idx + 1], r2 = rec[4 * (size_t)idx + 2];
+    const float4 r0 = rec[4 * (size_t)i], r1 = rec[4 * (size_t)i + 1], r2 = rec[4 * (size_t)i + 2];
     // view-space centre = z column of T (backward.cu:584-586, :684-686)
     const float u = r0.z, v = r1.y, w = r2.x;
     // raw accumulated dL_dT rows
@@ -508,13 +466,12 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
     }
     // dL_dM = P * dL_dT^T, P = rotation part of the view matrix as used in T = M^T P
     // (backward.cu:598): world-space gradients of L0, L1 and the mean.
-    // dL_dM[j] (j = 0: L0, 1: L1, 2: mean) = V^T-rotation applied to column j of dL_dT rows.
-    float3 dL0 = make_float3(vm0 * dTu_x + vm1 * dTv_x + vm2 * dTw_x, vm4 * dTu_x + vm5 * dTv_x + vm6 * dTw_x,
-                             vm8 * dTu_x + vm9 * dTv_x + vm10 * dTw_x);
-    float3 dL1 = make_float3(vm0 * dTu_y + vm1 * dTv_y + vm2 * dTw_y, vm4 * dTu_y + vm5 * dTv_y + vm6 * dTw_y,
-                             vm8 * dTu_y + vm9 * dTv_y + vm10 * dTw_y);
-    dmean = make_float3(vm0 * dTu_z + vm1 * dTv_z + vm2 * dTw_z, vm4 * dTu_z + vm5 * dTv_z + vm6 * dTw_z,
-                        vm8 * dTu_z + vm9 * dTv_z + vm10 * dTw_z);
+    const float3 dL0 = make_float3(vm0 * dTu_x + vm1 * dTv_x + vm2 * dTw_x, vm4 * dTu_x + vm5 * dTv_x + vm6 * dTw_x,
+                                   vm8 * dTu_x + vm9 * dTv_x + vm10 * dTw_x);
+    const float3 dL1 = make_float3(vm0 * dTu_y + vm1 * dTv_y + vm2 * dTw_y, vm4 * dTu_y + vm5 * dTv_y + vm6 * dTw_y,
+                                   vm8 * dTu_y + vm9 * dTv_y + vm10 * dTw_y);
+    float3 dmean = make_float3(vm0 * dTu_z + vm1 * dTv_z + vm2 * dTw_z, vm4 * dTu_z + vm5 * dTv_z + vm6 * dTw_z,
+                               vm8 * dTu_z + vm9 * dTv_z + vm10 * dTw_z);
     // normal gradient back to world, sign by the UNFLIPPED view normal's z (backward.cu:599-603)
     float3 dtn = make_float3(vm0 * gn.x + vm1 * gn.y + vm2 * gn.z, vm4 * gn.x + vm5 * gn.y + vm6 * gn.z,
                              vm8 * gn.x + vm9 * gn.y + vm10 * gn.z);
@@ -522,6 +479,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
     const float mult = nz_view < 0.f ? 1.f : -1.f;
     dtn.x *= mult; dtn.y *= mult; dtn.z *= mult;
     // dL_dscale, dL_dR (backward.cu:604-619)
+    float3 dscale;
     dscale.x = dL0.x * R.r00 + dL0.y * R.r01 + dL0.z * R.r02;
     dscale.y = dL1.x * R.r10 + dL1.y * R.r11 + dL1.z * R.r12;
     dscale.z = 0.f;
@@ -529,9 +487,10 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
     const float v00 = dL0.x * sx, v01 = dL0.y * sx, v02 = dL0.z * sx;
     const float v10 = dL1.x * sy, v11 = dL1.y * sy, v12 = dL1.z * sy;
     const float v20 = dtn.x, v21 = dtn.y, v22 = dtn.z;
+    float4 drot;
     {  // quat_to_rotmat_vjp (auxiliary.h:230-274)
-      float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
-      float qw = q.x * s, qx = q.y * s, qy = q.z * s, qz = q.w * s;
+      const float s = rsqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+      const float qw = q.x * s, qx = q.y * s, qy = q.z * s, qz = q.w * s;
       drot.x = 2.f * (qx * (v12 - v21) + qy * (v20 - v02) + qz * (v01 - v10));
       drot.y = 2.f * (-2.f * qx * (v11 + v22) + qy * (v01 + v10) + qz * (v02 + v20) + qw * (v12 - v21));
       drot.z = 2.f * (qx * (v01 + v10) - 2.f * qy * (v00 + v22) + qz * (v12 + v21) + qw * (v20 - v02));
@@ -539,34 +498,118 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
     }
     // SH (backward.cu:676-677)
     if (shs != nullptr) {
-      const uint8_t cl = clamped[idx];
-      float4 dRGB = make_float4((cl & 1) ? 0.f : dcol.x, (cl & 2) ? 0.f : dcol.y, (cl & 4) ? 0.f : dcol.z,
-                                (cl & 8) ? 0.f : dcol.w);
+      const uint8_t cl = clamped[i];
+      const float4 dRGB = make_float4((cl & 1) ? 0.f : dcol.x, (cl & 2) ? 0.f : dcol.y, (cl & 4) ? 0.f : dcol.z,
+                                      (cl & 8) ? 0.f : dcol.w);
       // the reference masks dL_dcolors only in a local copy; the returned tensor is discarded on the SH
-      // path by the Python wrapper semantics (colors_precomp is empty), so dcol stays as accumulated.
-      float3 dir = make_float3(means3D[3 * idx] - campos[0], means3D[3 * idx + 1] - campos[1],
-                               means3D[3 * idx + 2] - campos[2]);
-      float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)idx * pp.M;
-      float3 dm = sh_backward(pp.D, pp.M, reinterpret_cast<const float4*>(shs) + (size_t)idx * pp.M, dRGB, dir,
-                              out_sh);
-      for (int k = ncoef; k < pp.M; ++k) out_sh[k] = zero4;
+      // path by the Python wrapper semantics (colors_precomp is empty), so dL_dcolors stays as accumulated.
+      const float3 dir = make_float3(means3D[3 * (size_t)i] - campos[0], means3D[3 * (size_t)i + 1] - campos[1],
+                                     means3D[3 * (size_t)i + 2] - campos[2]);
+      float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * pp.M;
+      const float3 dm = sh_backward(pp.D, pp.M, reinterpret_cast<const float4*>(shs) + (size_t)i * pp.M, dRGB, dir,
+                                    out_sh);
+      // coefficients >= (D+1)^2 keep the zeros of the sweep
       dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
     }
     // densification proxy (backward.cu:684-711), from the RAW accumulated dT z-column
     const float phi = atan2f(u, w);
+    float2 dm2;
     dm2.x = (float)((raw_du * w + raw_dw * (-u)) * 0.5 * dHr);
     const float du_dth = -v * sinf(phi), dv_dth = sqrtf(u * u + w * w), dw_dth = -v * cosf(phi);
     dm2.y = (float)((raw_du * du_dth + raw_dv * dv_dth + raw_dw * dw_dth) * 0.5 * dVr * pp.W / pp.H);
-  } else if (shs != nullptr) {
-    float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)idx * pp.M;
-    for (int k = 0; k < pp.M; ++k) out_sh[k] = zero4;
+
+    dL_dmeans3D[3 * (size_t)i] = dmean.x; dL_dmeans3D[3 * (size_t)i + 1] = dmean.y; dL_dmeans3D[3 * (size_t)i + 2] = dmean.z;
+    dL_dscales[3 * (size_t)i] = dscale.x; dL_dscales[3 * (size_t)i + 1] = dscale.y; dL_dscales[3 * (size_t)i + 2] = dscale.z;
+    reinterpret_cast<float4*>(dL_drot)[i] = drot;
+    reinterpret_cast<float4*>(dL_dmeans2D)[i] = make_float4(dm2.x, dm2.y, 0.f, 0.f);
   }
-  dL_dmeans3D[3 * (size_t)idx] = dmean.x; dL_dmeans3D[3 * (size_t)idx + 1] = dmean.y; dL_dmeans3D[3 * (size_t)idx + 2] = dmean.z;
-  dL_dscales[3 * (size_t)idx] = dscale.x; dL_dscales[3 * (size_t)idx + 1] = dscale.y; dL_dscales[3 * (size_t)idx + 2] = dscale.z;
-  reinterpret_cast<float4*>(dL_drot)[idx] = drot;
-  reinterpret_cast<float4*>(dL_dmeans2D)[idx] = make_float4(dm2.x, dm2.y, 0.f, 0.f);
-  reinterpret_cast<float4*>(dL_dcolors)[idx] = dcol;
 }
+
+// Backward preprocess, 256 surfels per CTA, two phases.
+//  1. thread = surfel, pure streaming: read the packed accumulator record, re-zero it (it must be all-zero
+//     when the next backward starts), copy the pass-through gradients (opacity, colour, features), zero-fill
+//     every other dense output with coalesced stores and queue the surfels whose record is non-zero in
+//     shared memory.  A surfel no pixel contributed to -- culled, hidden behind saturated pixels, outside
+//     every box: about half of the 1M-surfel scene -- has all-zero gradients and its parameters / SH
+//     coefficients are never read.
+//  2. the queued surfels, densely packed over the CTA's threads: VJP of k_preprocess_fwd and of the SH
+//     evaluation (preprocess_vjp_one).  Every element of every dense output is written by one of the phases.
+__global__ void __launch_bounds__(256) k_preprocess_bwd(
+    PreBwdParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
+    const float* __restrict__ rotations, const float* __restrict__ shs,
+    const float* __restrict__ viewmatrix, const float* __restrict__ campos,
+    const int* __restrict__ radii, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
+    float* __restrict__ grad, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
+    float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors, float* __restrict__ dL_dfeatures,
+    float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
+    float* __restrict__ dL_dcov3D) {
+  __shared__ float4 s_g[5][256];  // queued accumulator records (dT, mean2D, opacity, colour, normal)
+  __shared__ uint16_t s_who[256];
+  __shared__ int s_count;
+  const bool have_sh = shs != nullptr;
+  const int cta0 = blockIdx.x * 256;
+  const int idx = cta0 + threadIdx.x;
+  const int S = pp.S;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  if (idx < pp.P) {
+    float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
+    const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
+    const bool any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
+                     (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f) | (g2.z != 0.f) | (g2.w != 0.f) |
+                     (gc.x != 0.f) | (gc.y != 0.f) | (gc.z != 0.f) | (gc.w != 0.f) | (gn.x != 0.f) | (gn.y != 0.f) |
+                     (gn.z != 0.f);
+    const int nf4 = (S + 3) / 4;
+    for (int k = 0; k < nf4; ++k) {
+      const float4 f = gq[5 + k];
+      const float fv[4] = {f.x, f.y, f.z, f.w};
+      bool fany = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = 4 * k + j;
+        if (ch < S) { dL_dfeatures[(size_t)idx * S + ch] = fv[j]; fany |= (fv[j] != 0.f); }
+      }
+      if (fany) gq[5 + k] = zero4;
+    }
+    dL_dopacity[idx] = g2.w;
+    reinterpret_cast<float4*>(dL_dcolors)[idx] = gc;
+    const bool heavy = any && radii[idx] > 0;
+    if (any) { gq[0] = zero4; gq[1] = zero4; gq[2] = zero4; gq[3] = zero4; gq[4] = zero4; }
+    if (heavy) {
+      const int slot = atomicAdd(&s_count, 1);
+      s_who[slot] = (uint16_t)threadIdx.x;
+      s_g[0][slot] = g0; s_g[1][slot] = g1; s_g[2][slot] = g2; s_g[3][slot] = gc; s_g[4][slot] = gn;
+    } else {
+      reinterpret_cast<float4*>(dL_drot)[idx] = zero4;
+      reinterpret_cast<float4*>(dL_dmeans2D)[idx] = zero4;
+    }
+  }
+  // coalesced zero-fill of the CTA's rows of the strided outputs (queued surfels overwrite theirs later)
+  const int nrows = min(256, pp.P - cta0);
+  if (have_sh) {
+    float4* o = reinterpret_cast<float4*>(dL_dsh) + (size_t)cta0 * pp.M;
+    for (int k = threadIdx.x; k < nrows * pp.M; k += 256) o[k] = zero4;
+  }
+  {
+    float* o = dL_dmeans3D + (size_t)cta0 * 3;
+    for (int k = threadIdx.x; k < nrows * 3; k += 256) o[k] = 0.f;
+    o = dL_dscales + (size_t)cta0 * 3;
+    for (int k = threadIdx.x; k < nrows * 3; k += 256) o[k] = 0.f;
+    if (dL_dcov3D) {
+      o = dL_dcov3D + (size_t)cta0 * 6;
+      for (int k = threadIdx.x; k < nrows * 6; k += 256) o[k] = 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: the queued surfels, densely packed over the CTA's threads
+  const int count = s_count;
+  for (int slot = threadIdx.x; slot < count; slot += 256)
+    preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
+                       s_g[4][slot], means3D, scales, rotations, shs, viewmatrix, campos, rec, clamped, dL_dmeans3D,
+                       dL_dmeans2D, dL_dsh, dL_dscales, dL_drot);
+}
+
 
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
                                gsl_bwd_outputs& gout, const GeomView& g, cudaStream_t st) {
