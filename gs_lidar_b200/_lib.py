@@ -69,6 +69,7 @@ SYMBOLS = {
                                          C.POINTER(gsl_fwd_outputs), C.POINTER(gsl_workspace), vp]),
     "gsl_forward_render": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs),
                                      C.POINTER(gsl_fwd_outputs), C.POINTER(gsl_workspace), vp]),
+    "gsl_wait_num_rendered": (C.c_int, [C.POINTER(gsl_workspace), C.POINTER(C.c_int32), vp]),
     "gsl_forward": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
                               C.POINTER(gsl_workspace), C.POINTER(C.c_int32), vp]),
     "gsl_backward": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
@@ -84,7 +85,7 @@ SYMBOLS = {
 GSL_K_COUNT = 8
 # kernels of THIS repo launched per forward / backward call (k_scan is three launches; the cub sort is
 # library code and not counted): used by bench.py for "gpu_launches".
-OWN_LAUNCHES_FWD = 1 + 3 + 1 + 1 + 1   # preprocess, scan x3, duplicate, tile ranges + block lists, render_fwd
+OWN_LAUNCHES_FWD = 1 + 3 + 1 + 1 + 1   # preprocess, bin count/scan/bases, bin scatter, tile block lists, render_fwd
 OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
 
 _lib = None

@@ -90,7 +90,7 @@ static int validate_ws(const gsl_params* p, const gsl_workspace* ws, bool need_b
   if (!ws) return set_error(GSL_EINVAL, "workspace is NULL");
   gsl_ws_sizes sz;
   GeomView g = geom_view(nullptr, p->P, p->S);
-  ImageView im = image_view(nullptr, p->W, p->H);
+  ImageView im = image_view(nullptr, p->W, p->H, p->P);
   sz.geom_bytes = g.bytes;
   sz.image_bytes = im.bytes;
   if (!ws->geom || ws->geom_bytes < sz.geom_bytes)
@@ -128,7 +128,7 @@ GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_
   if (!out) return set_error(GSL_EINVAL, "out is NULL");
   if (r_capacity < 0 || r_capacity > 0x7fffffffLL) return set_error(GSL_EINVAL, "r_capacity out of range");
   out->geom_bytes = geom_view(nullptr, p->P, p->S).bytes;
-  out->image_bytes = image_view(nullptr, p->W, p->H).bytes;
+  out->image_bytes = image_view(nullptr, p->W, p->H, p->P).bytes;
   out->binning_bytes = bin_view(nullptr, r_capacity).bytes;
   return 0;
 }
@@ -144,6 +144,10 @@ GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in
   GeomView g = geom_view(ws->geom, p->P, p->S);
   if ((rc = launch_preprocess(*p, *in, *out, g, st))) return rc;
   if ((rc = debug_sync(p, st, "preprocess"))) return rc;
+  if (fast_binning(p->W, p->H)) {
+    if ((rc = launch_surfel_sort(*p, g, st))) return rc;
+    return debug_sync(p, st, "surfel sort");
+  }
   if ((rc = launch_scan(*p, g, ws->num_rendered_host, st))) return rc;
   return debug_sync(p, st, "scan");
 }
@@ -158,7 +162,7 @@ GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gs
   if ((rc = validate_ws(p, ws, true))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
-  ImageView im = image_view(ws->image, p->W, p->H);
+  ImageView im = image_view(ws->image, p->W, p->H, p->P);
   BinView b = bin_view(ws->binning, ws->r_capacity);
   rc = launch_binning(*p, g, im, b, ws->r_capacity, ws->num_rendered_host, st);
   if (rc == GSL_ENOSPACE)
@@ -170,13 +174,27 @@ GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gs
   return debug_sync(p, st, "render_forward");
 }
 
+GSL_API int gsl_wait_num_rendered(gsl_workspace* ws, int32_t* num_rendered, void* stream) {
+  if (!ws || !ws->num_rendered_host) return set_error(GSL_EINVAL, "workspace / num_rendered_host is NULL");
+  int rc = wait_num_rendered(ws->num_rendered_host, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (num_rendered) *num_rendered = ws->num_rendered_host[0];
+  return 0;
+}
+
 GSL_API int gsl_forward(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out, gsl_workspace* ws,
                 int32_t* num_rendered, void* stream) {
   int rc = gsl_forward_preprocess(p, in, out, ws, stream);
   if (rc) return rc;
-  if ((rc = check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "forward: wait for instance count"))) return rc;
-  if (num_rendered) *num_rendered = ws->num_rendered_host[0];
-  return gsl_forward_render(p, in, out, ws, stream);
+  rc = gsl_forward_render(p, in, out, ws, stream);
+  if (rc && rc != GSL_ENOSPACE) return rc;
+  int32_t R = 0;
+  int rc2 = gsl_wait_num_rendered(ws, &R, stream);
+  if (rc2) return rc2;
+  if (num_rendered) *num_rendered = R;
+  if (rc == GSL_ENOSPACE || (int64_t)R > ws->r_capacity)
+    return set_error(GSL_ENOSPACE, "binning capacity %lld < num_rendered %d", (long long)ws->r_capacity, R);
+  return 0;
 }
 
 GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
@@ -196,7 +214,7 @@ GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gs
   if ((rc = validate_ws(p, ws, true))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
-  ImageView im = image_view(ws->image, p->W, p->H);
+  ImageView im = image_view(ws->image, p->W, p->H, p->P);
   BinView b = bin_view(ws->binning, ws->r_capacity);
   if ((rc = launch_render_backward(*p, *in, *fwd, *gin, g, im, b, ws->r_capacity, st))) return rc;
   if ((rc = debug_sync(p, st, "render_backward"))) return rc;
@@ -232,7 +250,7 @@ GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
 }
 
 GSL_API const char* gsl_kernel_name(int id) {
-  static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_scan_(reduce|sums|down)", "k_duplicate",
+  static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan|bases)", "k_bin_scatter",
                                            "cub::DeviceRadixSort (library)", "k_tile_blists", "k_render_fwd",
                                            "k_render_bwd", "k_preprocess_bwd"};
   return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
@@ -274,8 +292,11 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
   if (!ws || !dst) return set_error(GSL_EINVAL, "workspace / dst is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
-  ImageView im = image_view(ws->image, p->W, p->H);
+  ImageView im = image_view(ws->image, p->W, p->H, p->P);
   if (p->P > 0) {
+    if (dst->point_offsets) {  // the fast binning path does not need the scan; run it for the export
+      if ((rc = launch_scan(*p, g, nullptr, st))) return rc;
+    }
     k_export_geom<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, g.rec, g.rgb, g.clamped, g.pixbox, *dst);
     if (dst->tiles_touched)
       cudaMemcpyAsync(dst->tiles_touched, g.tiles, (size_t)p->P * 4, cudaMemcpyDeviceToDevice, st);
@@ -285,8 +306,13 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
   if (R > 0 && ws->binning) {
     if (R > ws->r_capacity) return set_error(GSL_EINVAL, "R exceeds the binning capacity");
     BinView b = bin_view(ws->binning, ws->r_capacity);
-    if (dst->point_list_keys)
-      cudaMemcpyAsync(dst->point_list_keys, b.keys_b, (size_t)R * 8, cudaMemcpyDeviceToDevice, st);
+    if (dst->point_list_keys) {
+      if (fast_binning(p->W, p->H)) {
+        if ((rc = launch_export_keys(*p, g, im, b.vals_b, dst->point_list_keys, st))) return rc;
+      } else {
+        cudaMemcpyAsync(dst->point_list_keys, b.keys_b, (size_t)R * 8, cudaMemcpyDeviceToDevice, st);
+      }
+    }
     if (dst->point_list) cudaMemcpyAsync(dst->point_list, b.vals_b, (size_t)R * 4, cudaMemcpyDeviceToDevice, st);
   }
   const size_t tiles = (size_t)((p->W + GSL_BLOCK_X - 1) / GSL_BLOCK_X) * ((p->H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y);

@@ -115,7 +115,10 @@ int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStr
     k_scan_sums<<<1, 1024, 0, st>>>(g.scan_state, nblocks, g.ctrl, nullptr);
     k_scan_down<<<nblocks, SCAN_THREADS, 0, st>>>(g.tiles, p.P, g.scan_state, g.offs);
   }
-  if (r_host) cudaMemcpyAsync(r_host, g.ctrl, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (r_host) {
+    r_host[0] = -1;  // sentinel for wait_num_rendered
+    cudaMemcpyAsync(r_host, g.ctrl, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  }
   return check_cuda(cudaGetLastError(), "scan launch");
 }
 
@@ -239,7 +242,7 @@ __device__ __forceinline__ uint32_t warp_lower_bound_tile(const uint64_t* __rest
 __global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
     const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, const short4* __restrict__ pixbox,
     const uint32_t* __restrict__ ctrl, uint32_t r_capacity, int gx, int W, int H, size_t plane_stride,
-    uint2* __restrict__ ranges, uint2* __restrict__ blist, uint4* __restrict__ bdesc) {
+    uint2* __restrict__ ranges, uint2* __restrict__ blist, uint4* __restrict__ bdesc, bool have_ranges) {
   const uint32_t R = ctrl[0];
   const uint32_t tile = blockIdx.x;
   constexpr int NW = TB_THREADS / 32;
@@ -254,14 +257,20 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
     if (threadIdx.x < 8) bdesc[tile * 8 + threadIdx.x] = make_uint4(0, 0, 0, 0);
     return;
   }
-  if (wv < 2) {
+  if (have_ranges) {  // written by k_bin_bases
+    if (threadIdx.x == 0) {
+      const uint2 r = ranges[tile];
+      s_bounds[0] = r.x;
+      s_bounds[1] = r.y;
+    }
+  } else if (wv < 2) {
     const uint32_t v = warp_lower_bound_tile(keys, R, tile + wv);
     if (lane == 0) s_bounds[wv] = v;
   }
   if (threadIdx.x < 8) s_run[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lo = s_bounds[0], hi = s_bounds[1];
-  if (threadIdx.x == 0) ranges[tile] = (hi > lo) ? make_uint2(lo, hi) : make_uint2(0, 0);
+  if (!have_ranges && threadIdx.x == 0) ranges[tile] = (hi > lo) ? make_uint2(lo, hi) : make_uint2(0, 0);
   const uint32_t lt = (1u << lane) - 1u;
   for (uint32_t base = lo; base < hi; base += ITEMS * TB_THREADS) {
     uint32_t id[ITEMS], m[ITEMS];
@@ -308,6 +317,146 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
   if (threadIdx.x < 8) bdesc[tile * 8 + threadIdx.x] = make_uint4(lo, lo + s_run[threadIdx.x], 0, 0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast binning (images of up to GSL_FAST_BIN_MAX_TILES tiles).  The reference sorts R (tile | depth) keys of 64
+// bits; the same permutation is obtained by
+//   1. sorting the P SURFELS once by (depth bits, id)  (library radix sort over 32-bit keys; P is known on the
+//      host, so nothing waits for the instance count), and
+//   2. one stable counting pass that distributes the instances, emitted in that surfel order, to their tiles:
+//      within a tile the instances then appear in (depth, id) order, which is exactly the order of the
+//      reference's stable sort (a surfel emits a tile at most once).
+// Step 2 works on chunks of 256 depth-ranked surfels (one CTA each):
+//   k_bin_count    per chunk, a shared-memory bitmap [tile][256 surfels]; hist[tile][chunk] = popcount
+//   k_bin_scan     per tile, exclusive scan of hist[tile][*] over the chunks + total[tile]
+//   k_bin_bases    exclusive scan of total[] -> ranges[tile], R, overflow flag
+//   k_bin_scatter  rebuilds the bitmap; instance of surfel thread t in tile b goes to
+//                  ranges[b].x + hist[b][chunk] + popcount(bitmap[b] below t)
+// ------------------------------------------------------------------------------------------------
+// Visits every tile of every surfel of the chunk: surfels covering up to BIG_RECT tiles are walked by their own
+// thread, larger ones (azimuth-seam surfels cover whole tile rows) by all 32 lanes of their warp together, so no
+// thread serialises a long loop.  f(tile, t_src, payload) is called with t_src = chunk-local index of the surfel
+// and the payload of the thread that owns it.
+constexpr int BIG_RECT = 12;
+template <typename F>
+__device__ __forceinline__ void for_each_chunk_tile(ushort4 rc, int gx, uint32_t payload, F f) {
+  const int lane = threadIdx.x & 31;
+  const int w = (int)rc.z - (int)rc.x, n = w * ((int)rc.w - (int)rc.y);
+  if (n > 0 && n <= BIG_RECT) {
+    for (int y = rc.y; y < rc.w; ++y)
+      for (int x = rc.x; x < rc.z; ++x) f(y * gx + x, (int)threadIdx.x, payload);
+  }
+  uint32_t big = __ballot_sync(0xffffffffu, n > BIG_RECT);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx = __shfl_sync(0xffffffffu, (int)rc.x, src), by = __shfl_sync(0xffffffffu, (int)rc.y, src);
+    const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
+    const uint32_t pl = __shfl_sync(0xffffffffu, payload, src);
+    const int t_src = (int)threadIdx.x - lane + src;
+    for (int k = lane; k < bn; k += 32) f((by + k / bw) * gx + bx + k % bw, t_src, pl);
+  }
+}
+
+__device__ __forceinline__ void chunk_bitmap(uint32_t* s_bits, int tiles, int gx, ushort4 rc) {
+  for (int k = threadIdx.x; k < tiles * 8; k += 256) s_bits[k] = 0u;
+  __syncthreads();
+  for_each_chunk_tile(rc, gx, 0u,
+                      [&](int tile, int t, uint32_t) { atomicOr(&s_bits[tile * 8 + (t >> 5)], 1u << (t & 31)); });
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(int P, const uint32_t* __restrict__ order,
+                                                   const ushort4* __restrict__ rect, int tiles, int gx, size_t ncta,
+                                                   uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t s_bits[];
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  ushort4 rc = make_ushort4(0, 0, 0, 0);
+  if (j < P) rc = rect[order[j]];
+  chunk_bitmap(s_bits, tiles, gx, rc);
+  for (int b = threadIdx.x; b < tiles; b += 256) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) c += __popc(s_bits[b * 8 + w]);
+    hist[(size_t)b * ncta + blockIdx.x] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_scan(uint32_t* __restrict__ hist, size_t ncta,
+                                                  uint32_t* __restrict__ bintotal) {
+  __shared__ uint32_t sm[33];
+  uint32_t* row = hist + (size_t)blockIdx.x * ncta;
+  uint32_t carry = 0;
+  for (size_t base = 0; base < ncta; base += 256 * 4) {
+    const size_t i0 = base + (size_t)threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < ncta) ? row[i0 + k] : 0u;
+    const uint32_t s = v[0] + v[1] + v[2] + v[3];
+    uint32_t total;
+    uint32_t ex = block_excl_scan(s, sm, &total) + carry;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < ncta) row[i0 + k] = ex;
+      ex += v[k];
+    }
+    carry += total;
+  }
+  if (threadIdx.x == 0) bintotal[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(1024) k_bin_bases(const uint32_t* __restrict__ bintotal, int tiles,
+                                                    uint2* __restrict__ ranges, uint32_t* __restrict__ ctrl,
+                                                    uint32_t r_capacity) {
+  __shared__ uint32_t sm[33];
+  uint32_t carry = 0;
+  for (int base = 0; base < tiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < tiles) ? bintotal[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan(v, sm, &total) + carry;
+    if (i < tiles) ranges[i] = v ? make_uint2(ex, ex + v) : make_uint2(0, 0);  // empty tiles: (0,0) like the memset
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    ctrl[0] = carry;                          // R
+    ctrl[1] = carry > r_capacity ? 1u : 0u;   // overflow: the instance buffers are too small, nothing is written
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(int P, const uint32_t* __restrict__ order,
+                                                     const ushort4* __restrict__ rect, int tiles, int gx, size_t ncta,
+                                                     const uint32_t* __restrict__ hist, const uint2* __restrict__ ranges,
+                                                     const uint32_t* __restrict__ ctrl, uint32_t r_capacity,
+                                                     uint32_t* __restrict__ point_list) {
+  extern __shared__ uint32_t s_bits[];  // [tiles][8] bitmap, then [tiles] first output slot of this chunk
+  if (ctrl[0] > r_capacity) return;
+  uint32_t* s_base = s_bits + tiles * 8;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  ushort4 rc = make_ushort4(0, 0, 0, 0);
+  uint32_t id = 0;
+  if (j < P) {
+    id = order[j];
+    rc = rect[id];
+  }
+  for (int b = threadIdx.x; b < tiles; b += 256) s_base[b] = ranges[b].x + hist[(size_t)b * ncta + blockIdx.x];
+  chunk_bitmap(s_bits, tiles, gx, rc);
+  for_each_chunk_tile(rc, gx, id, [&](int tile, int t, uint32_t sid) {
+    const int w = t >> 5;
+    uint32_t r = __popc(s_bits[tile * 8 + w] & ((1u << (t & 31)) - 1u));
+    for (int k = 0; k < w; ++k) r += __popc(s_bits[tile * 8 + k]);
+    point_list[s_base[tile] + r] = sid;
+  });
+}
+
+// keys of the sorted list, reconstructed for state export: (tile << 32) | depth bits of the surfel
+__global__ void __launch_bounds__(256) k_export_keys(const uint2* __restrict__ ranges,
+                                                     const uint32_t* __restrict__ point_list,
+                                                     const float4* __restrict__ rec, uint64_t* __restrict__ keys) {
+  const uint2 r = ranges[blockIdx.x];
+  for (uint32_t p = r.x + threadIdx.x; p < r.y; p += 256)
+    keys[p] = ((uint64_t)blockIdx.x << 32) | (uint64_t)__float_as_uint(rec[4 * (size_t)point_list[p] + 3].w);
+}
+
 __global__ void k_flag_overflow(uint32_t* ctrl, uint32_t r_capacity) {
   if (ctrl[0] > r_capacity) ctrl[1] = 1;
 }
@@ -335,12 +484,91 @@ size_t sort_temp_bytes(int64_t Rcap) {
   return cached_bytes;
 }
 
+size_t surfel_sort_temp_bytes(int64_t P) {
+  static thread_local int64_t cached_p = -1;
+  static thread_local size_t cached_bytes = 0;
+  if (P == cached_p) return cached_bytes;
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)P);
+  cached_p = P;
+  cached_bytes = bytes + 256;
+  return cached_bytes;
+}
+
+// surfel ids in (depth bits, id) order -> g.sval_b (fast binning only)
+int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  size_t tmp = g.ssort_tmp_bytes;
+  ProfScope prof(GSL_K_SORT, st);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(g.ssort_tmp, tmp, g.skey_a, g.skey_b, g.sval_a, g.sval_b, p.P, 0, 32, st);
+  return check_cuda(e, "cub::DeviceRadixSort::SortPairs (surfels)");
+}
+
+int wait_num_rendered(int32_t* r_host, cudaStream_t st) {
+  volatile int32_t* v = r_host;
+  while (v[0] < 0) {
+    cudaError_t q = cudaStreamQuery(st);
+    if (q == cudaSuccess) break;              // everything ran: the copy has landed
+    if (q != cudaErrorNotReady) return check_cuda(q, "waiting for the instance count");
+  }
+  if (v[0] < 0) return check_cuda(cudaStreamSynchronize(st), "waiting for the instance count");
+  return 0;
+}
+
+int launch_export_keys(const gsl_params& p, const GeomView& g, const ImageView& im, const uint32_t* point_list,
+                       uint64_t* keys_out, cudaStream_t st) {
+  const int tiles = tile_count(p.W, p.H);
+  k_export_keys<<<tiles, 256, 0, st>>>(im.ranges, point_list, g.rec, keys_out);
+  return check_cuda(cudaGetLastError(), "k_export_keys launch");
+}
+
 // r_host[0] must already hold R (the caller synchronised on the scan) -- cub needs the count on
 // the host.  TODO(round 2): device-count sort to drop this dependency.
 int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,
                    int64_t r_capacity, int32_t* r_host, cudaStream_t st) {
   const int gx = (p.W + GSL_BLOCK_X - 1) / GSL_BLOCK_X, gy = (p.H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
   const int tiles = gx * gy;
+  if (fast_binning(p.W, p.H)) {
+    // ---- surfels are already depth-sorted (launch_surfel_sort): one stable counting pass per tile
+    if (p.P == 0) {
+      cudaMemsetAsync(g.ctrl, 0, 8, st);
+      cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
+      cudaMemsetAsync(im.bdesc, 0, (size_t)tiles * 8 * sizeof(uint4), st);
+      if (r_host) {
+        r_host[0] = -1;
+        cudaMemcpyAsync(r_host, g.ctrl, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      }
+      return check_cuda(cudaGetLastError(), "binning (empty)");
+    }
+    const int ncta = (int)im.ncta;
+    const size_t smem = (size_t)tiles * 9 * sizeof(uint32_t);
+    {
+      ProfScope prof(GSL_K_SCAN, st);
+      k_bin_count<<<ncta, 256, smem, st>>>(p.P, g.sval_b, g.rect, tiles, gx, im.ncta, im.hist);
+      k_bin_scan<<<tiles, 256, 0, st>>>(im.hist, im.ncta, im.bintotal);
+      k_bin_bases<<<1, 1024, 0, st>>>(im.bintotal, tiles, im.ranges, g.ctrl, (uint32_t)r_capacity);
+    }
+    if (r_host) {
+      r_host[0] = -1;  // sentinel for wait_num_rendered
+      cudaMemcpyAsync(r_host, g.ctrl, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    }
+    {
+      ProfScope prof(GSL_K_DUPLICATE, st);
+      k_bin_scatter<<<ncta, 256, smem, st>>>(p.P, g.sval_b, g.rect, tiles, gx, im.ncta, im.hist, im.ranges, g.ctrl,
+                                            (uint32_t)r_capacity, b.vals_b);
+    }
+    ProfScope prof(GSL_K_RANGES, st);
+    k_tile_blists<<<tiles, TB_THREADS, 0, st>>>(nullptr, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W, p.H,
+                                               b.plane_stride, im.ranges, b.blist, im.bdesc, true);
+    return check_cuda(cudaGetLastError(), "binning launch");
+  }
+  // ---- general path: 64-bit (tile | depth) key sort like the reference; needs R on the host
+  if (r_host) {
+    int rc = wait_num_rendered(r_host, st);
+    if (rc) return rc;
+  }
+
   const int64_t R = r_host[0];
   if (p.P == 0 || R == 0) {
     cudaMemsetAsync(im.ranges, 0, (size_t)tiles * sizeof(uint2), st);
@@ -366,7 +594,7 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
   }
   ProfScope prof(GSL_K_RANGES, st);
   k_tile_blists<<<tiles, TB_THREADS, 0, st>>>(b.keys_b, b.vals_b, g.pixbox, g.ctrl, (uint32_t)r_capacity, gx, p.W, p.H,
-                                             b.plane_stride, im.ranges, b.blist, im.bdesc);
+                                             b.plane_stride, im.ranges, b.blist, im.bdesc, false);
   return check_cuda(cudaGetLastError(), "binning launch");
 }
 

@@ -44,6 +44,14 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // the record in lane c, so one 32-lane reduction instruction flushes a whole record.
 inline __host__ __device__ int grad_stride(int /*S*/) { return 32; }
 
+// Up to this many 16x16 tiles the binning runs as "depth-sort the surfels once, then one stable counting
+// pass per tile" (gsl_binning.cu); larger images take the 64-bit key sort of the reference.
+#define GSL_FAST_BIN_MAX_TILES 1024
+inline __host__ __device__ int tile_count(int W, int H) {
+  return ((W + GSL_BLOCK_X - 1) / GSL_BLOCK_X) * ((H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y);
+}
+inline bool fast_binning(int W, int H) { return tile_count(W, H) <= GSL_FAST_BIN_MAX_TILES; }
+
 struct GeomView {
   float4* rec;
   float4* rgb;
@@ -54,7 +62,13 @@ struct GeomView {
   uint8_t* clamped;
   float* grad;
   uint32_t* ctrl;
-  uint32_t* scan_state;  // decoupled look-back tile descriptors
+  uint32_t* scan_state;  // per-CTA sums of the tiles_touched scan
+  uint32_t* skey_a;      // surfel depth sort: keys (depth bits, 0xffffffff when invisible) and surfel ids,
+  uint32_t* skey_b;      // double buffered; sval_b = surfel ids in (depth, id) order
+  uint32_t* sval_a;
+  uint32_t* sval_b;
+  void* ssort_tmp;
+  size_t ssort_tmp_bytes;
   size_t bytes;
 };
 
@@ -62,6 +76,9 @@ struct ImageView {
   float* final_T;   // 3N
   uint2* ranges;    // tiles
   uint4* bdesc;     // tiles * 8
+  uint32_t* hist;   // [tiles][ncta]: instances of tile t emitted by surfel chunk c, then its exclusive prefix
+  uint32_t* bintotal;  // [tiles]
+  size_t ncta;      // surfel chunks of 256 (depth-rank order)
   size_t bytes;
 };
 
@@ -85,6 +102,8 @@ inline void carve(char*& p, T*& out, size_t count) {
   p = (char*)(a + count * sizeof(T));
 }
 
+size_t surfel_sort_temp_bytes(int64_t P);
+
 inline GeomView geom_view(void* base, int P, int S) {
   GeomView g;
   char* p = (char*)base;
@@ -99,18 +118,30 @@ inline GeomView geom_view(void* base, int P, int S) {
   carve(p, g.grad, Pp * grad_stride(S));
   carve(p, g.ctrl, 64);
   carve(p, g.scan_state, 2 * ((Pp + 1023) / 1024 + 1));
+  carve(p, g.skey_a, Pp);
+  carve(p, g.skey_b, Pp);
+  carve(p, g.sval_a, Pp);
+  carve(p, g.sval_b, Pp);
+  g.ssort_tmp_bytes = surfel_sort_temp_bytes((int64_t)Pp);
+  char* stmp;
+  carve(p, stmp, g.ssort_tmp_bytes);
+  g.ssort_tmp = stmp;
   g.bytes = (size_t)(p - (char*)base) + 256;
   return g;
 }
 
-inline ImageView image_view(void* base, int W, int H) {
+inline ImageView image_view(void* base, int W, int H, int P) {
   ImageView v;
   char* p = (char*)base;
   size_t N = (size_t)W * H;
-  size_t tiles = (size_t)((W + GSL_BLOCK_X - 1) / GSL_BLOCK_X) * ((H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y);
+  size_t tiles = (size_t)tile_count(W, H);
   carve(p, v.final_T, 3 * N);
   carve(p, v.ranges, tiles + 1);
   carve(p, v.bdesc, 8 * tiles + 8);
+  v.ncta = ((size_t)(P > 0 ? P : 1) + 255) / 256;
+  const bool fast = fast_binning(W, H);
+  carve(p, v.hist, fast ? tiles * v.ncta : 1);
+  carve(p, v.bintotal, fast ? tiles + 1 : 1);
   v.bytes = (size_t)(p - (char*)base) + 256;
   return v;
 }
@@ -175,8 +206,12 @@ int check_cuda(cudaError_t e, const char* what);
 int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
                       const GeomView& g, cudaStream_t st);
 int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st);
+int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st);
 int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,
                    int64_t r_capacity, int32_t* r_host, cudaStream_t st);
+int launch_export_keys(const gsl_params& p, const GeomView& g, const ImageView& im, const uint32_t* point_list,
+                       uint64_t* keys_out, cudaStream_t st);
+int wait_num_rendered(int32_t* r_host, cudaStream_t st);
 int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
                           const GeomView& g, const ImageView& im, const BinView& b,
                           int64_t r_capacity, cudaStream_t st);

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     const uint8_t* __restrict__ mask, const float* __restrict__ viewmatrix,
     const float* __restrict__ campos, int* __restrict__ radii, float4* __restrict__ rec,
     float4* __restrict__ rgb, ushort4* __restrict__ rect, short4* __restrict__ pixbox,
-    uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped) {
+    uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped, uint32_t* __restrict__ skey,
+    uint32_t* __restrict__ sval) {
   __shared__ float s_sin[12], s_cos[12];
   if (threadIdx.x < 12) {
     s_sin[threadIdx.x] = sinf(pp.samp[threadIdx.x]);
@@ -330,6 +331,9 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
   tiles[idx] = out_tiles;
   rect[idx] = out_rect;
   pixbox[idx] = out_box;
+  // key of the surfel depth sort (fast binning): depth bits, invisible surfels last
+  skey[idx] = out_tiles ? __float_as_uint(r) : 0xffffffffu;
+  sval[idx] = (uint32_t)idx;
 }
 
 int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
@@ -347,7 +351,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
   ProfScope prof(GSL_K_PREPROCESS_FWD, st);
   k_preprocess_fwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.opacities, in.shs,
                                           in.colors_precomp, in.mask, in.viewmatrix, in.campos, out.radii,
-                                          g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped);
+                                          g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped, g.skey_a, g.sval_a);
   return check_cuda(cudaGetLastError(), "k_preprocess_fwd launch");
 }
 

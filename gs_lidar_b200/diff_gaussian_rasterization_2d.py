@@ -198,15 +198,23 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
         st = _stream_ptr(dev)
         L.check(_lib.gsl_forward_preprocess(C.byref(params), C.byref(fin), C.byref(fout), C.byref(wss), st),
                 "gsl_forward_preprocess")
-        ws.event.record(torch.cuda.current_stream(dev))
-        ws.event.synchronize()
-        R = int(ws.host[0])
-        if R > ws.r_capacity:
+        # The render stage is enqueued speculatively against the current capacity; the instance count arrives on
+        # the host while the compositing kernels are still queued (no pipeline bubble in the middle of the
+        # forward pass like the reference's blocking copy, rasterizer_impl.cu:314-315).
+        r_host = C.c_int32(0)
+        for attempt in range(3):
+            rc = _lib.gsl_forward_render(C.byref(params), C.byref(fin), C.byref(fout), C.byref(wss), st)
+            if rc != L.GSL_ENOSPACE:
+                L.check(rc, "gsl_forward_render")
+            L.check(_lib.gsl_wait_num_rendered(C.byref(wss), C.byref(r_host), st), "gsl_wait_num_rendered")
+            R = int(r_host.value)
+            if R <= ws.r_capacity:
+                break
             ws.ensure(params, R + R // 4)
             wss = ws.as_struct()
+        else:
+            raise RuntimeError("gs_lidar_b200: could not size the binning workspace for %d instances" % R)
         _pool.r_hint[(dev, P, W, H)] = max(R + R // 4, 1024)
-        L.check(_lib.gsl_forward_render(C.byref(params), C.byref(fin), C.byref(fout), C.byref(wss), st),
-                "gsl_forward_render")
     outs = (out_contrib, out_color, out_feature, out_depth, out_alpha, radii)
     return outs, holder, params, inputs, R
 

@@ -79,7 +79,7 @@ typedef struct gsl_workspace {
   void* binning; size_t binning_bytes;
   void* image;   size_t image_bytes;
   int64_t r_capacity;     /* instance capacity the binning chunk was sized for */
-  int32_t* num_rendered_host; /* PINNED host int[2]: [0]=R (tile instances), [1]=overflow flag */
+  int32_t* num_rendered_host; /* PINNED host int[2]: [0]=R (tile instances; -1 while in flight), [1]=overflow flag */
 } gsl_workspace;
 
 typedef struct gsl_fwd_inputs {
@@ -132,17 +132,25 @@ GSL_API const char* gsl_last_error(void);
 /* Sizes of the scratch chunks for P surfels, r_capacity tile instances and W*H pixels. */
 GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_sizes* out);
 
-/* Stage 1 of the forward pass: preprocess + tile-count scan.  Enqueues an async copy of the
- * instance count R into ws->num_rendered_host[0]; never blocks the host. */
+/* Stage 1 of the forward pass: per-surfel preprocess, then the depth sort of the surfels (images of up to 1024
+ * tiles) or the tile-count scan (larger images).  Never blocks the host. */
 GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
                            gsl_workspace* ws, void* stream);
 
-/* Stage 2: key duplication, tile|depth sort, tile ranges and per-tile compositing.  Safe to
- * enqueue speculatively: if the device-side R exceeds ws->r_capacity the kernels do nothing and
- * num_rendered_host[1] is set to 1 (after the stream reaches that point); the caller then grows
- * the binning chunk and calls this function again. */
+/* Stage 2: binning (tile lists bit-identical to the reference's sorted list, tile ranges, block lists) and
+ * per-tile compositing.  Enqueued SPECULATIVELY against ws->r_capacity: if the device-side instance count R
+ * exceeds it the kernels write nothing and the overflow flag is raised; the caller then learns R with
+ * gsl_wait_num_rendered(), grows the binning chunk and calls this function again.  An asynchronous copy of
+ * (R, overflow) into ws->num_rendered_host is enqueued right after the counting kernels, long before the
+ * compositing finishes.  (Images of more than 1024 tiles use a 64-bit key sort that needs R on the host:
+ * there this call waits for the count itself and returns GSL_ENOSPACE without launching when R does not fit.) */
 GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
                        gsl_workspace* ws, void* stream);
+
+/* Waits (polling the pinned word, not the whole stream) until the instance count of the forward enqueued on
+ * `stream` with `ws` has arrived on the host and returns it.  Replaces the blocking cudaMemcpy of
+ * rasterizer_impl.cu:314-315, but sits AFTER all launches of the forward pass instead of in their middle. */
+GSL_API int gsl_wait_num_rendered(gsl_workspace* ws, int32_t* num_rendered, void* stream);
 
 /* Blocking convenience with the semantics of Rasterizer::forward: runs both stages, waits for
  * R, returns it in *num_rendered.  Returns GSL_ENOSPACE (with *num_rendered set) if the
@@ -183,10 +191,10 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
  * Kernel ids index the arrays of gsl_profile_read. */
 enum {
   GSL_K_PREPROCESS_FWD = 0,
-  GSL_K_SCAN = 1,
-  GSL_K_DUPLICATE = 2,
+  GSL_K_SCAN = 1,      /* k_bin_count + k_bin_scan + k_bin_bases (k_scan_* on the > 1024-tile path) */
+  GSL_K_DUPLICATE = 2, /* k_bin_scatter (k_duplicate on the > 1024-tile path) */
   GSL_K_SORT = 3,      /* library radix sort (cub) -- not one of this repo's kernels */
-  GSL_K_RANGES = 4,
+  GSL_K_RANGES = 4,    /* k_tile_blists */
   GSL_K_RENDER_FWD = 5,
   GSL_K_RENDER_BWD = 6,
   GSL_K_PREPROCESS_BWD = 7,
