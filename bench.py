@@ -146,7 +146,12 @@ def run_ours(args, rank, world, local):
     import gs_lidar_b200.diff_gaussian_rasterization_2d as G
     dev = torch.device("cuda", local)
     P, H, W, S = args.surfels, args.height, args.width, 4
-    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(rank)).to(dev)
+    # replicated surfels (the world-space set of frame 0 on every rank), one camera pose per rank
+    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(0))
+    if rank != 0:
+        cam = synth.make_scene(16, H=H, W=W, S=S, seed=0, **make_frame_pose(rank))
+        scene = scene._replace(viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, campos=cam.campos)
+    scene = scene.to(dev)
     cot_cpu = synth.make_cotangents(H, W, S, seed=1)
     cot = {k: v.to(dev) for k, v in cot_cpu.items()}
     settings = synth.settings_for(scene)
@@ -157,7 +162,10 @@ def run_ours(args, rank, world, local):
                   rotations=scene.rotations.clone())
     for v in leaves.values():
         v.requires_grad_(True)
-    bucket = parallel.GradBucket(parallel.surfel_grad_shapes(P, S, scene.shs.shape[1]), dev) if world > 1 else None
+    # N > 1: the gradient exchange is fused into the backward pass (parallel.GradientExchange): flat non-SH
+    # gradients all-reduced, 16-byte SH factors all-gathered, SH gradient rebuilt on the device.
+    bucket = None
+    exchange = parallel.GradientExchange().enable() if world > 1 else None
     last = {}
 
     def step(rasterizer=rast, cots=cot):
@@ -315,9 +323,9 @@ def run_ours(args, rank, world, local):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "visible_surfels": V, "tile_instances": R,
-                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, ", fp32 gradient all-reduce (NCCL) in the step" if world > 1 else ""),
+                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, ", fp32 gradient exchange (NCCL all-reduce of the non-SH gradients + all-gather of the SH factors) in the step" if world > 1 else ""),
                    "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6),
-                   "grad_bucket_bytes": bucket.nbytes if bucket is not None else 0},
+                   "grad_exchange_bytes": (exchange.flat.numel() * 4 + exchange.local.numel() * 4) if exchange is not None else 0},
         "clocks": clocks,
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,

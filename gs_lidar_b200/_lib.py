@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("GSL_B200_LIB", os.path.join(HERE, "libgsl_b200.so")) 
 GSL_ABI_VERSION = 1
 GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
 GSL_FLAG_DEBUG_SYNC = 1
+GSL_FLAG_BWD_SH_FACTORED = 2
 GSL_MAX_FEATURES = 10
 
 vp = C.c_void_p
@@ -76,6 +77,7 @@ SYMBOLS = {
                                C.POINTER(gsl_bwd_inputs), C.POINTER(gsl_bwd_outputs),
                                C.POINTER(gsl_workspace), vp]),
     "gsl_mark_visible": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
+    "gsl_sh_expand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_size_t, vp, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
                                    C.POINTER(gsl_state_export), vp]),
     "gsl_profile_enable": (C.c_int, [C.c_int]),

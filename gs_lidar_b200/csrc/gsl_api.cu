@@ -208,7 +208,7 @@ GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gs
     return set_error(GSL_EINVAL, "a cotangent pointer is NULL");
   if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dcolors || !gout->dL_dopacity ||
       !gout->dL_dscales || !gout->dL_drotations || (p->S > 0 && !gout->dL_dfeatures) ||
-      (in->shs && !gout->dL_dsh))
+      (in->shs && !gout->dL_dsh && !(p->flags & GSL_FLAG_BWD_SH_FACTORED)))
     return set_error(GSL_EINVAL, "a gradient output pointer is NULL");
   if (!fwd->radii || !fwd->out_contrib) return set_error(GSL_ESTATE, "forward outputs (radii, out_contrib) missing");
   if ((rc = validate_ws(p, ws, true))) return rc;
@@ -228,6 +228,16 @@ GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewm
   if (P > 0 && (!means3D || !viewmatrix || !projmatrix || !present))
     return set_error(GSL_EINVAL, "mark_visible: NULL pointer");
   return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_sh_expand(int32_t P, int32_t D, int32_t M, int32_t G, const float* means3D, const float* campos_all,
+                  const float* drgb_all, size_t drgb_stride, float* dL_dsh, void* stream) {
+  if (P < 0 || D < 0 || D > 3 || M < 0 || G < 1) return set_error(GSL_EINVAL, "sh_expand: bad sizes");
+  if (M > 0 && (D + 1) * (D + 1) > M) return set_error(GSL_EINVAL, "sh_expand: degree %d needs %d coefficients", D, (D + 1) * (D + 1));
+  if (P > 0 && M > 0 && (!means3D || !campos_all || !drgb_all || !dL_dsh))
+    return set_error(GSL_EINVAL, "sh_expand: NULL pointer");
+  if (drgb_stride < (size_t)4 * (size_t)P) return set_error(GSL_EINVAL, "sh_expand: drgb_stride < 4 P");
+  return launch_sh_expand(P, D, M, G, means3D, campos_all, drgb_all, drgb_stride, dL_dsh, (cudaStream_t)stream);
 }
 
 GSL_API int gsl_profile_enable(int on) { g_prof_on = on != 0; return 0; }

@@ -221,6 +221,8 @@ int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const 
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
                                cudaStream_t st);
+int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
+                     size_t drgb_stride, float* dL_dsh, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, cudaStream_t st);
 

@@ -361,6 +361,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
 
 struct PreBwdParams {
   int P, D, M, S, W, H, gstride;
+  int factored;  // GSL_FLAG_BWD_SH_FACTORED: dL_dcolors receives the clamp-masked dL_dRGB, dL_dsh is not written
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -382,39 +383,40 @@ __device__ __forceinline__ void operator+=(float4& a, float4 b) { a.x += b.x; a.
 
 // SH VJP (backward.cu:17-134).  Writes dL_dsh[0..(D+1)^2) and returns the gradient w.r.t. the
 // mean through the view direction.
+template <bool WRITE>
 __device__ __forceinline__ float3 sh_backward(int deg, int M, const float4* __restrict__ sh, float4 dL_dRGB,
                                               float3 dir_orig, float4* __restrict__ dL_dsh) {
   float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
   float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
   float4 dRGBdx = make_float4(0, 0, 0, 0), dRGBdy = dRGBdx, dRGBdz = dRGBdx;
-  dL_dsh[0] = kSH_C0 * dL_dRGB;
+  if (WRITE) dL_dsh[0] = kSH_C0 * dL_dRGB;
   if (deg > 0) {
-    dL_dsh[1] = (-kSH_C1 * y) * dL_dRGB;
-    dL_dsh[2] = (kSH_C1 * z) * dL_dRGB;
-    dL_dsh[3] = (-kSH_C1 * x) * dL_dRGB;
+    if (WRITE) dL_dsh[1] = (-kSH_C1 * y) * dL_dRGB;
+    if (WRITE) dL_dsh[2] = (kSH_C1 * z) * dL_dRGB;
+    if (WRITE) dL_dsh[3] = (-kSH_C1 * x) * dL_dRGB;
     dRGBdx = (-kSH_C1) * sh[3];
     dRGBdy = (-kSH_C1) * sh[1];
     dRGBdz = kSH_C1 * sh[2];
     if (deg > 1) {
       float xx = x * x, yy = y * y, zz = z * z;
       float xy = x * y, yz = y * z, xz = x * z;
-      dL_dsh[4] = (kSH_C2[0] * xy) * dL_dRGB;
-      dL_dsh[5] = (kSH_C2[1] * yz) * dL_dRGB;
-      dL_dsh[6] = (kSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB;
-      dL_dsh[7] = (kSH_C2[3] * xz) * dL_dRGB;
-      dL_dsh[8] = (kSH_C2[4] * (xx - yy)) * dL_dRGB;
+      if (WRITE) dL_dsh[4] = (kSH_C2[0] * xy) * dL_dRGB;
+      if (WRITE) dL_dsh[5] = (kSH_C2[1] * yz) * dL_dRGB;
+      if (WRITE) dL_dsh[6] = (kSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB;
+      if (WRITE) dL_dsh[7] = (kSH_C2[3] * xz) * dL_dRGB;
+      if (WRITE) dL_dsh[8] = (kSH_C2[4] * (xx - yy)) * dL_dRGB;
       float4 s4 = sh[4], s5 = sh[5], s6 = sh[6], s7 = sh[7], s8 = sh[8];
       dRGBdx += (kSH_C2[0] * y) * s4 + (kSH_C2[2] * 2.f * -x) * s6 + (kSH_C2[3] * z) * s7 + (kSH_C2[4] * 2.f * x) * s8;
       dRGBdy += (kSH_C2[0] * x) * s4 + (kSH_C2[1] * z) * s5 + (kSH_C2[2] * 2.f * -y) * s6 + (kSH_C2[4] * 2.f * -y) * s8;
       dRGBdz += (kSH_C2[1] * y) * s5 + (kSH_C2[2] * 2.f * 2.f * z) * s6 + (kSH_C2[3] * x) * s7;
       if (deg > 2) {
-        dL_dsh[9] = (kSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB;
-        dL_dsh[10] = (kSH_C3[1] * xy * z) * dL_dRGB;
-        dL_dsh[11] = (kSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB;
-        dL_dsh[12] = (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB;
-        dL_dsh[13] = (kSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB;
-        dL_dsh[14] = (kSH_C3[5] * z * (xx - yy)) * dL_dRGB;
-        dL_dsh[15] = (kSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB;
+        if (WRITE) dL_dsh[9] = (kSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB;
+        if (WRITE) dL_dsh[10] = (kSH_C3[1] * xy * z) * dL_dRGB;
+        if (WRITE) dL_dsh[11] = (kSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB;
+        if (WRITE) dL_dsh[12] = (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB;
+        if (WRITE) dL_dsh[13] = (kSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB;
+        if (WRITE) dL_dsh[14] = (kSH_C3[5] * z * (xx - yy)) * dL_dRGB;
+        if (WRITE) dL_dsh[15] = (kSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB;
         float4 s9 = sh[9], s10 = sh[10], s11 = sh[11], s12 = sh[12], s13 = sh[13], s14 = sh[14], s15 = sh[15];
         dRGBdx += (kSH_C3[0] * 3.f * 2.f * xy) * s9 + (kSH_C3[1] * yz) * s10 + (kSH_C3[2] * -2.f * xy) * s11 +
                   (kSH_C3[3] * -3.f * 2.f * xz) * s12 + (kSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
@@ -510,8 +512,9 @@ __device__ __forceinline__ void preprocess_vjp_one(
       const float3 dir = make_float3(means3D[3 * (size_t)i] - campos[0], means3D[3 * (size_t)i + 1] - campos[1],
                                      means3D[3 * (size_t)i + 2] - campos[2]);
       float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * pp.M;
-      const float3 dm = sh_backward(pp.D, pp.M, reinterpret_cast<const float4*>(shs) + (size_t)i * pp.M, dRGB, dir,
-                                    out_sh);
+      const float4* sh_i = reinterpret_cast<const float4*>(shs) + (size_t)i * pp.M;
+      const float3 dm = pp.factored ? sh_backward<false>(pp.D, pp.M, sh_i, dRGB, dir, out_sh)
+                                    : sh_backward<true>(pp.D, pp.M, sh_i, dRGB, dir, out_sh);
       // coefficients >= (D+1)^2 keep the zeros of the sweep
       dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
     }
@@ -577,7 +580,12 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
       if (fany) gq[5 + k] = zero4;
     }
     dL_dopacity[idx] = g2.w;
-    reinterpret_cast<float4*>(dL_dcolors)[idx] = gc;
+    float4 gc_out = gc;
+    if (pp.factored && any) {  // clamp-masked dL_dRGB: the factor the SH gradient is rebuilt from (k_sh_expand)
+      const uint8_t cl = clamped[idx];
+      gc_out = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
+    }
+    reinterpret_cast<float4*>(dL_dcolors)[idx] = gc_out;
     const bool heavy = any && radii[idx] > 0;
     if (any) { gq[0] = zero4; gq[1] = zero4; gq[2] = zero4; gq[3] = zero4; gq[4] = zero4; }
     if (heavy) {
@@ -591,7 +599,7 @@ __global__ void __launch_bounds__(256) k_preprocess_bwd(
   }
   // coalesced zero-fill of the CTA's rows of the strided outputs (queued surfels overwrite theirs later)
   const int nrows = min(256, pp.P - cta0);
-  if (have_sh) {
+  if (have_sh && !pp.factored) {
     float4* o = reinterpret_cast<float4*>(dL_dsh) + (size_t)cta0 * pp.M;
     for (int k = threadIdx.x; k < nrows * pp.M; k += 256) o[k] = zero4;
   }
@@ -631,6 +639,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
     if (!(p.tanfovy == p.tanfovy) || p.tanfovy == 0.f) pp.H = p.H;
   }
   pp.gstride = grad_stride(p.S);
+  pp.factored = (p.flags & GSL_FLAG_BWD_SH_FACTORED) ? 1 : 0;
   Fov f = make_fov(p);
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
   int blocks = (p.P + 255) / 256;
@@ -640,6 +649,67 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
                                           gout.dL_dmeans2D, gout.dL_dsh, gout.dL_dcolors, gout.dL_dfeatures,
                                           gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D);
   return check_cuda(cudaGetLastError(), "k_preprocess_bwd launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// SH gradient expansion for frame-parallel training (gsl_sh_expand).  The SH gradient a frame contributes to a
+// surfel is the outer product basis(dir) x dL_dRGB (backward.cu:17-134), so instead of all-reducing 16*M bytes
+// per surfel the ranks all-gather the 16-byte factor dL_dRGB (already clamp-masked) and every rank rebuilds
+//     dL_dsh[i] = sum_g basis((mean_i - campos_g) / |.|) x dL_dRGB_g[i]
+// -- the same sum an all-reduce of the dense gradients would produce, in a different order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sh_expand(int P, int D, int M, int G, const float* __restrict__ means3D,
+                                                   const float* __restrict__ campos_all, const float* __restrict__ drgb_all,
+                                                   size_t drgb_stride, float* __restrict__ dL_dsh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = zero4;
+  const float mx = means3D[3 * (size_t)i], my = means3D[3 * (size_t)i + 1], mz = means3D[3 * (size_t)i + 2];
+  for (int g = 0; g < G; ++g) {
+    const float4 d = reinterpret_cast<const float4*>(drgb_all + (size_t)g * drgb_stride)[i];
+    if (d.x == 0.f && d.y == 0.f && d.z == 0.f && d.w == 0.f) continue;
+    float x = mx - campos_all[3 * g], y = my - campos_all[3 * g + 1], z = mz - campos_all[3 * g + 2];
+    const float len = sqrtf(x * x + y * y + z * z);
+    x /= len; y /= len; z /= len;
+    acc[0] += kSH_C0 * d;
+    if (D > 0) {
+      acc[1] += (-kSH_C1 * y) * d;
+      acc[2] += (kSH_C1 * z) * d;
+      acc[3] += (-kSH_C1 * x) * d;
+      if (D > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        acc[4] += (kSH_C2[0] * xy) * d;
+        acc[5] += (kSH_C2[1] * yz) * d;
+        acc[6] += (kSH_C2[2] * (2.f * zz - xx - yy)) * d;
+        acc[7] += (kSH_C2[3] * xz) * d;
+        acc[8] += (kSH_C2[4] * (xx - yy)) * d;
+        if (D > 2) {
+          acc[9] += (kSH_C3[0] * y * (3.f * xx - yy)) * d;
+          acc[10] += (kSH_C3[1] * xy * z) * d;
+          acc[11] += (kSH_C3[2] * y * (4.f * zz - xx - yy)) * d;
+          acc[12] += (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * d;
+          acc[13] += (kSH_C3[4] * x * (4.f * zz - xx - yy)) * d;
+          acc[14] += (kSH_C3[5] * z * (xx - yy)) * d;
+          acc[15] += (kSH_C3[6] * x * (xx - 3.f * yy)) * d;
+        }
+      }
+    }
+  }
+  float4* out = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * M;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < M) out[k] = acc[k];
+  for (int k = 16; k < M; ++k) out[k] = zero4;
+}
+
+int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
+                     size_t drgb_stride, float* dL_dsh, cudaStream_t st) {
+  if (P == 0 || M == 0) return 0;
+  k_sh_expand<<<(P + 255) / 256, 256, 0, st>>>(P, D, M, G, means3D, campos_all, drgb_all, drgb_stride, dL_dsh);
+  return check_cuda(cudaGetLastError(), "k_sh_expand launch");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -98,6 +98,9 @@ class _Pool:
 
 _pool = _Pool()
 
+# frame-parallel training: a gs_lidar_b200.parallel.GradientExchange that the backward pass feeds directly
+_exchange = None
+
 
 class _Holder:
     """Keeps a workspace attached to one forward call until its backward ran (or it is dropped)."""
@@ -274,13 +277,24 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_depth = cot(grad_depth, (4, H, W))
         g_alpha = cot(grad_alpha, (1, H, W))
 
+        ex = _exchange if (_exchange is not None and M > 0 and P > 0 and _exchange.world_size() > 1) else None
         with torch.cuda.device(dev):
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-            d_means3D, d_means2D = e(P, 3), e(P, 4)
-            d_colors, d_features, d_opacity = e(P, NUM_CHANNELS), e(P, S), e(P, 1)
             d_cov3D = e(P, 6)
-            d_sh = e(P, M, NUM_CHANNELS)
-            d_scales, d_rot = e(P, 3), e(P, 4)
+            if ex is None:
+                d_means3D, d_means2D = e(P, 3), e(P, 4)
+                d_colors, d_features, d_opacity = e(P, NUM_CHANNELS), e(P, S), e(P, 1)
+                d_sh = e(P, M, NUM_CHANNELS)
+                d_scales, d_rot = e(P, 3), e(P, 4)
+            else:
+                # gradients go straight into the exchange's flat buffers; dL_dcolors receives the SH factor dL_dRGB
+                ex.prepare(P, S, M, dev)
+                v = ex.views
+                d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
+                d_scales, d_rot, d_features = v["scales"], v["rotations"], v["features"]
+                d_colors, d_sh = ex.local[:4 * P].view(P, NUM_CHANNELS), None
+                params = L.gsl_params.from_buffer_copy(params)
+                params.flags |= L.GSL_FLAG_BWD_SH_FACTORED
 
             fin = L.gsl_fwd_inputs()
             for k, t in inputs.items():
@@ -305,12 +319,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                 cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) + tuple(inputs.values()))
                 try:
                     run()
-                except Exception as ex:
+                except Exception as ex_:
                     torch.save(cpu_args, "snapshot_bw.dump")
                     print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                    raise ex
+                    raise ex_
             else:
                 run()
+            if ex is not None:
+                g = ex.finish(P, params.D, M, inputs["means3D"], inputs["campos"])
+                d_means3D, d_means2D, d_opacity = g["means3D"], g["means2D"], g["opacities"]
+                d_scales, d_rot, d_features, d_sh = g["scales"], g["rotations"], g["features"], g["shs"]
         if not _KEEP_WORKSPACE_AFTER_BACKWARD:
             holder.release()
 

@@ -71,3 +71,92 @@ def surfel_grad_shapes(P: int, S: int, M: int) -> Dict[str, Sequence[int]]:
     if M > 0:
         shapes["shs"] = (P, M, 4)
     return shapes
+
+
+class GradientExchange:
+    """Frame-parallel gradient exchange fused into the rasterizer's backward pass (SH colour path).
+
+    A dense all-reduce moves 4*(19+S... ) + 16*M bytes per surfel, 80 % of it SH gradient.  The SH gradient one
+    frame gives a surfel is the outer product basis(view direction) x dL_dRGB (backward.cu:17-134), so with this
+    exchange active the backward pass
+      1. writes its non-SH gradients straight into one flat fp32 buffer (no per-tensor copies) and the
+         clamp-masked 16-byte factor dL_dRGB into a second one (C-ABI flag GSL_FLAG_BWD_SH_FACTORED),
+      2. all-reduces the first buffer, all-gathers the second (with the rank's camera centre appended),
+      3. rebuilds dL_dsh = sum over ranks of basis x dL_dRGB on the device (gsl_sh_expand).
+    The gradients the autograd op then returns are already summed over the ranks -- do not all-reduce them
+    again.  Same result as an all-reduce of the dense gradients up to fp32 summation order.
+
+        ex = parallel.GradientExchange()            # default process group
+        with ex:                                    # or ex.enable() / ex.disable()
+            loss.backward()
+    """
+
+    NAMES = ("means3D", "means2D", "opacities", "scales", "rotations", "features")
+
+    def __init__(self, group=None):
+        self.group = group
+        self.key = None
+
+    # -- communication (overridable: the tests emulate the ranks in one process) ----------------------
+    def world_size(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.group)
+        return 1
+
+    def _all_reduce(self, flat):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _all_gather(self, out, local):
+        dist.all_gather_into_tensor(out, local, group=self.group)
+
+    # -- buffers -------------------------------------------------------------------------------------
+    def prepare(self, P, S, M, device):
+        G = self.world_size()
+        key = (P, S, M, G, str(device))
+        if self.key != key:
+            widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
+            self.flat = torch.zeros(P * sum(widths.values()), dtype=torch.float32, device=device)
+            self.views, off = {}, 0
+            for k in self.NAMES:
+                n = P * widths[k]
+                self.views[k] = self.flat[off:off + n].view(P, widths[k])
+                off += n
+            self.stride = 4 * P + 4                       # dL_dRGB (P,4) + camera centre (3) + pad
+            self.local = torch.zeros(self.stride, dtype=torch.float32, device=device)
+            self.gathered = torch.zeros(G * self.stride, dtype=torch.float32, device=device)
+            self.key = key
+        return self
+
+    def finish(self, P, D, M, means3D, campos):
+        """Runs the collectives and the SH expansion; returns the summed gradients (dict, `shs` included)."""
+        from . import _lib as L
+        import ctypes as C
+        G = self.world_size()
+        self.local[4 * P:4 * P + 3].copy_(campos.reshape(3))
+        self._all_reduce(self.flat)
+        self._all_gather(self.gathered, self.local)
+        campos_all = self.gathered.view(G, self.stride)[:, 4 * P:4 * P + 3].contiguous()
+        d_sh = torch.empty((P, M, 4), dtype=torch.float32, device=means3D.device)
+        stream = C.c_void_p(torch.cuda.current_stream(means3D.device).cuda_stream)
+        L.check(L.load().gsl_sh_expand(P, D, M, G, means3D.data_ptr(), campos_all.data_ptr(), self.gathered.data_ptr(),
+                                       self.stride, d_sh.data_ptr(), stream), "gsl_sh_expand")
+        out = dict(self.views)
+        out["shs"] = d_sh
+        return out
+
+    # -- activation ------------------------------------------------------------------------------------
+    def enable(self):
+        from . import diff_gaussian_rasterization_2d as G
+        G._exchange = self
+        return self
+
+    def disable(self):
+        from . import diff_gaussian_rasterization_2d as G
+        if G._exchange is self:
+            G._exchange = None
+
+    __enter__ = enable
+
+    def __exit__(self, *exc):
+        self.disable()
+        return False

@@ -48,6 +48,8 @@ extern "C" {
 
 /* flags */
 #define GSL_FLAG_DEBUG_SYNC 1u /* raster_settings.debug: sync + check after every stage */
+#define GSL_FLAG_BWD_SH_FACTORED 2u /* gsl_backward: write the clamp-masked dL_dRGB factor into dL_dcolors and do
+                                       not write dL_dsh (frame-parallel training rebuilds it with gsl_sh_expand) */
 
 /* Mirrors the scalar arguments of Rasterizer::forward / ::backward
  * (rasterizer.h:31-63) plus GaussianRasterizationSettings (diff_gaussian_rasterization_2d.py:194-209). */
@@ -162,6 +164,14 @@ GSL_API int gsl_forward(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_o
  * (no pre-zeroing needed by the caller). */
 GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                  const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream);
+
+/* Frame-parallel training (no counterpart in the reference, which is single-GPU): the SH gradient one frame gives
+ * a surfel is basis(view direction) x dL_dRGB, so ranks exchange the 16-byte factor (all-gather of the dL_dcolors
+ * written under GSL_FLAG_BWD_SH_FACTORED) instead of all-reducing 16*M bytes per surfel, and each rank rebuilds
+ *   dL_dsh[i] = sum_g basis(normalize(means3D[i] - campos_all[g])) x drgb_all[g * drgb_stride + 4 i .. +3].
+ * campos_all: (G,3) device floats; drgb_all: G blocks of >= 4*P floats, drgb_stride floats apart; dL_dsh (P,M,4). */
+GSL_API int gsl_sh_expand(int32_t P, int32_t D, int32_t M, int32_t G, const float* means3D, const float* campos_all,
+                  const float* drgb_all, size_t drgb_stride, float* dL_dsh, void* stream);
 
 /* Pinhole frustum test, present[i] = in_frustum(means3D[i]) (auxiliary.h:157-180). */
 GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

@@ -343,6 +343,51 @@ def test_pixel_box_is_conservative(kw):
         assert float(area[120:].median()) < 60.0
 
 
+def test_factored_gradient_exchange_equals_sum_of_dense_gradients():
+    """parallel.GradientExchange (flat non-SH all-reduce + all-gather of the 16-byte SH factors + gsl_sh_expand) must
+    give what an all-reduce of the dense gradients gives.  Two ranks are emulated in one process: rank 0's
+    backward parks its buffers, rank 1's combines both."""
+    from gs_lidar_b200 import parallel
+
+    class Loopback(parallel.GradientExchange):
+        def __init__(self):
+            super().__init__()
+            self.parked = None
+
+        def world_size(self):
+            return 2
+
+        def _all_reduce(self, flat):
+            if self.parked is not None:
+                flat.add_(self.parked[0])
+
+        def _all_gather(self, out, local):
+            o = out.view(2, -1)
+            if self.parked is None:
+                o[0].copy_(local)
+                o[1].zero_()
+            else:
+                o[0].copy_(self.parked[1])
+                o[1].copy_(local)
+
+    base = synth.make_scene(20000, seed=71)
+    frames = [synth.make_scene(20000, seed=71, view_yaw_deg=y, view_shift=sh) for y, sh in ((0.0, (0.0, 0.0, 0.0)), (3.0, (0.2, -0.1, 0.1)))]
+    assert torch.equal(frames[0].means3D, base.means3D)  # same surfels (world space differs only through the pose)
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(base.H, base.W, 4, seed=72).items()}
+    # world-space surfels are those of frame 0 for BOTH ranks (replicated parameters), cameras differ
+    scenes = [frames[0].to("cuda"), frames[1]._replace(means3D=frames[0].means3D).to("cuda")]
+    dense = [common.run_ours(sc, cot, export=False)[2] for sc in scenes]
+    expect = {k: dense[0][k] + dense[1][k] for k in dense[0]}
+    ex = Loopback()
+    with ex:
+        common.run_ours(scenes[0], cot, export=False)
+        ex.parked = (ex.flat.clone(), ex.local.clone())
+        _, _, got = common.run_ours(scenes[1], cot, export=False)
+    for k in ("means3D", "means2D", "opacities", "scales", "rotations", "features", "shs"):
+        elem, norm = common.grad_err(got[k], expect[k])
+        assert elem < TOL_GRAD and norm < TOL_GRAD, (k, elem, norm)
+
+
 # ----------------------------------------------------------------------------------------------
 # full size (BASELINE.json configs[2]): size-independent properties
 # ----------------------------------------------------------------------------------------------
