@@ -104,10 +104,11 @@ class GradientExchange:
         return 1
 
     def _all_reduce(self, flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        """Starts the sum of `flat` over the ranks; returns a handle with .wait() (or None when already done)."""
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _all_gather(self, out, local):
-        dist.all_gather_into_tensor(out, local, group=self.group)
+        return dist.all_gather_into_tensor(out, local, group=self.group, async_op=True)
 
     # -- buffers -------------------------------------------------------------------------------------
     def prepare(self, P, S, M, device):
@@ -133,13 +134,19 @@ class GradientExchange:
         import ctypes as C
         G = self.world_size()
         self.local[4 * P:4 * P + 3].copy_(campos.reshape(3))
-        self._all_reduce(self.flat)
-        self._all_gather(self.gathered, self.local)
+        # the small all-gather first, then the all-reduce: the SH expansion below only needs the gathered factors
+        # and runs while the all-reduce of the non-SH gradients is still on the wire
+        h_gather = self._all_gather(self.gathered, self.local)
+        h_reduce = self._all_reduce(self.flat)
+        if h_gather is not None:
+            h_gather.wait()
         campos_all = self.gathered.view(G, self.stride)[:, 4 * P:4 * P + 3].contiguous()
         d_sh = torch.empty((P, M, 4), dtype=torch.float32, device=means3D.device)
         stream = C.c_void_p(torch.cuda.current_stream(means3D.device).cuda_stream)
         L.check(L.load().gsl_sh_expand(P, D, M, G, means3D.data_ptr(), campos_all.data_ptr(), self.gathered.data_ptr(),
                                        self.stride, d_sh.data_ptr(), stream), "gsl_sh_expand")
+        if h_reduce is not None:
+            h_reduce.wait()
         out = dict(self.views)
         out["shs"] = d_sh
         return out

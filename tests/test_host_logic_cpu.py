@@ -116,3 +116,23 @@ def test_bench_byte_model_matches_survey():
     # P=V=1M, R=2M, N=67,980, S=4, K=M=16 -> ~326 + ~692 + 80 MB
     f, b, r = bench.algorithmic_bytes(10**6, 10**6, 2 * 10**6, 66 * 1030, 4, 16, 16)
     assert abs(f / 1e6 - 326) < 3 and abs(b / 1e6 - 692) < 3 and r == 80 * 10**6
+
+
+def test_gradient_exchange_buffers_alias_one_flat_allreduce_payload():
+    # layout contract of parallel.GradientExchange.prepare (the backward pass writes through these views)
+    ex = parallel.GradientExchange()
+    assert ex.world_size() == 1
+    ex.prepare(100, 4, 16, "cpu")
+    widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=4)
+    assert ex.flat.numel() == 100 * sum(widths.values())
+    off = 0
+    for k in ex.NAMES:
+        v = ex.views[k]
+        assert tuple(v.shape) == (100, widths[k]) and v.data_ptr() == ex.flat.data_ptr() + 4 * off
+        off += 100 * widths[k]
+    assert ex.local.numel() == ex.stride == 4 * 100 + 4 and ex.gathered.numel() == ex.stride
+    flat_before = ex.flat
+    ex.prepare(100, 4, 16, "cpu")
+    assert ex.flat is flat_before  # cached for the same (P, S, M, world, device)
+    ex.prepare(50, 0, 16, "cpu")
+    assert ex.views["features"].shape == (50, 0)
