@@ -20,6 +20,13 @@ namespace gsl {
 #define GSL_FF(a, b, c) __fmaf_rn((a), (b), (c))
 #define GSL_FD(a, b) __fdiv_rn((a), (b))
 
+// 1/x to ~1 ulp in one MUFU instruction (backward pass only; the forward pass keeps IEEE divisions)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // a*b + c*d + e*f as the reference evaluates 3-term dot products:
 // the middle product is rounded on its own, the others are fused.
 __device__ __forceinline__ float dot3_ref(float a, float b, float c, float d, float e, float f) {
@@ -86,7 +93,10 @@ struct PairEval {
 // The rounding sequence is the reference forward kernel's.  Written branch-free (the skip tests only
 // feed `valid`) so that the compiler can interleave the evaluation of consecutive candidates; values
 // computed past a failed test are never used.
-template <bool KEEP_KL>
+// FAST (backward pass only): the two IEEE divisions and expf are replaced by their approximate forms.  The
+// backward never re-decides which pairs contribute (the forward's pair masks do), so a last-ulp difference
+// cannot flip a threshold there; it only perturbs gradients at the 1e-7 level (contract: 1e-4).
+template <bool KEEP_KL, bool FAST = false>
 __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r, float near_, float far_) {
   PairEval e;
   // k = cos(phi)*Tu - sin(phi)*Tw            (x,y,z components over Tu/Tv... columns)
@@ -104,8 +114,15 @@ __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r,
   if (KEEP_KL) { e.kx = kx; e.ky = ky; e.kz = kz; e.lx = lx; e.ly = ly; e.lz = lz; }
   e.pz = pz;
   bool ok = pz != 0.0f;
-  float sx = GSL_FD(px, pz);
-  float sy = GSL_FD(py, pz);
+  float sx, sy;
+  if (FAST) {
+    const float ipz = fast_rcp(pz);
+    sx = px * ipz;
+    sy = py * ipz;
+  } else {
+    sx = GSL_FD(px, pz);
+    sy = GSL_FD(py, pz);
+  }
   float rho3d = GSL_FF(sx, sx, GSL_FM(sy, sy));
   float dx = GSL_FS(s.mx, r.px);
   float dy = GSL_FS(s.my, r.py);
@@ -122,7 +139,7 @@ __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r,
   ok = ok && !(depth < near_ || depth > far_);
   float power = GSL_FM(fminf(rho3d, rho2d), -0.5f);
   ok = ok && !(power > 0.0f);
-  float G = expf(power);
+  float G = expf(power);  // exact also in the backward: G scales every gradient term directly
   float alpha = fminf(GSL_FM(s.opacity, G), 0.99f);
   e.G = G;
   e.alpha = alpha;

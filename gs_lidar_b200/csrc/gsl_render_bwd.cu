@@ -138,8 +138,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
   float accum_n[3] = {0.f, 0.f, 0.f}, last_n[3] = {0.f, 0.f, 0.f};
   float accum_depth = 0.f, last_depth = 0.f, accum_mask = 0.f, last_alpha = 0.f, last_dL_dT = 0.f;
 
-  const float far_near = rp.far_ * rp.near_;
-  const float range_fn = rp.far_ - rp.near_;
+  const float far_near_over_range = rp.far_ * rp.near_ / (rp.far_ - rp.near_);
   int my_comp = butterfly_component(K, lane);
   if (my_comp == 19 || my_comp >= 20 + S) my_comp = -1;  // padding slots of the packed record
 #ifdef GSL_STATS
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
       if (active) {
         mine &= mine - 1;
         const Splat s = staged_splat(sb, j);
-        const PairEval e = eval_pair<true>(s, ray, rp.near_, rp.far_);
+        const PairEval e = eval_pair<true, true>(s, ray, rp.near_, rp.far_);
 #ifdef GSL_STATS
         st_valid++;
 #endif
@@ -224,7 +223,9 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         const int pos0 = (int)(ent.y - r0);  // 0-based list position == the reference's `contributor` after --
 
         const float alpha = e.alpha, G = e.G, depth = e.depth;
+        // the transmittance is a running product over the whole list: keep its division IEEE-exact
         T = T / (1.f - alpha);
+        const float inv_1ma = fast_rcp(1.f - alpha);
         const float wgt = alpha * T;
         float dL_dalpha = 0.f;
         const float4 c4 = sb.v[4][j];
@@ -241,8 +242,9 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         dL_dr += alpha * T * 2 * depth * dL_depth_sq;
         if (pos0 == median_contributor - 1) dL_dr += dL_dmedian;
 
-        const float m_d = rp.far_over_range * (1 - rp.near_ / depth);
-        const float dmd_dd = far_near / (range_fn * depth * depth);
+        const float inv_depth = fast_rcp(depth);
+        const float m_d = rp.far_over_range * (1 - rp.near_ * inv_depth);
+        const float dmd_dd = far_near_over_range * inv_depth * inv_depth;
         const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2 * m_d * final_D) * dL_ddist;
         dL_dalpha += dL_dweight - last_dL_dT;
         last_dL_dT = dL_dweight * alpha + (1 - alpha) * last_dL_dT;
@@ -264,17 +266,18 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         last_depth = depth;
         dL_dalpha += (depth - accum_depth) * dL_depth;
         accum_mask = last_alpha + (1.f - last_alpha) * accum_mask;
-        dL_dalpha = (float)((double)dL_dalpha + (1.0 - (double)accum_mask) * (double)dL_mask);
+        dL_dalpha += (1.f - accum_mask) * dL_mask;
         dL_dalpha *= T;
         last_alpha = alpha;
-        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+        dL_dalpha += (-T_final * inv_1ma) * bg_dot;
 
         const float dL_dG = s.opacity * dL_dalpha;
         if (e.rho3d <= e.rho2d) {
           const float ex = ray.sth * ray.sphi, ey = -ray.cth, ez = ray.sth * ray.cphi;
           const float dsx = dL_dG * -G * e.sx + dL_dr * (s.Tux * ex + s.Tvx * ey + s.Twx * ez);
           const float dsy = dL_dG * -G * e.sy + dL_dr * (s.Tuy * ex + s.Tvy * ey + s.Twy * ez);
-          const float qx = dsx / e.pz, qy = dsy / e.pz;
+          const float ipz = fast_rcp(e.pz);
+          const float qx = dsx * ipz, qy = dsy * ipz;
           const float dpx = qx, dpy = qy, dpz = -(qx * e.sx + qy * e.sy);
           // dL_dk = l x dL_dp ; dL_dl = dL_dp x k
           const float dkx = e.ly * dpz - e.lz * dpy, dky = e.lz * dpx - e.lx * dpz, dkz = e.lx * dpy - e.ly * dpx;
@@ -292,9 +295,10 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         } else {
           g[9] = dL_dG * (-G * 2.f * e.dx);
           g[10] = dL_dG * (-G * 2.f * e.dy);
-          g[2] = dL_dr * s.Tuz / depth;
-          g[5] = dL_dr * s.Tvz / depth;
-          g[8] = dL_dr * s.Twz / depth;
+          const float dr_d = dL_dr * inv_depth;
+          g[2] = dr_d * s.Tuz;
+          g[5] = dr_d * s.Tvz;
+          g[8] = dr_d * s.Twz;
         }
         g[11] = G * dL_dalpha;
 
