@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
   constexpr int KS = (S_T >= 0) ? S_T : GSL_MAX_FEATURES;  // feature slots held in registers
   constexpr int K = 20 + KS;                               // live components of the packed record
   const int S = (S_T >= 0) ? S_T : rp.S;
-  __shared__ ChunkStage stg[2];
+  __shared__ ChunkStage stg[3];
 
   const int lane = threadIdx.x;
   const BlockGeom bg_ = block_geom(rp, blockIdx.x, lane);
@@ -158,48 +158,57 @@ __global__ void __launch_bounds__(32) k_render_bwd(
     }
     cp_async_commit();
   };
-  auto load_entry = [&](int64_t c1, uint32_t& pm, uint2& ent) {
-    const int64_t e = c1 - 1 - lane;
+  // chunk c (0 = deepest) holds entries hi-1-32c ... hi-32-32c; slot j of a chunk = entry top(c) - j
+  const uint32_t hi = bs + nwalk;
+  const int nC = (int)((nwalk + 31u) >> 5);
+  auto load_entry = [&](int c, uint32_t& pm, uint2& ent) {
     pm = 0u;
     ent = make_uint2(0, 0);
-    if (e >= (int64_t)bs) {
+    const uint32_t back = 32u * (uint32_t)c + (uint32_t)lane;  // distance from the last walked entry
+    if (c < nC && back < nwalk) {
+      const uint32_t e = hi - 1u - back;
       pm = __ldg(pmk + e);
       if (pm != 0u) ent = __ldg(bl + e);
     }
   };
 
-  const int64_t hi = (int64_t)bs + nwalk;
-  int cur = 0;
-  uint32_t pmCur, pmN;
-  uint2 entN;
+  // Two chunks are live at a time (A = deeper, B = next towards the sensor); a lane that has finished its pairs of A
+  // goes on with its pairs of B while slower lanes are still in A -- see gsl_render_fwd.cu.
+  int a = 0;
+  int bufA = 0, bufB = 1, bufC = 2;  // stage buffers of A, B and of the chunk in flight
+  uint32_t mineA, mineB = 0;
+  uint32_t pmI;
+  uint2 entI;
   {
-    uint2 ent0;
-    load_entry(hi, pmCur, ent0);
-    load_entry(hi - 32, pmN, entN);
-    issue(stg[0], ent0, pmCur != 0u);
-  }
-  for (int64_t c1 = hi; c1 > (int64_t)bs; c1 -= 32) {
+    uint32_t pm0, pm1;
+    uint2 e0, e1;
+    load_entry(0, pm0, e0);
+    load_entry(1, pm1, e1);
+    load_entry(2, pmI, entI);
+    issue(stg[0], e0, pm0 != 0u);
+    if (nC > 1) issue(stg[1], e1, pm1 != 0u);
     cp_async_wait_all();
     __syncwarp();
-    issue(stg[cur ^ 1], entN, pmN != 0u);
-    uint32_t pmNN;
-    uint2 entNN;
-    load_entry(c1 - 64, pmNN, entNN);
-
-    const ChunkStage& sb = stg[cur];
-    uint32_t mine = transpose32(pmCur, lane);  // bit j: my pixel contributed to the entry staged in slot j
+    mineA = transpose32(pm0, lane);  // bit j: my pixel contributed to the entry staged in slot j
+    if (nC > 1) mineB = transpose32(pm1, lane);
 #ifdef GSL_STATS
-    if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pmCur != 0u));
-    else __ballot_sync(0xffffffffu, pmCur != 0u);
+    if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pm0 != 0u)) + __popc(__ballot_sync(0xffffffffu, pm1 != 0u));
+    else { __ballot_sync(0xffffffffu, pm0 != 0u); __ballot_sync(0xffffffffu, pm1 != 0u); }
 #endif
-    for (;;) {
+  }
+  uint32_t pmB2 = pmI;  // pair masks of chunk a + 2 (gathers in flight)
+  if (nC > 2) issue(stg[2], entI, pmI != 0u);
+  load_entry(3, pmI, entI);
+  for (;;) {
+    while (__any_sync(0xffffffffu, mineA != 0)) {
       // Lanes normally sit on different entries.  When (almost) every pixel of the block is on the SAME entry --
       // splats much larger than the block -- the pairs are summed by a transposing butterfly and the record is
       // updated by one coalesced reduction instead of 32 colliding ones (also a more accurate sum).
-      const bool active = mine != 0;
+      const bool inA = mineA != 0;
+      const bool active = inA || mineB != 0;
       const uint32_t amask = __ballot_sync(0xffffffffu, active);
-      if (amask == 0u) break;
-      const int j = active ? (__ffs(mine) - 1) : -1;
+      // slot key: bit 5 = chunk B
+      const int j = inA ? (__ffs(mineA) - 1) : (mineB != 0 ? 32 + (__ffs(mineB) - 1) : -1);
       const int j0 = __shfl_sync(0xffffffffu, j, __ffs(amask) - 1);
       const bool uniform = __popc(amask) >= 8 && __all_sync(0xffffffffu, !active || j == j0);
 #ifdef GSL_STATS
@@ -212,13 +221,16 @@ __global__ void __launch_bounds__(32) k_render_bwd(
       for (int i = 0; i < 32; ++i) g[i] = 0.f;
       uint32_t sid = 0;
       if (active) {
-        mine &= mine - 1;
-        const Splat s = staged_splat(sb, j);
+        if (inA) mineA &= mineA - 1;
+        else mineB &= mineB - 1;
+        const ChunkStage& sb = stg[inA ? bufA : bufB];
+        const int js = j & 31;
+        const Splat s = staged_splat(sb, js);
         const PairEval e = eval_pair<true, true>(s, ray, rp.near_, rp.far_);
 #ifdef GSL_STATS
         st_valid++;
 #endif
-        const uint2 ent = sb.ent[j];
+        const uint2 ent = sb.ent[js];
         sid = ent.x;
         const int pos0 = (int)(ent.y - r0);  // 0-based list position == the reference's `contributor` after --
 
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         const float inv_1ma = fast_rcp(1.f - alpha);
         const float wgt = alpha * T;
         float dL_dalpha = 0.f;
-        const float4 c4 = sb.v[4][j];
+        const float4 c4 = sb.v[4][js];
         const float col[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -320,10 +332,24 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         if (my_comp >= 0) red_add_f32(grad + (size_t)sid0 * 32 + my_comp, g[0]);
       }
     }
-    cur ^= 1;
-    pmCur = pmN;
-    pmN = pmNN;
-    entN = entNN;
+    // every lane is through chunk A: retire it, B becomes A, the chunk whose gathers were in flight becomes B
+    if (a + 1 >= nC) break;
+    ++a;
+    mineA = mineB;
+    mineB = 0;
+    { const int t = bufA; bufA = bufB; bufB = bufC; bufC = t; }  // the retired buffer receives the next gathers
+    if (a + 1 < nC) {
+      cp_async_wait_all();
+      __syncwarp();
+      mineB = transpose32(pmB2, lane);
+#ifdef GSL_STATS
+      if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pmB2 != 0u));
+      else __ballot_sync(0xffffffffu, pmB2 != 0u);
+#endif
+      pmB2 = pmI;
+      if (a + 2 < nC) issue(stg[bufC], entI, pmI != 0u);
+      load_entry(a + 3, pmI, entI);
+    }
   }
   cp_async_wait_all();
 #ifdef GSL_STATS
