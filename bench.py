@@ -304,17 +304,30 @@ def run_ours(args, rank, world, local):
     for i in range(L.GSL_K_COUNT):
         if kn[i] > 0:
             per_kernel[L.load().gsl_kernel_name(i).decode()] = dict(ms_per_launch=kms[i] / kn[i], launches=int(kn[i]))
-    dom_id = max(range(L.GSL_K_COUNT), key=lambda i: kms[i] if i != 3 else -1.0)
+    # algorithmic bytes of each of this repo's kernels per launch and, where a full ncu capture
+    # exists (profiles/r01_*_ncu_full.md), the DRAM traffic ncu measured for it at this workload
+    kern_bytes = {
+        0: 45 * P + V * (16 * K) + P * (64 + 16 + 8 + 8 + 4 + 4 + 8),                 # k_preprocess_fwd
+        1: 12 * P + 3 * 4 * (((W + 15) // 16) * ((H + 15) // 16)) * ((P + 255) // 256),   # k_bin_count/scan/bases (order + rect in, hist out/in/out)
+        2: 12 * P + 4 * R,                                                             # k_bin_scatter
+        4: 12 * R,                                                                     # k_tile_blists (id + box in, entry out)
+        5: N * (8 + 16 + 4 * (S + 3) + 16 + 4 + 12) + V * (64 + 16 + 4 * S),           # k_render_fwd
+        6: render_bwd_algorithmic_bytes(V, N, S),                                      # k_render_bwd
+        7: P * (96 + 4) + V * (48 + 45 + 16 * M) // 2 + P * (12 + 16 + 16 + 4 * S + 4 + 24 + 16 * M + 12 + 16),  # k_preprocess_bwd
+    }
+    ncu_traffic = {0: 401.2e6, 4: 19.5e6, 5: 115.4e6, 6: 131.5e6, 7: 667.5e6}
+    dom_id = max(kern_bytes, key=lambda i: kms[i])
     dom_ms = kms[dom_id] / max(kn[dom_id], 1)
     dom_name = L.load().gsl_kernel_name(dom_id).decode()
-    if dom_id == 6:
-        dom_bytes = render_bwd_algorithmic_bytes(V, N, S)
-    elif dom_id == 5:
-        dom_bytes = N * (8 + 16 + 4 * (S + 3) + 16 + 4 + 12) + V * (64 + 16 + 4 * S)
-    else:
-        dom_bytes = fwd_b if dom_id < 5 else bwd_b
+    dom_bytes = kern_bytes[dom_id]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = {6: 156.6e6, 5: 102.7e6}.get(dom_id)  # ncu --set full, profiles/r01_render_kernels.md
+    traffic = ncu_traffic.get(dom_id)
+    per_kernel_roofline = {}
+    for i, b in kern_bytes.items():
+        if kn[i] > 0 and kms[i] > 0:
+            gbs = b / (kms[i] / kn[i] * 1e-3) / 1e9
+            per_kernel_roofline[L.load().gsl_kernel_name(i).decode()] = dict(
+                algorithmic_bytes=int(b), achieved_gbs=gbs, frac=gbs / hbm_peak, traffic=ncu_traffic.get(i))
     step_bytes = fwd_b + bwd_b + bin_b
     step_ms = ms / args.steps
     value = world * args.steps / (ms * 1e-3)
@@ -334,7 +347,9 @@ def run_ours(args, rank, world, local):
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-                     "note": "compositing is FP32/latency-bound at 325 tiles, not HBM-bound; see profiles/"},
+                     "note": "the two compositors are FP32-issue / L2-reduction bound at this shape, not HBM-bound (ncu: profiles/); "
+                             "the streaming kernels' fractions are in kernel_rooflines"},
+        "kernel_rooflines": per_kernel_roofline,
         "step_roofline": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak,
                           "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak},
         "kernels": per_kernel,
