@@ -541,7 +541,10 @@ __device__ __forceinline__ void preprocess_vjp_one(
 //     coefficients are never read.
 //  2. the queued surfels, densely packed over the CTA's threads: VJP of k_preprocess_fwd and of the SH
 //     evaluation (preprocess_vjp_one).  Every element of every dense output is written by one of the phases.
-__global__ void __launch_bounds__(256) k_preprocess_bwd(
+#ifndef GSL_PBWD_MINB
+#define GSL_PBWD_MINB 2
+#endif
+__global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     PreBwdParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ shs,
     const float* __restrict__ viewmatrix, const float* __restrict__ campos,

@@ -64,15 +64,17 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// 32x32 bit-matrix transpose across the warp: bit i of the result in lane j = bit j of `m` in lane i.
-__device__ __forceinline__ uint32_t transpose32(uint32_t m, int lane) {
-  uint32_t out = 0;
+// 32x32 bit-matrix transpose across the warp: bit i of the result in lane j = bit j of `x` in lane i.
+// Five butterfly steps (swap the off-diagonal k x k blocks with lane ^ k), 5 shuffles instead of 32 ballots.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const uint32_t b = __ballot_sync(0xffffffffu, (m >> j) & 1u);
-    if (lane == j) out = b;
+  for (int k = 16; k >= 1; k >>= 1) {
+    const uint32_t m = (k == 16) ? 0x0000ffffu : (k == 8) ? 0x00ff00ffu : (k == 4) ? 0x0f0f0f0fu
+                     : (k == 2) ? 0x33333333u : 0x55555555u;
+    const uint32_t t = __shfl_xor_sync(0xffffffffu, x, k);
+    x = (lane & k) ? ((x & ~m) | ((t >> k) & m)) : ((x & m) | ((t << k) & ~m));
   }
-  return out;
+  return x;
 }
 
 // Which of the 32 pixels of the 8x4 block at (bx0, by0) lie inside the (possibly azimuth-wrapped) pixel box;

@@ -280,7 +280,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         ex = _exchange if (_exchange is not None and M > 0 and P > 0 and _exchange.world_size() > 1) else None
         with torch.cuda.device(dev):
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-            d_cov3D = e(P, 6)
+            # dL_dcov3D is all-zero (forward.cu never reads cov3D_precomp); only materialised when the caller passed one
+            d_cov3D = e(P, 6) if ctx.cov_shape == (P, 6) else None
             if ex is None:
                 d_means3D, d_means2D = e(P, 3), e(P, 4)
                 d_colors, d_features, d_opacity = e(P, NUM_CHANNELS), e(P, S), e(P, 1)
@@ -332,7 +333,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         if not _KEEP_WORKSPACE_AFTER_BACKWARD:
             holder.release()
 
-        grad_cov = d_cov3D if tuple(d_cov3D.shape) == ctx.cov_shape else None
+        grad_cov = d_cov3D
         grads = (d_means3D, d_means2D, d_sh if M > 0 else None, d_colors if inputs["colors_precomp"].numel() else None,
                  d_features, d_opacity, d_scales, d_rot, grad_cov, None, None)
         return grads
