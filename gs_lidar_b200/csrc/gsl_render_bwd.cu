@@ -177,6 +177,11 @@ __global__ void __launch_bounds__(32) k_render_bwd(
   int a = 0;
   int bufA = 0, bufB = 1, bufC = 2;  // stage buffers of A, B and of the chunk in flight
   uint32_t mineA, mineB = 0;
+  // A chunk whose entries are used by many pixels of the block each (splats larger than the block) is walked in
+  // LOCK-STEP instead: all lanes take the warp's lowest pending entry together, so that its pairs are summed by the
+  // butterfly below -- one reduction per entry instead of one per pair, and a tree sum instead of a serial one.
+  constexpr uint32_t DENSE_BITS = 32u * 10u;  // >= 10 pixels per entry on average
+  bool denseA, denseB = false;
   uint32_t pmI;
   uint2 entI;
   {
@@ -190,7 +195,11 @@ __global__ void __launch_bounds__(32) k_render_bwd(
     cp_async_wait_all();
     __syncwarp();
     mineA = transpose32(pm0, lane);  // bit j: my pixel contributed to the entry staged in slot j
-    if (nC > 1) mineB = transpose32(pm1, lane);
+    denseA = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pm0)) >= DENSE_BITS;
+    if (nC > 1) {
+      mineB = transpose32(pm1, lane);
+      denseB = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pm1)) >= DENSE_BITS;
+    }
 #ifdef GSL_STATS
     if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pm0 != 0u)) + __popc(__ballot_sync(0xffffffffu, pm1 != 0u));
     else { __ballot_sync(0xffffffffu, pm0 != 0u); __ballot_sync(0xffffffffu, pm1 != 0u); }
@@ -204,8 +213,12 @@ __global__ void __launch_bounds__(32) k_render_bwd(
       // Lanes normally sit on different entries.  When (almost) every pixel of the block is on the SAME entry --
       // splats much larger than the block -- the pairs are summed by a transposing butterfly and the record is
       // updated by one coalesced reduction instead of 32 colliding ones (also a more accurate sum).
-      const bool inA = mineA != 0;
-      const bool active = inA || mineB != 0;
+      bool inA = mineA != 0;
+      if (denseA) {  // lock-step: only the warp's lowest pending entry of A, no running ahead into B
+        const uint32_t pending = __reduce_or_sync(0xffffffffu, mineA);
+        inA = (mineA & (pending & (0u - pending))) != 0;
+      }
+      const bool active = inA || (!denseA && mineB != 0);
       const uint32_t amask = __ballot_sync(0xffffffffu, active);
       // slot key: bit 5 = chunk B
       const int j = inA ? (__ffs(mineA) - 1) : (mineB != 0 ? 32 + (__ffs(mineB) - 1) : -1);
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(32) k_render_bwd(
         const ChunkStage& sb = stg[inA ? bufA : bufB];
         const int js = j & 31;
         const Splat s = staged_splat(sb, js);
-        const PairEval e = eval_pair<true, true>(s, ray, rp.near_, rp.far_);
+        const PairEval e = eval_pair<true>(s, ray, rp.near_, rp.far_);  // exact like the forward: alpha feeds every term
 #ifdef GSL_STATS
         st_valid++;
 #endif
@@ -337,11 +350,14 @@ __global__ void __launch_bounds__(32) k_render_bwd(
     ++a;
     mineA = mineB;
     mineB = 0;
+    denseA = denseB;
+    denseB = false;
     { const int t = bufA; bufA = bufB; bufB = bufC; bufC = t; }  // the retired buffer receives the next gathers
     if (a + 1 < nC) {
       cp_async_wait_all();
       __syncwarp();
       mineB = transpose32(pmB2, lane);
+      denseB = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(pmB2)) >= DENSE_BITS;
 #ifdef GSL_STATS
       if (lane == 0) st_cand += __popc(__ballot_sync(0xffffffffu, pmB2 != 0u));
       else __ballot_sync(0xffffffffu, pmB2 != 0u);

@@ -125,6 +125,8 @@ def _ptr(t):
 
 
 def _f32c(t):
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
@@ -178,11 +180,14 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
     params = _make_params(settings, P, S, M)
 
     with torch.cuda.device(dev):
-        out_contrib = torch.empty((2, H, W), dtype=torch.int32, device=dev)
-        out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
-        out_feature = torch.empty((S + 3, H, W), dtype=torch.float32, device=dev)
-        out_depth = torch.empty((4, H, W), dtype=torch.float32, device=dev)
-        out_alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        # one allocation for all maps (planes of H*W 4-byte elements), one for radii
+        n_planes = 2 + NUM_CHANNELS + (S + 3) + 4 + 1
+        maps = torch.empty((n_planes, H, W), dtype=torch.float32, device=dev)
+        out_contrib = maps[0:2].view(torch.int32)
+        out_color = maps[2:2 + NUM_CHANNELS]
+        out_feature = maps[2 + NUM_CHANNELS:2 + NUM_CHANNELS + S + 3]
+        out_depth = maps[n_planes - 5:n_planes - 1]
+        out_alpha = maps[n_planes - 1:n_planes]
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
 
         fin = L.gsl_fwd_inputs()
@@ -219,6 +224,7 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
             raise RuntimeError("gs_lidar_b200: could not size the binning workspace for %d instances" % R)
         _pool.r_hint[(dev, P, W, H)] = max(R + R // 4, 1024)
     outs = (out_contrib, out_color, out_feature, out_depth, out_alpha, radii)
+    inputs["_fin"] = fin  # the backward passes the same pointer struct again
     return outs, holder, params, inputs, R
 
 
@@ -283,10 +289,16 @@ class _RasterizeGaussians(torch.autograd.Function):
             # dL_dcov3D is all-zero (forward.cu never reads cov3D_precomp); only materialised when the caller passed one
             d_cov3D = e(P, 6) if ctx.cov_shape == (P, 6) else None
             if ex is None:
-                d_means3D, d_means2D = e(P, 3), e(P, 4)
-                d_colors, d_features, d_opacity = e(P, NUM_CHANNELS), e(P, S), e(P, 1)
-                d_sh = e(P, M, NUM_CHANNELS)
-                d_scales, d_rot = e(P, 3), e(P, 4)
+                # one allocation for all dense gradients; the returned tensors are contiguous views of it
+                widths = (3, 4, NUM_CHANNELS, S, 1, 3, 4, M * NUM_CHANNELS)
+                starts, off = [], 0
+                for w in widths:  # every tensor starts 256-B aligned (the kernels use 16-byte stores)
+                    starts.append(off)
+                    off += (P * w + 63) // 64 * 64
+                flat = e(off)
+                views = [flat[o:o + P * w].view(P, w) for o, w in zip(starts, widths)]
+                d_means3D, d_means2D, d_colors, d_features, d_opacity, d_scales, d_rot, d_sh = views
+                d_sh = d_sh.view(P, M, NUM_CHANNELS)
             else:
                 # gradients go straight into the exchange's flat buffers; dL_dcolors receives the SH factor dL_dRGB
                 ex.prepare(P, S, M, dev)
@@ -297,10 +309,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 params = L.gsl_params.from_buffer_copy(params)
                 params.flags |= L.GSL_FLAG_BWD_SH_FACTORED
 
-            fin = L.gsl_fwd_inputs()
-            for k, t in inputs.items():
-                setattr(fin, k, _ptr(t))
-            fin.cov3D_precomp = None
+            fin = inputs["_fin"]
             ffwd = L.gsl_fwd_outputs()
             ffwd.out_contrib, ffwd.radii = contrib.data_ptr(), _ptr(radii)
             gin = L.gsl_bwd_inputs()
@@ -317,7 +326,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                                           C.byref(wss), _stream_ptr(dev)), "gsl_backward")
 
             if settings.debug:
-                cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) + tuple(inputs.values()))
+                cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) +
+                                               tuple(v for k, v in inputs.items() if k != "_fin"))
                 try:
                     run()
                 except Exception as ex_:

@@ -116,12 +116,12 @@ class GradientExchange:
         key = (P, S, M, G, str(device))
         if self.key != key:
             widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
-            self.flat = torch.zeros(P * sum(widths.values()), dtype=torch.float32, device=device)
-            self.views, off = {}, 0
-            for k in self.NAMES:
-                n = P * widths[k]
-                self.views[k] = self.flat[off:off + n].view(P, widths[k])
-                off += n
+            starts, off = {}, 0
+            for k in self.NAMES:  # every tensor starts 256-B aligned (the kernels use 16-byte stores)
+                starts[k] = off
+                off += (P * widths[k] + 63) // 64 * 64
+            self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+            self.views = {k: self.flat[starts[k]:starts[k] + P * widths[k]].view(P, widths[k]) for k in self.NAMES}
             self.stride = 4 * P + 4                       # dL_dRGB (P,4) + camera centre (3) + pad
             self.local = torch.zeros(self.stride, dtype=torch.float32, device=device)
             self.gathered = torch.zeros(G * self.stride, dtype=torch.float32, device=device)

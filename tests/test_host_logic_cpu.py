@@ -124,12 +124,13 @@ def test_gradient_exchange_buffers_alias_one_flat_allreduce_payload():
     assert ex.world_size() == 1
     ex.prepare(100, 4, 16, "cpu")
     widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=4)
-    assert ex.flat.numel() == 100 * sum(widths.values())
     off = 0
     for k in ex.NAMES:
         v = ex.views[k]
         assert tuple(v.shape) == (100, widths[k]) and v.data_ptr() == ex.flat.data_ptr() + 4 * off
-        off += 100 * widths[k]
+        assert (v.data_ptr() - ex.flat.data_ptr()) % 256 == 0  # the kernels store 16 bytes at a time
+        off += (100 * widths[k] + 63) // 64 * 64
+    assert ex.flat.numel() == off
     assert ex.local.numel() == ex.stride == 4 * 100 + 4 and ex.gathered.numel() == ex.stride
     flat_before = ex.flat
     ex.prepare(100, 4, 16, "cpu")

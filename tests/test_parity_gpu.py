@@ -53,8 +53,11 @@ def scene_from_golden(g):
     return sc, cp, cot
 
 
-def check_against(out, state, grads, r_out, r_state, r_grads, precomp):
-    """Shared assertions: `r_*` are the reference's outputs as torch tensors (any device)."""
+def check_against(out, state, grads, r_out, r_state, r_grads, precomp, r_grads_again=None):
+    """Shared assertions: `r_*` are the reference's outputs as torch tensors (any device).  `r_grads_again` = the
+    gradients of a second run of the reference on the same inputs: its atomicAdd order is not reproducible, and the
+    product cannot be asked to match the reference more closely than the reference matches itself, so the
+    element-wise bound is max(1e-4, 3 x the reference's own run-to-run error) (measured: 1e-6 ... 5e-5)."""
     dev = out["radii"].device
     to = lambda x: x.to(dev)
     # --- integer state: bit exact
@@ -81,8 +84,12 @@ def check_against(out, state, grads, r_out, r_state, r_grads, precomp):
         for k, rk in GRAD_KEYS.items():
             if grads.get(k) is None or rk not in r_grads:
                 continue
-            elem, norm = common.grad_err(grads[k], to(r_grads[rk]).reshape(grads[k].shape))
-            assert elem < TOL_GRAD and norm < TOL_GRAD, (k, elem, norm)
+            ref_k = to(r_grads[rk]).reshape(grads[k].shape)
+            elem, norm = common.grad_err(grads[k], ref_k)
+            tol_elem = TOL_GRAD
+            if r_grads_again is not None and rk in r_grads_again:
+                tol_elem = max(TOL_GRAD, 3.0 * common.grad_err(to(r_grads_again[rk]).reshape(grads[k].shape), ref_k)[0])
+            assert elem < tol_elem and norm < TOL_GRAD, (k, elem, norm, tol_elem)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -110,7 +117,7 @@ CASES = [
     dict(P=30000, H=66, W=515, hfov=(-90.0, 90.0), seed=2, view_yaw_deg=-35.0, view_shift=(0.3, 0.1, -0.2)),
     dict(P=20000, H=128, W=2048, vfov=synth.OPV2V_VFOV, hfov=(-180.0, 180.0), seed=3),
     dict(P=5000, H=66, W=1030, hfov=(-180.0, 180.0), seed=4, footprint_px=12.0),      # big splats, many tiles each
-    dict(P=5000, H=50, W=70, vfov=(-60.0, 60.0), hfov=(-100.0, 100.0), seed=5, footprint_px=3.0, S=0, sh_degree=0),
+    dict(P=5003, H=50, W=70, vfov=(-60.0, 60.0), hfov=(-100.0, 100.0), seed=5, footprint_px=3.0, S=0, sh_degree=0),  # odd P: alignment of packed buffers
     dict(P=8000, H=66, W=515, hfov=(-90.0, 90.0), seed=6, S=10, sh_degree=2),          # S at the cap, generic-S kernels
     dict(P=8000, H=33, W=1030, vfov=(-85.0, 85.0), hfov=(-180.0, 180.0), seed=7, footprint_px=4.0),  # near the poles
     dict(P=20000, H=272, W=1040, vfov=(-40.0, 20.0), hfov=(-180.0, 180.0), seed=8, footprint_px=2.0),  # 1105 tiles: 64-bit key-sort path
@@ -126,12 +133,15 @@ def test_matches_reference_cuda(kw):
     S = scene.features.shape[1]
     cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, S, seed=99).items()}
     out, state, grads = common.run_ours(scene, cot)
-    r_out, r_state, r_grads, _ = common.run_ref(scene, cot)
-    if S > 0:
-        r_grads["dL_dfeatures"] = r_grads["dL_dfeatures"][:, :S]
-    else:
-        r_grads.pop("dL_dfeatures", None)
-    check_against(out, state, grads, r_out, r_state, r_grads, False)
+    r_out, r_state, r_grads, ref = common.run_ref(scene, cot)
+    r_grads = {k: v.clone() for k, v in r_grads.items()}
+    r_again = {k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()}
+    for rg in (r_grads, r_again):
+        if S > 0:
+            rg["dL_dfeatures"] = rg["dL_dfeatures"][:, :S]
+        else:
+            rg.pop("dL_dfeatures", None)
+    check_against(out, state, grads, r_out, r_state, r_grads, False, r_again)
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
@@ -145,9 +155,11 @@ def test_matches_reference_cuda_colors_precomp_and_close_range():
     cp = torch.rand(6000, 4, generator=torch.Generator().manual_seed(5)).cuda()
     cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=98).items()}
     out, state, grads = common.run_ours(scene, cot, colors_precomp=cp)
-    r_out, r_state, r_grads, _ = common.run_ref(scene, cot, colors_precomp=cp)
+    r_out, r_state, r_grads, ref = common.run_ref(scene, cot, colors_precomp=cp)
+    r_grads = {k: v.clone() for k, v in r_grads.items()}
+    r_again = {k: v.clone() for k, v in common.run_ref(scene, cot, colors_precomp=cp, ref=ref)[2].items()}
     r_grads.pop("dL_dsh", None)
-    check_against(out, state, grads, r_out, r_state, r_grads, True)
+    check_against(out, state, grads, r_out, r_state, r_grads, True, r_again)
 
 
 def test_matches_cpu_oracle_small():
@@ -444,8 +456,44 @@ def test_full_size_render_invariants(full_run):
 @pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
 def test_full_size_matches_reference_cuda(full_run):
     scene, cot, out, state, grads = full_run
-    r_out, r_state, r_grads, _ = common.run_ref(scene, cot)
-    check_against(out, state, grads, r_out, r_state, r_grads, False)
+    r_out, r_state, r_grads, ref = common.run_ref(scene, cot)
+    r_grads = {k: v.clone() for k, v in r_grads.items()}
+    r_again = {k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()}
+    check_against(out, state, grads, r_out, r_state, r_grads, False, r_again)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
+def test_forward_only_100k_matches_reference_cuda():
+    """BASELINE.json configs[1]: forward-only render of 100k surfels at 66x1030 (inference path, no autograd state)."""
+    scene = synth.make_scene(100000, seed=81).to("cuda")
+    with torch.no_grad():
+        contrib, color, feature, depth, alpha, radii = _call(scene)
+    r_out, _, _, _ = common.run_ref(scene, None)
+    assert torch.equal(radii, r_out["radii"].int()) and torch.equal(contrib, r_out["out_contrib"].int())
+    for a, b in ((color, r_out["out_color"]), (feature, r_out["out_feature"]), (depth, r_out["out_depth"]), (alpha, r_out["out_alpha"])):
+        assert common.rel_err(a, b) < TOL_MAP
+
+
+def test_stress_inference_shape_frames_sharded():
+    """BASELINE.json configs[4] shape: 4M surfels, 128x2048 OPV2V panorama, frames sharded by rank (no collective on
+    the inference path).  One rank's share of a 512-frame batch on one GPU: size-independent checks."""
+    from gs_lidar_b200 import parallel
+    frames = parallel.shard_frames(512, rank=3, world_size=8)
+    assert len(frames) == 64 and frames[:3] == [3, 11, 19]
+    scene = synth.make_scene(4000000, H=128, W=2048, vfov=synth.OPV2V_VFOV, seed=82).to("cuda")
+    outs = []
+    with torch.no_grad():
+        for f in frames[:2]:
+            cam = synth.make_scene(16, H=128, W=2048, vfov=synth.OPV2V_VFOV, seed=82, view_yaw_deg=0.05 * f,
+                                   view_shift=(0.002 * f, 0.0, 0.0))
+            sc = scene._replace(viewmatrix=cam.viewmatrix.cuda(), projmatrix=cam.projmatrix.cuda(), campos=cam.campos.cuda())
+            outs.append(_call(sc))
+    for contrib, color, feature, depth, alpha, radii in outs:
+        assert color.shape == (4, 128, 2048) and int((radii > 0).sum()) > 3000000
+        assert bool(torch.isfinite(color).all()) and bool(torch.isfinite(depth).all())
+        assert float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0 and float(alpha.mean()) > 0.9
+        assert bool((contrib[1] <= contrib[0]).all())
+    assert not torch.equal(outs[0][1], outs[1][1])  # different frames render differently
 
 
 def test_full_size_gradients_are_finite_and_sparse(full_run):
