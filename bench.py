@@ -384,10 +384,17 @@ def cpu_baseline(args, full=True):
         P = args.surfels if t_small * (args.surfels / 50000.0) < 25.0 else int(50000 * 25.0 / max(t_small, 1e-3))
         P = max(50000, min(P, args.surfels))
     t = run(P)
-    sample = "1 panorama fwd+bwd, %d of %d surfels, %dx%d" % (P, args.surfels, H, W)
+    reps = 1
+    if t < 10.0:  # bounded sample of ~10-15 s of CPU work
+        reps = max(1, min(40, int(12.0 / max(t, 1e-3))))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            run(P)
+        t = (time.perf_counter() - t0) / reps
+    sample = "%d panorama(s) fwd+bwd, %d of %d surfels, %dx%d" % (reps, P, args.surfels, H, W)
     if P < args.surfels:
         sample += " (value = 1/time of this reduced sample; the full workload is slower)"
-    return {"value": 1.0 / t, "unit": UNIT, "cores": o.threads, "kind": "port", "sample": sample, "seconds": t}
+    return {"value": 1.0 / t, "unit": UNIT, "cores": o.threads, "kind": "port", "sample": sample, "seconds": t * reps}
 
 
 def run_reference(args, rank, world, local):

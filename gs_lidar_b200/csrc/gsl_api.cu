@@ -107,6 +107,25 @@ static int validate_ws(const gsl_params* p, const gsl_workspace* ws, bool need_b
   return 0;
 }
 
+// One side stream + fork/join events per host thread and device (the surfel sort runs on it).
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream* side_stream() {
+  static thread_local SideStream aux[64];
+  static thread_local bool have[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!have[dev]) {
+    // highest priority: the sort's few CTAs must slip in between the preprocess kernel's CTAs, not queue behind them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&aux[dev].stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&aux[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    have[dev] = true;
+  }
+  return &aux[dev];
+}
+
 static int debug_sync(const gsl_params* p, cudaStream_t st, const char* stage) {
   if (!(p->flags & GSL_FLAG_DEBUG_SYNC)) return 0;
   return check_cuda(cudaStreamSynchronize(st), stage);
@@ -142,12 +161,22 @@ GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in
   if ((rc = validate_ws(p, ws, false))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
+  if (fast_binning(p->W, p->H) && p->P > 0) {
+    // fork: depth keys, then the surfel sort on a side stream UNDER the preprocess kernel; join before binning
+    SideStream* aux = side_stream();
+    if (!aux) return set_error(GSL_EINVAL, "could not create the side stream");
+    if ((rc = launch_depth_keys(*p, *in, g, st))) return rc;
+    cudaEventRecord(aux->fork, st);
+    cudaStreamWaitEvent(aux->stream, aux->fork, 0);
+    if ((rc = launch_surfel_sort(*p, g, aux->stream))) return rc;
+    cudaEventRecord(aux->join, aux->stream);
+    if ((rc = launch_preprocess(*p, *in, *out, g, st))) return rc;
+    cudaStreamWaitEvent(st, aux->join, 0);
+    return debug_sync(p, st, "preprocess + surfel sort");
+  }
   if ((rc = launch_preprocess(*p, *in, *out, g, st))) return rc;
   if ((rc = debug_sync(p, st, "preprocess"))) return rc;
-  if (fast_binning(p->W, p->H)) {
-    if ((rc = launch_surfel_sort(*p, g, st))) return rc;
-    return debug_sync(p, st, "surfel sort");
-  }
+  if (fast_binning(p->W, p->H)) return 0;
   if ((rc = launch_scan(*p, g, ws->num_rendered_host, st))) return rc;
   return debug_sync(p, st, "scan");
 }

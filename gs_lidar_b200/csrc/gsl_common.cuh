@@ -206,6 +206,7 @@ int check_cuda(cudaError_t e, const char* what);
 int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
                       const GeomView& g, cudaStream_t st);
 int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st);
+int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st);
 int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st);
 int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,
                    int64_t r_capacity, int32_t* r_host, cudaStream_t st);

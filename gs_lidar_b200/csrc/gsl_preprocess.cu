@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     const uint8_t* __restrict__ mask, const float* __restrict__ viewmatrix,
     const float* __restrict__ campos, int* __restrict__ radii, float4* __restrict__ rec,
     float4* __restrict__ rgb, ushort4* __restrict__ rect, short4* __restrict__ pixbox,
-    uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped, uint32_t* __restrict__ skey,
-    uint32_t* __restrict__ sval) {
+    uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped) {
   __shared__ float s_sin[12], s_cos[12];
   if (threadIdx.x < 12) {
     s_sin[threadIdx.x] = sinf(pp.samp[threadIdx.x]);
@@ -331,9 +330,36 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
   tiles[idx] = out_tiles;
   rect[idx] = out_rect;
   pixbox[idx] = out_box;
-  // key of the surfel depth sort (fast binning): depth bits, invisible surfels last
-  skey[idx] = out_tiles ? __float_as_uint(r) : 0xffffffffu;
+}
+
+// Keys of the surfel depth sort (fast binning): bits of the view-space range r, computed with exactly the
+// instruction sequence of k_preprocess_fwd (forward.cu:116-125) so that the order is the order of the stored
+// depths.  Culled surfels get a key too -- they emit no instances, so where they sort does not matter.  Kept
+// separate from k_preprocess_fwd so that the (latency-bound, library) sort can run on a side stream UNDER the
+// (issue-bound) preprocess kernel.
+__global__ void __launch_bounds__(256) k_depth_keys(int P, const float* __restrict__ means3D,
+                                                    const float* __restrict__ viewmatrix, uint32_t* __restrict__ skey,
+                                                    uint32_t* __restrict__ sval) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
+  const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
+  const float vm8 = viewmatrix[8], vm9 = viewmatrix[9], vm10 = viewmatrix[10];
+  const float vm12 = viewmatrix[12], vm13 = viewmatrix[13], vm14 = viewmatrix[14];
+  const float px = means3D[3 * idx], py = means3D[3 * idx + 1], pz = means3D[3 * idx + 2];
+  const float tx = GSL_FA(vm12, dot3_ref(px, vm0, py, vm4, pz, vm8));
+  const float ty = GSL_FA(vm13, dot3_ref(px, vm1, py, vm5, pz, vm9));
+  const float tz = GSL_FA(vm14, dot3_ref(px, vm2, py, vm6, pz, vm10));
+  const float tx2 = GSL_FM(tx, tx), tz2 = GSL_FM(tz, tz);
+  const float r = sqrtf(GSL_FA(GSL_FF(ty, ty, tx2), tz2));
+  skey[idx] = __float_as_uint(r);
   sval[idx] = (uint32_t)idx;
+}
+
+int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  k_depth_keys<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, in.means3D, in.viewmatrix, g.skey_a, g.sval_a);
+  return check_cuda(cudaGetLastError(), "k_depth_keys launch");
 }
 
 int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_outputs& out,
@@ -351,7 +377,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
   ProfScope prof(GSL_K_PREPROCESS_FWD, st);
   k_preprocess_fwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.opacities, in.shs,
                                           in.colors_precomp, in.mask, in.viewmatrix, in.campos, out.radii,
-                                          g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped, g.skey_a, g.sval_a);
+                                          g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped);
   return check_cuda(cudaGetLastError(), "k_preprocess_fwd launch");
 }
 
