@@ -245,9 +245,24 @@ GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gs
   GeomView g = geom_view(ws->geom, p->P, p->S);
   ImageView im = image_view(ws->image, p->W, p->H, p->P);
   BinView b = bin_view(ws->binning, ws->r_capacity);
+  // fork: the dense gradient outputs are zero-filled on the side stream while the compositor (which touches only
+  // the packed accumulators, and is not DRAM-bound) runs; the per-surfel kernel then writes non-zero rows only
+  SideStream* aux = side_stream();
+  bool prezeroed = false;
+#ifdef GSL_NO_PREZERO
+  aux = nullptr;
+#endif
+  if (aux) {
+    cudaEventRecord(aux->fork, st);
+    cudaStreamWaitEvent(aux->stream, aux->fork, 0);
+    if ((rc = launch_zero_outputs(*p, *in, *gout, aux->stream))) return rc;
+    cudaEventRecord(aux->join, aux->stream);
+    prezeroed = true;
+  }
   if ((rc = launch_render_backward(*p, *in, *fwd, *gin, g, im, b, ws->r_capacity, st))) return rc;
   if ((rc = debug_sync(p, st, "render_backward"))) return rc;
-  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, st))) return rc;
+  if (prezeroed) cudaStreamWaitEvent(st, aux->join, 0);
+  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, prezeroed, st))) return rc;
   return debug_sync(p, st, "preprocess_backward");
 }
 

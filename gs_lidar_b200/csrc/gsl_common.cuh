@@ -219,9 +219,10 @@ int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd
 int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
                            const gsl_bwd_inputs& gin, const GeomView& g, const ImageView& im,
                            const BinView& b, int64_t r_capacity, cudaStream_t st);
+int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st);
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
-                               cudaStream_t st);
+                               bool prezeroed, cudaStream_t st);
 int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
                      size_t drgb_stride, float* dL_dsh, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,

@@ -388,6 +388,8 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
 struct PreBwdParams {
   int P, D, M, S, W, H, gstride;
   int factored;  // GSL_FLAG_BWD_SH_FACTORED: dL_dcolors receives the clamp-masked dL_dRGB, dL_dsh is not written
+  int prezeroed; // the dense outputs were zero-filled already (side stream, under the backward compositor):
+                 // only non-zero values are written here
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -604,35 +606,44 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int ch = 4 * k + j;
-        if (ch < S) { dL_dfeatures[(size_t)idx * S + ch] = fv[j]; fany |= (fv[j] != 0.f); }
+        if (ch < S) fany |= (fv[j] != 0.f);
+      }
+      if (fany || !pp.prezeroed) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = 4 * k + j;
+          if (ch < S) dL_dfeatures[(size_t)idx * S + ch] = fv[j];
+        }
       }
       if (fany) gq[5 + k] = zero4;
     }
-    dL_dopacity[idx] = g2.w;
+    if (any || !pp.prezeroed) dL_dopacity[idx] = g2.w;
     float4 gc_out = gc;
     if (pp.factored && any) {  // clamp-masked dL_dRGB: the factor the SH gradient is rebuilt from (k_sh_expand)
       const uint8_t cl = clamped[idx];
       gc_out = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
     }
-    reinterpret_cast<float4*>(dL_dcolors)[idx] = gc_out;
+    if (any || !pp.prezeroed) reinterpret_cast<float4*>(dL_dcolors)[idx] = gc_out;
     const bool heavy = any && radii[idx] > 0;
     if (any) { gq[0] = zero4; gq[1] = zero4; gq[2] = zero4; gq[3] = zero4; gq[4] = zero4; }
     if (heavy) {
       const int slot = atomicAdd(&s_count, 1);
       s_who[slot] = (uint16_t)threadIdx.x;
       s_g[0][slot] = g0; s_g[1][slot] = g1; s_g[2][slot] = g2; s_g[3][slot] = gc; s_g[4][slot] = gn;
-    } else {
+    } else if (!pp.prezeroed) {
       reinterpret_cast<float4*>(dL_drot)[idx] = zero4;
       reinterpret_cast<float4*>(dL_dmeans2D)[idx] = zero4;
     }
   }
   // coalesced zero-fill of the CTA's rows of the strided outputs (queued surfels overwrite theirs later)
   const int nrows = min(256, pp.P - cta0);
-  if (have_sh && !pp.factored) {
+  if (pp.prezeroed) {
+    // nothing to fill
+  } else if (have_sh && !pp.factored) {
     float4* o = reinterpret_cast<float4*>(dL_dsh) + (size_t)cta0 * pp.M;
     for (int k = threadIdx.x; k < nrows * pp.M; k += 256) o[k] = zero4;
   }
-  {
+  if (!pp.prezeroed) {
     float* o = dL_dmeans3D + (size_t)cta0 * 3;
     for (int k = threadIdx.x; k < nrows * 3; k += 256) o[k] = 0.f;
     o = dL_dscales + (size_t)cta0 * 3;
@@ -652,8 +663,39 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
 }
 
 
+// zero-fill of every dense gradient output (enqueued on a side stream under the backward compositor)
+int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st) {
+  const size_t P = (size_t)p.P;
+  if (P == 0) return 0;
+  struct Range { char* ptr; size_t bytes; };
+  Range r[9];
+  int n = 0;
+  auto add = [&](float* ptr, size_t bytes) { if (ptr && bytes) { r[n].ptr = (char*)ptr; r[n].bytes = bytes; ++n; } };
+  add(gout.dL_dmeans3D, P * 12);
+  add(gout.dL_dmeans2D, P * 16);
+  add(gout.dL_dcolors, P * 16);
+  add(gout.dL_dopacity, P * 4);
+  add(gout.dL_dscales, P * 12);
+  add(gout.dL_drotations, P * 16);
+  if (p.S > 0) add(gout.dL_dfeatures, P * 4 * (size_t)p.S);
+  if (in.shs && !(p.flags & GSL_FLAG_BWD_SH_FACTORED)) add(gout.dL_dsh, P * 16 * (size_t)p.M);
+  add(gout.dL_dcov3D, P * 24);
+  // exactly adjacent tensors (the Python wrapper packs all gradients into one allocation) become one memset
+  for (int i = 1; i < n; ++i)
+    for (int j = i; j > 0 && r[j].ptr < r[j - 1].ptr; --j) { Range t = r[j]; r[j] = r[j - 1]; r[j - 1] = t; }
+  for (int i = 0; i < n;) {
+    char* start = r[i].ptr;
+    size_t bytes = r[i].bytes;
+    int j = i + 1;
+    while (j < n && r[j].ptr == start + bytes) { bytes += r[j].bytes; ++j; }
+    cudaMemsetAsync(start, 0, bytes, st);
+    i = j;
+  }
+  return check_cuda(cudaGetLastError(), "zero-fill of the gradient outputs");
+}
+
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
-                               gsl_bwd_outputs& gout, const GeomView& g, cudaStream_t st) {
+                               gsl_bwd_outputs& gout, const GeomView& g, bool prezeroed, cudaStream_t st) {
   if (p.P == 0) return 0;
   PreBwdParams pp;
   pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.S = p.S;
@@ -669,6 +711,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   }
   pp.gstride = grad_stride(p.S);
   pp.factored = (p.flags & GSL_FLAG_BWD_SH_FACTORED) ? 1 : 0;
+  pp.prezeroed = prezeroed ? 1 : 0;
   Fov f = make_fov(p);
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
   int blocks = (p.P + 255) / 256;

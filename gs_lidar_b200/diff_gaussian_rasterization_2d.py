@@ -290,14 +290,15 @@ class _RasterizeGaussians(torch.autograd.Function):
             d_cov3D = e(P, 6) if ctx.cov_shape == (P, 6) else None
             if ex is None:
                 # one allocation for all dense gradients; the returned tensors are contiguous views of it
-                widths = (3, 4, NUM_CHANNELS, S, 1, 3, 4, M * NUM_CHANNELS)
-                starts, off = [], 0
-                for w in widths:  # every tensor starts 256-B aligned (the kernels use 16-byte stores)
-                    starts.append(off)
-                    off += (P * w + 63) // 64 * 64
-                flat = e(off)
-                views = [flat[o:o + P * w].view(P, w) for o, w in zip(starts, widths)]
-                d_means3D, d_means2D, d_colors, d_features, d_opacity, d_scales, d_rot, d_sh = views
+                # 16-byte-stored tensors first (their sizes are multiples of 16 B), scalar-stored ones after: every
+                # tensor is aligned for its stores and the buffer has no gaps (the C side zero-fills it as one range)
+                widths = (4, NUM_CHANNELS, 4, M * NUM_CHANNELS, 3, 3, 1, S)
+                flat = e(P * sum(widths))
+                views, off = [], 0
+                for w in widths:
+                    views.append(flat[off:off + P * w].view(P, w))
+                    off += P * w
+                d_means2D, d_colors, d_rot, d_sh, d_means3D, d_scales, d_opacity, d_features = views
                 d_sh = d_sh.view(P, M, NUM_CHANNELS)
             else:
                 # gradients go straight into the exchange's flat buffers; dL_dcolors receives the SH factor dL_dRGB
