@@ -76,6 +76,11 @@ SYMBOLS = {
     "gsl_backward": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
                                C.POINTER(gsl_bwd_inputs), C.POINTER(gsl_bwd_outputs),
                                C.POINTER(gsl_workspace), vp]),
+    "gsl_backward_composite": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
+                                         C.POINTER(gsl_bwd_inputs), C.POINTER(gsl_bwd_outputs),
+                                         C.POINTER(gsl_workspace), vp, vp]),
+    "gsl_backward_surfels": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
+                                       C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), vp]),
     "gsl_mark_visible": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
     "gsl_sh_expand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_size_t, vp, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,

@@ -226,21 +226,34 @@ GSL_API int gsl_forward(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_o
   return 0;
 }
 
-GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
-                 const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream) {
+static int backward_validate(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                             const gsl_bwd_outputs* gout, gsl_workspace* ws) {
   int rc = validate(p);
   if (rc) return rc;
   if ((rc = validate_inputs(p, in))) return rc;
-  if (!fwd || !gin || !gout) return set_error(GSL_EINVAL, "fwd / grad inputs / grad outputs is NULL");
+  if (!fwd || !gout) return set_error(GSL_EINVAL, "fwd / grad outputs is NULL");
   if (p->P == 0) return 0;
-  if (!gin->dL_dout_color || !gin->dL_dout_depth || !gin->dL_dout_alpha || !gin->dL_dout_feature)
-    return set_error(GSL_EINVAL, "a cotangent pointer is NULL");
   if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dcolors || !gout->dL_dopacity ||
       !gout->dL_dscales || !gout->dL_drotations || (p->S > 0 && !gout->dL_dfeatures) ||
       (in->shs && !gout->dL_dsh && !(p->flags & GSL_FLAG_BWD_SH_FACTORED)))
     return set_error(GSL_EINVAL, "a gradient output pointer is NULL");
   if (!fwd->radii || !fwd->out_contrib) return set_error(GSL_ESTATE, "forward outputs (radii, out_contrib) missing");
-  if ((rc = validate_ws(p, ws, true))) return rc;
+  return validate_ws(p, ws, true);
+}
+
+// true while the zero-fill forked by gsl_backward_composite has not been joined by gsl_backward_surfels (per thread)
+static thread_local bool g_prezero_pending = false;
+
+GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                           const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, float* sh_factor_out,
+                           void* stream) {
+  int rc = backward_validate(p, in, fwd, gout, ws);
+  if (rc) return rc;
+  if (!gin) return set_error(GSL_EINVAL, "grad inputs is NULL");
+  g_prezero_pending = false;
+  if (p->P == 0) return 0;
+  if (!gin->dL_dout_color || !gin->dL_dout_depth || !gin->dL_dout_alpha || !gin->dL_dout_feature)
+    return set_error(GSL_EINVAL, "a cotangent pointer is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
   ImageView im = image_view(ws->image, p->W, p->H, p->P);
@@ -248,7 +261,6 @@ GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gs
   // fork: the dense gradient outputs are zero-filled on the side stream while the compositor (which touches only
   // the packed accumulators, and is not DRAM-bound) runs; the per-surfel kernel then writes non-zero rows only
   SideStream* aux = side_stream();
-  bool prezeroed = false;
 #ifdef GSL_NO_PREZERO
   aux = nullptr;
 #endif
@@ -257,13 +269,40 @@ GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gs
     cudaStreamWaitEvent(aux->stream, aux->fork, 0);
     if ((rc = launch_zero_outputs(*p, *in, *gout, aux->stream))) return rc;
     cudaEventRecord(aux->join, aux->stream);
-    prezeroed = true;
+    g_prezero_pending = true;
   }
   if ((rc = launch_render_backward(*p, *in, *fwd, *gin, g, im, b, ws->r_capacity, st))) return rc;
   if ((rc = debug_sync(p, st, "render_backward"))) return rc;
-  if (prezeroed) cudaStreamWaitEvent(st, aux->join, 0);
+  if (sh_factor_out) {
+    if ((rc = launch_extract_sh_factor(*p, g, sh_factor_out, st))) return rc;
+    return debug_sync(p, st, "extract_sh_factor");
+  }
+  return 0;
+}
+
+GSL_API int gsl_backward_surfels(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                         gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream) {
+  int rc = backward_validate(p, in, fwd, gout, ws);
+  if (rc) return rc;
+  const bool prezeroed = g_prezero_pending;
+  g_prezero_pending = false;
+  if (p->P == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  GeomView g = geom_view(ws->geom, p->P, p->S);
+  if (prezeroed) {
+    SideStream* aux = side_stream();
+    if (!aux) return set_error(GSL_ESTATE, "side stream lost between the two backward stages");
+    cudaStreamWaitEvent(st, aux->join, 0);
+  }
   if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, prezeroed, st))) return rc;
   return debug_sync(p, st, "preprocess_backward");
+}
+
+GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                 const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream) {
+  int rc = gsl_backward_composite(p, in, fwd, gin, gout, ws, nullptr, stream);
+  if (rc) return rc;
+  return gsl_backward_surfels(p, in, fwd, gout, ws, stream);
 }
 
 GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -219,6 +219,7 @@ int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd
 int launch_render_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
                            const gsl_bwd_inputs& gin, const GeomView& g, const ImageView& im,
                            const BinView& b, int64_t r_capacity, cudaStream_t st);
+int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out, cudaStream_t st);
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st);
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,

@@ -663,6 +663,28 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
 }
 
 
+// The SH factor of frame-parallel training, extracted from the packed accumulators right after the backward
+// compositor (so that its all-gather can run under k_preprocess_bwd): clamp-masked dL_dRGB per surfel.
+__global__ void __launch_bounds__(256) k_extract_sh_factor(int P, int gstride, const float* __restrict__ grad,
+                                                           const uint8_t* __restrict__ clamped, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float4 gc = reinterpret_cast<const float4*>(grad + (size_t)i * gstride)[3];
+  float4 o = gc;
+  if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
+    const uint8_t cl = clamped[i];
+    o = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
+  }
+  out[i] = o;
+}
+
+int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  k_extract_sh_factor<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, grad_stride(p.S), g.grad, g.clamped,
+                                                        reinterpret_cast<float4*>(out));
+  return check_cuda(cudaGetLastError(), "k_extract_sh_factor launch");
+}
+
 // zero-fill of every dense gradient output (enqueued on a side stream under the backward compositor)
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st) {
   const size_t P = (size_t)p.P;

@@ -306,7 +306,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 v = ex.views
                 d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
                 d_scales, d_rot, d_features = v["scales"], v["rotations"], v["features"]
-                d_colors, d_sh = ex.local[:4 * P].view(P, NUM_CHANNELS), None
+                d_colors, d_sh = e(P, NUM_CHANNELS), None  # scratch: the factor itself goes to ex.local (see below)
                 params = L.gsl_params.from_buffer_copy(params)
                 params.flags |= L.GSL_FLAG_BWD_SH_FACTORED
 
@@ -323,8 +323,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             wss = holder.ws.as_struct()
 
             def run():
-                L.check(_lib.gsl_backward(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gin), C.byref(gout),
-                                          C.byref(wss), _stream_ptr(dev)), "gsl_backward")
+                if ex is None:
+                    L.check(_lib.gsl_backward(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gin), C.byref(gout),
+                                              C.byref(wss), _stream_ptr(dev)), "gsl_backward")
+                    return
+                # frame-parallel: compositor + SH factor, start the all-gather, then the per-surfel kernel under it
+                L.check(_lib.gsl_backward_composite(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gin),
+                                                    C.byref(gout), C.byref(wss), ex.local.data_ptr(), _stream_ptr(dev)),
+                        "gsl_backward_composite")
+                ex.start_gather(P, inputs["campos"])
+                L.check(_lib.gsl_backward_surfels(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gout),
+                                                  C.byref(wss), _stream_ptr(dev)), "gsl_backward_surfels")
 
             if settings.debug:
                 cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) +
@@ -338,7 +347,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             else:
                 run()
             if ex is not None:
-                g = ex.finish(P, params.D, M, inputs["means3D"], inputs["campos"])
+                g = ex.finish(P, params.D, M, inputs["means3D"])
                 d_means3D, d_means2D, d_opacity = g["means3D"], g["means2D"], g["opacities"]
                 d_scales, d_rot, d_features, d_sh = g["scales"], g["rotations"], g["features"], g["shs"]
         if not _KEEP_WORKSPACE_AFTER_BACKWARD:

@@ -79,10 +79,13 @@ class GradientExchange:
     A dense all-reduce moves 4*(19+S... ) + 16*M bytes per surfel, 80 % of it SH gradient.  The SH gradient one
     frame gives a surfel is the outer product basis(view direction) x dL_dRGB (backward.cu:17-134), so with this
     exchange active the backward pass
-      1. writes its non-SH gradients straight into one flat fp32 buffer (no per-tensor copies) and the
-         clamp-masked 16-byte factor dL_dRGB into a second one (C-ABI flag GSL_FLAG_BWD_SH_FACTORED),
-      2. all-reduces the first buffer, all-gathers the second (with the rank's camera centre appended),
-      3. rebuilds dL_dsh = sum over ranks of basis x dL_dRGB on the device (gsl_sh_expand).
+      1. extracts the clamp-masked 16-byte factor dL_dRGB right after the backward compositor
+         (gsl_backward_composite) and starts its all-gather (camera centre appended) -- it travels while the
+         per-surfel backward kernel runs,
+      2. writes its non-SH gradients straight into one flat fp32 buffer (gsl_backward_surfels under
+         GSL_FLAG_BWD_SH_FACTORED, no per-tensor copies) and all-reduces it,
+      3. rebuilds dL_dsh = sum over ranks of basis x dL_dRGB on the device (gsl_sh_expand) while that all-reduce is
+         on the wire.
     The gradients the autograd op then returns are already summed over the ranks -- do not all-reduce them
     again.  Same result as an all-reduce of the dense gradients up to fp32 summation order.
 
@@ -128,18 +131,22 @@ class GradientExchange:
             self.key = key
         return self
 
-    def finish(self, P, D, M, means3D, campos):
-        """Runs the collectives and the SH expansion; returns the summed gradients (dict, `shs` included)."""
+    def start_gather(self, P, campos):
+        """After the backward compositor wrote the SH factor into `local`: append the camera centre and start the
+        all-gather, so that it runs while the per-surfel backward kernel is still computing."""
+        self.local[4 * P:4 * P + 3].copy_(campos.reshape(3))
+        self._h_gather = self._all_gather(self.gathered, self.local)
+
+    def finish(self, P, D, M, means3D):
+        """Starts the all-reduce of the non-SH gradients, rebuilds the SH gradient from the gathered factors while it
+        is on the wire, and returns the summed gradients (dict, `shs` included)."""
         from . import _lib as L
         import ctypes as C
         G = self.world_size()
-        self.local[4 * P:4 * P + 3].copy_(campos.reshape(3))
-        # the small all-gather first, then the all-reduce: the SH expansion below only needs the gathered factors
-        # and runs while the all-reduce of the non-SH gradients is still on the wire
-        h_gather = self._all_gather(self.gathered, self.local)
         h_reduce = self._all_reduce(self.flat)
-        if h_gather is not None:
-            h_gather.wait()
+        if self._h_gather is not None:
+            self._h_gather.wait()
+        self._h_gather = None
         campos_all = self.gathered.view(G, self.stride)[:, 4 * P:4 * P + 3].contiguous()
         d_sh = torch.empty((P, M, 4), dtype=torch.float32, device=means3D.device)
         stream = C.c_void_p(torch.cuda.current_stream(means3D.device).cuda_stream)

@@ -173,6 +173,17 @@ GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gs
 GSL_API int gsl_sh_expand(int32_t P, int32_t D, int32_t M, int32_t G, const float* means3D, const float* campos_all,
                   const float* drgb_all, size_t drgb_stride, float* dL_dsh, void* stream);
 
+/* gsl_backward in two stages, for callers that start communication between them: _composite runs the backward
+ * compositor (and forks the zero-fill of the dense outputs onto a side stream); when sh_factor_out is non-NULL it
+ * also writes the clamp-masked dL_dRGB factor (P,4) there, so that a frame-parallel caller can all-gather it while
+ * _surfels (the per-surfel VJP, which joins the zero-fill) is still running.  Must be called in this order by the
+ * same host thread. */
+GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                           const gsl_bwd_inputs* gin, gsl_bwd_outputs* gout, gsl_workspace* ws, float* sh_factor_out,
+                           void* stream);
+GSL_API int gsl_backward_surfels(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                         gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream);
+
 /* Pinhole frustum test, present[i] = in_frustum(means3D[i]) (auxiliary.h:157-180). */
 GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
