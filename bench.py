@@ -24,6 +24,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # the VERSION banner is printf'ed to stdout
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -338,7 +342,7 @@ def run_ours(args, rank, world, local):
         "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "visible_surfels": V, "tile_instances": R,
                    "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, ", fp32 gradient exchange (NCCL all-reduce of the non-SH gradients + all-gather of the SH factors) in the step" if world > 1 else ""),
                    "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6),
-                   "grad_exchange_bytes": (exchange.flat.numel() * 4 + exchange.local.numel() * 4) if exchange is not None else 0},
+                   "grad_exchange_bytes": (exchange.flat_nbytes + exchange.local.numel() * 4) if exchange is not None else 0},
         "clocks": clocks,
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -94,7 +94,9 @@ class GradientExchange:
             loss.backward()
     """
 
-    NAMES = ("means3D", "means2D", "opacities", "scales", "rotations", "features")
+    # 16-byte-stored tensors first (sizes are multiples of 16 B), scalar-stored ones after: every tensor is aligned
+    # for its stores and the buffer has no gaps (one zero-fill, one all-reduce payload)
+    NAMES = ("means2D", "rotations", "means3D", "scales", "opacities", "features")
 
     def __init__(self, group=None):
         self.group = group
@@ -116,15 +118,17 @@ class GradientExchange:
     # -- buffers -------------------------------------------------------------------------------------
     def prepare(self, P, S, M, device):
         G = self.world_size()
-        key = (P, S, M, G, str(device))
+        widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
+        starts, off = {}, 0
+        for k in self.NAMES:
+            starts[k] = off
+            off += P * widths[k]
+        # a fresh flat buffer per backward: the gradients handed to autograd are views of it and nothing else keeps
+        # it alive, so AccumulateGrad adopts them instead of copying (the caching allocator makes this cheap)
+        self.flat = torch.empty(off, dtype=torch.float32, device=device)
+        self.views = {k: self.flat[starts[k]:starts[k] + P * widths[k]].view(P, widths[k]) for k in self.NAMES}
+        key = (P, G, str(device))
         if self.key != key:
-            widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
-            starts, off = {}, 0
-            for k in self.NAMES:  # every tensor starts 256-B aligned (the kernels use 16-byte stores)
-                starts[k] = off
-                off += (P * widths[k] + 63) // 64 * 64
-            self.flat = torch.zeros(off, dtype=torch.float32, device=device)
-            self.views = {k: self.flat[starts[k]:starts[k] + P * widths[k]].view(P, widths[k]) for k in self.NAMES}
             self.stride = 4 * P + 4                       # dL_dRGB (P,4) + camera centre (3) + pad
             self.local = torch.zeros(self.stride, dtype=torch.float32, device=device)
             self.gathered = torch.zeros(G * self.stride, dtype=torch.float32, device=device)
@@ -156,6 +160,9 @@ class GradientExchange:
             h_reduce.wait()
         out = dict(self.views)
         out["shs"] = d_sh
+        self.views = None  # drop our references: autograd owns the gradients now
+        self.flat_nbytes = self.flat.numel() * 4
+        self.flat = None
         return out
 
     # -- activation ------------------------------------------------------------------------------------

@@ -370,22 +370,25 @@ def test_factored_gradient_exchange_equals_sum_of_dense_gradients():
     class Loopback(parallel.GradientExchange):
         def __init__(self):
             super().__init__()
-            self.parked = None
+            self.first, self.flat0, self.local0 = True, None, None
 
         def world_size(self):
             return 2
 
         def _all_reduce(self, flat):
-            if self.parked is not None:
-                flat.add_(self.parked[0])
+            if self.first:
+                self.flat0 = flat.clone()
+            else:
+                flat.add_(self.flat0)
 
         def _all_gather(self, out, local):
             o = out.view(2, -1)
-            if self.parked is None:
+            if self.first:
+                self.local0 = local.clone()
                 o[0].copy_(local)
                 o[1].zero_()
             else:
-                o[0].copy_(self.parked[1])
+                o[0].copy_(self.local0)
                 o[1].copy_(local)
 
     base = synth.make_scene(20000, seed=71)
@@ -399,7 +402,7 @@ def test_factored_gradient_exchange_equals_sum_of_dense_gradients():
     ex = Loopback()
     with ex:
         common.run_ours(scenes[0], cot, export=False)
-        ex.parked = (ex.flat.clone(), ex.local.clone())
+        ex.first = False
         _, _, got = common.run_ours(scenes[1], cot, export=False)
     for k in ("means3D", "means2D", "opacities", "scales", "rotations", "features", "shs"):
         elem, norm = common.grad_err(got[k], expect[k])
