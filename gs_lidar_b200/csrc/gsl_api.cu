@@ -344,7 +344,7 @@ GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
 
 GSL_API const char* gsl_kernel_name(int id) {
   static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan|bases)", "k_bin_scatter",
-                                           "cub::DeviceRadixSort (library)", "k_tile_blists", "k_render_fwd",
+                                           "k_sort_(hist|scan|scatter|buckets)", "k_tile_blists", "k_render_fwd",
                                            "k_render_bwd", "k_preprocess_bwd"};
   return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
 }

@@ -484,27 +484,6 @@ size_t sort_temp_bytes(int64_t Rcap) {
   return cached_bytes;
 }
 
-size_t surfel_sort_temp_bytes(int64_t P) {
-  static thread_local int64_t cached_p = -1;
-  static thread_local size_t cached_bytes = 0;
-  if (P == cached_p) return cached_bytes;
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)P);
-  cached_p = P;
-  cached_bytes = bytes + 256;
-  return cached_bytes;
-}
-
-// surfel ids in (depth bits, id) order -> g.sval_b (fast binning only)
-int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st) {
-  if (p.P == 0) return 0;
-  size_t tmp = g.ssort_tmp_bytes;
-  ProfScope prof(GSL_K_SORT, st);
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(g.ssort_tmp, tmp, g.skey_a, g.skey_b, g.sval_a, g.sval_b, p.P, 0, 32, st);
-  return check_cuda(e, "cub::DeviceRadixSort::SortPairs (surfels)");
-}
-
 int wait_num_rendered(int32_t* r_host, cudaStream_t st) {
   volatile int32_t* v = r_host;
   while (v[0] < 0) {

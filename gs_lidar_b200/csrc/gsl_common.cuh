@@ -17,7 +17,7 @@
 //     grad[i]     float[32] packed gradient accumulators, kept all-zero between steps:
 //         [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity,
 //         [12..15] dL_dcolor, [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature, pad to 32
-//     ctrl        u32[64]  [0]=R, [1]=overflow
+//     ctrl        u32[64]  [0]=R, [1]=overflow, [8]=max(~depth key), [9]=max(depth key)
 //   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2),
 //     bdesc uint4[tiles*8]  per 8x4 pixel block (tile, b): (start, end) of its block list inside plane b,
 //                     .z = number of leading entries the backward pass has to walk (written by the forward)
@@ -63,12 +63,11 @@ struct GeomView {
   float* grad;
   uint32_t* ctrl;
   uint32_t* scan_state;  // per-CTA sums of the tiles_touched scan
-  uint32_t* skey_a;      // surfel depth sort: keys (depth bits, 0xffffffff when invisible) and surfel ids,
-  uint32_t* skey_b;      // double buffered; sval_b = surfel ids in (depth, id) order
+  uint32_t* skey_a;      // surfel depth sort (gsl_sort.cu): depth-bit keys,
+  uint32_t* skey_b;      //   keys / ids scattered into their buckets,
   uint32_t* sval_a;
-  uint32_t* sval_b;
-  void* ssort_tmp;
-  size_t ssort_tmp_bytes;
+  uint32_t* sval_b;      //   surfel ids in (depth, id) order
+  uint32_t* sort_buckets;  // count / start / cursor arrays of the bucket sort, 3 x (16384 + 64)
   size_t bytes;
 };
 
@@ -102,8 +101,6 @@ inline void carve(char*& p, T*& out, size_t count) {
   p = (char*)(a + count * sizeof(T));
 }
 
-size_t surfel_sort_temp_bytes(int64_t P);
-
 inline GeomView geom_view(void* base, int P, int S) {
   GeomView g;
   char* p = (char*)base;
@@ -122,10 +119,7 @@ inline GeomView geom_view(void* base, int P, int S) {
   carve(p, g.skey_b, Pp);
   carve(p, g.sval_a, Pp);
   carve(p, g.sval_b, Pp);
-  g.ssort_tmp_bytes = surfel_sort_temp_bytes((int64_t)Pp);
-  char* stmp;
-  carve(p, stmp, g.ssort_tmp_bytes);
-  g.ssort_tmp = stmp;
+  carve(p, g.sort_buckets, 3 * (16384 + 64));
   g.bytes = (size_t)(p - (char*)base) + 256;
   return g;
 }

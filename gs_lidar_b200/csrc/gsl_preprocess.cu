@@ -335,13 +335,33 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
 // Keys of the surfel depth sort (fast binning): bits of the view-space range r, computed with exactly the
 // instruction sequence of k_preprocess_fwd (forward.cu:116-125) so that the order is the order of the stored
 // depths.  Culled surfels get a key too -- they emit no instances, so where they sort does not matter.  Kept
-// separate from k_preprocess_fwd so that the (latency-bound, library) sort can run on a side stream UNDER the
+// separate from k_preprocess_fwd so that the (latency-bound) sort of gsl_sort.cu can run on a side stream UNDER the
 // (issue-bound) preprocess kernel.
+__device__ __forceinline__ void depth_key_of(int idx, const float* __restrict__ means3D, const float* __restrict__ viewmatrix,
+                                             uint32_t* __restrict__ skey, uint32_t& key);
 __global__ void __launch_bounds__(256) k_depth_keys(int P, const float* __restrict__ means3D,
                                                     const float* __restrict__ viewmatrix, uint32_t* __restrict__ skey,
-                                                    uint32_t* __restrict__ sval) {
+                                                    uint32_t* __restrict__ ctrl) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P) return;
+  uint32_t key = 0;
+  const bool live = idx < P;
+  if (live) depth_key_of(idx, means3D, viewmatrix, skey, key);
+  // key range for the bucket sort: ctrl[8] = max(~key), ctrl[9] = max(key), one pair of atomics per CTA
+  __shared__ uint32_t s_max[2];
+  if (threadIdx.x < 2) s_max[threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t kmax = __reduce_max_sync(0xffffffffu, live ? key : 0u);
+  const uint32_t nmin = __reduce_max_sync(0xffffffffu, live ? ~key : 0u);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&s_max[0], nmin);
+    atomicMax(&s_max[1], kmax);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) atomicMax(&ctrl[8 + threadIdx.x], s_max[threadIdx.x]);
+}
+
+__device__ __forceinline__ void depth_key_of(int idx, const float* __restrict__ means3D, const float* __restrict__ viewmatrix,
+                                             uint32_t* __restrict__ skey, uint32_t& key) {
   const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
   const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
   const float vm8 = viewmatrix[8], vm9 = viewmatrix[9], vm10 = viewmatrix[10];
@@ -352,13 +372,14 @@ __global__ void __launch_bounds__(256) k_depth_keys(int P, const float* __restri
   const float tz = GSL_FA(vm14, dot3_ref(px, vm2, py, vm6, pz, vm10));
   const float tx2 = GSL_FM(tx, tx), tz2 = GSL_FM(tz, tz);
   const float r = sqrtf(GSL_FA(GSL_FF(ty, ty, tx2), tz2));
-  skey[idx] = __float_as_uint(r);
-  sval[idx] = (uint32_t)idx;
+  key = __float_as_uint(r);
+  skey[idx] = key;
 }
 
 int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st) {
   if (p.P == 0) return 0;
-  k_depth_keys<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, in.means3D, in.viewmatrix, g.skey_a, g.sval_a);
+  cudaMemsetAsync(g.ctrl + 8, 0, 2 * sizeof(uint32_t), st);
+  k_depth_keys<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, in.means3D, in.viewmatrix, g.skey_a, g.ctrl);
   return check_cuda(cudaGetLastError(), "k_depth_keys launch");
 }
 
