@@ -350,9 +350,11 @@ def run_ours(args, rank, world, local):
         4: 12 * R,                                                                     # k_tile_blists (id + box in, entry out)
         5: N * (8 + 16 + 4 * (S + 3) + 16 + 4 + 12) + V * (64 + 16 + 4 * S),           # k_render_fwd
         6: render_bwd_algorithmic_bytes(V, N, S),                                      # k_render_bwd
-        7: P * (96 + 4) + V * (48 + 45 + 16 * M) // 2 + P * (12 + 16 + 16 + 4 * S + 4 + 24 + 16 * M + 12 + 16),  # k_preprocess_bwd
+        # k_preprocess_bwd: accumulator + radii of every surfel; record, parameters and SH in, dense gradient rows out for
+        # the surfels that contributed (measured: half of the visible ones); the zero rows are a memset on the side stream
+        7: P * (96 + 4) + (V // 2) * (48 + 45 + 16 * M) + (V // 2) * (12 + 16 + 16 + 4 * S + 4 + 16 * M + 12 + 16),
     }
-    ncu_traffic = {0: 401.2e6, 4: 19.5e6, 5: 115.4e6, 6: 131.5e6, 7: 667.5e6}
+    ncu_traffic = {0: 401.2e6, 1: 17.1e6, 2: 17.1e6, 4: 19.4e6, 5: 114.5e6, 6: 129.7e6, 7: 519.9e6}  # profiles/r01_v9_ncu_full.md
     dom_id = max(kern_bytes, key=lambda i: kms[i])
     dom_ms = kms[dom_id] / max(kn[dom_id], 1)
     dom_name = L.load().gsl_kernel_name(dom_id).decode()

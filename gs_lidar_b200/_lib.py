@@ -90,9 +90,10 @@ SYMBOLS = {
     "gsl_kernel_name": (C.c_char_p, [C.c_int]),
 }
 GSL_K_COUNT = 8
-# kernels of THIS repo launched per forward / backward call (k_scan is three launches; the cub sort is
-# library code and not counted): used by bench.py for "gpu_launches".
-OWN_LAUNCHES_FWD = 1 + 1 + 3 + 1 + 1 + 1   # depth keys, preprocess, bin count/scan/bases, bin scatter, tile block lists, render_fwd
+# kernels of THIS repo launched per forward / backward call on the fast binning path (<= 1024 tiles; no library
+# kernel is launched there): used by bench.py for "gpu_launches".
+OWN_LAUNCHES_FWD = 1 + 4 + 1 + 3 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan/bases,
+                                            # bin scatter, tile block lists, render_fwd
 OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
 
 _lib = None

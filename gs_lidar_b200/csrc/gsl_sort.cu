@@ -132,9 +132,9 @@ __device__ void sort_one_bucket(unsigned long long* s_v, uint32_t lo, uint32_t n
           o = __shfl_xor_sync(0xffffffffu, v, j);
         }
         if (warp_live) {
-          const bool lower = (i & j) == 0;  // keep the smaller value in the lower partner when sorting upwards
-          const bool take_min = (lower == up);
-          v = take_min ? (v < o ? v : o) : (v > o ? v : o);
+          // the lower partner keeps the smaller value when sorting upwards: one 64-bit compare, one select
+          const bool take_min = (((i & j) == 0) == up);
+          v = ((v < o) == take_min) ? v : o;
         }
       }
     }
