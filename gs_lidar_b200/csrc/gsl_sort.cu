@@ -104,6 +104,36 @@ __global__ void __launch_bounds__(256) k_sort_scatter(int P, const uint32_t* __r
 }
 
 // compare-exchange network step of the bitonic sort over m = 2^x virtual elements (indices >= n hold +inf)
+// Bitonic network over M <= SORT_THREADS elements, one per thread (threads >= M idle): partners closer than a warp are
+// exchanged with shuffles, only the steps with j >= 32 go through shared memory.  Fully unrolled: the directions and
+// partner tests fold into constants per step.  Must be called by all threads of the CTA.
+template <int M>
+__device__ __forceinline__ unsigned long long bitonic_one_per_thread(unsigned long long v, unsigned long long* s_v) {
+  const uint32_t i = threadIdx.x;
+  const bool warp_live = (i & ~31u) < (uint32_t)M;
+#pragma unroll
+  for (int k = 2; k <= M; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long o = 0;
+      if (j >= 32) {
+        __syncthreads();
+        if (warp_live) s_v[i] = v;
+        __syncthreads();
+        if (warp_live) o = s_v[i ^ j];
+      } else if (warp_live) {
+        o = __shfl_xor_sync(0xffffffffu, v, j);
+      }
+      if (warp_live) {
+        // the lower partner keeps the smaller value when sorting upwards: one 64-bit compare, one select
+        const bool take_min = (((i & j) == 0) == ((i & k) == 0));
+        v = ((v < o) == take_min) ? v : o;
+      }
+    }
+  }
+  return v;
+}
+
 __device__ void sort_one_bucket(unsigned long long* s_v, uint32_t lo, uint32_t n, uint32_t* __restrict__ tmp_key,
                                 uint32_t* __restrict__ tmp_id, uint32_t* __restrict__ order) {
   if (n == 0) return;
@@ -114,30 +144,13 @@ __device__ void sort_one_bucket(unsigned long long* s_v, uint32_t lo, uint32_t n
   uint32_t m = 2;
   while (m < n) m <<= 1;
   if (n <= (uint32_t)SORT_THREADS) {
-    // the common case: one element per thread; partners closer than a warp are exchanged with shuffles, only the
-    // steps with j >= 32 go through shared memory
+    // the common case: one element per thread, network fully unrolled for the padded size
     const uint32_t i = threadIdx.x;
-    const bool warp_live = (i & ~31u) < m;  // warps beyond the padded size only keep the barriers company
     unsigned long long v = (i < n) ? (((unsigned long long)tmp_key[lo + i] << 32) | tmp_id[lo + i]) : ~0ull;
-    for (uint32_t k = 2; k <= m; k <<= 1) {
-      const bool up = (i & k) == 0;
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        unsigned long long o = 0;
-        if (j >= 32) {
-          __syncthreads();
-          if (warp_live) s_v[i] = v;
-          __syncthreads();
-          if (warp_live) o = s_v[i ^ j];
-        } else if (warp_live) {
-          o = __shfl_xor_sync(0xffffffffu, v, j);
-        }
-        if (warp_live) {
-          // the lower partner keeps the smaller value when sorting upwards: one 64-bit compare, one select
-          const bool take_min = (((i & j) == 0) == up);
-          v = ((v < o) == take_min) ? v : o;
-        }
-      }
-    }
+    if (m <= 32) v = bitonic_one_per_thread<32>(v, s_v);
+    else if (m == 64) v = bitonic_one_per_thread<64>(v, s_v);
+    else if (m == 128) v = bitonic_one_per_thread<128>(v, s_v);
+    else v = bitonic_one_per_thread<256>(v, s_v);
     if (i < n) order[lo + i] = (uint32_t)v;
     return;
   }
