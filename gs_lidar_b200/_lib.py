@@ -61,6 +61,23 @@ class gsl_state_export(C.Structure):
                                   "final_T", "pixbox")]
 
 
+class gsl_glue_params(C.Structure):
+    _fields_ = [("P", C.c_int32), ("timestamp", C.c_float), ("time_shift", C.c_float), ("cycle", C.c_float),
+                ("velocity_decay", C.c_float), ("dynamic", C.c_int32)]
+
+
+class gsl_glue_inputs(C.Structure):
+    _fields_ = [(n, vp) for n in ("xyz", "velocity", "t", "scaling_t", "opacity", "scaling", "rotation", "mask")]
+
+
+class gsl_glue_outputs(C.Structure):
+    _fields_ = [(n, vp) for n in ("means3D", "opacity", "scales", "rotations", "marginal_t", "mask")]
+
+
+class gsl_glue_inputs_grad(C.Structure):
+    _fields_ = [(n, vp) for n in ("xyz", "velocity", "t", "scaling_t", "opacity", "scaling", "rotation")]
+
+
 # name -> (restype, argtypes); every symbol include/gsl_b200.h declares
 SYMBOLS = {
     "gsl_abi_version": (C.c_int, []),
@@ -81,6 +98,9 @@ SYMBOLS = {
                                          C.POINTER(gsl_workspace), vp, vp]),
     "gsl_backward_surfels": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
                                        C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), vp]),
+    "gsl_glue_forward": (C.c_int, [C.POINTER(gsl_glue_params), C.POINTER(gsl_glue_inputs), C.POINTER(gsl_glue_outputs), vp]),
+    "gsl_glue_backward": (C.c_int, [C.POINTER(gsl_glue_params), C.POINTER(gsl_glue_inputs), C.POINTER(gsl_glue_outputs),
+                                    C.POINTER(gsl_glue_inputs_grad), vp]),
     "gsl_mark_visible": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
     "gsl_sh_expand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_size_t, vp, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
@@ -89,7 +109,7 @@ SYMBOLS = {
     "gsl_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "gsl_kernel_name": (C.c_char_p, [C.c_int]),
 }
-GSL_K_COUNT = 8
+GSL_K_COUNT = 10
 # kernels of THIS repo launched per forward / backward call on the fast binning path (<= 1024 tiles; no library
 # kernel is launched there): used by bench.py for "gpu_launches".
 OWN_LAUNCHES_FWD = 1 + 4 + 1 + 3 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan/bases,

@@ -323,6 +323,33 @@ GSL_API int gsl_sh_expand(int32_t P, int32_t D, int32_t M, int32_t G, const floa
   return launch_sh_expand(P, D, M, G, means3D, campos_all, drgb_all, drgb_stride, dL_dsh, (cudaStream_t)stream);
 }
 
+static int validate_glue(const gsl_glue_params* p, const gsl_glue_inputs* in) {
+  if (!p || !in) return set_error(GSL_EINVAL, "glue: params / inputs is NULL");
+  if (p->P < 0) return set_error(GSL_EINVAL, "glue: P must be >= 0");
+  if (!(p->cycle > 0.f)) return set_error(GSL_EINVAL, "glue: cycle (GaussianModel.T) must be positive");
+  if (p->P > 0 && (!in->xyz || !in->velocity || !in->t || !in->scaling_t || !in->opacity || !in->scaling || !in->rotation))
+    return set_error(GSL_EINVAL, "glue: a raw parameter pointer is NULL");
+  return 0;
+}
+
+GSL_API int gsl_glue_forward(const gsl_glue_params* p, const gsl_glue_inputs* in, const gsl_glue_outputs* out, void* stream) {
+  int rc = validate_glue(p, in);
+  if (rc) return rc;
+  if (!out || (p->P > 0 && (!out->means3D || !out->opacity || !out->scales || !out->rotations || !out->mask)))
+    return set_error(GSL_EINVAL, "glue: an output pointer is NULL");
+  return launch_glue_forward(*p, *in, *out, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_glue_backward(const gsl_glue_params* p, const gsl_glue_inputs* in, const gsl_glue_outputs* gout,
+                      const gsl_glue_inputs_grad* gin, void* stream) {
+  int rc = validate_glue(p, in);
+  if (rc) return rc;
+  if (!gout || !gin) return set_error(GSL_EINVAL, "glue: cotangents / gradient outputs is NULL");
+  if (p->P > 0 && (!gin->xyz || !gin->velocity || !gin->t || !gin->scaling_t || !gin->opacity || !gin->scaling || !gin->rotation))
+    return set_error(GSL_EINVAL, "glue: a gradient output pointer is NULL");
+  return launch_glue_backward(*p, *in, *gout, *gin, (cudaStream_t)stream);
+}
+
 GSL_API int gsl_profile_enable(int on) { g_prof_on = on != 0; return 0; }
 
 GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
@@ -345,7 +372,7 @@ GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
 GSL_API const char* gsl_kernel_name(int id) {
   static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan|bases)", "k_bin_scatter",
                                            "k_sort_(hist|scan|scatter|buckets)", "k_tile_blists", "k_render_fwd",
-                                           "k_render_bwd", "k_preprocess_bwd"};
+                                           "k_render_bwd", "k_preprocess_bwd", "k_glue_fwd", "k_glue_bwd"};
   return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
 }
 

@@ -220,6 +220,9 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                bool prezeroed, cudaStream_t st);
 int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
                      size_t drgb_stride, float* dL_dsh, cudaStream_t st);
+int launch_glue_forward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& out, cudaStream_t st);
+int launch_glue_backward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& gout,
+                         const gsl_glue_inputs_grad& gin, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, cudaStream_t st);
 

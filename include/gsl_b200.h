@@ -184,6 +184,42 @@ GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in
 GSL_API int gsl_backward_surfels(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                          gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream);
 
+/* ---- render() glue: the per-surfel element-wise work gaussian_renderer/__init__.py:64-115 and
+ * scene/gaussian_model.py:139-186 run in PyTorch before the rasterizer, as one kernel per direction. ---- */
+typedef struct gsl_glue_params {
+  int32_t P;
+  float timestamp;      /* viewpoint_camera.timestamp */
+  float time_shift;     /* render(time_shift=...), 0 when None */
+  float cycle;          /* GaussianModel.T (args.cycle) */
+  float velocity_decay; /* GaussianModel.velocity_decay */
+  int32_t dynamic;      /* pipe.dynamic */
+} gsl_glue_params;
+typedef struct gsl_glue_inputs {   /* raw (pre-activation) parameters of GaussianModel */
+  const float* xyz;        /* _xyz (P,3) */
+  const float* velocity;   /* _velocity (P,3) */
+  const float* t;          /* _t (P,1) */
+  const float* scaling_t;  /* _scaling_t (P,1), log */
+  const float* opacity;    /* _opacity (P,1), logit */
+  const float* scaling;    /* _scaling (P,3), log */
+  const float* rotation;   /* _rotation (P,4), unnormalised */
+  const uint8_t* mask;     /* optional user mask (P), may be NULL */
+} gsl_glue_inputs;
+typedef struct gsl_glue_outputs {  /* what render() feeds the rasterizer (also used for their cotangents) */
+  float* means3D;    /* (P,3) */
+  float* opacity;    /* (P,1) */
+  float* scales;     /* (P,3) */
+  float* rotations;  /* (P,4) */
+  float* marginal_t; /* (P,1), may be NULL */
+  uint8_t* mask;     /* (P) prefilter mask */
+} gsl_glue_outputs;
+typedef struct gsl_glue_inputs_grad {
+  float* xyz; float* velocity; float* t; float* scaling_t; float* opacity; float* scaling; float* rotation;
+} gsl_glue_inputs_grad;
+GSL_API int gsl_glue_forward(const gsl_glue_params* p, const gsl_glue_inputs* in, const gsl_glue_outputs* out, void* stream);
+/* gout: cotangents of (means3D, opacity, scales, rotations); NULL members count as zero. */
+GSL_API int gsl_glue_backward(const gsl_glue_params* p, const gsl_glue_inputs* in, const gsl_glue_outputs* gout,
+                      const gsl_glue_inputs_grad* gin, void* stream);
+
 /* Pinhole frustum test, present[i] = in_frustum(means3D[i]) (auxiliary.h:157-180). */
 GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
@@ -219,7 +255,9 @@ enum {
   GSL_K_RENDER_FWD = 5,
   GSL_K_RENDER_BWD = 6,
   GSL_K_PREPROCESS_BWD = 7,
-  GSL_K_COUNT = 8
+  GSL_K_GLUE_FWD = 8,  /* k_glue_fwd (render() glue, next-1) */
+  GSL_K_GLUE_BWD = 9,  /* k_glue_bwd */
+  GSL_K_COUNT = 10
 };
 GSL_API int gsl_profile_enable(int on);
 /* Waits for all recorded events, then returns accumulated milliseconds and launch counts per id. */

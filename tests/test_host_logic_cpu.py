@@ -138,3 +138,15 @@ def test_gradient_exchange_buffers_alias_one_flat_allreduce_payload():
     assert ex.gathered is gathered_before  # the persistent comm buffers are cached for the same (P, world, device)
     ex.prepare(50, 0, 16, "cpu")
     assert ex.views["features"].shape == (50, 0)
+
+
+def test_glue_restatement_is_differentiable_and_masks_like_render():
+    # tests/glue_oracle.py restates gaussian_renderer/__init__.py:64-115 in torch; sanity of the checker itself on CPU
+    import glue_oracle as GO
+    pc = GO.make_model(500, seed=1)
+    m3, op, sc, rot, mt, msk = GO.reference_glue(pc, 0.1, 0.02, True, None)
+    assert m3.shape == (500, 3) and op.shape == (500, 1) and rot.shape == (500, 4) and msk.dtype == torch.bool
+    assert torch.allclose(rot.norm(dim=1), torch.ones(500), atol=1e-6)
+    assert bool((msk == ((op[:, 0] > 1 / 255) & (mt[:, 0] > 0.05))).all())
+    g = torch.autograd.grad(m3.sum() + op.sum(), [pc._xyz, pc._velocity, pc._t, pc._scaling_t, pc._opacity])
+    assert all(torch.isfinite(x).all() for x in g)
