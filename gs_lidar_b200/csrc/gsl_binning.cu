@@ -1,9 +1,15 @@
-// gsl_binning.cu -- tile binning: scan of tile counts, key duplication, tile|depth sort, tile ranges.
-// Semantics of rasterizer_impl.cu:68-142 and :310-354 (K2-K7 in SURVEY.md):
+// gsl_binning.cu -- tile binning.  What must come out, bit for bit, is what rasterizer_impl.cu:68-142 and :310-354
+// (K2-K7 in SURVEY.md) produce:
 //   offsets = inclusive_scan(tiles_touched); R = offsets[P-1]
 //   key = (tile_id << 32) | float_bits(depth), value = surfel id, emitted y-major/x-minor per surfel
 //   stable sort over key bits [0, 32 + bits(tiles));  ranges[tile] = [first, last+1)
-// All of it is integer work and must be bit-exact.
+// Two ways to get there:
+//   * fast path (images of up to GSL_FAST_BIN_MAX_TILES tiles, every BASELINE.json config): the surfels are depth-
+//     sorted once (gsl_sort.cu) and ONE stable counting pass distributes their instances to the tiles
+//     (k_bin_count / k_bin_scan / k_bin_bases / k_bin_scatter below) -- no 64-bit keys, no library;
+//   * general path: the reference's own scheme -- scan (k_scan_*), key duplication (k_duplicate) and the library
+//     64-bit radix sort (the same cub call the reference makes).
+// Both end in k_tile_blists, which also builds the per-8x4-block lists of this design.
 #include <cub/cub.cuh>
 #include "gsl_common.cuh"
 

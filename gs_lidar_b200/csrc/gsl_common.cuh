@@ -12,7 +12,9 @@
 //     rgb[i]      float4   SH colour (forward.cu:275-278); unused with colors_precomp
 //     rect[i]     ushort4  tile rect (min.x, min.y, max.x, max.y) of getRect (auxiliary.h:47-55)
 //     pixbox[i]   short4   conservative pixel box of the surfel's support (this design)
-//     tiles[i]    u32      tiles_touched;  offs[i] u32 inclusive scan
+//     tiles[i]    u32      tiles_touched;  offs[i] u32 inclusive scan (general binning path, state export) /
+//                          scratch of the surfel sort (fast path)
+//     skey_a/b, sval_a/b u32  surfel depth sort: keys, bucket-scattered (key, id), ids in (depth, id) order
 //     clamped[i]  u8       bit c set when SH channel c was clamped (forward.cu:64-67)
 //     grad[i]     float[32] packed gradient accumulators, kept all-zero between steps:
 //         [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity,
@@ -21,7 +23,9 @@
 //   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2),
 //     bdesc uint4[tiles*8]  per 8x4 pixel block (tile, b): (start, end) of its block list inside plane b,
 //                     .z = number of leading entries the backward pass has to walk (written by the forward)
-//   binning chunk (capacity Rcap): keys_a u64, keys_b u64, vals_a u32, vals_b u32, sort temp,
+//     hist u32[tiles][ceil(P/256)], bintotal u32[tiles]  counting pass of the fast binning path
+//   binning chunk (capacity Rcap): vals_b u32 = point_list (sorted surfel ids); keys_a/keys_b u64, vals_a u32 and the
+//     sort scratch of the general path;
 //     blist uint2[8][Rcap]  BLOCK LISTS: plane b holds, for tile t at [ranges[t].x, ...), in list order, the
 //                     (surfel id, list position) of every entry of t whose conservative pixel box overlaps
 //                     8x4 pixel block b = (row/4)*2 + col/8 of the tile -- the list of block (t, b)
