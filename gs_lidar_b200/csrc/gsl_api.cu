@@ -162,12 +162,12 @@ GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
   if (fast_binning(p->W, p->H) && p->P > 0) {
-    // fork: depth keys, then the surfel sort on a side stream UNDER the preprocess kernel; join before binning
+    // fork: depth keys + surfel sort on a side stream UNDER the preprocess kernel; join before binning
     SideStream* aux = side_stream();
     if (!aux) return set_error(GSL_EINVAL, "could not create the side stream");
-    if ((rc = launch_depth_keys(*p, *in, g, st))) return rc;
     cudaEventRecord(aux->fork, st);
     cudaStreamWaitEvent(aux->stream, aux->fork, 0);
+    if ((rc = launch_depth_keys(*p, *in, g, aux->stream))) return rc;
     if ((rc = launch_surfel_sort(*p, g, aux->stream))) return rc;
     cudaEventRecord(aux->join, aux->stream);
     if ((rc = launch_preprocess(*p, *in, *out, g, st))) return rc;
