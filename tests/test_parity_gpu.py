@@ -517,3 +517,72 @@ def test_full_size_gradients_are_finite_and_sparse(full_run):
         assert float(g[culled].abs().sum()) == 0.0, k   # culled surfels get exactly zero gradient
     assert float(grads["scales"][:, 2].abs().sum()) == 0.0  # dL_dscale.z is always 0 (backward.cu:618)
     assert float(grads["means2D"][:, 2:].abs().sum()) == 0.0
+
+
+def test_capacity_overflow_is_detected_and_rerun():
+    """The render stage is enqueued speculatively against the workspace capacity; when the device-side instance count
+    does not fit, nothing is written, the wrapper grows the binning chunk and re-runs -- results must be identical."""
+    import gs_lidar_b200.diff_gaussian_rasterization_2d as G
+    scene = synth.make_scene(40000, seed=91).to("cuda")
+    with torch.no_grad():
+        ref = _call(scene)
+    # forget every sizing hint and pooled workspace, then force a far too small first guess
+    G._pool.free.clear()
+    G._pool.r_hint.clear()
+    G._pool.r_hint[(scene.means3D.device, 40000, scene.W, scene.H)] = 1024
+    with torch.no_grad():
+        out = _call(scene)
+    for a, b in zip(ref, out):
+        assert torch.equal(a, b)
+    assert G._pool.r_hint[(scene.means3D.device, 40000, scene.W, scene.H)] > 100000  # learnt the real size
+
+
+def test_c_abi_called_directly_matches_the_wrapper():
+    """gsl_forward / gsl_backward through plain ctypes structs (what a non-Python host would do), no wrapper code."""
+    import ctypes as C
+    from gs_lidar_b200 import _lib as L
+    lib = L.load()
+    scene = synth.make_scene(15000, seed=92).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=93).items()}
+    out_w, _, g_w = common.run_ours(scene, cot, export=False)
+    P, H, W, S, M = 15000, scene.H, scene.W, 4, 16
+    p = L.gsl_params(P, S, 3, M, W, H, math.tan(-0.5), math.tan(-0.5), 1.0, scene.vfov[0], scene.vfov[1], scene.hfov[0],
+                     scene.hfov[1], scene.scale_factor, 0, 0)
+    sz = L.gsl_ws_sizes()
+    rcap = 200000
+    assert lib.gsl_workspace_sizes(C.byref(p), rcap, C.byref(sz)) == 0
+    geom = torch.zeros(sz.geom_bytes, dtype=torch.uint8, device="cuda")
+    binning = torch.empty(sz.binning_bytes, dtype=torch.uint8, device="cuda")
+    image = torch.empty(sz.image_bytes, dtype=torch.uint8, device="cuda")
+    host = torch.zeros(2, dtype=torch.int32).pin_memory()
+    ws = L.gsl_workspace(geom.data_ptr(), sz.geom_bytes, binning.data_ptr(), sz.binning_bytes, image.data_ptr(),
+                         sz.image_bytes, rcap, host.data_ptr())
+    mask8 = scene.mask.view(torch.uint8)
+    fin = L.gsl_fwd_inputs(scene.bg.data_ptr(), scene.means3D.data_ptr(), scene.shs.data_ptr(), None, scene.features.data_ptr(),
+                           scene.opacities.data_ptr(), scene.scales.data_ptr(), scene.rotations.data_ptr(), None,
+                           mask8.data_ptr(), scene.viewmatrix.data_ptr(), scene.projmatrix.data_ptr(), scene.campos.data_ptr())
+    e = lambda *s: torch.empty(s, device="cuda")
+    contrib = torch.empty((2, H, W), dtype=torch.int32, device="cuda")
+    color, feature, depth, alpha = e(4, H, W), e(S + 3, H, W), e(4, H, W), e(1, H, W)
+    radii = torch.empty(P, dtype=torch.int32, device="cuda")
+    fout = L.gsl_fwd_outputs(contrib.data_ptr(), color.data_ptr(), feature.data_ptr(), depth.data_ptr(), alpha.data_ptr(),
+                             radii.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    R = C.c_int32(0)
+    assert lib.gsl_forward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(ws), C.byref(R), st) == 0, L.last_error()
+    assert 0 < R.value <= rcap
+    assert torch.equal(color, out_w["out_color"]) and torch.equal(contrib, out_w["out_contrib"]) and torch.equal(radii, out_w["radii"])
+    gin = L.gsl_bwd_inputs(cot["color"].data_ptr(), cot["depth"].data_ptr(), cot["alpha"].data_ptr(), cot["feature"].data_ptr())
+    d = dict(means3D=e(P, 3), means2D=e(P, 4), shs=e(P, M, 4), colors=e(P, 4), features=e(P, S), opacities=e(P, 1),
+             scales=e(P, 3), rotations=e(P, 4))
+    gout = L.gsl_bwd_outputs(d["means3D"].data_ptr(), d["means2D"].data_ptr(), d["shs"].data_ptr(), d["colors"].data_ptr(),
+                             d["features"].data_ptr(), d["opacities"].data_ptr(), d["scales"].data_ptr(),
+                             d["rotations"].data_ptr(), None)
+    assert lib.gsl_backward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(gin), C.byref(gout), C.byref(ws), st) == 0, L.last_error()
+    torch.cuda.synchronize()
+    for k in ("means3D", "means2D", "shs", "features", "opacities", "scales", "rotations"):
+        assert max(common.grad_err(d[k], g_w[k])) < TOL_GRAD, k
+    # too small a capacity is reported, not silently wrong
+    ws.r_capacity = 1000
+    rc = lib.gsl_forward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(ws), C.byref(R), st)
+    assert rc == L.GSL_ENOSPACE and R.value > 1000 and b"capacity" in lib.gsl_last_error()
