@@ -13,6 +13,7 @@ GSL_ABI_VERSION = 1
 GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
 GSL_FLAG_DEBUG_SYNC = 1
 GSL_FLAG_BWD_SH_FACTORED = 2
+GSL_FLAG_WRAP_AZIMUTH = 4
 GSL_MAX_FEATURES = 10
 
 vp = C.c_void_p

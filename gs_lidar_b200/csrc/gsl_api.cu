@@ -1,5 +1,6 @@
 // gsl_api.cu -- extern "C" entry points declared in include/gsl_b200.h.
 // Validation, workspace carving and stage orchestration only; all arithmetic lives in the kernels.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -68,6 +69,12 @@ static int validate(const gsl_params* p) {
     return set_error(GSL_EINVAL, "sh has %d coefficients but degree %d needs %d", p->M, p->D, (p->D + 1) * (p->D + 1));
   if (p->W <= 0 || p->H <= 0) return set_error(GSL_EINVAL, "image size must be positive (got %dx%d)", p->W, p->H);
   if (p->W > 32767 || p->H > 32767) return set_error(GSL_EINVAL, "image side > 32767 not supported");
+  if (p->flags & GSL_FLAG_WRAP_AZIMUTH) {
+    if (fabsf((p->hfov_max - p->hfov_min) - 360.f) > 1e-3f)
+      return set_error(GSL_EINVAL, "azimuth wrap-around needs a 360 degree hfov (got %g .. %g)", p->hfov_min, p->hfov_max);
+    if (!fast_binning(p->W, p->H))
+      return set_error(GSL_EINVAL, "azimuth wrap-around supports images of up to %d tiles", GSL_FAST_BIN_MAX_TILES);
+  }
   return 0;
 }
 

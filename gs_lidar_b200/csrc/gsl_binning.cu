@@ -347,9 +347,10 @@ template <typename F>
 __device__ __forceinline__ void for_each_chunk_tile(ushort4 rc, int gx, uint32_t payload, F f) {
   const int lane = threadIdx.x & 31;
   const int w = (int)rc.z - (int)rc.x, n = w * ((int)rc.w - (int)rc.y);
+  // rc.z may exceed gx in azimuth wrap-around mode: the column is x mod gx (gsl_preprocess.cu)
   if (n > 0 && n <= BIG_RECT) {
     for (int y = rc.y; y < rc.w; ++y)
-      for (int x = rc.x; x < rc.z; ++x) f(y * gx + x, (int)threadIdx.x, payload);
+      for (int x = rc.x; x < rc.z; ++x) f(y * gx + (x >= gx ? x - gx : x), (int)threadIdx.x, payload);
   }
   uint32_t big = __ballot_sync(0xffffffffu, n > BIG_RECT);
   while (big) {
@@ -359,7 +360,10 @@ __device__ __forceinline__ void for_each_chunk_tile(ushort4 rc, int gx, uint32_t
     const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
     const uint32_t pl = __shfl_sync(0xffffffffu, payload, src);
     const int t_src = (int)threadIdx.x - lane + src;
-    for (int k = lane; k < bn; k += 32) f((by + k / bw) * gx + bx + k % bw, t_src, pl);
+    for (int k = lane; k < bn; k += 32) {
+      const int x = bx + k % bw;
+      f((by + k / bw) * gx + (x >= gx ? x - gx : x), t_src, pl);
+    }
   }
 }
 

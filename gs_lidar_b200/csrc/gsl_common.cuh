@@ -183,6 +183,7 @@ struct RenderParams {
   int W, H, gx, gy, S;
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
   float near_, far_, far_over_range;  // 2*sf, 300*sf, far/(far-near) (forward.cu:366-367,453)
+  float wrapW;                        // azimuth wrap-around mode: period in pixels (= W), else 0
   uint32_t r_capacity;
 };
 RenderParams make_render_params(const gsl_params& p, int64_t r_capacity);

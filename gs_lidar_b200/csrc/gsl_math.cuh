@@ -39,6 +39,7 @@ struct PixelRay {
   float sphi_cth;  // sin(phi)*cos(theta)
   float cphi_cth;  // cos(phi)*cos(theta)
   float px, py;    // float pixel coordinates (integer valued)
+  float wrapW;     // > 0 in azimuth wrap-around mode: the period of the panorama in pixels
 };
 
 __device__ __forceinline__ PixelRay make_pixel_ray(float px, float py, float hfov_min, float hfov_max,
@@ -46,6 +47,7 @@ __device__ __forceinline__ PixelRay make_pixel_ray(float px, float py, float hfo
   PixelRay r;
   r.px = px;
   r.py = py;
+  r.wrapW = 0.f;
   // phi = pixf.x * (HFOV_max - HFOV_min) / W + HFOV_min : mul, div, add (no contraction possible)
   float phi = GSL_FA(GSL_FD(GSL_FM(GSL_FS(hfov_max, hfov_min), px), (float)W), hfov_min);
   float theta = GSL_FA(GSL_FD(GSL_FM(GSL_FS(vfov_max, vfov_min), py), (float)H), vfov_min);
@@ -125,6 +127,10 @@ __device__ __forceinline__ PairEval eval_pair(const Splat& s, const PixelRay& r,
   }
   float rho3d = GSL_FF(sx, sx, GSL_FM(sy, sy));
   float dx = GSL_FS(s.mx, r.px);
+  if (r.wrapW > 0.f) {  // wrap-around mode: distance to the nearest periodic image of the projected centre
+    if (dx > 0.5f * r.wrapW) dx -= r.wrapW;
+    else if (dx < -0.5f * r.wrapW) dx += r.wrapW;
+  }
   float dy = GSL_FS(s.my, r.py);
   float h = GSL_FF(dx, dx, GSL_FM(dy, dy));
   float rho2d = GSL_FA(h, h);  // FilterInvSquare (=2) * |d|^2

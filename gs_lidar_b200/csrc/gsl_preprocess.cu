@@ -23,6 +23,7 @@ __device__ __constant__ float kSH_C3[7] = {-0.5900435899266435f, 2.8906114426405
 
 struct PreParams {
   int P, D, M, W, H, gx, gy;
+  int wrap;  // GSL_FLAG_WRAP_AZIMUTH: the panorama is periodic in azimuth (opt-in; the reference has no wrap-around)
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
   float scale_factor;
   float samp[12];  // (float)(2*MY_PI*i/12), forward.cu:155
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     const float cutoff = sqrtf((float)fmax((double)GSL_FF(logf(opacity), 2.f, 9.f), 0.000001));
     float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
     const float Wf = (float)pp.W, Hf = (float)pp.H;
+    const float cx = GSL_FD(GSL_FM(GSL_FS(phi, pp.HFOV_min), Wf), dH);
+    const float cy = GSL_FD(GSL_FM(GSL_FS(theta, pp.VFOV_min), Hf), dV);
 #pragma unroll 1
     for (int i = 0; i < 12; ++i) {
       float vx = GSL_FM(s_sin[i], cutoff), vy = GSL_FM(s_cos[i], cutoff);
@@ -195,12 +198,16 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
       float ph = atan2f(X, Z);
       float th = atan2f(sqrtf(GSL_FF(X, X, GSL_FM(Z, Z))), -Y);
       float ppx = GSL_FD(GSL_FM(GSL_FS(ph, pp.HFOV_min), Wf), dH);
+      if (pp.wrap) {  // azimuth of the sample RELATIVE to the centre, so that a splat on the seam keeps its true extent
+        float dphi = ph - phi;
+        if (dphi > 3.14159265f) dphi -= 6.2831853f;
+        else if (dphi < -3.14159265f) dphi += 6.2831853f;
+        ppx = cx + dphi * Wf / dH;
+      }
       float ppy = GSL_FD(GSL_FM(GSL_FS(th, pp.VFOV_min), Hf), dV);
       minx = fminf(minx, ppx); maxx = fmaxf(maxx, ppx);
       miny = fminf(miny, ppy); maxy = fmaxf(maxy, ppy);
     }
-    const float cx = GSL_FD(GSL_FM(GSL_FS(phi, pp.HFOV_min), Wf), dH);
-    const float cy = GSL_FD(GSL_FM(GSL_FS(theta, pp.VFOV_min), Hf), dV);
     const float rad = fmaxf(fmaxf(GSL_FS(maxx, cx), GSL_FS(cx, minx)), fmaxf(GSL_FS(maxy, cy), GSL_FS(cy, miny)));
     if (!((double)rad < 0.3)) {
       const int my_radius = (int)ceilf(rad);
@@ -210,6 +217,23 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
       int rminy = min(pp.gy, max(0, (int)(GSL_FM(GSL_FS(cy, rf), 0.0625f))));
       int rmaxx = min(pp.gx, max(0, (int)(GSL_FM(GSL_FS(GSL_FA(GSL_FA(cx, rf), 16.f), 1.f), 0.0625f))));
       int rmaxy = min(pp.gy, max(0, (int)(GSL_FM(GSL_FS(GSL_FA(GSL_FA(cy, rf), 16.f), 1.f), 0.0625f))));
+      if (pp.wrap) {
+        // Tile columns as a modular range [rminx, rmaxx) over gx columns, rmaxx may exceed gx: column = x mod gx.
+        // The part of the footprint left of pixel 0 continues at pixel W, the part right of pixel W - 1 at pixel 0
+        // (same rounding rules as getRect for each part).
+        const int tx0 = (int)floorf((cx - rf) * 0.0625f), tx1 = (int)floorf((cx + rf + 15.f) * 0.0625f);
+        const bool left = (cx - rf) < 0.f, right = (cx + rf) >= Wf;
+        int start = max(tx0, 0), len = min(tx1, pp.gx) - max(tx0, 0);
+        if (left) {
+          const int a0 = min(pp.gx, max(0, (int)floorf((Wf + cx - rf) * 0.0625f)));
+          start = a0;
+          len += pp.gx - a0;
+        }
+        if (right) len += min(pp.gx, max(0, (int)floorf((cx + rf - Wf + 15.f) * 0.0625f)));
+        if ((left && right) || len >= pp.gx) { start = 0; len = pp.gx; }
+        rminx = start;
+        rmaxx = start + max(len, 0);
+      }
       const int area = (rmaxx - rminx) * (rmaxy - rminy);
       if (area != 0) {
         // colour: SH or precomputed (forward.cu:269-279)
@@ -393,6 +417,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
   Fov f = make_fov(p);
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
   pp.scale_factor = p.scale_factor;
+  pp.wrap = (p.flags & GSL_FLAG_WRAP_AZIMUTH) ? 1 : 0;
   for (int i = 0; i < 12; ++i) pp.samp[i] = (float)(2 * GSL_MY_PI * i / 12);
   int blocks = (p.P + 255) / 256;
   ProfScope prof(GSL_K_PREPROCESS_FWD, st);

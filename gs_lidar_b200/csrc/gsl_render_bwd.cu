@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(32) k_render_bwd(
   const uint2* __restrict__ bl = blist + (size_t)bg_.bbit * plane_stride;
   const uint32_t* __restrict__ pmk = pairmask + (size_t)bg_.bbit * plane_stride;
 
-  const PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min,
-                                      rp.VFOV_max, rp.W, rp.H);
+  PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min, rp.VFOV_max,
+                                rp.W, rp.H);
+  ray.wrapW = rp.wrapW;
   const float T_final = inside ? final_T[pix_id] : 0.f;
   float T = T_final;
   const int median_contributor = inside ? n_contrib[pix_id + N] : 0;

@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(32) k_render_fwd(
   const uint2* __restrict__ bl = blist + (size_t)bg_.bbit * plane_stride;
   uint32_t* __restrict__ pmk = pairmask + (size_t)bg_.bbit * plane_stride;
 
-  const PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min,
-                                      rp.VFOV_max, rp.W, rp.H);
+  PixelRay ray = make_pixel_ray((float)bg_.pxi, (float)bg_.pyi, rp.HFOV_min, rp.HFOV_max, rp.VFOV_min, rp.VFOV_max,
+                                rp.W, rp.H);
+  ray.wrapW = rp.wrapW;
   bool done = !inside;
   float T = 1.0f;
   int last_contributor = 0, median_contributor = 0;
@@ -218,6 +219,7 @@ RenderParams make_render_params(const gsl_params& p, int64_t r_capacity) {
   volatile float range = fr - nr;
   volatile float q = fr / range;
   rp.near_ = nr; rp.far_ = fr; rp.far_over_range = q;
+  rp.wrapW = (p.flags & GSL_FLAG_WRAP_AZIMUTH) ? (float)p.W : 0.f;
   rp.r_capacity = (uint32_t)(r_capacity < 0 ? 0 : (r_capacity > 0xffffffffLL ? 0xffffffffLL : r_capacity));
   return rp;
 }

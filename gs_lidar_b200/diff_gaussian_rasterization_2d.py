@@ -101,6 +101,17 @@ _pool = _Pool()
 # frame-parallel training: a gs_lidar_b200.parallel.GradientExchange that the backward pass feeds directly
 _exchange = None
 
+# Opt-in extension, OFF by default (= the reference's semantics): treat a 360-degree panorama as periodic in azimuth.
+# The reference clamps tile rects at the image border (auxiliary.h:47-55), so a splat on the +-180 degree seam gets an
+# AABB spanning the whole width and is binned into every tile of its rows; with wrap-around it keeps its true footprint
+# and its low-pass distance is measured to the nearest periodic image.
+_wrap_azimuth = False
+
+
+def set_wrap_azimuth(flag: bool):
+    global _wrap_azimuth
+    _wrap_azimuth = bool(flag)
+
 
 class _Holder:
     """Keeps a workspace attached to one forward call until its backward ran (or it is dropped)."""
@@ -143,6 +154,8 @@ def _make_params(settings, P, S, M):
     p.scale_factor = float(settings.scale_factor)
     p.prefiltered = int(bool(settings.prefiltered))
     p.flags = L.GSL_FLAG_DEBUG_SYNC if settings.debug else 0
+    if _wrap_azimuth:
+        p.flags |= L.GSL_FLAG_WRAP_AZIMUTH
     return p
 
 

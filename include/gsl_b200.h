@@ -48,6 +48,10 @@ extern "C" {
 
 /* flags */
 #define GSL_FLAG_DEBUG_SYNC 1u /* raster_settings.debug: sync + check after every stage */
+#define GSL_FLAG_WRAP_AZIMUTH 4u /* opt-in, NOT the reference's semantics (it clamps rects, auxiliary.h:47-55): the
+                                    panorama is periodic in azimuth -- a splat on the +-180 deg seam keeps its true
+                                    footprint (modular tile columns) and its low-pass distance wraps.  Needs
+                                    hfov_max - hfov_min = 360 and an image of <= 1024 tiles. */
 #define GSL_FLAG_BWD_SH_FACTORED 2u /* gsl_backward: write the clamp-masked dL_dRGB factor into dL_dcolors and do
                                        not write dL_dsh (frame-parallel training rebuilds it with gsl_sh_expand) */
 

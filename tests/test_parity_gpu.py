@@ -36,6 +36,8 @@ GRAD_KEYS = dict(means3D="dL_dmeans3D", means2D="dL_dmeans2D", shs="dL_dsh", col
 def test_extension_is_the_cuda_library():
     """The product path must be the in-tree CUDA .so; there is no fallback to fall back to."""
     from gs_lidar_b200 import _lib as L
+    import gs_lidar_b200
+    assert gs_lidar_b200.GaussianRasterizer is not None  # first access of an API name dlopens the library
     assert os.path.basename(L.LIB_PATH).startswith("libgsl_b200") and os.path.exists(L.LIB_PATH)
     with open("/proc/self/maps") as f:
         assert "libgsl_b200" in f.read()
