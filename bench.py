@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=66)
     ap.add_argument("--width", type=int, default=1030)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wrap-azimuth", action="store_true",
+                    help="opt-in extension, NOT the reference's semantics and not the headline: periodic panorama")
     ap.add_argument("--cpu-sample-surfels", type=int, default=0, help="0 = pick from a quick calibration")
     return ap.parse_args()
 
@@ -150,6 +152,8 @@ def run_ours(args, rank, world, local):
     import gs_lidar_b200.diff_gaussian_rasterization_2d as G
     dev = torch.device("cuda", local)
     P, H, W, S = args.surfels, args.height, args.width, 4
+    if args.wrap_azimuth:
+        G.set_wrap_azimuth(True)
     # replicated surfels (the world-space set of frame 0 on every rank), one camera pose per rank
     scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(0))
     if rank != 0:
@@ -294,7 +298,7 @@ def run_ours(args, rank, world, local):
     # ---- M2: the reference-faithful pair of half panoramas, two calls of H x W/2 with hfov +-90 and the
     # front / back view matrices of scene/kitti360_loader.py:215-218, gradients summed; reported next to the headline
     m2 = None
-    if world == 1 and W % 2 == 0:
+    if world == 1 and W % 2 == 0 and not args.wrap_azimuth:
         flip = torch.diag(torch.tensor([-1.0, 1.0, -1.0, 1.0], device=dev))
         half = dict(image_width=W // 2, hfov=(-90.0, 90.0))
         st_front = settings._replace(**half)
@@ -375,6 +379,7 @@ def run_ours(args, rank, world, local):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "visible_surfels": V, "tile_instances": R,
+                   "azimuth_wrap_around": bool(args.wrap_azimuth),
                    "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, ", fp32 gradient exchange (NCCL all-reduce of the non-SH gradients + all-gather of the SH factors) in the step" if world > 1 else ""),
                    "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6),
                    "grad_exchange_bytes": (exchange.flat_nbytes + exchange.local.numel() * 4) if exchange is not None else 0},
