@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSL_B200_LIB", os.path.join(HERE, "libgsl_b200.so"))  # override: dev builds only
 
-GSL_ABI_VERSION = 1
+GSL_ABI_VERSION = 2
 GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
 GSL_FLAG_DEBUG_SYNC = 1
 GSL_FLAG_BWD_SH_FACTORED = 2
@@ -40,7 +40,7 @@ class gsl_workspace(C.Structure):
 class gsl_fwd_inputs(C.Structure):
     _fields_ = [(n, vp) for n in ("background", "means3D", "shs", "colors_precomp", "features", "opacities",
                                   "scales", "rotations", "cov3D_precomp", "mask", "viewmatrix", "projmatrix",
-                                  "campos")]
+                                  "campos", "shs_rest")]
 
 
 class gsl_fwd_outputs(C.Structure):
@@ -53,7 +53,7 @@ class gsl_bwd_inputs(C.Structure):
 
 class gsl_bwd_outputs(C.Structure):
     _fields_ = [(n, vp) for n in ("dL_dmeans3D", "dL_dmeans2D", "dL_dsh", "dL_dcolors", "dL_dfeatures",
-                                  "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D")]
+                                  "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D", "dL_dsh_rest")]
 
 
 class gsl_state_export(C.Structure):

@@ -89,6 +89,7 @@ static int validate_inputs(const gsl_params* p, const gsl_fwd_inputs* in) {
   if ((in->shs == nullptr) == (in->colors_precomp == nullptr))
     return set_error(GSL_EINVAL, "Please provide exactly one of either SHs or precomputed colors!");
   if (in->shs && p->M == 0) return set_error(GSL_EINVAL, "shs given but M == 0");
+  if (in->shs_rest && (!in->shs || p->M < 2)) return set_error(GSL_EINVAL, "shs_rest needs shs (coefficient 0) and M >= 2");
   if (p->S > 0 && !in->features) return set_error(GSL_EINVAL, "features is NULL but S = %d", p->S);
   return 0;
 }
@@ -242,7 +243,8 @@ static int backward_validate(const gsl_params* p, const gsl_fwd_inputs* in, cons
   if (p->P == 0) return 0;
   if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dcolors || !gout->dL_dopacity ||
       !gout->dL_dscales || !gout->dL_drotations || (p->S > 0 && !gout->dL_dfeatures) ||
-      (in->shs && !gout->dL_dsh && !(p->flags & GSL_FLAG_BWD_SH_FACTORED)))
+      (in->shs && !gout->dL_dsh && !(p->flags & GSL_FLAG_BWD_SH_FACTORED)) ||
+      (in->shs_rest && !gout->dL_dsh_rest && !(p->flags & GSL_FLAG_BWD_SH_FACTORED)))
     return set_error(GSL_EINVAL, "a gradient output pointer is NULL");
   if (!fwd->radii || !fwd->out_contrib) return set_error(GSL_ESTATE, "forward outputs (radii, out_contrib) missing");
   return validate_ws(p, ws, true);

@@ -59,13 +59,49 @@ __device__ __forceinline__ Rot3 quat_to_rot(float q0, float q1, float q2, float 
   return R;
 }
 
-// SH -> 4 channels (forward.cu:17-69).  sh points at this surfel's M float4 coefficients.
-__device__ __forceinline__ float4 eval_sh(int deg, const float4* __restrict__ sh, float x, float y, float z) {
-  float4 c0 = sh[0];
+// The M float4 SH coefficients of one surfel: either one (P, M, 4) tensor like the reference's `shs`, or GS-LiDAR's two
+// parameter tensors _features_dc (P, 1, 4) and _features_rest (P, M - 1, 4) taken as they are (the reference
+// concatenates them on every call, scene/gaussian_model.py:167-171: 256 MB written and read again at 1M surfels).
+struct ShView {
+  const float4* c0;  // coefficient 0
+  const float4* cr;  // coefficients 1 .. M-1
+  __device__ __forceinline__ float4 at(int k) const { return k == 0 ? c0[0] : cr[k - 1]; }
+};
+struct ShOut {
+  float4* c0;
+  float4* cr;
+  __device__ __forceinline__ void set(int k, float4 v) const { if (k == 0) c0[0] = v; else cr[k - 1] = v; }
+};
+__device__ __forceinline__ ShView sh_view(const float* shs, const float* shs_rest, size_t idx, int M) {
+  ShView v;
+  if (shs_rest) {
+    v.c0 = reinterpret_cast<const float4*>(shs) + idx;
+    v.cr = reinterpret_cast<const float4*>(shs_rest) + idx * (size_t)(M - 1);
+  } else {
+    v.c0 = reinterpret_cast<const float4*>(shs) + idx * (size_t)M;
+    v.cr = v.c0 + 1;
+  }
+  return v;
+}
+__device__ __forceinline__ ShOut sh_out(float* d, float* d_rest, size_t idx, int M) {
+  ShOut v;
+  if (d_rest) {
+    v.c0 = reinterpret_cast<float4*>(d) + idx;
+    v.cr = reinterpret_cast<float4*>(d_rest) + idx * (size_t)(M - 1);
+  } else {
+    v.c0 = reinterpret_cast<float4*>(d) + idx * (size_t)M;
+    v.cr = v.c0 + 1;
+  }
+  return v;
+}
+
+// SH -> 4 channels (forward.cu:17-69).
+__device__ __forceinline__ float4 eval_sh(int deg, const ShView sh, float x, float y, float z) {
+  float4 c0 = sh.at(0);
   float r[4] = {kSH_C0 * c0.x, kSH_C0 * c0.y, kSH_C0 * c0.z, kSH_C0 * c0.w};
 #define GSL_ACC(coef, idx, sign)                         \
   {                                                      \
-    float4 c = sh[idx];                                  \
+    float4 c = sh.at(idx);                               \
     float k = (coef);                                    \
     r[0] = r[0] sign k * c.x;                            \
     r[1] = r[1] sign k * c.y;                            \
@@ -102,7 +138,7 @@ __device__ __forceinline__ float4 eval_sh(int deg, const float4* __restrict__ sh
 __global__ void __launch_bounds__(256) k_preprocess_fwd(
     PreParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ opacities,
-    const float* __restrict__ shs, const float* __restrict__ colors_precomp,
+    const float* __restrict__ shs, const float* __restrict__ shs_rest, const float* __restrict__ colors_precomp,
     const uint8_t* __restrict__ mask, const float* __restrict__ viewmatrix,
     const float* __restrict__ campos, int* __restrict__ radii, float4* __restrict__ rec,
     float4* __restrict__ rgb, ushort4* __restrict__ rect, short4* __restrict__ pixbox,
@@ -241,7 +277,7 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
           float dx = px - campos[0], dy = py - campos[1], dz = pz - campos[2];
           float len = sqrtf(dx * dx + dy * dy + dz * dz);
           dx = dx / len; dy = dy / len; dz = dz / len;
-          float4 c = eval_sh(pp.D, reinterpret_cast<const float4*>(shs) + (size_t)idx * pp.M, dx, dy, dz);
+          float4 c = eval_sh(pp.D, sh_view(shs, shs_rest, (size_t)idx, pp.M), dx, dy, dz);
           uint8_t cl = (uint8_t)((c.x < 0.f ? 1 : 0) | (c.y < 0.f ? 2 : 0) | (c.z < 0.f ? 4 : 0) | (c.w < 0.f ? 8 : 0));
           clamped[idx] = cl;
           rgb[idx] = make_float4(fmaxf(c.x, 0.f), fmaxf(c.y, 0.f), fmaxf(c.z, 0.f), fmaxf(c.w, 0.f));
@@ -421,7 +457,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
   for (int i = 0; i < 12; ++i) pp.samp[i] = (float)(2 * GSL_MY_PI * i / 12);
   int blocks = (p.P + 255) / 256;
   ProfScope prof(GSL_K_PREPROCESS_FWD, st);
-  k_preprocess_fwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.opacities, in.shs,
+  k_preprocess_fwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.opacities, in.shs, in.shs_rest,
                                           in.colors_precomp, in.mask, in.viewmatrix, in.campos, out.radii,
                                           g.rec, g.rgb, g.rect, g.pixbox, g.tiles, g.clamped);
   return check_cuda(cudaGetLastError(), "k_preprocess_fwd launch");
@@ -458,40 +494,40 @@ __device__ __forceinline__ void operator+=(float4& a, float4 b) { a.x += b.x; a.
 // SH VJP (backward.cu:17-134).  Writes dL_dsh[0..(D+1)^2) and returns the gradient w.r.t. the
 // mean through the view direction.
 template <bool WRITE>
-__device__ __forceinline__ float3 sh_backward(int deg, int M, const float4* __restrict__ sh, float4 dL_dRGB,
-                                              float3 dir_orig, float4* __restrict__ dL_dsh) {
+__device__ __forceinline__ float3 sh_backward(int deg, int M, const ShView sh, float4 dL_dRGB, float3 dir_orig,
+                                              const ShOut dL_dsh) {
   float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
   float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
   float4 dRGBdx = make_float4(0, 0, 0, 0), dRGBdy = dRGBdx, dRGBdz = dRGBdx;
-  if (WRITE) dL_dsh[0] = kSH_C0 * dL_dRGB;
+  if (WRITE) dL_dsh.set(0, kSH_C0 * dL_dRGB);
   if (deg > 0) {
-    if (WRITE) dL_dsh[1] = (-kSH_C1 * y) * dL_dRGB;
-    if (WRITE) dL_dsh[2] = (kSH_C1 * z) * dL_dRGB;
-    if (WRITE) dL_dsh[3] = (-kSH_C1 * x) * dL_dRGB;
-    dRGBdx = (-kSH_C1) * sh[3];
-    dRGBdy = (-kSH_C1) * sh[1];
-    dRGBdz = kSH_C1 * sh[2];
+    if (WRITE) dL_dsh.set(1, (-kSH_C1 * y) * dL_dRGB);
+    if (WRITE) dL_dsh.set(2, (kSH_C1 * z) * dL_dRGB);
+    if (WRITE) dL_dsh.set(3, (-kSH_C1 * x) * dL_dRGB);
+    dRGBdx = (-kSH_C1) * sh.at(3);
+    dRGBdy = (-kSH_C1) * sh.at(1);
+    dRGBdz = kSH_C1 * sh.at(2);
     if (deg > 1) {
       float xx = x * x, yy = y * y, zz = z * z;
       float xy = x * y, yz = y * z, xz = x * z;
-      if (WRITE) dL_dsh[4] = (kSH_C2[0] * xy) * dL_dRGB;
-      if (WRITE) dL_dsh[5] = (kSH_C2[1] * yz) * dL_dRGB;
-      if (WRITE) dL_dsh[6] = (kSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB;
-      if (WRITE) dL_dsh[7] = (kSH_C2[3] * xz) * dL_dRGB;
-      if (WRITE) dL_dsh[8] = (kSH_C2[4] * (xx - yy)) * dL_dRGB;
-      float4 s4 = sh[4], s5 = sh[5], s6 = sh[6], s7 = sh[7], s8 = sh[8];
+      if (WRITE) dL_dsh.set(4, (kSH_C2[0] * xy) * dL_dRGB);
+      if (WRITE) dL_dsh.set(5, (kSH_C2[1] * yz) * dL_dRGB);
+      if (WRITE) dL_dsh.set(6, (kSH_C2[2] * (2.f * zz - xx - yy)) * dL_dRGB);
+      if (WRITE) dL_dsh.set(7, (kSH_C2[3] * xz) * dL_dRGB);
+      if (WRITE) dL_dsh.set(8, (kSH_C2[4] * (xx - yy)) * dL_dRGB);
+      float4 s4 = sh.at(4), s5 = sh.at(5), s6 = sh.at(6), s7 = sh.at(7), s8 = sh.at(8);
       dRGBdx += (kSH_C2[0] * y) * s4 + (kSH_C2[2] * 2.f * -x) * s6 + (kSH_C2[3] * z) * s7 + (kSH_C2[4] * 2.f * x) * s8;
       dRGBdy += (kSH_C2[0] * x) * s4 + (kSH_C2[1] * z) * s5 + (kSH_C2[2] * 2.f * -y) * s6 + (kSH_C2[4] * 2.f * -y) * s8;
       dRGBdz += (kSH_C2[1] * y) * s5 + (kSH_C2[2] * 2.f * 2.f * z) * s6 + (kSH_C2[3] * x) * s7;
       if (deg > 2) {
-        if (WRITE) dL_dsh[9] = (kSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB;
-        if (WRITE) dL_dsh[10] = (kSH_C3[1] * xy * z) * dL_dRGB;
-        if (WRITE) dL_dsh[11] = (kSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB;
-        if (WRITE) dL_dsh[12] = (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB;
-        if (WRITE) dL_dsh[13] = (kSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB;
-        if (WRITE) dL_dsh[14] = (kSH_C3[5] * z * (xx - yy)) * dL_dRGB;
-        if (WRITE) dL_dsh[15] = (kSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB;
-        float4 s9 = sh[9], s10 = sh[10], s11 = sh[11], s12 = sh[12], s13 = sh[13], s14 = sh[14], s15 = sh[15];
+        if (WRITE) dL_dsh.set(9, (kSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB);
+        if (WRITE) dL_dsh.set(10, (kSH_C3[1] * xy * z) * dL_dRGB);
+        if (WRITE) dL_dsh.set(11, (kSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB);
+        if (WRITE) dL_dsh.set(12, (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * dL_dRGB);
+        if (WRITE) dL_dsh.set(13, (kSH_C3[4] * x * (4.f * zz - xx - yy)) * dL_dRGB);
+        if (WRITE) dL_dsh.set(14, (kSH_C3[5] * z * (xx - yy)) * dL_dRGB);
+        if (WRITE) dL_dsh.set(15, (kSH_C3[6] * x * (xx - 3.f * yy)) * dL_dRGB);
+        float4 s9 = sh.at(9), s10 = sh.at(10), s11 = sh.at(11), s12 = sh.at(12), s13 = sh.at(13), s14 = sh.at(14), s15 = sh.at(15);
         dRGBdx += (kSH_C3[0] * 3.f * 2.f * xy) * s9 + (kSH_C3[1] * yz) * s10 + (kSH_C3[2] * -2.f * xy) * s11 +
                   (kSH_C3[3] * -3.f * 2.f * xz) * s12 + (kSH_C3[4] * (-3.f * xx + 4.f * zz - yy)) * s13 +
                   (kSH_C3[5] * 2.f * xz) * s14 + (kSH_C3[6] * 3.f * (xx - yy)) * s15;
@@ -513,10 +549,10 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const float4* __re
 __device__ __forceinline__ void preprocess_vjp_one(
     const PreBwdParams& pp, int i, float4 g0, float4 g1, float4 g2, float4 dcol, float4 gn,
     const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rotations,
-    const float* __restrict__ shs, const float* __restrict__ viewmatrix, const float* __restrict__ campos,
-    const float4* __restrict__ rec, const uint8_t* __restrict__ clamped, float* __restrict__ dL_dmeans3D,
-    float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
-    float* __restrict__ dL_drot) {
+    const float* __restrict__ shs, const float* __restrict__ shs_rest, const float* __restrict__ viewmatrix,
+    const float* __restrict__ campos, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
+    float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh,
+    float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dscales, float* __restrict__ dL_drot) {
   {
     const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
     const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
@@ -585,8 +621,8 @@ __device__ __forceinline__ void preprocess_vjp_one(
       // path by the Python wrapper semantics (colors_precomp is empty), so dL_dcolors stays as accumulated.
       const float3 dir = make_float3(means3D[3 * (size_t)i] - campos[0], means3D[3 * (size_t)i + 1] - campos[1],
                                      means3D[3 * (size_t)i + 2] - campos[2]);
-      float4* out_sh = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * pp.M;
-      const float4* sh_i = reinterpret_cast<const float4*>(shs) + (size_t)i * pp.M;
+      const ShOut out_sh = sh_out(dL_dsh, dL_dsh_rest, (size_t)i, pp.M);
+      const ShView sh_i = sh_view(shs, shs_rest, (size_t)i, pp.M);
       const float3 dm = pp.factored ? sh_backward<false>(pp.D, pp.M, sh_i, dRGB, dir, out_sh)
                                     : sh_backward<true>(pp.D, pp.M, sh_i, dRGB, dir, out_sh);
       // coefficients >= (D+1)^2 keep the zeros of the sweep
@@ -620,11 +656,12 @@ __device__ __forceinline__ void preprocess_vjp_one(
 #endif
 __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     PreBwdParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
-    const float* __restrict__ rotations, const float* __restrict__ shs,
+    const float* __restrict__ rotations, const float* __restrict__ shs, const float* __restrict__ shs_rest,
     const float* __restrict__ viewmatrix, const float* __restrict__ campos,
     const int* __restrict__ radii, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
     float* __restrict__ grad, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
-    float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors, float* __restrict__ dL_dfeatures,
+    float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dcolors,
+    float* __restrict__ dL_dfeatures,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
     float* __restrict__ dL_dcov3D) {
   __shared__ float4 s_g[5][256];  // queued accumulator records (dT, mean2D, opacity, colour, normal)
@@ -686,8 +723,13 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
   if (pp.prezeroed) {
     // nothing to fill
   } else if (have_sh && !pp.factored) {
-    float4* o = reinterpret_cast<float4*>(dL_dsh) + (size_t)cta0 * pp.M;
-    for (int k = threadIdx.x; k < nrows * pp.M; k += 256) o[k] = zero4;
+    const int m0 = dL_dsh_rest ? 1 : pp.M;
+    float4* o = reinterpret_cast<float4*>(dL_dsh) + (size_t)cta0 * m0;
+    for (int k = threadIdx.x; k < nrows * m0; k += 256) o[k] = zero4;
+    if (dL_dsh_rest) {
+      o = reinterpret_cast<float4*>(dL_dsh_rest) + (size_t)cta0 * (pp.M - 1);
+      for (int k = threadIdx.x; k < nrows * (pp.M - 1); k += 256) o[k] = zero4;
+    }
   }
   if (!pp.prezeroed) {
     float* o = dL_dmeans3D + (size_t)cta0 * 3;
@@ -704,8 +746,8 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
   const int count = s_count;
   for (int slot = threadIdx.x; slot < count; slot += 256)
     preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
-                       s_g[4][slot], means3D, scales, rotations, shs, viewmatrix, campos, rec, clamped, dL_dmeans3D,
-                       dL_dmeans2D, dL_dsh, dL_dscales, dL_drot);
+                       s_g[4][slot], means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec, clamped,
+                       dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot);
 }
 
 
@@ -736,7 +778,7 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
   const size_t P = (size_t)p.P;
   if (P == 0) return 0;
   struct Range { char* ptr; size_t bytes; };
-  Range r[9];
+  Range r[10];
   int n = 0;
   auto add = [&](float* ptr, size_t bytes) { if (ptr && bytes) { r[n].ptr = (char*)ptr; r[n].bytes = bytes; ++n; } };
   add(gout.dL_dmeans3D, P * 12);
@@ -746,7 +788,10 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
   add(gout.dL_dscales, P * 12);
   add(gout.dL_drotations, P * 16);
   if (p.S > 0) add(gout.dL_dfeatures, P * 4 * (size_t)p.S);
-  if (in.shs && !(p.flags & GSL_FLAG_BWD_SH_FACTORED)) add(gout.dL_dsh, P * 16 * (size_t)p.M);
+  if (in.shs && !(p.flags & GSL_FLAG_BWD_SH_FACTORED)) {
+    add(gout.dL_dsh, P * 16 * (size_t)(in.shs_rest ? 1 : p.M));
+    if (in.shs_rest) add(gout.dL_dsh_rest, P * 16 * (size_t)(p.M - 1));
+  }
   add(gout.dL_dcov3D, P * 24);
   // exactly adjacent tensors (the Python wrapper packs all gradients into one allocation) become one memset
   for (int i = 1; i < n; ++i)
@@ -784,9 +829,10 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
   int blocks = (p.P + 255) / 256;
   ProfScope prof(GSL_K_PREPROCESS_BWD, st);
-  k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.viewmatrix,
+  k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.shs_rest, in.viewmatrix,
                                           in.campos, fwd.radii, g.rec, g.clamped, g.grad, gout.dL_dmeans3D,
-                                          gout.dL_dmeans2D, gout.dL_dsh, gout.dL_dcolors, gout.dL_dfeatures,
+                                          gout.dL_dmeans2D, gout.dL_dsh, in.shs_rest ? gout.dL_dsh_rest : nullptr,
+                                          gout.dL_dcolors, gout.dL_dfeatures,
                                           gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D);
   return check_cuda(cudaGetLastError(), "k_preprocess_bwd launch");
 }

@@ -164,12 +164,14 @@ def _stream_ptr(device):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
-                        cov3Ds_precomp, mask, raster_settings):
+                        cov3Ds_precomp, mask, raster_settings, sh_rest=None):
+    if sh_rest is None:
+        sh_rest = torch.empty(0, dtype=torch.float32, device=means3D.device)
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, features, opacities, scales,
-                                     rotations, cov3Ds_precomp, mask, raster_settings)
+                                     rotations, cov3Ds_precomp, mask, raster_settings, sh_rest)
 
 
-def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rotations, mask, settings):
+def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rotations, mask, settings, sh_rest):
     """Runs the forward pass; returns (outputs..., holder, params, keepalive inputs)."""
     if means3D.dim() != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -179,6 +181,12 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
     P = means3D.shape[0]
     S = features.shape[1] if features.dim() == 2 else 0
     M = sh.shape[1] if (sh.numel() != 0 and sh.dim() == 3) else 0
+    split = sh_rest.numel() != 0
+    if split:
+        if M != 1 or sh_rest.dim() != 3 or sh_rest.shape[0] != P or sh_rest.shape[2] != NUM_CHANNELS:
+            raise RuntimeError("shs_rest (P, M-1, %d) goes with shs = the DC coefficient (P, 1, %d)"
+                               % (NUM_CHANNELS, NUM_CHANNELS))
+        M = 1 + sh_rest.shape[1]
     H, W = int(settings.image_height), int(settings.image_width)
     if scales.numel() == 0 or rotations.numel() == 0:
         if P > 0:
@@ -186,7 +194,8 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
                                "(forward.cu:237) the cov3D_precomp path is not computed")
 
     inputs = dict(
-        background=_f32c(settings.bg), means3D=_f32c(means3D), shs=_f32c(sh), colors_precomp=_f32c(colors_precomp),
+        background=_f32c(settings.bg), means3D=_f32c(means3D), shs=_f32c(sh),
+        shs_rest=_f32c(sh_rest) if split else sh_rest, colors_precomp=_f32c(colors_precomp),
         features=_f32c(features), opacities=_f32c(opacities), scales=_f32c(scales), rotations=_f32c(rotations),
         mask=mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous(),
         viewmatrix=_f32c(settings.viewmatrix), projmatrix=_f32c(settings.projmatrix), campos=_f32c(settings.campos))
@@ -244,10 +253,10 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
-                cov3Ds_precomp, mask, raster_settings):
-        args = (means3D, sh, colors_precomp, features, opacities, scales, rotations, mask, raster_settings)
+                cov3Ds_precomp, mask, raster_settings, sh_rest):
+        args = (means3D, sh, colors_precomp, features, opacities, scales, rotations, mask, raster_settings, sh_rest)
         if raster_settings.debug:
-            cpu_args = cpu_deep_copy_tuple(args[:-1])  # copy them before they can be corrupted
+            cpu_args = cpu_deep_copy_tuple(args[:-2] + args[-1:])  # copy them before they can be corrupted
             try:
                 outs, holder, params, inputs, R = _forward_impl(*args)
             except Exception as ex:
@@ -296,6 +305,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_depth = cot(grad_depth, (4, H, W))
         g_alpha = cot(grad_alpha, (1, H, W))
 
+        split = inputs["shs_rest"].numel() != 0  # never together with the exchange (GaussianRasterizer.forward)
         ex = _exchange if (_exchange is not None and M > 0 and P > 0 and _exchange.world_size() > 1) else None
         with torch.cuda.device(dev):
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
@@ -312,14 +322,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                     views.append(flat[off:off + P * w].view(P, w))
                     off += P * w
                 d_means2D, d_colors, d_rot, d_sh, d_means3D, d_scales, d_opacity, d_features = views
-                d_sh = d_sh.view(P, M, NUM_CHANNELS)
+                d_sh_rest = None
+                if split:  # the flat range holds dL/d(dc) (P,1,4) followed by dL/d(rest) (P,M-1,4)
+                    d_sh, d_sh_rest = d_sh.view(-1)[:P * NUM_CHANNELS], d_sh.view(-1)[P * NUM_CHANNELS:]
+                    d_sh, d_sh_rest = d_sh.view(P, 1, NUM_CHANNELS), d_sh_rest.view(P, M - 1, NUM_CHANNELS)
+                else:
+                    d_sh = d_sh.view(P, M, NUM_CHANNELS)
             else:
                 # gradients go straight into the exchange's flat buffers; dL_dcolors receives the SH factor dL_dRGB
                 ex.prepare(P, S, M, dev)
                 v = ex.views
                 d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
                 d_scales, d_rot, d_features = v["scales"], v["rotations"], v["features"]
-                d_colors, d_sh = e(P, NUM_CHANNELS), None  # scratch: the factor itself goes to ex.local (see below)
+                d_colors, d_sh, d_sh_rest = e(P, NUM_CHANNELS), None, None  # scratch: the factor itself goes to ex.local (see below)
                 params = L.gsl_params.from_buffer_copy(params)
                 params.flags |= L.GSL_FLAG_BWD_SH_FACTORED
 
@@ -331,6 +346,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             gin.dL_dout_alpha, gin.dL_dout_feature = g_alpha.data_ptr(), g_feature.data_ptr()
             gout = L.gsl_bwd_outputs()
             gout.dL_dmeans3D, gout.dL_dmeans2D, gout.dL_dsh = _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh)
+            gout.dL_dsh_rest = _ptr(d_sh_rest)
             gout.dL_dcolors, gout.dL_dfeatures, gout.dL_dopacity = _ptr(d_colors), _ptr(d_features), _ptr(d_opacity)
             gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D = _ptr(d_scales), _ptr(d_rot), _ptr(d_cov3D)
             wss = holder.ws.as_struct()
@@ -368,7 +384,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         grad_cov = d_cov3D
         grads = (d_means3D, d_means2D, d_sh if M > 0 else None, d_colors if inputs["colors_precomp"].numel() else None,
-                 d_features, d_opacity, d_scales, d_rot, grad_cov, None, None)
+                 d_features, d_opacity, d_scales, d_rot, grad_cov, None, None, d_sh_rest)
         return grads
 
 
@@ -420,7 +436,11 @@ class GaussianRasterizer(nn.Module):
         return present
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, features=None, scales=None,
-                rotations=None, cov3D_precomp=None, mask=None):
+                rotations=None, cov3D_precomp=None, mask=None, shs_rest=None):
+        """Same keyword arguments as the reference (diff_gaussian_rasterization_2d.py:224-267).  Extension:
+        `shs_rest` -- pass GaussianModel._features_dc as `shs` (P,1,4) and _features_rest as `shs_rest` (P,M-1,4)
+        and the kernels read/write the two parameter tensors directly, without the concatenated copy
+        `get_features` builds per call (scene/gaussian_model.py:167-171) and its split in backward."""
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -432,6 +452,10 @@ class GaussianRasterizer(nn.Module):
 
         dev = means3D.device
         empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
+        if shs_rest is not None and shs is None:
+            raise Exception('shs_rest needs shs (the DC coefficient)')
+        if shs_rest is not None and _exchange is not None and _exchange.world_size() > 1:
+            shs, shs_rest = torch.cat((shs, shs_rest), dim=1), None  # the factored exchange works on one (P,M,4) tensor
         if shs is None:
             shs = empty()
         if colors_precomp is None:
@@ -449,4 +473,4 @@ class GaussianRasterizer(nn.Module):
 
         # Invoke the CUDA rasterization routine
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, features, opacities, scales, rotations,
-                                   cov3D_precomp, mask, raster_settings)
+                                   cov3D_precomp, mask, raster_settings, shs_rest)

@@ -94,7 +94,13 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
     means3D, opacity, scales, rotations, marginal_t, pre_mask = activate_surfels(
         pc, viewpoint_camera.timestamp, time_shift, bool(getattr(pipe, "dynamic", False)), mask)
 
-    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
+    shs, shs_rest, colors_precomp = None, None, override_color
+    if override_color is None:
+        dc, rest = getattr(pc, "_features_dc", None), getattr(pc, "_features_rest", None)
+        if dc is not None and rest is not None and rest.shape[1] > 0:
+            shs, shs_rest = dc, rest  # the two parameter tensors as they are: no get_features concatenation (:167-171)
+        else:
+            shs = pc.get_features
     if len(other) > 0:
         features = torch.cat(other, dim=1)
         S_other = features.shape[1]
@@ -104,7 +110,8 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
 
     contrib, rendered_image, rendered_feature, rendered_depth, rendered_opacity, radii = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp, features=features,
-        opacities=opacity, scales=scales, rotations=rotations, cov3D_precomp=None, mask=pre_mask.view(-1, 1))
+        opacities=opacity, scales=scales, rotations=rotations, cov3D_precomp=None, mask=pre_mask.view(-1, 1),
+        shs_rest=shs_rest)
 
     _, rendered_intensity_sh, rendered_raydrop = rendered_image.split([2, 1, 1], dim=0)
     rendered_other, rendered_normal = rendered_feature.split([S_other, 3], dim=0)

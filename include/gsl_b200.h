@@ -37,7 +37,7 @@ extern "C" {
 #define GSL_API
 #endif
 
-#define GSL_ABI_VERSION 1
+#define GSL_ABI_VERSION 2
 #define GSL_NUM_CHANNELS 4 /* cuda_rasterizer/config.h:12 */
 #define GSL_TILE 16        /* cuda_rasterizer/config.h:13-14 */
 #define GSL_MAX_FEATURES 10 /* forward.cu:348: F[13] holds S features + 3 normal channels */
@@ -91,7 +91,7 @@ typedef struct gsl_workspace {
 typedef struct gsl_fwd_inputs {
   const float* background;     /* (4) */
   const float* means3D;        /* (P,3) */
-  const float* shs;            /* (P,M,4) or NULL */
+  const float* shs;            /* (P,M,4) or NULL; with shs_rest: coefficient 0 only, (P,1,4) */
   const float* colors_precomp; /* (P,4) or NULL */
   const float* features;       /* (P,S) or NULL when S==0 */
   const float* opacities;      /* (P,1) */
@@ -102,6 +102,9 @@ typedef struct gsl_fwd_inputs {
   const float* viewmatrix;     /* (4,4) transposed world->camera, as scene/cameras.py:62 */
   const float* projmatrix;     /* (4,4), only used by gsl_mark_visible */
   const float* campos;         /* (3) */
+  /* ABI 2, appended so that ABI-1 initialisers keep their meaning: */
+  const float* shs_rest;       /* NULL, or coefficients 1..M-1 as (P,M-1,4): GaussianModel._features_dc /
+                                  _features_rest taken without the torch.cat of get_features (gaussian_model.py:167-171) */
 } gsl_fwd_inputs;
 
 typedef struct gsl_fwd_outputs {
@@ -123,13 +126,14 @@ typedef struct gsl_bwd_inputs {
 typedef struct gsl_bwd_outputs {
   float* dL_dmeans3D;  /* (P,3) */
   float* dL_dmeans2D;  /* (P,4): densification proxy in .xy, zeros in .zw (backward.cu:700-711) */
-  float* dL_dsh;       /* (P,M,4) or NULL */
+  float* dL_dsh;       /* (P,M,4) or NULL; (P,1,4) when the input came as shs + shs_rest */
   float* dL_dcolors;   /* (P,4) */
   float* dL_dfeatures; /* (P,S) or NULL */
   float* dL_dopacity;  /* (P,1) */
   float* dL_dscales;   /* (P,3) */
   float* dL_drotations;/* (P,4) */
   float* dL_dcov3D;    /* (P,6) all zero, like the reference; may be NULL */
+  float* dL_dsh_rest;  /* ABI 2: (P,M-1,4) when the input came as shs + shs_rest, else ignored */
 } gsl_bwd_outputs;
 
 GSL_API int gsl_abi_version(void);

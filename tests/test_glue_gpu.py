@@ -99,7 +99,7 @@ def test_render_matches_reference_glue_plus_rasterizer():
     # gradients w.r.t. the raw parameters through render()
     w = torch.randn(pkg["depth"].shape, generator=torch.Generator().manual_seed(3)).cuda()
     loss = (pkg["depth"] * w).sum() + pkg["intensity_sh"].sum() + (pkg["alpha"] * w).sum()
-    leaves = [getattr(pc, n) for n in GO.RAW] + [pc._features_dc]
+    leaves = [getattr(pc, n) for n in GO.RAW] + [pc._features_dc, pc._features_rest]  # render() takes dc/rest unconcatenated
     g_got = torch.autograd.grad(loss, leaves, retain_graph=False)
     loss_ref = (depth[0:1] * w).sum() + img[2:3].sum() + (alpha * w).sum()
     g_ref = torch.autograd.grad(loss_ref, leaves, allow_unused=True)

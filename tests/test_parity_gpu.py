@@ -272,6 +272,39 @@ def test_backward_is_linear_in_cotangents_and_accumulators_self_clean():
         assert max(common.grad_err(g2[k], 2 * g1[k])) < TOL_GRAD, k
 
 
+@pytest.mark.parametrize("P", [20000, 5003])
+def test_split_sh_inputs_equal_the_concatenated_tensor(P):
+    """shs = _features_dc (P,1,4) + shs_rest = _features_rest (P,M-1,4) is the same operator as the reference's
+    shs = torch.cat((dc, rest), 1) (scene/gaussian_model.py:167-171): identical maps, same gradients."""
+    scene = synth.make_scene(P, seed=47).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=48).items()}
+
+    def run(split):
+        leaves = dict(means3D=scene.means3D, opacities=scene.opacities, scales=scene.scales, rotations=scene.rotations,
+                      features=scene.features, dc=scene.shs[:, :1].contiguous(), rest=scene.shs[:, 1:].contiguous())
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
+        sh_kw = dict(shs=leaves["dc"], shs_rest=leaves["rest"]) if split else \
+            dict(shs=torch.cat((leaves["dc"], leaves["rest"]), dim=1))
+        outs = _call(scene, means3D=leaves["means3D"], opacities=leaves["opacities"], scales=leaves["scales"],
+                     rotations=leaves["rotations"], features=leaves["features"], **sh_kw)
+        contrib, color, feature, depth, alpha, radii = outs
+        loss = (color * cot["color"]).sum() + (feature * cot["feature"]).sum() + (depth * cot["depth"]).sum() + \
+               (alpha * cot["alpha"]).sum()
+        loss.backward()
+        return outs, {k: v.grad for k, v in leaves.items()}
+
+    o_cat, g_cat = run(False)
+    o_split, g_split = run(True)
+    for a, b in zip(o_cat, o_split):
+        assert torch.equal(a, b)
+    assert g_split["dc"].shape == (P, 1, 4) and g_split["rest"].shape == (P, 15, 4)
+    for k in g_cat:
+        assert max(common.grad_err(g_split[k], g_cat[k])) < TOL_GRAD, k
+    # wrong shapes are refused, not read out of bounds
+    with pytest.raises(RuntimeError, match="shs_rest"):
+        _call(scene, shs=scene.shs, shs_rest=scene.shs[:, 1:].contiguous())
+
+
 def test_unused_arguments_are_ignored_like_the_reference():
     # scale_modifier, scales.z, projmatrix, tanfov are not used by the math (SURVEY.md 8a parity trap 1)
     scene = synth.make_scene(3000, seed=47).to("cuda")
@@ -584,6 +617,19 @@ def test_c_abi_called_directly_matches_the_wrapper():
     torch.cuda.synchronize()
     for k in ("means3D", "means2D", "shs", "features", "opacities", "scales", "rotations"):
         assert max(common.grad_err(d[k], g_w[k])) < TOL_GRAD, k
+    # ABI 2: the same call with the SH coefficients as two tensors (dc, rest)
+    dc, rest = scene.shs[:, :1].contiguous(), scene.shs[:, 1:].contiguous()
+    fin.shs, fin.shs_rest = dc.data_ptr(), rest.data_ptr()
+    assert lib.gsl_forward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(ws), C.byref(R), st) == 0, L.last_error()
+    assert torch.equal(color, out_w["out_color"])
+    assert lib.gsl_backward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(gin), C.byref(gout), C.byref(ws), st) == \
+        L.GSL_EINVAL and b"null" in lib.gsl_last_error().lower()  # dL_dsh_rest missing
+    d_dc, d_rest = e(P, 1, 4), e(P, M - 1, 4)
+    gout.dL_dsh, gout.dL_dsh_rest = d_dc.data_ptr(), d_rest.data_ptr()
+    assert lib.gsl_backward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(gin), C.byref(gout), C.byref(ws), st) == 0, L.last_error()
+    torch.cuda.synchronize()
+    assert max(common.grad_err(torch.cat((d_dc, d_rest), 1), g_w["shs"])) < TOL_GRAD
+    fin.shs, fin.shs_rest = scene.shs.data_ptr(), None
     # too small a capacity is reported, not silently wrong
     ws.r_capacity = 1000
     rc = lib.gsl_forward(C.byref(p), C.byref(fin), C.byref(fout), C.byref(ws), C.byref(R), st)
