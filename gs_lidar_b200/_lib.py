@@ -9,11 +9,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSL_B200_LIB", os.path.join(HERE, "libgsl_b200.so"))  # override: dev builds only
 
-GSL_ABI_VERSION = 2
+GSL_ABI_VERSION = 3
 GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
 GSL_FLAG_DEBUG_SYNC = 1
 GSL_FLAG_BWD_SH_FACTORED = 2
 GSL_FLAG_WRAP_AZIMUTH = 4
+GSL_FLAG_BWD_PEER_ROWS = 8
 GSL_MAX_FEATURES = 10
 
 vp = C.c_void_p
@@ -53,7 +54,8 @@ class gsl_bwd_inputs(C.Structure):
 
 class gsl_bwd_outputs(C.Structure):
     _fields_ = [(n, vp) for n in ("dL_dmeans3D", "dL_dmeans2D", "dL_dsh", "dL_dcolors", "dL_dfeatures",
-                                  "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D", "dL_dsh_rest")]
+                                  "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dcov3D", "dL_dsh_rest",
+                                  "peer")]
 
 
 class gsl_state_export(C.Structure):
@@ -77,6 +79,19 @@ class gsl_glue_outputs(C.Structure):
 
 class gsl_glue_inputs_grad(C.Structure):
     _fields_ = [(n, vp) for n in ("xyz", "velocity", "t", "scaling_t", "opacity", "scaling", "rotation")]
+
+
+GSL_PEER_MAX = 8
+GSL_PEER_CAMPOS_OFFSET = 1024
+
+
+class gsl_peer_handle(C.Structure):
+    _fields_ = [("reserved", C.c_ubyte * 64)]
+
+
+class gsl_peer_ctx(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
+                ("buf", vp * GSL_PEER_MAX), ("error_flag", vp)]
 
 
 # name -> (restype, argtypes); every symbol include/gsl_b200.h declares
@@ -104,6 +119,21 @@ SYMBOLS = {
                                     C.POINTER(gsl_glue_inputs_grad), vp]),
     "gsl_mark_visible": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp]),
     "gsl_sh_expand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_size_t, vp, vp]),
+    "gsl_peer_buffer_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "gsl_peer_row_width": (C.c_int32, [C.c_int32]),
+    "gsl_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.POINTER(gsl_peer_handle)]),
+    "gsl_peer_open": (C.c_int, [C.POINTER(gsl_peer_handle), C.POINTER(vp)]),
+    "gsl_peer_close": (C.c_int, [vp]),
+    "gsl_peer_free": (C.c_int, [vp]),
+    "gsl_peer_barrier": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
+    "gsl_peer_signal": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
+    "gsl_peer_wait": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
+    "gsl_peer_sh_expand": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, vp, vp, vp]),
+    "gsl_peer_reduce": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "gsl_peer_unpack": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.POINTER(gsl_bwd_outputs), vp]),
+    "gsl_backward_surfels_rows": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
+                                            C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), C.c_int32, C.c_int32, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
                                    C.POINTER(gsl_state_export), vp]),
     "gsl_profile_enable": (C.c_int, [C.c_int]),

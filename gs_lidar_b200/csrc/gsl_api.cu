@@ -234,6 +234,15 @@ GSL_API int gsl_forward(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_o
   return 0;
 }
 
+static int validate_peer(const gsl_peer_ctx* c) {
+  if (!c) return set_error(GSL_EINVAL, "peer: ctx is NULL");
+  if (c->world < 1 || c->world > GSL_PEER_MAX || c->rank < 0 || c->rank >= c->world)
+    return set_error(GSL_EINVAL, "peer: bad rank/world %d/%d (at most %d ranks)", c->rank, c->world, GSL_PEER_MAX);
+  for (int g = 0; g < c->world; ++g)
+    if (!c->buf[g]) return set_error(GSL_EINVAL, "peer: buffer of rank %d is not mapped", g);
+  return 0;
+}
+
 static int backward_validate(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                              const gsl_bwd_outputs* gout, gsl_workspace* ws) {
   int rc = validate(p);
@@ -241,6 +250,10 @@ static int backward_validate(const gsl_params* p, const gsl_fwd_inputs* in, cons
   if ((rc = validate_inputs(p, in))) return rc;
   if (!fwd || !gout) return set_error(GSL_EINVAL, "fwd / grad outputs is NULL");
   if (p->P == 0) return 0;
+  if (p->flags & GSL_FLAG_BWD_PEER_ROWS) {
+    if (!in->shs) return set_error(GSL_EINVAL, "GSL_FLAG_BWD_PEER_ROWS needs the SH colour path");
+    if ((rc = validate_peer(gout->peer))) return rc;
+  } else
   if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dcolors || !gout->dL_dopacity ||
       !gout->dL_dscales || !gout->dL_drotations || (p->S > 0 && !gout->dL_dfeatures) ||
       (in->shs && !gout->dL_dsh && !(p->flags & GSL_FLAG_BWD_SH_FACTORED)) ||
@@ -273,6 +286,10 @@ GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in
 #ifdef GSL_NO_PREZERO
   aux = nullptr;
 #endif
+  if (p->flags & GSL_FLAG_BWD_PEER_ROWS) {
+    aux = nullptr;  // packed rows: nothing is zero-filled
+    if (sh_factor_out) return set_error(GSL_EINVAL, "GSL_FLAG_BWD_PEER_ROWS: the SH factors are pushed by the per-surfel kernel; sh_factor_out must be NULL");
+  }
   if (aux) {
     cudaEventRecord(aux->fork, st);
     cudaStreamWaitEvent(aux->stream, aux->fork, 0);
@@ -291,8 +308,17 @@ GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in
 
 GSL_API int gsl_backward_surfels(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                          gsl_bwd_outputs* gout, gsl_workspace* ws, void* stream) {
+  return gsl_backward_surfels_rows(p, in, fwd, gout, ws, 0, p ? p->P : 0, stream);
+}
+
+GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                              gsl_bwd_outputs* gout, gsl_workspace* ws, int32_t row_begin, int32_t row_end, void* stream) {
   int rc = backward_validate(p, in, fwd, gout, ws);
   if (rc) return rc;
+  if (row_begin < 0 || row_end > p->P || row_begin > row_end || (row_begin & 255))
+    return set_error(GSL_EINVAL, "backward_surfels_rows: bad row range [%d, %d)", row_begin, row_end);
+  if ((row_begin != 0 || row_end != p->P) && !(p->flags & GSL_FLAG_BWD_PEER_ROWS))
+    return set_error(GSL_EINVAL, "backward_surfels_rows: partial ranges need GSL_FLAG_BWD_PEER_ROWS");
   const bool prezeroed = g_prezero_pending;
   g_prezero_pending = false;
   if (p->P == 0) return 0;
@@ -303,7 +329,7 @@ GSL_API int gsl_backward_surfels(const gsl_params* p, const gsl_fwd_inputs* in, 
     if (!aux) return set_error(GSL_ESTATE, "side stream lost between the two backward stages");
     cudaStreamWaitEvent(st, aux->join, 0);
   }
-  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, prezeroed, st))) return rc;
+  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, prezeroed, row_begin, row_end, st))) return rc;
   return debug_sync(p, st, "preprocess_backward");
 }
 
@@ -330,6 +356,90 @@ GSL_API int gsl_sh_expand(int32_t P, int32_t D, int32_t M, int32_t G, const floa
     return set_error(GSL_EINVAL, "sh_expand: NULL pointer");
   if (drgb_stride < (size_t)4 * (size_t)P) return set_error(GSL_EINVAL, "sh_expand: drgb_stride < 4 P");
   return launch_sh_expand(P, D, M, G, means3D, campos_all, drgb_all, drgb_stride, dL_dsh, (cudaStream_t)stream);
+}
+
+// ---- peer-memory gradient exchange (gsl_peer.cu) -----------------------------------------------------------------
+GSL_API size_t gsl_peer_buffer_bytes(int64_t P, int32_t S, int32_t world) {
+  return peer_layout((size_t)(P < 0 ? 0 : P), S, world).total;
+}
+GSL_API int32_t gsl_peer_row_width(int32_t S) { return peer_row_width(S); }
+
+GSL_API int gsl_peer_alloc(size_t bytes, void** dptr, gsl_peer_handle* handle) {
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(gsl_peer_handle), "handle size");
+  if (!dptr || bytes == 0) return set_error(GSL_EINVAL, "peer_alloc: bad arguments");
+  void* p = nullptr;
+  int rc = check_cuda(cudaMalloc(&p, bytes), "peer_alloc cudaMalloc");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemset(p, 0, bytes), "peer_alloc memset");
+  if (!rc && handle) {
+    cudaIpcMemHandle_t h;
+    rc = check_cuda(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle");
+    if (!rc) {
+      memset(handle, 0, sizeof(*handle));
+      memcpy(handle, &h, sizeof(h));
+    }
+  }
+  if (rc) {
+    cudaFree(p);
+    return rc;
+  }
+  *dptr = p;
+  return 0;
+}
+
+GSL_API int gsl_peer_open(const gsl_peer_handle* handle, void** dptr) {
+  if (!handle || !dptr) return set_error(GSL_EINVAL, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  return check_cuda(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+GSL_API int gsl_peer_close(void* dptr) { return dptr ? check_cuda(cudaIpcCloseMemHandle(dptr), "cudaIpcCloseMemHandle") : 0; }
+GSL_API int gsl_peer_free(void* dptr) { return dptr ? check_cuda(cudaFree(dptr), "peer_free") : 0; }
+
+static int peer_barrier(const gsl_peer_ctx* ctx, int32_t phase, int mode, void* stream) {
+  int rc = validate_peer(ctx);
+  if (rc) return rc;
+  if (phase < 0 || phase > 3) return set_error(GSL_EINVAL, "peer_barrier: phase must be 0..3");
+  return launch_peer_barrier(ctx, phase, mode, (cudaStream_t)stream);
+}
+GSL_API int gsl_peer_barrier(const gsl_peer_ctx* ctx, int32_t phase, void* stream) { return peer_barrier(ctx, phase, 3, stream); }
+GSL_API int gsl_peer_signal(const gsl_peer_ctx* ctx, int32_t phase, void* stream) { return peer_barrier(ctx, phase, 1, stream); }
+GSL_API int gsl_peer_wait(const gsl_peer_ctx* ctx, int32_t phase, void* stream) { return peer_barrier(ctx, phase, 2, stream); }
+
+static int validate_rows(const char* what, int32_t P, int32_t S, int32_t row_begin, int32_t row_end) {
+  if (P < 0 || S < 0 || S > 10 || row_begin < 0 || row_end > P || row_begin > row_end || (row_begin & 255) ||
+      ((row_end & 255) && row_end != P))
+    return set_error(GSL_EINVAL, "%s: bad sizes / row range [%d, %d) of %d", what, row_begin, row_end, P);
+  return 0;
+}
+
+GSL_API int gsl_peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
+                               int32_t row_end, const float* means3D, float* dL_dsh, void* stream) {
+  int rc = validate_peer(ctx);
+  if (rc) return rc;
+  if ((rc = validate_rows("peer_sh_expand", P, S, row_begin, row_end))) return rc;
+  if (D < 0 || D > 3 || M < 0) return set_error(GSL_EINVAL, "peer_sh_expand: bad sizes");
+  if (M > 0 && (D + 1) * (D + 1) > M) return set_error(GSL_EINVAL, "peer_sh_expand: degree %d needs %d coefficients", D, (D + 1) * (D + 1));
+  if (P > 0 && M > 0 && (!means3D || !dL_dsh)) return set_error(GSL_EINVAL, "peer_sh_expand: NULL pointer");
+  return launch_peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, means3D, dL_dsh, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_peer_reduce(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t row_begin, int32_t row_end, void* stream) {
+  int rc = validate_peer(ctx);
+  if (rc) return rc;
+  if ((rc = validate_rows("peer_reduce", P, S, row_begin, row_end))) return rc;
+  return launch_peer_reduce_rows(ctx, P, S, row_begin, row_end, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const gsl_bwd_outputs* out, void* stream) {
+  int rc = validate_peer(ctx);
+  if (rc) return rc;
+  if (P < 0 || S < 0 || S > 10) return set_error(GSL_EINVAL, "peer_unpack: bad sizes");
+  if (P > 0 && (!out || !out->dL_dmeans3D || !out->dL_dmeans2D || !out->dL_dscales || !out->dL_drotations ||
+                !out->dL_dopacity || (S > 0 && !out->dL_dfeatures)))
+    return set_error(GSL_EINVAL, "peer_unpack: an output pointer is NULL");
+  return launch_peer_unpack(ctx, P, S, *out, (cudaStream_t)stream);
 }
 
 static int validate_glue(const gsl_glue_params* p, const gsl_glue_inputs* in) {

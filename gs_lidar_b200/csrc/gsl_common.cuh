@@ -222,7 +222,7 @@ int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out,
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st);
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
-                               bool prezeroed, cudaStream_t st);
+                               bool prezeroed, int row0, int row1, cudaStream_t st);
 int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
                      size_t drgb_stride, float* dL_dsh, cudaStream_t st);
 int launch_glue_forward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& out, cudaStream_t st);
@@ -230,5 +230,44 @@ int launch_glue_backward(const gsl_glue_params& p, const gsl_glue_inputs& in, co
                          const gsl_glue_inputs_grad& gin, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, cudaStream_t st);
+
+// ---- peer-memory gradient exchange (gsl_peer.cu) -------------------------------------------------------------
+constexpr int PEER_MAX = GSL_PEER_MAX;
+constexpr size_t PEER_HEADER = 4096;      // flags: u32[4 phases][PEER_MAX]; camera centre at PEER_CAMPOS_OFF
+constexpr size_t PEER_CAMPOS_OFF = GSL_PEER_CAMPOS_OFFSET;
+constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[PEER_MAX]: camera centres of all ranks, pushed by barrier 0
+struct PeerView {  // gsl_peer_ctx by value, as the kernels take it
+  int rank, world;
+  uint32_t epoch;
+  char* own;  // buf[rank]
+  char* buf[PEER_MAX];
+};
+inline PeerView make_view(const gsl_peer_ctx* c) {
+  PeerView v;
+  v.rank = c->rank;
+  v.world = c->world;
+  v.epoch = c->epoch;
+  for (int g = 0; g < PEER_MAX; ++g) v.buf[g] = g < c->world ? (char*)c->buf[g] : nullptr;
+  v.own = (char*)c->buf[c->rank];
+  return v;
+}
+// Byte offsets inside an exchange buffer for P surfels (tiles of 256), S feature channels and `world` ranks.
+struct PeerLayout {
+  int tiles, tiles_per_rank;  // ceil(P / 256); tiles a rank owns (tile t belongs to rank t % world)
+  size_t off_fmeta;      // uint2 [world][tiles * 8]: (factor bits, non-zero factors of the tile before this word), per source rank
+  size_t off_factor;     // float4 [world][tiles * 256]: SH factors per source rank, the non-zero ones of a tile packed to its front
+  size_t off_stagebits;  // u32 [world][tiles_per_rank * 8]: row bits of the tiles this rank owns, per source rank
+  size_t off_stage;      // float [world][tiles_per_rank * 256][rw]: packed rows of the tiles this rank owns, per source rank
+  size_t off_rowbits;    // u32 [tiles * 8]: OR of the row bits over the ranks (written by the tile owners)
+  size_t off_rows;       // float [tiles * 256][rw]: summed rows (written by the tile owners)
+  size_t total;
+};
+int peer_row_width(int S);
+PeerLayout peer_layout(size_t P, int S, int world);
+int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
+int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, const float* means3D,
+                          float* dL_dsh, cudaStream_t st);
+int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st);
+int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, const gsl_bwd_outputs& out, cudaStream_t st);
 
 }  // namespace gsl

@@ -1,0 +1,194 @@
+// gsl_peer.cu -- frame-parallel gradient exchange over NVLink peer memory (no library collective on the data path).
+//
+// The reference is single-GPU; SURVEY.md 8(e) shards the path by LiDAR frame and sums the surfel gradients of the
+// ranks before the optimizer step.  With a ~0.9 ms compute step the two NCCL collectives of the first design (a 76 MB
+// all-reduce + a G x 16 MB all-gather at 1M surfels) cost 0.31 + 0.21 ms on 8 B200s, most of it exposed, and P2P LOADS
+// turned out latency-bound (~2 us per dependent round trip).  Here every rank keeps ONE peer-visible exchange buffer
+// (cudaMalloc + CUDA IPC, mapped into the other ranks' address spaces) and all NVLink traffic is remote STORES issued
+// by the kernels that produce the data:
+//   * k_preprocess_bwd (gsl_preprocess.cu, GSL_FLAG_BWD_PEER_ROWS) pushes, per 256-surfel tile, the packed 64-byte
+//     gradient rows of the surfels a pixel touched (~half of them) + their row bits into the staging area of the rank
+//     that owns the tile (tile % world), and the non-zero 16-byte SH factors (packed to the front of the tile's
+//     segment, + bits / prefix words) into every rank's factor table;
+//   * k_peer_barrier   -- one warp: release-store of a ticket into the flag slot this rank owns in every peer's buffer,
+//                         then acquire-spin on the own slots (with a time-out that reports instead of hanging).  A few
+//                         microseconds instead of a collective's launch + protocol latency;
+//   * k_peer_reduce_rows -- the owner sums the staged rows of its tiles (local reads, fixed rank order) and pushes the
+//                         sums + OR-ed bits into every rank's result area: every rank ends up with bit-identical sums;
+//   * k_peer_sh_expand (gsl_preprocess.cu) -- gsl_sh_expand over the local factor tables;
+//   * k_peer_unpack    -- summed packed rows -> the dense tensors autograd returns.
+// All of it works on row ranges, so the exchange of one range runs (on a side stream) while k_preprocess_bwd computes
+// the next.  Layout of an exchange buffer: PeerLayout (gsl_common.cuh).
+#include "gsl_common.cuh"
+#include <algorithm>
+
+namespace gsl {
+
+// floats per packed exchange row: means2D.xy scales.xy | rot | means3D opacity | features (padded to whole 32-B sectors)
+int peer_row_width(int S) { return S <= 4 ? 16 : 24; }
+
+PeerLayout peer_layout(size_t P, int S, int world) {
+  PeerLayout l;
+  if (world < 1) world = 1;
+  l.tiles = (int)((P + 255) / 256);
+  l.tiles_per_rank = (l.tiles + world - 1) / world;
+  const size_t rowbytes = (size_t)peer_row_width(S) * 4;
+  l.off_fmeta = PEER_HEADER;
+  l.off_factor = align_up(l.off_fmeta + (size_t)world * l.tiles * 8 * 8, 256);
+  l.off_stagebits = align_up(l.off_factor + (size_t)world * l.tiles * 256 * 16, 256);
+  l.off_stage = align_up(l.off_stagebits + (size_t)world * l.tiles_per_rank * 8 * 4, 256);
+  l.off_rowbits = align_up(l.off_stage + (size_t)world * l.tiles_per_rank * 256 * rowbytes, 256);
+  l.off_rows = align_up(l.off_rowbits + (size_t)l.tiles * 8 * 4, 256);
+  l.total = align_up(l.off_rows + (size_t)l.tiles * 256 * rowbytes, 256);
+  return l;
+}
+
+// ---- barrier ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Lane g tells rank g "rank `rank` reached `phase` of step `epoch`" and waits for the same news from rank g.  Everything
+// this rank's stream did before (kernel boundary) is visible to a peer that has seen the flag; a peer that never
+// arrives makes the wait give up after timeout_ns and raise *error (the results of the step are then undefined).
+__global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long long timeout_ns, int* error) {
+  const int g = threadIdx.x;
+  if (g >= pv.world) return;
+  if (phase == 0 && (mode & 1)) {  // publish this rank's camera centre into rank g's table: k_peer_sh_expand then reads it locally
+    const float* own = reinterpret_cast<const float*>(pv.own + PEER_CAMPOS_OFF);
+    float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * pv.rank;
+    dst[0] = own[0]; dst[1] = own[1]; dst[2] = own[2];
+  }
+  if (mode & 1) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(pv.buf[g]) + phase * PEER_MAX + pv.rank, pv.epoch);
+  }
+  if (!(mode & 2)) return;
+  const uint32_t* mine = reinterpret_cast<const uint32_t*>(pv.own) + phase * PEER_MAX + g;
+  const unsigned long long t0 = global_timer_ns();
+  while ((int32_t)(ld_acquire_sys(mine) - pv.epoch) < 0) {
+    if (global_timer_ns() - t0 > timeout_ns) {
+      if (error) *error = 1 + phase;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
+// mode: 1 = signal, 2 = wait, 3 = both (the barrier)
+int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st) {
+  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, 2000000000ull, c->error_flag);
+  return check_cuda(cudaGetLastError(), "k_peer_barrier launch");
+}
+
+// ---- sum of the packed gradient rows -------------------------------------------------------------------------------
+// Tile t (256 rows) belongs to rank t % world; every rank pushed its rows of the tile (and their bits) into the owner's
+// staging area.  The owner reads the staged rows whose bit is set (local memory), sums them in rank order and pushes the
+// sum row and the OR of the bits into every rank's result area -- remote STORES only, every rank gets the same bits.
+// Rows nobody touched are neither read nor written (k_peer_unpack looks at the OR-ed bits).
+__global__ void __launch_bounds__(256) k_peer_reduce_rows(const PeerView pv, const PeerLayout pl, int rw4, int tile0,
+                                                          int tile1) {
+  __shared__ uint32_t s_bits[PEER_MAX][8];
+  __shared__ uint32_t s_union[8];
+  const uint32_t* stagebits = reinterpret_cast<const uint32_t*>(pv.own + pl.off_stagebits);
+  const float4* stage = reinterpret_cast<const float4*>(pv.own + pl.off_stage);
+  // my tiles in [tile0, tile1): the first one is tile0 rounded up to rank (mod world)
+  const int first = tile0 + ((pv.rank - tile0 % pv.world) + pv.world) % pv.world;
+  for (int tile = first + blockIdx.x * pv.world; tile < tile1; tile += gridDim.x * pv.world) {
+    const int lt = tile / pv.world;  // index among my tiles
+    __syncthreads();
+    if (threadIdx.x < 8 * PEER_MAX) {
+      const int g = threadIdx.x >> 3, w = threadIdx.x & 7;
+      s_bits[g][w] = g < pv.world ? stagebits[((size_t)g * pl.tiles_per_rank + lt) * 8 + w] : 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      uint32_t u = 0u;
+#pragma unroll
+      for (int g = 0; g < PEER_MAX; ++g) u |= s_bits[g][threadIdx.x];
+      s_union[threadIdx.x] = u;
+#pragma unroll
+      for (int g = 0; g < PEER_MAX; ++g)
+        if (g < pv.world) reinterpret_cast<uint32_t*>(pv.buf[g] + pl.off_rowbits)[tile * 8 + threadIdx.x] = u;
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < 256 * rw4; item += 256) {
+      const int r = item / rw4, q = item - r * rw4;
+      if (!((s_union[r >> 5] >> (r & 31)) & 1u)) continue;
+      float4 v[PEER_MAX];
+#pragma unroll
+      for (int g = 0; g < PEER_MAX; ++g) {
+        v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < pv.world && ((s_bits[g][r >> 5] >> (r & 31)) & 1u))
+          v[g] = stage[(((size_t)g * pl.tiles_per_rank + lt) * 256 + r) * rw4 + q];
+      }
+      float4 acc = v[0];
+#pragma unroll
+      for (int g = 1; g < PEER_MAX; ++g)
+        if (g < pv.world) { acc.x += v[g].x; acc.y += v[g].y; acc.z += v[g].z; acc.w += v[g].w; }
+      const size_t at = ((size_t)tile * 256 + r) * rw4 + q;
+#pragma unroll
+      for (int g = 0; g < PEER_MAX; ++g)
+        if (g < pv.world) reinterpret_cast<float4*>(pv.buf[g] + pl.off_rows)[at] = acc;
+    }
+  }
+}
+
+int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st) {
+  if (row_end <= row_begin) return 0;
+  const int tile0 = row_begin / 256, tile1 = (row_end + 255) / 256;
+  const int per_rank = (tile1 - tile0 + c->world - 1) / c->world;
+  const int blocks = std::max(1, std::min(per_rank, 148 * 8));
+  k_peer_reduce_rows<<<blocks, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), peer_row_width(S) / 4, tile0,
+                                             tile1);
+  return check_cuda(cudaGetLastError(), "k_peer_reduce_rows launch");
+}
+
+// ---- summed packed rows -> the dense gradient tensors autograd returns (local) ------------------------------------------
+__global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, const float* __restrict__ rows,
+                                                     const uint32_t* __restrict__ bits, float* __restrict__ d_means3D,
+                                                     float* __restrict__ d_means2D, float* __restrict__ d_scales,
+                                                     float* __restrict__ d_rot, float* __restrict__ d_opacity,
+                                                     float* __restrict__ d_features) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 r0 = zero4, r1 = zero4, r2 = zero4, f[3] = {zero4, zero4, zero4};
+  if ((bits[i >> 5] >> (i & 31)) & 1u) {
+    const float4* r = reinterpret_cast<const float4*>(rows + (size_t)i * rw);
+    r0 = r[0]; r1 = r[1]; r2 = r[2];
+    for (int k = 0; k < rw / 4 - 3; ++k) f[k] = r[3 + k];
+  }
+  reinterpret_cast<float4*>(d_means2D)[i] = make_float4(r0.x, r0.y, 0.f, 0.f);
+  d_scales[3 * (size_t)i] = r0.z; d_scales[3 * (size_t)i + 1] = r0.w; d_scales[3 * (size_t)i + 2] = 0.f;
+  reinterpret_cast<float4*>(d_rot)[i] = r1;
+  d_means3D[3 * (size_t)i] = r2.x; d_means3D[3 * (size_t)i + 1] = r2.y; d_means3D[3 * (size_t)i + 2] = r2.z;
+  d_opacity[i] = r2.w;
+  for (int ch = 0; ch < S; ++ch) {
+    const float4 v = f[ch >> 2];
+    d_features[(size_t)i * S + ch] = (ch & 3) == 0 ? v.x : (ch & 3) == 1 ? v.y : (ch & 3) == 2 ? v.z : v.w;
+  }
+}
+
+int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, const gsl_bwd_outputs& out, cudaStream_t st) {
+  if (P == 0) return 0;
+  const char* own = (const char*)c->buf[c->rank];
+  const PeerLayout pl = peer_layout((size_t)P, S, c->world);
+  k_peer_unpack<<<(P + 255) / 256, 256, 0, st>>>(P, S, peer_row_width(S), reinterpret_cast<const float*>(own + pl.off_rows),
+                                                 reinterpret_cast<const uint32_t*>(own + pl.off_rowbits), out.dL_dmeans3D,
+                                                 out.dL_dmeans2D, out.dL_dscales, out.dL_drotations, out.dL_dopacity,
+                                                 out.dL_dfeatures);
+  return check_cuda(cudaGetLastError(), "k_peer_unpack launch");
+}
+
+}  // namespace gsl

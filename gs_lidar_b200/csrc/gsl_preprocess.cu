@@ -472,6 +472,8 @@ struct PreBwdParams {
   int factored;  // GSL_FLAG_BWD_SH_FACTORED: dL_dcolors receives the clamp-masked dL_dRGB, dL_dsh is not written
   int prezeroed; // the dense outputs were zero-filled already (side stream, under the backward compositor):
                  // only non-zero values are written here
+  int row0, row1; // surfel range of this launch (chunked launches pipeline the peer exchange behind the kernel)
+  int rw;         // > 0: GSL_FLAG_BWD_PEER_ROWS -- floats per packed exchange row (peer_row_width(S))
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -552,7 +554,8 @@ __device__ __forceinline__ void preprocess_vjp_one(
     const float* __restrict__ shs, const float* __restrict__ shs_rest, const float* __restrict__ viewmatrix,
     const float* __restrict__ campos, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
     float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh,
-    float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dscales, float* __restrict__ dL_drot) {
+    float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
+    float* __restrict__ rows) {
   {
     const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
     const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
@@ -635,6 +638,13 @@ __device__ __forceinline__ void preprocess_vjp_one(
     const float du_dth = -v * sinf(phi), dv_dth = sqrtf(u * u + w * w), dw_dth = -v * cosf(phi);
     dm2.y = (float)((raw_du * du_dth + raw_dv * dv_dth + raw_dw * dw_dth) * 0.5 * dVr * pp.W / pp.H);
 
+    if (pp.rw > 0) {  // packed exchange row: [means2D.xy scales.xy | rot | means3D opacity | features...]
+      float4* r = reinterpret_cast<float4*>(rows + (size_t)i * pp.rw);
+      r[0] = make_float4(dm2.x, dm2.y, dscale.x, dscale.y);
+      r[1] = drot;
+      r[2] = make_float4(dmean.x, dmean.y, dmean.z, g2.w);
+      return;
+    }
     dL_dmeans3D[3 * (size_t)i] = dmean.x; dL_dmeans3D[3 * (size_t)i + 1] = dmean.y; dL_dmeans3D[3 * (size_t)i + 2] = dmean.z;
     dL_dscales[3 * (size_t)i] = dscale.x; dL_dscales[3 * (size_t)i + 1] = dscale.y; dL_dscales[3 * (size_t)i + 2] = dscale.z;
     reinterpret_cast<float4*>(dL_drot)[i] = drot;
@@ -663,18 +673,94 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dcolors,
     float* __restrict__ dL_dfeatures,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
-    float* __restrict__ dL_dcov3D) {
+    float* __restrict__ dL_dcov3D, const PeerView pv, const PeerLayout pl) {
   __shared__ float4 s_g[5][256];  // queued accumulator records (dT, mean2D, opacity, colour, normal)
   __shared__ uint16_t s_who[256];
   __shared__ int s_count;
   const bool have_sh = shs != nullptr;
-  const int cta0 = blockIdx.x * 256;
+  const int cta0 = pp.row0 + blockIdx.x * 256;
   const int idx = cta0 + threadIdx.x;
   const int S = pp.S;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  if (idx < pp.P) {
+  if (pp.rw > 0) {
+    // ---- peer-memory gradient exchange: this CTA's 256 surfels are one tile; its packed rows (only those with a
+    // non-zero record, + a row bitmap) are PUSHED into the staging area of the rank that owns the tile, its non-zero SH
+    // factors (packed to the front of the tile's segment, + bits / prefix words) into every rank's factor table.  Remote
+    // stores only: nothing here waits for NVLink.  Nothing is zero-filled (readers look at the bits first).
+    __shared__ int s_warp[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = cta0 >> 8;
+    const int owner = tile % pv.world;
+    char* obuf = nullptr;
+#pragma unroll
+    for (int g = 0; g < PEER_MAX; ++g)
+      if (g == owner) obuf = pv.buf[g];
+    const size_t slot0 = ((size_t)pv.rank * pl.tiles_per_rank + tile / pv.world) * 256;  // staging row of the tile's row 0
+    float* rows = reinterpret_cast<float*>(obuf + pl.off_stage) + (ptrdiff_t)(slot0 - (size_t)cta0) * pp.rw;
+    bool any = false;
+    float4 fac = zero4;
+    if (idx < pp.row1) {
+      float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
+      const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
+      any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
+            (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f) | (g2.z != 0.f) | (g2.w != 0.f) |
+            (gc.x != 0.f) | (gc.y != 0.f) | (gc.z != 0.f) | (gc.w != 0.f) | (gn.x != 0.f) | (gn.y != 0.f) |
+            (gn.z != 0.f);
+      if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
+        const uint8_t cl = clamped[idx];
+        fac = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
+      }
+      const int nf4 = (S + 3) / 4;
+      float4 f[3] = {zero4, zero4, zero4};
+      for (int k = 0; k < nf4; ++k) {
+        f[k] = gq[5 + k];
+        if (f[k].x != 0.f || f[k].y != 0.f || f[k].z != 0.f || f[k].w != 0.f) {
+          any = true;
+          gq[5 + k] = zero4;
+        }
+      }
+      if (any) {
+        float4* r = reinterpret_cast<float4*>(rows + (size_t)idx * pp.rw);
+        for (int k = 0; k < pp.rw / 4 - 3; ++k) r[3 + k] = k < nf4 ? f[k] : zero4;
+        gq[0] = zero4; gq[1] = zero4; gq[2] = zero4; gq[3] = zero4; gq[4] = zero4;
+        if (radii[idx] > 0) {
+          const int slot = atomicAdd(&s_count, 1);
+          s_who[slot] = (uint16_t)threadIdx.x;
+          s_g[0][slot] = g0; s_g[1][slot] = g1; s_g[2][slot] = g2; s_g[3][slot] = gc; s_g[4][slot] = gn;
+        } else {
+          r[0] = zero4; r[1] = zero4; r[2] = make_float4(0.f, 0.f, 0.f, g2.w);
+        }
+      }
+    }
+    const bool live = cta0 + warp * 32 < pp.row1;  // this warp's word exists
+    const uint32_t bits = __ballot_sync(0xffffffffu, any);
+    if (lane == 0 && live) reinterpret_cast<uint32_t*>(obuf + pl.off_stagebits)[(slot0 >> 5) + warp] = bits;
+    // SH factors: block-local compaction, pushed to every rank
+    const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
+    const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) s_warp[warp] = __popc(fbits);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const size_t fpos = ((size_t)pv.rank * pl.tiles + tile) * 256 + before + __popc(fbits & ((1u << lane) - 1u));
+    const size_t mpos = ((size_t)pv.rank * pl.tiles + tile) * 8 + warp;
+#pragma unroll
+    for (int g = 0; g < PEER_MAX; ++g) {
+      if (g < pv.world) {
+        if (nz) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[fpos] = fac;
+        if (lane == 0 && live) reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[mpos] = make_uint2(fbits, (uint32_t)before);
+      }
+    }
+    const int count = s_count;
+    for (int slot = threadIdx.x; slot < count; slot += 256)
+      preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
+                         s_g[4][slot], means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec, clamped,
+                         dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, rows);
+    return;
+  }
+  if (idx < pp.row1) {
     float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
     const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
     const bool any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
@@ -719,7 +805,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     }
   }
   // coalesced zero-fill of the CTA's rows of the strided outputs (queued surfels overwrite theirs later)
-  const int nrows = min(256, pp.P - cta0);
+  const int nrows = min(256, pp.row1 - cta0);
   if (pp.prezeroed) {
     // nothing to fill
   } else if (have_sh && !pp.factored) {
@@ -747,7 +833,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
   for (int slot = threadIdx.x; slot < count; slot += 256)
     preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
                        s_g[4][slot], means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec, clamped,
-                       dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot);
+                       dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, nullptr);
 }
 
 
@@ -808,8 +894,9 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
 }
 
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
-                               gsl_bwd_outputs& gout, const GeomView& g, bool prezeroed, cudaStream_t st) {
-  if (p.P == 0) return 0;
+                               gsl_bwd_outputs& gout, const GeomView& g, bool prezeroed, int row0, int row1,
+                               cudaStream_t st) {
+  if (p.P == 0 || row1 <= row0) return 0;
   PreBwdParams pp;
   pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.S = p.S;
   {
@@ -825,15 +912,25 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   pp.gstride = grad_stride(p.S);
   pp.factored = (p.flags & GSL_FLAG_BWD_SH_FACTORED) ? 1 : 0;
   pp.prezeroed = prezeroed ? 1 : 0;
+  pp.row0 = row0; pp.row1 = row1;
+  pp.rw = (p.flags & GSL_FLAG_BWD_PEER_ROWS) ? peer_row_width(p.S) : 0;
+  PeerView pv = {};
+  PeerLayout pl = {};
+  if (pp.rw > 0) {
+    pp.factored = 1;
+    pv = make_view(gout.peer);
+    pl = peer_layout((size_t)p.P, p.S, gout.peer->world);
+  }
   Fov f = make_fov(p);
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
-  int blocks = (p.P + 255) / 256;
+  int blocks = (row1 - row0 + 255) / 256;
   ProfScope prof(GSL_K_PREPROCESS_BWD, st);
   k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.shs_rest, in.viewmatrix,
                                           in.campos, fwd.radii, g.rec, g.clamped, g.grad, gout.dL_dmeans3D,
                                           gout.dL_dmeans2D, gout.dL_dsh, in.shs_rest ? gout.dL_dsh_rest : nullptr,
                                           gout.dL_dcolors, gout.dL_dfeatures,
-                                          gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D);
+                                          gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D,
+                                          pv, pl);
   return check_cuda(cudaGetLastError(), "k_preprocess_bwd launch");
 }
 
@@ -844,6 +941,35 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
 //     dL_dsh[i] = sum_g basis((mean_i - campos_g) / |.|) x dL_dRGB_g[i]
 // -- the same sum an all-reduce of the dense gradients would produce, in a different order.
 // ------------------------------------------------------------------------------------------------
+// acc[k] += basis_k(normalize(x, y, z)) * d for the coefficients of degree <= D (the dL_dsh rows of backward.cu:17-134)
+__device__ __forceinline__ void sh_basis_accumulate(float4 (&acc)[16], int D, float x, float y, float z, const float4 d) {
+  const float len = sqrtf(x * x + y * y + z * z);
+  x /= len; y /= len; z /= len;
+  acc[0] += kSH_C0 * d;
+  if (D > 0) {
+    acc[1] += (-kSH_C1 * y) * d;
+    acc[2] += (kSH_C1 * z) * d;
+    acc[3] += (-kSH_C1 * x) * d;
+    if (D > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      acc[4] += (kSH_C2[0] * xy) * d;
+      acc[5] += (kSH_C2[1] * yz) * d;
+      acc[6] += (kSH_C2[2] * (2.f * zz - xx - yy)) * d;
+      acc[7] += (kSH_C2[3] * xz) * d;
+      acc[8] += (kSH_C2[4] * (xx - yy)) * d;
+      if (D > 2) {
+        acc[9] += (kSH_C3[0] * y * (3.f * xx - yy)) * d;
+        acc[10] += (kSH_C3[1] * xy * z) * d;
+        acc[11] += (kSH_C3[2] * y * (4.f * zz - xx - yy)) * d;
+        acc[12] += (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * d;
+        acc[13] += (kSH_C3[4] * x * (4.f * zz - xx - yy)) * d;
+        acc[14] += (kSH_C3[5] * z * (xx - yy)) * d;
+        acc[15] += (kSH_C3[6] * x * (xx - 3.f * yy)) * d;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_sh_expand(int P, int D, int M, int G, const float* __restrict__ means3D,
                                                    const float* __restrict__ campos_all, const float* __restrict__ drgb_all,
                                                    size_t drgb_stride, float* __restrict__ dL_dsh) {
@@ -857,32 +983,7 @@ __global__ void __launch_bounds__(256) k_sh_expand(int P, int D, int M, int G, c
   for (int g = 0; g < G; ++g) {
     const float4 d = reinterpret_cast<const float4*>(drgb_all + (size_t)g * drgb_stride)[i];
     if (d.x == 0.f && d.y == 0.f && d.z == 0.f && d.w == 0.f) continue;
-    float x = mx - campos_all[3 * g], y = my - campos_all[3 * g + 1], z = mz - campos_all[3 * g + 2];
-    const float len = sqrtf(x * x + y * y + z * z);
-    x /= len; y /= len; z /= len;
-    acc[0] += kSH_C0 * d;
-    if (D > 0) {
-      acc[1] += (-kSH_C1 * y) * d;
-      acc[2] += (kSH_C1 * z) * d;
-      acc[3] += (-kSH_C1 * x) * d;
-      if (D > 1) {
-        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        acc[4] += (kSH_C2[0] * xy) * d;
-        acc[5] += (kSH_C2[1] * yz) * d;
-        acc[6] += (kSH_C2[2] * (2.f * zz - xx - yy)) * d;
-        acc[7] += (kSH_C2[3] * xz) * d;
-        acc[8] += (kSH_C2[4] * (xx - yy)) * d;
-        if (D > 2) {
-          acc[9] += (kSH_C3[0] * y * (3.f * xx - yy)) * d;
-          acc[10] += (kSH_C3[1] * xy * z) * d;
-          acc[11] += (kSH_C3[2] * y * (4.f * zz - xx - yy)) * d;
-          acc[12] += (kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy)) * d;
-          acc[13] += (kSH_C3[4] * x * (4.f * zz - xx - yy)) * d;
-          acc[14] += (kSH_C3[5] * z * (xx - yy)) * d;
-          acc[15] += (kSH_C3[6] * x * (xx - 3.f * yy)) * d;
-        }
-      }
-    }
+    sh_basis_accumulate(acc, D, mx - campos_all[3 * g], my - campos_all[3 * g + 1], mz - campos_all[3 * g + 2], d);
   }
   float4* out = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * M;
 #pragma unroll
@@ -896,6 +997,57 @@ int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const flo
   if (P == 0 || M == 0) return 0;
   k_sh_expand<<<(P + 255) / 256, 256, 0, st>>>(P, D, M, G, means3D, campos_all, drgb_all, drgb_stride, dL_dsh);
   return check_cuda(cudaGetLastError(), "k_sh_expand launch");
+}
+
+// ---- SH expansion straight from the peers' factor buffers --------------------------------------------------------
+// gsl_sh_expand over the factor tables the ranks pushed into this rank's buffer (local reads only), rows [row0, row1).
+__global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const PeerLayout pl, int row0, int row1, int D,
+                                                        int M, const float* __restrict__ means3D,
+                                                        float* __restrict__ dL_dsh) {
+  const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int word = i >> 5;  // warp-uniform (row0 is a multiple of 256)
+  const uint2* fmeta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta);
+  const float4* factor = reinterpret_cast<const float4*>(pv.own + pl.off_factor);
+  uint2 mine = make_uint2(0u, 0u);
+  if (lane < pv.world && word * 32 < row1) mine = fmeta[(size_t)lane * pl.tiles * 8 + word];
+  float4 d[PEER_MAX];
+#pragma unroll
+  for (int g = 0; g < PEER_MAX; ++g) {
+    d[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < pv.world) {  // warp-uniform
+      const uint32_t bits = __shfl_sync(0xffffffffu, mine.x, g);
+      const uint32_t before = __shfl_sync(0xffffffffu, mine.y, g);
+      if ((bits >> lane) & 1u)
+        d[g] = factor[((size_t)g * pl.tiles + (word >> 3)) * 256 + before + __popc(bits & ((1u << lane) - 1u))];
+    }
+  }
+  if (i >= row1) return;
+  float4 acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float mx = means3D[3 * (size_t)i], my = means3D[3 * (size_t)i + 1], mz = means3D[3 * (size_t)i + 2];
+  const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF);
+#pragma unroll
+  for (int g = 0; g < PEER_MAX; ++g) {
+    const float4 dg = d[g];
+    if (g >= pv.world || (dg.x == 0.f && dg.y == 0.f && dg.z == 0.f && dg.w == 0.f)) continue;
+    const float4 cpos = campos_all[g];
+    sh_basis_accumulate(acc, D, mx - cpos.x, my - cpos.y, mz - cpos.z, dg);
+  }
+  float4* out = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * M;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (k < M) out[k] = acc[k];
+  for (int k = 16; k < M; ++k) out[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, const float* means3D,
+                          float* dL_dsh, cudaStream_t st) {
+  if (row1 <= row0 || M == 0) return 0;
+  k_peer_sh_expand<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0, row1, D,
+                                                             M, means3D, dL_dsh);
+  return check_cuda(cudaGetLastError(), "k_peer_sh_expand launch");
 }
 
 // ------------------------------------------------------------------------------------------------

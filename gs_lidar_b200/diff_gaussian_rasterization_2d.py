@@ -331,12 +331,16 @@ class _RasterizeGaussians(torch.autograd.Function):
             else:
                 # gradients go straight into the exchange's flat buffers; dL_dcolors receives the SH factor dL_dRGB
                 ex.prepare(P, S, M, dev)
-                v = ex.views
-                d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
-                d_scales, d_rot, d_features = v["scales"], v["rotations"], v["features"]
-                d_colors, d_sh, d_sh_rest = e(P, NUM_CHANNELS), None, None  # scratch: the factor itself goes to ex.local (see below)
+                d_sh = d_sh_rest = None
+                if ex.packed:  # the kernels write the exchange's packed rows; the dense tensors come from ex.finish
+                    d_means3D = d_means2D = d_opacity = d_scales = d_rot = d_features = d_colors = None
+                else:
+                    v = ex.views
+                    d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
+                    d_scales, d_rot, d_features = v["scales"], v["rotations"], v["features"]
+                    d_colors = e(P, NUM_CHANNELS)  # scratch: the factor itself goes to ex.local (see below)
                 params = L.gsl_params.from_buffer_copy(params)
-                params.flags |= L.GSL_FLAG_BWD_SH_FACTORED
+                params.flags |= ex.flags()
 
             fin = inputs["_fin"]
             ffwd = L.gsl_fwd_outputs()
@@ -347,6 +351,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             gout = L.gsl_bwd_outputs()
             gout.dL_dmeans3D, gout.dL_dmeans2D, gout.dL_dsh = _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh)
             gout.dL_dsh_rest = _ptr(d_sh_rest)
+            if ex is not None and ex.packed:
+                gout.peer = ex.ctx_ptr
             gout.dL_dcolors, gout.dL_dfeatures, gout.dL_dopacity = _ptr(d_colors), _ptr(d_features), _ptr(d_opacity)
             gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D = _ptr(d_scales), _ptr(d_rot), _ptr(d_cov3D)
             wss = holder.ws.as_struct()
@@ -357,12 +363,14 @@ class _RasterizeGaussians(torch.autograd.Function):
                                               C.byref(wss), _stream_ptr(dev)), "gsl_backward")
                     return
                 # frame-parallel: compositor + SH factor, start the all-gather, then the per-surfel kernel under it
+                factor_out = None if ex.packed else ex.local.data_ptr()  # packed: the per-surfel kernel pushes the factors
                 L.check(_lib.gsl_backward_composite(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gin),
-                                                    C.byref(gout), C.byref(wss), ex.local.data_ptr(), _stream_ptr(dev)),
+                                                    C.byref(gout), C.byref(wss), factor_out, _stream_ptr(dev)),
                         "gsl_backward_composite")
-                ex.start_gather(P, inputs["campos"])
-                L.check(_lib.gsl_backward_surfels(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gout),
-                                                  C.byref(wss), _stream_ptr(dev)), "gsl_backward_surfels")
+                ex.start_gather(P, inputs["campos"], params.D, M, inputs["means3D"])
+                ex.run_surfels(P, lambda rb, re: L.check(
+                    _lib.gsl_backward_surfels_rows(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gout),
+                                                   C.byref(wss), rb, re, _stream_ptr(dev)), "gsl_backward_surfels_rows"))
 
             if settings.debug:
                 cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) +

@@ -102,6 +102,15 @@ class GradientExchange:
         self.group = group
         self.key = None
 
+    packed = False  # True: the backward kernels write the exchange's own packed format (PeerExchange)
+
+    def flags(self):
+        from . import _lib as L
+        return L.GSL_FLAG_BWD_SH_FACTORED
+
+    def run_surfels(self, P, launch):
+        launch(0, P)
+
     # -- communication (overridable: the tests emulate the ranks in one process) ----------------------
     def world_size(self):
         if dist.is_available() and dist.is_initialized():
@@ -135,7 +144,7 @@ class GradientExchange:
             self.key = key
         return self
 
-    def start_gather(self, P, campos):
+    def start_gather(self, P, campos, D=None, M=None, means3D=None):
         """After the backward compositor wrote the SH factor into `local`: append the camera centre and start the
         all-gather, so that it runs while the per-surfel backward kernel is still computing."""
         self.local[4 * P:4 * P + 3].copy_(campos.reshape(3))
@@ -181,3 +190,211 @@ class GradientExchange:
     def __exit__(self, *exc):
         self.disable()
         return False
+
+
+class _DeviceMemory:
+    """Zero-copy torch view of device memory this package allocated itself (torch.as_tensor reads the interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = dict(shape=(int(nbytes),), typestr="|u1", data=(int(ptr), False), version=3)
+
+
+class PeerExchange(GradientExchange):
+    """GradientExchange without a collective library on the data path: the ranks of one NVLink domain (<= 8) map each
+    other's exchange buffers (CUDA IPC) and all traffic is remote stores issued by this package's own kernels
+    (csrc/gsl_peer.cu, GSL_FLAG_BWD_PEER_ROWS):
+
+      the per-surfel backward kernel runs in `chunks` row ranges; for every 256-surfel tile it pushes the packed 64-byte
+      gradient rows of the surfels a pixel touched (+ row bits) to the rank that owns the tile and the non-zero 16-byte
+      SH factors to every rank.  Behind every range, on a side stream: barrier -> gsl_peer_reduce (the owner sums its
+      tiles in rank order and pushes the sums to every rank) -> gsl_peer_sh_expand (dL_dsh from the local factor
+      tables) -- the exchange of range c travels while range c+1 is computed.  Then one barrier and gsl_peer_unpack
+      writes the dense gradient tensors.
+
+    Every rank ends up with bit-identical sums.  torch.distributed is used once, at set-up, to exchange the IPC handles.
+    Same interface as GradientExchange (`with PeerExchange(): loss.backward()`)."""
+
+    packed = True
+
+    def __init__(self, group=None, sync=True, chunks=4):
+        super().__init__(group)
+        self.sync = sync          # False: single-process emulation (tests) -- no barriers, caller orders the pieces
+        self.chunks = max(1, min(int(chunks), 32))
+        self.pkey = None
+        self.epoch = 0
+        self.ctx = None
+        self._own = None
+        self._opened = []
+        self.side = None
+
+    def rank(self):
+        return dist.get_rank(self.group) if (dist.is_available() and dist.is_initialized()) else 0
+
+    def flags(self):
+        from . import _lib as L
+        return L.GSL_FLAG_BWD_SH_FACTORED | L.GSL_FLAG_BWD_PEER_ROWS
+
+    # -- set-up: allocate, exchange handles, map ------------------------------------------------------------------
+    def _exchange_handles(self, handle_bytes):
+        out = [None] * self.world_size()
+        dist.all_gather_object(out, handle_bytes, group=self.group)
+        return out
+
+    def setup(self, P, S, device, buffers=None):
+        """Allocates this rank's exchange buffer and maps the peers' (`buffers`: already-mapped device pointers of all
+        ranks, for single-process emulation)."""
+        from . import _lib as L
+        import ctypes as C
+        lib = L.load()
+        self.close()
+        G, r = self.world_size(), self.rank()
+        if G > L.GSL_PEER_MAX:
+            raise RuntimeError("PeerExchange: %d ranks, at most %d (one NVLink domain)" % (G, L.GSL_PEER_MAX))
+        self.nbytes = int(lib.gsl_peer_buffer_bytes(P, S, G))
+        ctx = L.gsl_peer_ctx()
+        ctx.rank, ctx.world, ctx.epoch = r, G, 0
+        with torch.cuda.device(device):
+            if buffers is None:
+                ptr, handle = C.c_void_p(), L.gsl_peer_handle()
+                L.check(lib.gsl_peer_alloc(self.nbytes, C.byref(ptr), C.byref(handle)), "gsl_peer_alloc")
+                self._own = ptr.value
+                handles = self._exchange_handles(bytes(handle.reserved))
+                for g in range(G):
+                    if g == r:
+                        ctx.buf[g] = self._own
+                        continue
+                    h = L.gsl_peer_handle()
+                    C.memmove(C.byref(h), handles[g], 64)
+                    q = C.c_void_p()
+                    L.check(lib.gsl_peer_open(C.byref(h), C.byref(q)), "gsl_peer_open (rank %d)" % g)
+                    self._opened.append(q.value)
+                    ctx.buf[g] = q.value
+            else:
+                for g in range(G):
+                    ctx.buf[g] = buffers[g]
+            self._err = torch.zeros(1, dtype=torch.int32).pin_memory()
+            ctx.error_flag = self._err.data_ptr()
+            self._mem = _DeviceMemory(ctx.buf[r] + L.GSL_PEER_CAMPOS_OFFSET, 16)
+            self._campos = torch.as_tensor(self._mem, device=device).view(torch.float32)[:3]
+            self.side = torch.cuda.Stream(device=device, priority=-1)
+            self._events = [torch.cuda.Event() for _ in range(self.chunks)]
+        self.ctx = ctx
+        self.ctx_ptr = C.addressof(ctx)
+        self.pkey = (P, S, G, str(device))
+
+    def close(self):
+        from . import _lib as L
+        if self.ctx is None:
+            return
+        lib = L.load()
+        torch.cuda.synchronize()
+        for q in self._opened:
+            lib.gsl_peer_close(q)
+        self._opened = []
+        if self._own is not None:
+            lib.gsl_peer_free(self._own)
+            self._own = None
+        self.ctx = None
+        self.pkey = None
+
+    # -- per backward ---------------------------------------------------------------------------------------------
+    def prepare(self, P, S, M, device):
+        G = self.world_size()
+        if self.pkey != (P, S, G, str(device)):
+            self.setup(P, S, device)
+        if int(self._err[0]) != 0:
+            raise RuntimeError("PeerExchange: a rank did not reach a barrier (flag slot %d) of an earlier step within the "
+                               "time-out; the gradients of that step are invalid" % (int(self._err[0]) - 1))
+        self.epoch += 1
+        self._S = S
+        self.views = None
+        return self
+
+    @staticmethod
+    def _sp(stream):
+        import ctypes as C
+        return C.c_void_p(stream.cuda_stream)
+
+    def _barrier(self, slot, ticket, stream):
+        """Flag slot 0: first range of a step (also pushes the camera centres), 1: later ranges, 2: end of the step;
+        tickets grow monotonically per slot."""
+        if self.sync:
+            from . import _lib as L
+            import ctypes as C
+            self.ctx.epoch = ticket & 0xFFFFFFFF
+            L.check(L.load().gsl_peer_barrier(C.byref(self.ctx), slot, self._sp(stream)), "gsl_peer_barrier")
+
+    def launch_expand(self, P, D, M, means3D, d_sh, row_begin, row_end, stream):
+        from . import _lib as L
+        import ctypes as C
+        L.check(L.load().gsl_peer_sh_expand(C.byref(self.ctx), P, self._S, D, M, row_begin, row_end, means3D.data_ptr(),
+                                            d_sh.data_ptr(), self._sp(stream)), "gsl_peer_sh_expand")
+
+    def launch_reduce(self, P, row_begin, row_end, stream):
+        from . import _lib as L
+        import ctypes as C
+        L.check(L.load().gsl_peer_reduce(C.byref(self.ctx), P, self._S, row_begin, row_end, self._sp(stream)),
+                "gsl_peer_reduce")
+
+    def start_gather(self, P, campos, D=None, M=None, means3D=None):
+        """Publishes the camera centre (the first barrier of the step pushes it to every rank) and allocates dL_dsh."""
+        self._campos.copy_(campos.reshape(3))
+        self._d_sh = torch.empty((P, M, 4), dtype=torch.float32, device=means3D.device)
+        self._expand_args = (D, M, means3D)
+
+    def ranges(self, P):
+        step = ((P + self.chunks - 1) // self.chunks + 255) // 256 * 256
+        return [(rb, min(P, rb + step)) for rb in range(0, P, max(step, 256))]
+
+    def run_surfels(self, P, launch):
+        """`launch(row_begin, row_end)` enqueues the per-surfel backward kernel (which pushes its results to the ranks)
+        for a row range on the current stream; the exchange of every finished range runs on the side stream under the
+        next one."""
+        if not self.sync:
+            launch(0, P)
+            return
+        D, M, means3D = self._expand_args
+        main = torch.cuda.current_stream(means3D.device)
+        for c, (rb, re) in enumerate(self.ranges(P)):
+            launch(rb, re)
+            ev = self._events[c]
+            ev.record(main)
+            self.side.wait_event(ev)
+            if c == 0:
+                self._barrier(0, self.epoch, self.side)       # every rank pushed this range (and its camera centre)
+            else:
+                self._barrier(1, self.epoch * 64 + c, self.side)
+            self.launch_reduce(P, rb, re, self.side)           # my tiles: summed in rank order, pushed to every rank
+            self.launch_expand(P, D, M, means3D, self._d_sh, rb, re, self.side)
+
+    def unpack(self, P):
+        """Summed packed rows of the own buffer -> fresh dense gradient tensors (one allocation, NAMES order)."""
+        from . import _lib as L
+        import ctypes as C
+        S = self._S
+        dev = self._campos.device
+        widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
+        flat = torch.empty(P * (15 + S), dtype=torch.float32, device=dev)
+        out, off = {}, 0
+        for k in self.NAMES:
+            out[k] = flat[off:off + P * widths[k]].view(P, widths[k])
+            off += P * widths[k]
+        g = L.gsl_bwd_outputs()
+        g.dL_dmeans3D, g.dL_dmeans2D, g.dL_dscales = out["means3D"].data_ptr(), out["means2D"].data_ptr(), out["scales"].data_ptr()
+        g.dL_drotations, g.dL_dopacity = out["rotations"].data_ptr(), out["opacities"].data_ptr()
+        g.dL_dfeatures = out["features"].data_ptr() if S > 0 and P > 0 else None
+        L.check(L.load().gsl_peer_unpack(C.byref(self.ctx), P, S, C.byref(g), self._sp(torch.cuda.current_stream(dev))),
+                "gsl_peer_unpack")
+        self.flat_nbytes = flat.numel() * 4
+        return out
+
+    def finish(self, P, D, M, means3D):
+        main = torch.cuda.current_stream(means3D.device)
+        if self.sync:
+            main.wait_stream(self.side)         # my tiles are summed and published, my dL_dsh is complete
+            self._barrier(2, self.epoch, main)  # every tile arrived; every rank is done reading what was pushed to it
+        out = self.unpack(P)
+        out["shs"] = self._d_sh
+        self._d_sh = None
+        self._expand_args = None
+        return out

@@ -37,7 +37,7 @@ extern "C" {
 #define GSL_API
 #endif
 
-#define GSL_ABI_VERSION 2
+#define GSL_ABI_VERSION 3
 #define GSL_NUM_CHANNELS 4 /* cuda_rasterizer/config.h:12 */
 #define GSL_TILE 16        /* cuda_rasterizer/config.h:13-14 */
 #define GSL_MAX_FEATURES 10 /* forward.cu:348: F[13] holds S features + 3 normal channels */
@@ -54,6 +54,10 @@ extern "C" {
                                     hfov_max - hfov_min = 360 and an image of <= 1024 tiles. */
 #define GSL_FLAG_BWD_SH_FACTORED 2u /* gsl_backward: write the clamp-masked dL_dRGB factor into dL_dcolors and do
                                        not write dL_dsh (frame-parallel training rebuilds it with gsl_sh_expand) */
+
+#define GSL_FLAG_BWD_PEER_ROWS 8u /* backward for the peer-memory gradient exchange (gsl_peer_*): implies SH_FACTORED;
+                                    gsl_backward_surfels[_rows] writes no dense tensor but pushes packed gradient rows
+                                    and SH factors into the exchange buffers of gsl_bwd_outputs.peer (remote stores). */
 
 /* Mirrors the scalar arguments of Rasterizer::forward / ::backward
  * (rasterizer.h:31-63) plus GaussianRasterizationSettings (diff_gaussian_rasterization_2d.py:194-209). */
@@ -123,6 +127,7 @@ typedef struct gsl_bwd_inputs {
   const float* dL_dout_feature; /* (S+3,H,W) */
 } gsl_bwd_inputs;
 
+struct gsl_peer_ctx;
 typedef struct gsl_bwd_outputs {
   float* dL_dmeans3D;  /* (P,3) */
   float* dL_dmeans2D;  /* (P,4): densification proxy in .xy, zeros in .zw (backward.cu:700-711) */
@@ -134,6 +139,7 @@ typedef struct gsl_bwd_outputs {
   float* dL_drotations;/* (P,4) */
   float* dL_dcov3D;    /* (P,6) all zero, like the reference; may be NULL */
   float* dL_dsh_rest;  /* ABI 2: (P,M-1,4) when the input came as shs + shs_rest, else ignored */
+  const struct gsl_peer_ctx* peer; /* ABI 3, GSL_FLAG_BWD_PEER_ROWS only: the mapped exchange buffers (see below) */
 } gsl_bwd_outputs;
 
 GSL_API int gsl_abi_version(void);
@@ -251,6 +257,58 @@ typedef struct gsl_state_export {
 } gsl_state_export;
 GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64_t R,
                      const gsl_state_export* dst, void* stream);
+
+/* ---- Frame-parallel gradient exchange over NVLink peer memory (no counterpart in the reference, which is single-GPU;
+ * SURVEY.md 8e).  Every rank owns one exchange buffer that all ranks of the node map (CUDA IPC).  Under
+ * GSL_FLAG_BWD_PEER_ROWS the per-surfel backward kernel PUSHES its results into the ranks' buffers with remote stores
+ * (packed gradient rows of a 256-surfel tile -> the rank that owns the tile, tile % world; SH factors -> every rank),
+ * the owners sum their tiles and push the sums to everybody, and each rank rebuilds dL_dsh and the dense gradient
+ * tensors locally -- no collective library and no remote load on the data path.  All calls take row ranges (multiples
+ * of 256), so the exchange of one range can run on a side stream while the backward kernel computes the next one.
+ * Per step and rank (ticket = a number that grows with every barrier on a flag slot, same sequence on all ranks):
+ *   camera centre -> own buffer + GSL_PEER_CAMPOS_OFFSET;  gsl_backward_composite(sh_factor_out = NULL);
+ *   for each row range:  gsl_backward_surfels_rows();  [side stream] gsl_peer_barrier(slot 0 on the first range, else 1);
+ *                        gsl_peer_reduce();  gsl_peer_sh_expand();
+ *   join;  gsl_peer_barrier(slot 2);  gsl_peer_unpack().
+ * After the last barrier every rank holds bit-identical sums and may start the next step. */
+#define GSL_PEER_MAX 8 /* ranks of one NVLink domain */
+#define GSL_PEER_CAMPOS_OFFSET 1024 /* float[3] at this byte offset of the own buffer: this rank's camera centre
+                                       (pushed to every rank's table by a barrier on flag slot 0) */
+typedef struct gsl_peer_handle { unsigned char reserved[64]; } gsl_peer_handle; /* cudaIpcMemHandle_t */
+typedef struct gsl_peer_ctx {
+  int32_t rank, world;       /* world <= GSL_PEER_MAX */
+  uint32_t epoch;            /* the ticket of the next barrier call; barriers wait for flags >= ticket (wrap-safe) */
+  uint32_t reserved;
+  void* buf[GSL_PEER_MAX];   /* exchange buffer of every rank as mapped into THIS process; buf[rank] is the own one */
+  int32_t* error_flag;       /* device-visible int (pinned host memory): set to 1 + slot when a barrier timed out */
+} gsl_peer_ctx;
+GSL_API size_t gsl_peer_buffer_bytes(int64_t P, int32_t S, int32_t world);
+/* floats per packed row: [means2D.xy scales.xy | rotations | means3D opacity | features (S), zero padded] */
+GSL_API int32_t gsl_peer_row_width(int32_t S);
+GSL_API int gsl_peer_alloc(size_t bytes, void** dptr, gsl_peer_handle* handle); /* cudaMalloc, zero, export */
+GSL_API int gsl_peer_open(const gsl_peer_handle* handle, void** dptr);          /* map a peer's buffer (other process) */
+GSL_API int gsl_peer_close(void* dptr);
+GSL_API int gsl_peer_free(void* dptr);
+/* Signal "this rank reached ticket ctx->epoch on flag slot `slot` (0..3)" to all ranks and wait for all of them. */
+GSL_API int gsl_peer_barrier(const gsl_peer_ctx* ctx, int32_t slot, void* stream);
+/* The two halves of the barrier (signal: publish + flag stores to all ranks; wait: spin on the own flag slots), for
+ * callers that put work between them.  Slot 0's signal also pushes the camera centre into every rank's table. */
+GSL_API int gsl_peer_signal(const gsl_peer_ctx* ctx, int32_t slot, void* stream);
+GSL_API int gsl_peer_wait(const gsl_peer_ctx* ctx, int32_t slot, void* stream);
+/* gsl_sh_expand for the surfels [row_begin, row_end) over the factor tables and camera centres the ranks pushed into
+ * the own buffer (local reads); dL_dsh is the full (P,M,4) tensor. */
+GSL_API int gsl_peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
+                               int32_t row_end, const float* means3D, float* dL_dsh, void* stream);
+/* Sum of the staged packed rows [row_begin, row_end) (multiples of 256, or row_end = P): this rank sums the tiles it
+ * owns (every world-th) in rank order and pushes sums + OR-ed row bits into every rank's result area; complete after
+ * the next barrier. */
+GSL_API int gsl_peer_reduce(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t row_begin, int32_t row_end, void* stream);
+/* Summed packed rows + OR-ed row bits of the own buffer -> dense dL_dmeans3D, dL_dmeans2D, dL_dscales, dL_drotations,
+ * dL_dopacity, dL_dfeatures of `out` (every element written). */
+GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const gsl_bwd_outputs* out, void* stream);
+/* gsl_backward_surfels for the surfels [row_begin, row_end) only (GSL_FLAG_BWD_PEER_ROWS; row_begin a multiple of 256). */
+GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                              gsl_bwd_outputs* gout, gsl_workspace* ws, int32_t row_begin, int32_t row_end, void* stream);
 
 /* Per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline block.
  * Kernel ids index the arrays of gsl_profile_read. */
