@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--height", type=int, default=66)
     ap.add_argument("--width", type=int, default=1030)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange by this repo's own kernels over NVLink peer memory (default) or by "
+                         "NCCL collectives (all-reduce + all-gather)")
+    ap.add_argument("--exchange-chunks", type=int, default=1)
     ap.add_argument("--wrap-azimuth", action="store_true",
                     help="opt-in extension, NOT the reference's semantics and not the headline: periodic panorama")
     ap.add_argument("--cpu-sample-surfels", type=int, default=0, help="0 = pick from a quick calibration")
@@ -173,7 +177,10 @@ def run_ours(args, rank, world, local):
     # N > 1: the gradient exchange is fused into the backward pass (parallel.GradientExchange): flat non-SH
     # gradients all-reduced, 16-byte SH factors all-gathered, SH gradient rebuilt on the device.
     bucket = None
-    exchange = parallel.GradientExchange().enable() if world > 1 else None
+    exchange = None
+    if world > 1:
+        exchange = (parallel.PeerExchange(chunks=args.exchange_chunks) if args.exchange == "peer"
+                    else parallel.GradientExchange()).enable()
     last = {}
 
     def step(rasterizer=rast, cots=cot):
@@ -380,14 +387,19 @@ def run_ours(args, rank, world, local):
         "data": "synthetic", "impl": "ours",
         "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "visible_surfels": V, "tile_instances": R,
                    "azimuth_wrap_around": bool(args.wrap_azimuth),
-                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, ", fp32 gradient exchange (NCCL all-reduce of the non-SH gradients + all-gather of the SH factors) in the step" if world > 1 else ""),
+                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, "" if world == 1 else (
+                       ", fp32 gradient exchange in the step: packed rows + SH factors pushed over NVLink peer memory by the backward kernel, "
+                       "summed by the tile owners (own kernels, no collective library)" if args.exchange == "peer" else
+                       ", fp32 gradient exchange (NCCL all-reduce of the non-SH gradients + all-gather of the SH factors) in the step")),
                    "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6),
-                   "grad_exchange_bytes": (exchange.flat_nbytes + exchange.local.numel() * 4) if exchange is not None else 0},
+                   "grad_exchange": None if exchange is None else args.exchange,
+                   "grad_exchange_bytes": 0 if exchange is None else (exchange.flat_nbytes + (0 if exchange.packed else exchange.local.numel() * 4))},
         "clocks": clocks,
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "note": "per-step camera + cotangent maps from pinned host memory, rendered maps + a gradient checksum read back; surfel parameters stay resident like model weights"},
-        "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD) * args.steps,
+        "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD +
+                         (0 if exchange is None or not exchange.packed else L.OWN_LAUNCHES_PEER(len(exchange.ranges(P))))) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,

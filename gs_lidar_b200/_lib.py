@@ -132,6 +132,8 @@ SYMBOLS = {
                                      C.c_int32, vp, vp, vp]),
     "gsl_peer_reduce": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "gsl_peer_unpack": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.POINTER(gsl_bwd_outputs), vp]),
+    "gsl_backward_surfels_exchange": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
+                                                C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), C.c_uint32, C.c_int32, vp]),
     "gsl_backward_surfels_rows": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
                                             C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), C.c_int32, C.c_int32, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
@@ -146,6 +148,14 @@ GSL_K_COUNT = 10
 OWN_LAUNCHES_FWD = 1 + 4 + 1 + 3 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan/bases,
                                             # bin scatter, tile block lists, render_fwd
 OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
+
+
+
+def OWN_LAUNCHES_PEER(ranges):
+    """extra launches of a backward with the peer-memory exchange: per row range the per-surfel kernel (one is already
+    counted in OWN_LAUNCHES_BWD), a barrier, the reduce and the expand; then the last barrier and the unpack."""
+    return 4 * ranges - 1 + 2
+
 
 _lib = None
 

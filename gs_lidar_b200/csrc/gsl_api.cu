@@ -116,7 +116,8 @@ static int validate_ws(const gsl_params* p, const gsl_workspace* ws, bool need_b
 }
 
 // One side stream + fork/join events per host thread and device (the surfel sort runs on it).
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+constexpr int SIDE_CHUNK_EVENTS = 32;
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; cudaEvent_t chunk[SIDE_CHUNK_EVENTS]; };
 static SideStream* side_stream() {
   static thread_local SideStream aux[64];
   static thread_local bool have[64] = {false};
@@ -129,6 +130,8 @@ static SideStream* side_stream() {
     if (cudaStreamCreateWithPriority(&aux[dev].stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&aux[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int k = 0; k < SIDE_CHUNK_EVENTS; ++k)
+      if (cudaEventCreateWithFlags(&aux[dev].chunk[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     have[dev] = true;
   }
   return &aux[dev];
@@ -287,7 +290,9 @@ GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in
   aux = nullptr;
 #endif
   if (p->flags & GSL_FLAG_BWD_PEER_ROWS) {
-    aux = nullptr;  // packed rows: nothing is zero-filled
+    // the dense outputs given here (the targets of gsl_backward_surfels_exchange) are zero-filled on the side stream;
+    // without them (the piecewise calls) there is nothing to fill
+    if (!gout->dL_dsh && !gout->dL_dmeans3D) aux = nullptr;
     if (sh_factor_out) return set_error(GSL_EINVAL, "GSL_FLAG_BWD_PEER_ROWS: the SH factors are pushed by the per-surfel kernel; sh_factor_out must be NULL");
   }
   if (aux) {
@@ -331,6 +336,52 @@ GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs*
   }
   if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, prezeroed, row_begin, row_end, st))) return rc;
   return debug_sync(p, st, "preprocess_backward");
+}
+
+// The whole second half of a frame-parallel backward pass in one call (see include/gsl_b200.h).
+GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                                  gsl_bwd_outputs* gout, gsl_workspace* ws, uint32_t step, int32_t chunks, void* stream) {
+  int rc = backward_validate(p, in, fwd, gout, ws);
+  if (rc) return rc;
+  if (!(p->flags & GSL_FLAG_BWD_PEER_ROWS)) return set_error(GSL_EINVAL, "backward_surfels_exchange needs GSL_FLAG_BWD_PEER_ROWS");
+  if (p->P == 0) return 0;
+  if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dopacity || !gout->dL_dscales || !gout->dL_drotations ||
+      (p->S > 0 && !gout->dL_dfeatures) || !gout->dL_dsh)
+    return set_error(GSL_EINVAL, "backward_surfels_exchange: a dense gradient output pointer is NULL");
+  if (chunks < 1) chunks = 1;
+  if (chunks > SIDE_CHUNK_EVENTS) chunks = SIDE_CHUNK_EVENTS;
+  SideStream* aux = side_stream();
+  if (!aux) return set_error(GSL_ESTATE, "no side stream");
+  // zero-fill forked by gsl_backward_composite onto the same side stream the exchange runs on: ordered before every
+  // kernel below that writes the dense outputs (expand on the side stream, unpack after the join)
+  const bool prezeroed = g_prezero_pending;
+  g_prezero_pending = false;
+  cudaStream_t st = (cudaStream_t)stream;
+  GeomView g = geom_view(ws->geom, p->P, p->S);
+  gsl_peer_ctx ctx = *gout->peer;  // tickets are set per barrier below
+  // this rank's camera centre: pushed to every rank's table by the first barrier
+  if ((rc = check_cuda(cudaMemcpyAsync((char*)ctx.buf[ctx.rank] + GSL_PEER_CAMPOS_OFFSET, in->campos, 12,
+                                       cudaMemcpyDeviceToDevice, st), "camera centre copy"))) return rc;
+  const int P = p->P;
+  const int rows_per = (((P + chunks - 1) / chunks) + 255) / 256 * 256;
+  int c = 0;
+  for (int rb = 0; rb < P; rb += rows_per, ++c) {
+    const int re = rb + rows_per < P ? rb + rows_per : P;
+    // main stream: VJP of the range, results pushed to the ranks; side stream: its exchange, under the next range
+    if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, false, rb, re, st))) return rc;
+    cudaEventRecord(aux->chunk[c], st);
+    cudaStreamWaitEvent(aux->stream, aux->chunk[c], 0);
+    ctx.epoch = c == 0 ? step : step * 64u + (uint32_t)c;
+    if ((rc = launch_peer_barrier(&ctx, c == 0 ? 0 : 1, 3, aux->stream))) return rc;
+    if ((rc = launch_peer_reduce_rows(&ctx, P, p->S, rb, re, aux->stream))) return rc;
+    if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, rb, re, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
+  }
+  cudaEventRecord(aux->join, aux->stream);
+  cudaStreamWaitEvent(st, aux->join, 0);
+  ctx.epoch = step;
+  if ((rc = launch_peer_barrier(&ctx, 2, 3, st))) return rc;  // every tile arrived; everybody is done with my pushes
+  if ((rc = launch_peer_unpack(&ctx, P, p->S, prezeroed, *gout, st))) return rc;
+  return debug_sync(p, st, "backward_surfels_exchange");
 }
 
 GSL_API int gsl_backward(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
@@ -422,7 +473,7 @@ GSL_API int gsl_peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, in
   if (D < 0 || D > 3 || M < 0) return set_error(GSL_EINVAL, "peer_sh_expand: bad sizes");
   if (M > 0 && (D + 1) * (D + 1) > M) return set_error(GSL_EINVAL, "peer_sh_expand: degree %d needs %d coefficients", D, (D + 1) * (D + 1));
   if (P > 0 && M > 0 && (!means3D || !dL_dsh)) return set_error(GSL_EINVAL, "peer_sh_expand: NULL pointer");
-  return launch_peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, means3D, dL_dsh, (cudaStream_t)stream);
+  return launch_peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, false, means3D, dL_dsh, (cudaStream_t)stream);
 }
 
 GSL_API int gsl_peer_reduce(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t row_begin, int32_t row_end, void* stream) {
@@ -439,7 +490,7 @@ GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const
   if (P > 0 && (!out || !out->dL_dmeans3D || !out->dL_dmeans2D || !out->dL_dscales || !out->dL_drotations ||
                 !out->dL_dopacity || (S > 0 && !out->dL_dfeatures)))
     return set_error(GSL_EINVAL, "peer_unpack: an output pointer is NULL");
-  return launch_peer_unpack(ctx, P, S, *out, (cudaStream_t)stream);
+  return launch_peer_unpack(ctx, P, S, false, *out, (cudaStream_t)stream);
 }
 
 static int validate_glue(const gsl_glue_params* p, const gsl_glue_inputs* in) {

@@ -265,9 +265,9 @@ struct PeerLayout {
 int peer_row_width(int S);
 PeerLayout peer_layout(size_t P, int S, int world);
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
-int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, const float* means3D,
-                          float* dL_dsh, cudaStream_t st);
+int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
+                          const float* means3D, float* dL_dsh, cudaStream_t st);
 int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st);
-int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, const gsl_bwd_outputs& out, cudaStream_t st);
+int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st);
 
 }  // namespace gsl

@@ -155,7 +155,7 @@ int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, 
 }
 
 // ---- summed packed rows -> the dense gradient tensors autograd returns (local) ------------------------------------------
-__global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, const float* __restrict__ rows,
+__global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, int prezeroed, const float* __restrict__ rows,
                                                      const uint32_t* __restrict__ bits, float* __restrict__ d_means3D,
                                                      float* __restrict__ d_means2D, float* __restrict__ d_scales,
                                                      float* __restrict__ d_rot, float* __restrict__ d_opacity,
@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, const
   if (i >= P) return;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 r0 = zero4, r1 = zero4, r2 = zero4, f[3] = {zero4, zero4, zero4};
-  if ((bits[i >> 5] >> (i & 31)) & 1u) {
+  const bool set = (bits[i >> 5] >> (i & 31)) & 1u;
+  if (!set && prezeroed) return;  // the dense outputs were zero-filled under the backward compositor
+  if (set) {
     const float4* r = reinterpret_cast<const float4*>(rows + (size_t)i * rw);
     r0 = r[0]; r1 = r[1]; r2 = r[2];
     for (int k = 0; k < rw / 4 - 3; ++k) f[k] = r[3 + k];
@@ -180,11 +182,12 @@ __global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, const
   }
 }
 
-int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, const gsl_bwd_outputs& out, cudaStream_t st) {
+int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st) {
   if (P == 0) return 0;
   const char* own = (const char*)c->buf[c->rank];
   const PeerLayout pl = peer_layout((size_t)P, S, c->world);
-  k_peer_unpack<<<(P + 255) / 256, 256, 0, st>>>(P, S, peer_row_width(S), reinterpret_cast<const float*>(own + pl.off_rows),
+  k_peer_unpack<<<(P + 255) / 256, 256, 0, st>>>(P, S, peer_row_width(S), prezeroed ? 1 : 0,
+                                                 reinterpret_cast<const float*>(own + pl.off_rows),
                                                  reinterpret_cast<const uint32_t*>(own + pl.off_rowbits), out.dL_dmeans3D,
                                                  out.dL_dmeans2D, out.dL_dscales, out.dL_drotations, out.dL_dopacity,
                                                  out.dL_dfeatures);

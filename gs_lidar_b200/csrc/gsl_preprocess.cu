@@ -874,7 +874,9 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
   add(gout.dL_dscales, P * 12);
   add(gout.dL_drotations, P * 16);
   if (p.S > 0) add(gout.dL_dfeatures, P * 4 * (size_t)p.S);
-  if (in.shs && !(p.flags & GSL_FLAG_BWD_SH_FACTORED)) {
+  if (in.shs && (p.flags & GSL_FLAG_BWD_PEER_ROWS)) {
+    add(gout.dL_dsh, P * 16 * (size_t)p.M);  // summed over the ranks by k_peer_sh_expand, non-zero rows only
+  } else if (in.shs && !(p.flags & GSL_FLAG_BWD_SH_FACTORED)) {
     add(gout.dL_dsh, P * 16 * (size_t)(in.shs_rest ? 1 : p.M));
     if (in.shs_rest) add(gout.dL_dsh_rest, P * 16 * (size_t)(p.M - 1));
   }
@@ -1002,7 +1004,7 @@ int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const flo
 // ---- SH expansion straight from the peers' factor buffers --------------------------------------------------------
 // gsl_sh_expand over the factor tables the ranks pushed into this rank's buffer (local reads only), rows [row0, row1).
 __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const PeerLayout pl, int row0, int row1, int D,
-                                                        int M, const float* __restrict__ means3D,
+                                                        int M, int prezeroed, const float* __restrict__ means3D,
                                                         float* __restrict__ dL_dsh) {
   const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -1022,11 +1024,18 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
         d[g] = factor[((size_t)g * pl.tiles + (word >> 3)) * 256 + before + __popc(bits & ((1u << lane) - 1u))];
     }
   }
-  if (i >= row1) return;
   float4 acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float mx = means3D[3 * (size_t)i], my = means3D[3 * (size_t)i + 1], mz = means3D[3 * (size_t)i + 2];
+  bool some = false;  // a rank has a non-zero factor for this surfel
+#pragma unroll
+  for (int g = 0; g < PEER_MAX; ++g) some |= (d[g].x != 0.f) | (d[g].y != 0.f) | (d[g].z != 0.f) | (d[g].w != 0.f);
+  // rows to store: all of them, or -- when dL_dsh was zero-filled under the backward compositor -- the non-zero ones
+  const uint32_t rowmask = prezeroed ? __ballot_sync(0xffffffffu, some) : 0xffffffffu;
+  if (rowmask == 0u) return;
+  const bool in_range = i < row1;
+  const size_t ic = in_range ? (size_t)i : 0;
+  const float mx = means3D[3 * ic], my = means3D[3 * ic + 1], mz = means3D[3 * ic + 2];
   const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF);
 #pragma unroll
   for (int g = 0; g < PEER_MAX; ++g) {
@@ -1035,18 +1044,37 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
     const float4 cpos = campos_all[g];
     sh_basis_accumulate(acc, D, mx - cpos.x, my - cpos.y, mz - cpos.z, dg);
   }
-  float4* out = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * M;
+  // coalesced stores: a warp's 32 rows x 16 float4 go through shared memory, 8 coefficients at a time, so that one
+  // store instruction writes 4 rows x 128 contiguous bytes instead of 32 pieces of 16 bytes 256 bytes apart
+  __shared__ float4 s_t[8][32][9];
+  const int warp = threadIdx.x >> 5;
+  const int row_base = i - lane;  // first row of this warp
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
-    if (k < M) out[k] = acc[k];
-  for (int k = 16; k < M; ++k) out[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int half = 0; half < 2; ++half) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_t[warp][lane][k] = acc[8 * half + k];
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx >> 3, q = idx & 7;
+      const int row = row_base + r, k = 8 * half + q;
+      if (row < row1 && k < M && ((rowmask >> r) & 1u)) reinterpret_cast<float4*>(dL_dsh)[(size_t)row * M + k] = s_t[warp][r][q];
+    }
+  }
+  if (i < row1 && !prezeroed) {
+    float4* out = reinterpret_cast<float4*>(dL_dsh) + (size_t)i * M;
+    for (int k = 16; k < M; ++k) out[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
-int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, const float* means3D,
-                          float* dL_dsh, cudaStream_t st) {
+
+int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
+                          const float* means3D, float* dL_dsh, cudaStream_t st) {
   if (row1 <= row0 || M == 0) return 0;
   k_peer_sh_expand<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0, row1, D,
-                                                             M, means3D, dL_dsh);
+                                                             M, prezeroed ? 1 : 0, means3D, dL_dsh);
   return check_cuda(cudaGetLastError(), "k_peer_sh_expand launch");
 }
 

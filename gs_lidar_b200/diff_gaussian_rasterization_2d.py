@@ -306,11 +306,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_alpha = cot(grad_alpha, (1, H, W))
 
         split = inputs["shs_rest"].numel() != 0  # never together with the exchange (GaussianRasterizer.forward)
-        ex = _exchange if (_exchange is not None and M > 0 and P > 0 and _exchange.world_size() > 1) else None
+        ex = _exchange if (_exchange is not None and M > 0 and P > 0 and
+                           (_exchange.world_size() > 1 or getattr(_exchange, "force", False))) else None
         with torch.cuda.device(dev):
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
             # dL_dcov3D is all-zero (forward.cu never reads cov3D_precomp); only materialised when the caller passed one
             d_cov3D = e(P, 6) if ctx.cov_shape == (P, 6) else None
+            fused = False
             if ex is None:
                 # one allocation for all dense gradients; the returned tensors are contiguous views of it
                 # 16-byte-stored tensors first (their sizes are multiples of 16 B), scalar-stored ones after: every
@@ -332,7 +334,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 # gradients go straight into the exchange's flat buffers; dL_dcolors receives the SH factor dL_dRGB
                 ex.prepare(P, S, M, dev)
                 d_sh = d_sh_rest = None
-                if ex.packed:  # the kernels write the exchange's packed rows; the dense tensors come from ex.finish
+                fused = ex.packed and ex.sync  # the whole exchange is one C call writing the summed dense gradients
+                if fused:
+                    v = ex.alloc_outputs(P, S, M, dev)
+                    d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
+                    d_scales, d_rot, d_features, d_sh = v["scales"], v["rotations"], v["features"], v["shs"]
+                    d_colors = None
+                elif ex.packed:  # emulation (tests): the pieces are driven one by one, the tensors come from ex.finish
                     d_means3D = d_means2D = d_opacity = d_scales = d_rot = d_features = d_colors = None
                 else:
                     v = ex.views
@@ -367,6 +375,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                 L.check(_lib.gsl_backward_composite(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gin),
                                                     C.byref(gout), C.byref(wss), factor_out, _stream_ptr(dev)),
                         "gsl_backward_composite")
+                if fused:
+                    L.check(_lib.gsl_backward_surfels_exchange(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gout),
+                                                               C.byref(wss), ex.epoch & 0xFFFFFFFF, ex.chunks,
+                                                               _stream_ptr(dev)), "gsl_backward_surfels_exchange")
+                    return
                 ex.start_gather(P, inputs["campos"], params.D, M, inputs["means3D"])
                 ex.run_surfels(P, lambda rb, re: L.check(
                     _lib.gsl_backward_surfels_rows(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gout),
@@ -383,7 +396,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     raise ex_
             else:
                 run()
-            if ex is not None:
+            if ex is not None and not fused:
                 g = ex.finish(P, params.D, M, inputs["means3D"])
                 d_means3D, d_means2D, d_opacity = g["means3D"], g["means2D"], g["opacities"]
                 d_scales, d_rot, d_features, d_sh = g["scales"], g["rotations"], g["features"], g["shs"]
@@ -462,7 +475,7 @@ class GaussianRasterizer(nn.Module):
         empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
         if shs_rest is not None and shs is None:
             raise Exception('shs_rest needs shs (the DC coefficient)')
-        if shs_rest is not None and _exchange is not None and _exchange.world_size() > 1:
+        if shs_rest is not None and _exchange is not None and (_exchange.world_size() > 1 or getattr(_exchange, "force", False)):
             shs, shs_rest = torch.cat((shs, shs_rest), dim=1), None  # the factored exchange works on one (P,M,4) tensor
         if shs is None:
             shs = empty()

@@ -216,9 +216,10 @@ class PeerExchange(GradientExchange):
 
     packed = True
 
-    def __init__(self, group=None, sync=True, chunks=4):
+    def __init__(self, group=None, sync=True, chunks=1, force=False):
         super().__init__(group)
         self.sync = sync          # False: single-process emulation (tests) -- no barriers, caller orders the pieces
+        self.force = force        # run the exchange even with a single rank (tests: the whole path on one GPU)
         self.chunks = max(1, min(int(chunks), 32))
         self.pkey = None
         self.epoch = 0
@@ -236,6 +237,8 @@ class PeerExchange(GradientExchange):
 
     # -- set-up: allocate, exchange handles, map ------------------------------------------------------------------
     def _exchange_handles(self, handle_bytes):
+        if self.world_size() == 1:
+            return [handle_bytes]
         out = [None] * self.world_size()
         dist.all_gather_object(out, handle_bytes, group=self.group)
         return out
@@ -363,9 +366,21 @@ class PeerExchange(GradientExchange):
             if c == 0:
                 self._barrier(0, self.epoch, self.side)       # every rank pushed this range (and its camera centre)
             else:
-                self._barrier(1, self.epoch * 64 + c, self.side)
+                self._barrier(1, (self.epoch & 0xFFFFFFFF) * 64 + c, self.side)
             self.launch_reduce(P, rb, re, self.side)           # my tiles: summed in rank order, pushed to every rank
             self.launch_expand(P, D, M, means3D, self._d_sh, rb, re, self.side)
+
+    def alloc_outputs(self, P, S, M, device):
+        """Fresh dense gradient tensors (one allocation for the non-SH ones, NAMES order, + dL_dsh)."""
+        widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
+        flat = torch.empty(P * (15 + S), dtype=torch.float32, device=device)
+        out, off = {}, 0
+        for k in self.NAMES:
+            out[k] = flat[off:off + P * widths[k]].view(P, widths[k])
+            off += P * widths[k]
+        out["shs"] = torch.empty((P, M, 4), dtype=torch.float32, device=device)
+        self.flat_nbytes = flat.numel() * 4
+        return out
 
     def unpack(self, P):
         """Summed packed rows of the own buffer -> fresh dense gradient tensors (one allocation, NAMES order)."""

@@ -309,6 +309,12 @@ GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const
 /* gsl_backward_surfels for the surfels [row_begin, row_end) only (GSL_FLAG_BWD_PEER_ROWS; row_begin a multiple of 256). */
 GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                               gsl_bwd_outputs* gout, gsl_workspace* ws, int32_t row_begin, int32_t row_end, void* stream);
+/* The sequence above from "for each row range" to gsl_peer_unpack in one call (after gsl_backward_composite): `chunks`
+ * row ranges, their exchange on the library's side stream, `step` = the step counter the tickets derive from (same on
+ * all ranks, > 0, growing).  gout: peer = the mapped exchange buffers, the dense non-SH pointers and dL_dsh receive
+ * the gradients summed over the ranks. */
+GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
+                                  gsl_bwd_outputs* gout, gsl_workspace* ws, uint32_t step, int32_t chunks, void* stream);
 
 /* Per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline block.
  * Kernel ids index the arrays of gsl_profile_read. */

@@ -86,7 +86,7 @@ for name, kw in NCCL_VARIANTS:
     res[name] = timed(step, STEPS)
     ex.disable()
 # the peer-memory exchange (own kernels over NVLink, parallel.PeerExchange)
-for chunks in ((8,) if PARTS_ONLY else (1, 4, 8)):
+for chunks in ((8,) if PARTS_ONLY else (1, 2, 4, 8)):
     pex = parallel.PeerExchange(chunks=chunks).enable()
     res["peer_chunks%d" % chunks] = timed(step, STEPS)
     pex.disable()

@@ -126,6 +126,31 @@ def test_emulated_two_ranks_equal_the_sum_of_dense_gradients(P, split):
             lib.gsl_peer_free(q)
 
 
+@pytest.mark.parametrize("P,chunks", [(20000, 1), (5003, 3), (70000, 4)])
+def test_single_rank_exchange_equals_the_plain_backward(P, chunks):
+    """The complete fused path (gsl_backward_surfels_exchange: pushes, barriers, reduce, expand, unpack, zero-fill under
+    the compositor, row ranges on the side stream) with one rank: the 'sum' must be the plain backward's gradients."""
+    from gs_lidar_b200 import parallel
+    scene = synth.make_scene(P, seed=75).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=76).items()}
+    dense = common.run_ours(scene, cot, export=False)[2]
+    ex = parallel.PeerExchange(force=True, chunks=chunks)
+    try:
+        for it in range(3):  # the buffers are reused: stale rows / factors of earlier steps must never leak
+            sc = scene if it != 1 else scene._replace(opacities=scene.opacities * 0.5)
+            with ex:
+                got = common.run_ours(sc, cot, export=False)[2]
+        torch.cuda.synchronize()
+        assert int(ex._err[0]) == 0
+        for k in NAMES:
+            elem, norm = common.grad_err(got[k], dense[k])
+            assert elem < TOL_GRAD and norm < TOL_GRAD, (k, elem, norm)
+        culled = dense["shs"].abs().sum(dim=(1, 2)) == 0
+        assert float(got["shs"][culled].abs().sum()) == 0.0  # untouched surfels: exact zeros from the zero-fill
+    finally:
+        ex.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
