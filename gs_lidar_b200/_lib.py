@@ -90,7 +90,7 @@ class gsl_peer_handle(C.Structure):
 
 
 class gsl_peer_ctx(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("parity", C.c_uint32),
                 ("buf", vp * GSL_PEER_MAX), ("error_flag", vp)]
 
 

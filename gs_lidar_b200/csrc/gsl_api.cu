@@ -358,7 +358,13 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   g_prezero_pending = false;
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
+  // the zero-fill of the dense outputs (side stream, forked by gsl_backward_composite) precedes the expand kernels on
+  // that stream; the unpack on this stream waits for its event here (long complete)
+  if (prezeroed) cudaStreamWaitEvent(st, aux->join, 0);
   gsl_peer_ctx ctx = *gout->peer;  // tickets are set per barrier below
+  ctx.parity = step & 1u;
+  gsl_bwd_outputs go = *gout;
+  go.peer = &ctx;
   // this rank's camera centre: pushed to every rank's table by the first barrier
   if ((rc = check_cuda(cudaMemcpyAsync((char*)ctx.buf[ctx.rank] + GSL_PEER_CAMPOS_OFFSET, in->campos, 12,
                                        cudaMemcpyDeviceToDevice, st), "camera centre copy"))) return rc;
@@ -367,20 +373,22 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   int c = 0;
   for (int rb = 0; rb < P; rb += rows_per, ++c) {
     const int re = rb + rows_per < P ? rb + rows_per : P;
-    // main stream: VJP of the range, results pushed to the ranks; side stream: its exchange, under the next range
-    if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, false, rb, re, st))) return rc;
+    // main stream: VJP of the range (results pushed to the ranks), barrier, sum of the tiles this rank owns (pushed to the
+    // ranks); side stream, behind the barrier: dL_dsh of the range from the local factor tables -- it overlaps the
+    // reduce / unpack and the next range
+    if ((rc = launch_preprocess_backward(*p, *in, *fwd, go, g, false, rb, re, st))) return rc;
+    ctx.epoch = c == 0 ? step : step * 64u + (uint32_t)c;
+    if ((rc = launch_peer_barrier(&ctx, c == 0 ? 0 : 1, 3, st))) return rc;
     cudaEventRecord(aux->chunk[c], st);
     cudaStreamWaitEvent(aux->stream, aux->chunk[c], 0);
-    ctx.epoch = c == 0 ? step : step * 64u + (uint32_t)c;
-    if ((rc = launch_peer_barrier(&ctx, c == 0 ? 0 : 1, 3, aux->stream))) return rc;
-    if ((rc = launch_peer_reduce_rows(&ctx, P, p->S, rb, re, aux->stream))) return rc;
     if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, rb, re, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
+    if ((rc = launch_peer_reduce_rows(&ctx, P, p->S, rb, re, st))) return rc;
   }
   cudaEventRecord(aux->join, aux->stream);
-  cudaStreamWaitEvent(st, aux->join, 0);
   ctx.epoch = step;
-  if ((rc = launch_peer_barrier(&ctx, 2, 3, st))) return rc;  // every tile arrived; everybody is done with my pushes
+  if ((rc = launch_peer_barrier(&ctx, 2, 3, st))) return rc;  // every tile's sum arrived; staging may be rewritten
   if ((rc = launch_peer_unpack(&ctx, P, p->S, prezeroed, *gout, st))) return rc;
+  cudaStreamWaitEvent(st, aux->join, 0);  // dL_dsh complete
   return debug_sync(p, st, "backward_surfels_exchange");
 }
 

@@ -239,6 +239,7 @@ constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[PEER_MAX]: camera centre
 struct PeerView {  // gsl_peer_ctx by value, as the kernels take it
   int rank, world;
   uint32_t epoch;
+  int parity;  // which factor table (step & 1)
   char* own;  // buf[rank]
   char* buf[PEER_MAX];
 };
@@ -249,13 +250,14 @@ inline PeerView make_view(const gsl_peer_ctx* c) {
   v.epoch = c->epoch;
   for (int g = 0; g < PEER_MAX; ++g) v.buf[g] = g < c->world ? (char*)c->buf[g] : nullptr;
   v.own = (char*)c->buf[c->rank];
+  v.parity = (int)(c->parity & 1u);
   return v;
 }
 // Byte offsets inside an exchange buffer for P surfels (tiles of 256), S feature channels and `world` ranks.
 struct PeerLayout {
   int tiles, tiles_per_rank;  // ceil(P / 256); tiles a rank owns (tile t belongs to rank t % world)
-  size_t off_fmeta;      // uint2 [world][tiles * 8]: (factor bits, non-zero factors of the tile before this word), per source rank
-  size_t off_factor;     // float4 [world][tiles * 256]: SH factors per source rank, the non-zero ones of a tile packed to its front
+  size_t off_fmeta;      // uint2 [2 parities][world][tiles * 8]: (factor bits, non-zero factors of the tile before this word), per source rank
+  size_t off_factor;     // float4 [2 parities][world][tiles * 256]: SH factors per source rank, the non-zero ones of a tile packed to its front
   size_t off_stagebits;  // u32 [world][tiles_per_rank * 8]: row bits of the tiles this rank owns, per source rank
   size_t off_stage;      // float [world][tiles_per_rank * 256][rw]: packed rows of the tiles this rank owns, per source rank
   size_t off_rowbits;    // u32 [tiles * 8]: OR of the row bits over the ranks (written by the tile owners)

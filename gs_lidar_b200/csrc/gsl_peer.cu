@@ -34,8 +34,8 @@ PeerLayout peer_layout(size_t P, int S, int world) {
   l.tiles_per_rank = (l.tiles + world - 1) / world;
   const size_t rowbytes = (size_t)peer_row_width(S) * 4;
   l.off_fmeta = PEER_HEADER;
-  l.off_factor = align_up(l.off_fmeta + (size_t)world * l.tiles * 8 * 8, 256);
-  l.off_stagebits = align_up(l.off_factor + (size_t)world * l.tiles * 256 * 16, 256);
+  l.off_factor = align_up(l.off_fmeta + 2 * (size_t)world * l.tiles * 8 * 8, 256);
+  l.off_stagebits = align_up(l.off_factor + 2 * (size_t)world * l.tiles * 256 * 16, 256);
   l.off_stage = align_up(l.off_stagebits + (size_t)world * l.tiles_per_rank * 8 * 4, 256);
   l.off_rowbits = align_up(l.off_stage + (size_t)world * l.tiles_per_rank * 256 * rowbytes, 256);
   l.off_rows = align_up(l.off_rowbits + (size_t)l.tiles * 8 * 4, 256);

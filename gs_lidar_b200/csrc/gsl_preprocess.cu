@@ -744,8 +744,9 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     __syncthreads();
     int before = 0;
     for (int w = 0; w < warp; ++w) before += s_warp[w];
-    const size_t fpos = ((size_t)pv.rank * pl.tiles + tile) * 256 + before + __popc(fbits & ((1u << lane) - 1u));
-    const size_t mpos = ((size_t)pv.rank * pl.tiles + tile) * 8 + warp;
+    const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;  // [parity][source rank][tile]
+    const size_t fpos = table * 256 + before + __popc(fbits & ((1u << lane) - 1u));
+    const size_t mpos = table * 8 + warp;
 #pragma unroll
     for (int g = 0; g < PEER_MAX; ++g) {
       if (g < pv.world) {
@@ -945,8 +946,8 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
 // ------------------------------------------------------------------------------------------------
 // acc[k] += basis_k(normalize(x, y, z)) * d for the coefficients of degree <= D (the dL_dsh rows of backward.cu:17-134)
 __device__ __forceinline__ void sh_basis_accumulate(float4 (&acc)[16], int D, float x, float y, float z, const float4 d) {
-  const float len = sqrtf(x * x + y * y + z * z);
-  x /= len; y /= len; z /= len;
+  const float inv = 1.f / sqrtf(x * x + y * y + z * z);
+  x *= inv; y *= inv; z *= inv;
   acc[0] += kSH_C0 * d;
   if (D > 0) {
     acc[1] += (-kSH_C1 * y) * d;
@@ -1012,7 +1013,7 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
   const uint2* fmeta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta);
   const float4* factor = reinterpret_cast<const float4*>(pv.own + pl.off_factor);
   uint2 mine = make_uint2(0u, 0u);
-  if (lane < pv.world && word * 32 < row1) mine = fmeta[(size_t)lane * pl.tiles * 8 + word];
+  if (lane < pv.world && word * 32 < row1) mine = fmeta[(size_t)(pv.parity * pv.world + lane) * pl.tiles * 8 + word];
   float4 d[PEER_MAX];
 #pragma unroll
   for (int g = 0; g < PEER_MAX; ++g) {
@@ -1021,7 +1022,8 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
       const uint32_t bits = __shfl_sync(0xffffffffu, mine.x, g);
       const uint32_t before = __shfl_sync(0xffffffffu, mine.y, g);
       if ((bits >> lane) & 1u)
-        d[g] = factor[((size_t)g * pl.tiles + (word >> 3)) * 256 + before + __popc(bits & ((1u << lane) - 1u))];
+        d[g] = factor[((size_t)(pv.parity * pv.world + g) * pl.tiles + (word >> 3)) * 256 + before +
+                      __popc(bits & ((1u << lane) - 1u))];
     }
   }
   float4 acc[16];

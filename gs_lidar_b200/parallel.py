@@ -309,6 +309,7 @@ class PeerExchange(GradientExchange):
             raise RuntimeError("PeerExchange: a rank did not reach a barrier (flag slot %d) of an earlier step within the "
                                "time-out; the gradients of that step are invalid" % (int(self._err[0]) - 1))
         self.epoch += 1
+        self.ctx.parity = self.epoch & 1
         self._S = S
         self.views = None
         return self
@@ -350,25 +351,10 @@ class PeerExchange(GradientExchange):
         return [(rb, min(P, rb + step)) for rb in range(0, P, max(step, 256))]
 
     def run_surfels(self, P, launch):
-        """`launch(row_begin, row_end)` enqueues the per-surfel backward kernel (which pushes its results to the ranks)
-        for a row range on the current stream; the exchange of every finished range runs on the side stream under the
-        next one."""
-        if not self.sync:
-            launch(0, P)
-            return
-        D, M, means3D = self._expand_args
-        main = torch.cuda.current_stream(means3D.device)
-        for c, (rb, re) in enumerate(self.ranges(P)):
-            launch(rb, re)
-            ev = self._events[c]
-            ev.record(main)
-            self.side.wait_event(ev)
-            if c == 0:
-                self._barrier(0, self.epoch, self.side)       # every rank pushed this range (and its camera centre)
-            else:
-                self._barrier(1, (self.epoch & 0xFFFFFFFF) * 64 + c, self.side)
-            self.launch_reduce(P, rb, re, self.side)           # my tiles: summed in rank order, pushed to every rank
-            self.launch_expand(P, D, M, means3D, self._d_sh, rb, re, self.side)
+        """Piecewise path (sync=False, tests / scripts): the per-surfel backward kernel for all rows; the caller drives
+        barrier / reduce / expand / unpack itself.  With sync=True the rasterizer's backward makes ONE call instead,
+        gsl_backward_surfels_exchange, which runs the whole sequence (row ranges, side stream) inside the library."""
+        launch(0, P)
 
     def alloc_outputs(self, P, S, M, device):
         """Fresh dense gradient tensors (one allocation for the non-SH ones, NAMES order, + dL_dsh)."""
@@ -404,10 +390,6 @@ class PeerExchange(GradientExchange):
         return out
 
     def finish(self, P, D, M, means3D):
-        main = torch.cuda.current_stream(means3D.device)
-        if self.sync:
-            main.wait_stream(self.side)         # my tiles are summed and published, my dL_dsh is complete
-            self._barrier(2, self.epoch, main)  # every tile arrived; every rank is done reading what was pushed to it
         out = self.unpack(P)
         out["shs"] = self._d_sh
         self._d_sh = None

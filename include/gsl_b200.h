@@ -267,9 +267,9 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
  * of 256), so the exchange of one range can run on a side stream while the backward kernel computes the next one.
  * Per step and rank (ticket = a number that grows with every barrier on a flag slot, same sequence on all ranks):
  *   camera centre -> own buffer + GSL_PEER_CAMPOS_OFFSET;  gsl_backward_composite(sh_factor_out = NULL);
- *   for each row range:  gsl_backward_surfels_rows();  [side stream] gsl_peer_barrier(slot 0 on the first range, else 1);
- *                        gsl_peer_reduce();  gsl_peer_sh_expand();
- *   join;  gsl_peer_barrier(slot 2);  gsl_peer_unpack().
+ *   for each row range:  gsl_backward_surfels_rows();  gsl_peer_barrier(slot 0 on the first range, else 1);
+ *                        gsl_peer_reduce();  [side stream, after the barrier] gsl_peer_sh_expand();
+ *   gsl_peer_barrier(slot 2);  gsl_peer_unpack();  join.
  * After the last barrier every rank holds bit-identical sums and may start the next step. */
 #define GSL_PEER_MAX 8 /* ranks of one NVLink domain */
 #define GSL_PEER_CAMPOS_OFFSET 1024 /* float[3] at this byte offset of the own buffer: this rank's camera centre
@@ -278,7 +278,8 @@ typedef struct gsl_peer_handle { unsigned char reserved[64]; } gsl_peer_handle; 
 typedef struct gsl_peer_ctx {
   int32_t rank, world;       /* world <= GSL_PEER_MAX */
   uint32_t epoch;            /* the ticket of the next barrier call; barriers wait for flags >= ticket (wrap-safe) */
-  uint32_t reserved;
+  uint32_t parity;           /* step & 1: which of the two SH-factor tables this step pushes into / expands from (two
+                                tables, so that a fast rank's next step never overwrites factors a slow rank still reads) */
   void* buf[GSL_PEER_MAX];   /* exchange buffer of every rank as mapped into THIS process; buf[rank] is the own one */
   int32_t* error_flag;       /* device-visible int (pinned host memory): set to 1 + slot when a barrier timed out */
 } gsl_peer_ctx;
