@@ -690,6 +690,8 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     // factors (packed to the front of the tile's segment, + bits / prefix words) into every rank's factor table.  Remote
     // stores only: nothing here waits for NVLink.  Nothing is zero-filled (readers look at the bits first).
     __shared__ int s_warp[8];
+    __shared__ uint32_t s_any[8];
+    __shared__ float4 s_rows[256][4];  // the tile's 64-byte rows, flushed with 64 contiguous bytes per 4 lanes at the end
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = cta0 >> 8;
     const int owner = tile % pv.world;
@@ -698,7 +700,10 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     for (int g = 0; g < PEER_MAX; ++g)
       if (g == owner) obuf = pv.buf[g];
     const size_t slot0 = ((size_t)pv.rank * pl.tiles_per_rank + tile / pv.world) * 256;  // staging row of the tile's row 0
-    float* rows = reinterpret_cast<float*>(obuf + pl.off_stage) + (ptrdiff_t)(slot0 - (size_t)cta0) * pp.rw;
+    float* rows_remote = reinterpret_cast<float*>(obuf + pl.off_stage) + (ptrdiff_t)(slot0 - (size_t)cta0) * pp.rw;
+    // 16-byte stores 64 bytes apart make poor NVLink packets: 64-byte rows are staged in shared memory first
+    const bool staged = pp.rw == 16;
+    float* rows = staged ? reinterpret_cast<float*>(&s_rows[0][0]) - (ptrdiff_t)cta0 * 16 : rows_remote;
     bool any = false;
     float4 fac = zero4;
     if (idx < pp.row1) {
@@ -737,6 +742,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     const bool live = cta0 + warp * 32 < pp.row1;  // this warp's word exists
     const uint32_t bits = __ballot_sync(0xffffffffu, any);
     if (lane == 0 && live) reinterpret_cast<uint32_t*>(obuf + pl.off_stagebits)[(slot0 >> 5) + warp] = bits;
+    if (lane == 0) s_any[warp] = bits;
     // SH factors: block-local compaction, pushed to every rank
     const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
     const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
@@ -759,6 +765,16 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
       preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
                          s_g[4][slot], means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec, clamped,
                          dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, rows);
+    if (staged) {
+      __syncthreads();
+      float4* dst = reinterpret_cast<float4*>(obuf + pl.off_stage) + slot0 * 4;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int item = it * 256 + threadIdx.x;
+        const int r = item >> 2, q = item & 3;
+        if ((s_any[r >> 5] >> (r & 31)) & 1u) dst[(size_t)r * 4 + q] = s_rows[r][q];
+      }
+    }
     return;
   }
   if (idx < pp.row1) {
