@@ -87,7 +87,7 @@ __global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long l
 
 // mode: 1 = signal, 2 = wait, 3 = both (the barrier)
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st) {
-  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, 2000000000ull, c->error_flag);
+  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, 20000000000ull, c->error_flag);
   return check_cuda(cudaGetLastError(), "k_peer_barrier launch");
 }
 

@@ -103,6 +103,36 @@ def test_null_arguments_are_rejected_before_any_launch():
     assert rc == L.GSL_EINVAL
 
 
+def test_peer_exchange_layout_and_validation_without_a_gpu():
+    """The exchange-buffer layout is plain arithmetic and every gsl_peer_* entry point validates its context before it
+    touches CUDA."""
+    from gs_lidar_b200 import _lib as L
+    lib = L.load()
+    assert lib.gsl_peer_row_width(0) == 16 and lib.gsl_peer_row_width(4) == 16 and lib.gsl_peer_row_width(5) == 24
+    P = 1000000
+    one, eight = lib.gsl_peer_buffer_bytes(P, 4, 1), lib.gsl_peer_buffer_bytes(P, 4, 8)
+    tiles = (P + 255) // 256
+    # header + two factor tables per source rank + staging of the owned tiles per source rank + result area
+    assert one >= 4096 + 2 * tiles * 256 * 16 + tiles * 256 * 64 + tiles * 256 * 64
+    assert eight - one >= 7 * 2 * tiles * 256 * 16            # factor tables grow with the number of source ranks
+    assert eight < one + 7 * 2 * tiles * 256 * 16 + 2 * tiles * 256 * 64  # staging does not: 1/8 of the tiles x 8 sources
+    assert one % 256 == 0 and eight % 256 == 0
+    assert lib.gsl_peer_buffer_bytes(0, 4, 8) >= 4096
+    ctx = L.gsl_peer_ctx()
+    ctx.rank, ctx.world = 0, 0
+    assert lib.gsl_peer_barrier(C.byref(ctx), 0, None) == L.GSL_EINVAL and b"rank/world" in lib.gsl_last_error()
+    ctx.world = 2
+    assert lib.gsl_peer_reduce(C.byref(ctx), 1000, 4, 0, 1000, None) == L.GSL_EINVAL and b"not mapped" in lib.gsl_last_error()
+    assert lib.gsl_peer_sh_expand(None, 1000, 4, 3, 16, 0, 1000, None, None, None) == L.GSL_EINVAL
+    assert lib.gsl_peer_unpack(None, 1000, 4, None, None) == L.GSL_EINVAL
+    # the peer backward needs a mapped context in gsl_bwd_outputs.peer
+    p = _params()
+    p.flags = L.GSL_FLAG_BWD_PEER_ROWS
+    fin, ffwd, gout, ws = L.gsl_fwd_inputs(), L.gsl_fwd_outputs(), L.gsl_bwd_outputs(), L.gsl_workspace()
+    assert lib.gsl_backward_surfels_exchange(C.byref(p), C.byref(fin), C.byref(ffwd), C.byref(gout), C.byref(ws), 1, 1,
+                                             None) == L.GSL_EINVAL
+
+
 def test_python_api_validation_matches_reference_messages():
     import torch
     from gs_lidar_b200 import GaussianRasterizer, synth

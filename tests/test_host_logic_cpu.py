@@ -150,3 +150,13 @@ def test_glue_restatement_is_differentiable_and_masks_like_render():
     assert bool((msk == ((op[:, 0] > 1 / 255) & (mt[:, 0] > 0.05))).all())
     g = torch.autograd.grad(m3.sum() + op.sum(), [pc._xyz, pc._velocity, pc._t, pc._scaling_t, pc._opacity])
     assert all(torch.isfinite(x).all() for x in g)
+
+
+def test_peer_exchange_row_ranges_cover_the_surfels_on_tile_boundaries():
+    from gs_lidar_b200 import parallel
+    for P in (1, 255, 256, 5003, 1000000):
+        for chunks in (1, 3, 4, 8):
+            r = parallel.PeerExchange(chunks=chunks, sync=False).ranges(P)
+            assert r[0][0] == 0 and r[-1][1] == P and len(r) <= chunks
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))          # contiguous
+            assert all(rb % 256 == 0 for rb, _ in r)                    # ranges start on a 256-surfel tile
