@@ -292,7 +292,7 @@ GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in
   if (p->flags & GSL_FLAG_BWD_PEER_ROWS) {
     // the dense outputs given here (the targets of gsl_backward_surfels_exchange) are zero-filled on the side stream;
     // without them (the piecewise calls) there is nothing to fill
-    if (!gout->dL_dsh && !gout->dL_dmeans3D) aux = nullptr;
+    if (!gout->dL_dsh && !gout->dL_dmeans3D && !gout->dL_dcov3D) aux = nullptr;
     if (sh_factor_out) return set_error(GSL_EINVAL, "GSL_FLAG_BWD_PEER_ROWS: the SH factors are pushed by the per-surfel kernel; sh_factor_out must be NULL");
   }
   if (aux) {
