@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=66)
     ap.add_argument("--width", type=int, default=1030)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--toy-only", action="store_true", help="only time the pure-PyTorch toy splat on the host cores (no GPU needed)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange by this repo's own kernels over NVLink peer memory (default) or by "
                          "NCCL collectives (all-reduce + all-gather)")
@@ -454,6 +455,29 @@ def cpu_baseline(args, full=True):
     return {"value": 1.0 / t, "unit": UNIT, "cores": o.threads, "kind": "port", "sample": sample, "seconds": t * reps}
 
 
+def cpu_toy_baseline(args, budget_s=15.0):
+    """BASELINE.json configs[0]: the reference's pure-PyTorch panorama surfel splatting (scripts/compare_2dgs_3dgs.py
+    `surface_splatting`; restated for CPU tensors in oracle/toy_splat.py and pinned against the reference function's own
+    outputs) timed on the host cores at the panorama shape.  Forward only -- the toy has no backward -- and every pixel
+    evaluates every surfel, so it is quoted at the surfel counts it can hold; a context number, not a target."""
+    from oracle import toy_splat
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H, W = args.height, args.width
+    out, spent = [], 0.0
+    for P in (64, 1024, 4096):
+        a = toy_splat.make_inputs(P, W, H, seed=0)
+        t0 = time.perf_counter()
+        img, _, _, _ = toy_splat.surface_splatting(*a)
+        t = time.perf_counter() - t0
+        spent += t
+        out.append({"surfels": P, "seconds": t, "value": 1.0 / t, "covered_pixels": int((torch.nan_to_num(img).sum(-1) > 0).sum())})
+        if spent + 4.5 * t > budget_s:  # the next size costs ~4x
+            break
+    return {"what": "pure-PyTorch toy panorama splat (compare_2dgs_3dgs.py surface_splatting), forward only, %dx%d, fov +-90 x +-20 deg" % (H, W),
+            "unit": "panoramas/s", "cores": cores, "kind": "port", "runs": out}
+
+
 def run_reference(args, rank, world, local):
     """Reference arm: the UNMODIFIED reference CUDA rasterizer (oracle/_ref) on the same GPU, same scene,
     same cotangents; falls back to the CPU oracle port when the compiled reference is absent."""
@@ -541,6 +565,9 @@ def run_reference(args, rank, world, local):
 
 def main():
     args = parse_args()
+    if args.toy_only:
+        print(json.dumps(cpu_toy_baseline(args)))
+        return
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
         sys.exit(1)
@@ -554,6 +581,10 @@ def main():
                 res["cpu_baseline"] = cpu_baseline(args)
             except Exception as ex:  # the baseline must never take the measurement down
                 res["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+            try:
+                res["cpu_toy_baseline"] = cpu_toy_baseline(args)
+            except Exception as ex:
+                res["cpu_toy_baseline"] = {"runs": [], "kind": "port", "what": "failed: %r" % (ex,)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
