@@ -15,7 +15,7 @@ import pytest
 import oracle
 from gs_lidar_b200 import synth
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "g[0-9]*.npz")))
 TANFOV = math.tan(-0.5)
 
 
