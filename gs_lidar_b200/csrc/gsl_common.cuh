@@ -235,7 +235,8 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
 constexpr int PEER_MAX = GSL_PEER_MAX;
 constexpr size_t PEER_HEADER = 4096;      // flags: u32[4 phases][PEER_MAX]; camera centre at PEER_CAMPOS_OFF
 constexpr size_t PEER_CAMPOS_OFF = GSL_PEER_CAMPOS_OFFSET;
-constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[PEER_MAX]: camera centres of all ranks, pushed by barrier 0
+constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[2 parities][PEER_MAX]: camera centres of all ranks, pushed by barrier 0
+static_assert(PEER_CAMPOS_ALL_OFF + 2 * PEER_MAX * 16 <= PEER_HEADER, "header too small");
 struct PeerView {  // gsl_peer_ctx by value, as the kernels take it
   int rank, world;
   uint32_t epoch;

@@ -66,7 +66,7 @@ __global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long l
   if (g >= pv.world) return;
   if (phase == 0 && (mode & 1)) {  // publish this rank's camera centre into rank g's table: k_peer_sh_expand then reads it locally
     const float* own = reinterpret_cast<const float*>(pv.own + PEER_CAMPOS_OFF);
-    float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * pv.rank;
+    float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * (pv.parity * PEER_MAX + pv.rank);
     dst[0] = own[0]; dst[1] = own[1]; dst[2] = own[2];
   }
   if (mode & 1) {

@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
   const bool in_range = i < row1;
   const size_t ic = in_range ? (size_t)i : 0;
   const float mx = means3D[3 * ic], my = means3D[3 * ic + 1], mz = means3D[3 * ic + 2];
-  const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF);
+  const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF) + pv.parity * PEER_MAX;
 #pragma unroll
   for (int g = 0; g < PEER_MAX; ++g) {
     const float4 dg = d[g];
