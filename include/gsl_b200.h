@@ -323,7 +323,8 @@ enum {
   GSL_K_PREPROCESS_FWD = 0,
   GSL_K_SCAN = 1,      /* k_bin_count + k_bin_scan + k_bin_bases (k_scan_* on the > 1024-tile path) */
   GSL_K_DUPLICATE = 2, /* k_bin_scatter (k_duplicate on the > 1024-tile path) */
-  GSL_K_SORT = 3,      /* library radix sort (cub) -- not one of this repo's kernels */
+  GSL_K_SORT = 3,      /* k_depth_keys + k_sort_hist/scan/scatter/buckets: this repo's depth sort of the surfels (the
+                          64-bit cub radix sort only on the > 1024-tile path) */
   GSL_K_RANGES = 4,    /* k_tile_blists */
   GSL_K_RENDER_FWD = 5,
   GSL_K_RENDER_BWD = 6,

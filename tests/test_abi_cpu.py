@@ -61,6 +61,34 @@ int main(void) {
                     L.gsl_workspace.num_rendered_host.offset]
 
 
+def test_extension_struct_layouts_match_header():
+    """The structs added after ABI 1 (glue, peer exchange) and the fields appended to the ABI-1 structs."""
+    from gs_lidar_b200 import _lib as L
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "gsl_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(gsl_peer_ctx), sizeof(gsl_peer_handle), sizeof(gsl_glue_params),
+         sizeof(gsl_glue_inputs), sizeof(gsl_glue_outputs), sizeof(gsl_glue_inputs_grad));
+  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(gsl_fwd_inputs, shs_rest), offsetof(gsl_bwd_outputs, dL_dsh_rest),
+         offsetof(gsl_bwd_outputs, peer), offsetof(gsl_peer_ctx, parity), offsetof(gsl_peer_ctx, buf),
+         offsetof(gsl_peer_ctx, error_flag));
+  printf("%d %d %u %u\n", GSL_PEER_MAX, GSL_PEER_CAMPOS_OFFSET, GSL_FLAG_BWD_PEER_ROWS, GSL_FLAG_BWD_SH_FACTORED);
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        cfile, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(cfile, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), cfile, "-o", exe])
+        out = [int(x) for x in subprocess.check_output([exe]).decode().split()]
+    assert out[:6] == [C.sizeof(t) for t in (L.gsl_peer_ctx, L.gsl_peer_handle, L.gsl_glue_params, L.gsl_glue_inputs,
+                                             L.gsl_glue_outputs, L.gsl_glue_inputs_grad)]
+    assert out[6:12] == [L.gsl_fwd_inputs.shs_rest.offset, L.gsl_bwd_outputs.dL_dsh_rest.offset, L.gsl_bwd_outputs.peer.offset,
+                         L.gsl_peer_ctx.parity.offset, L.gsl_peer_ctx.buf.offset, L.gsl_peer_ctx.error_flag.offset]
+    assert out[12:] == [L.GSL_PEER_MAX, L.GSL_PEER_CAMPOS_OFFSET, L.GSL_FLAG_BWD_PEER_ROWS, L.GSL_FLAG_BWD_SH_FACTORED]
+
+
 def _params(**kw):
     from gs_lidar_b200 import _lib as L
     p = L.gsl_params()
