@@ -9,6 +9,7 @@
 // One thread per surfel, 256-thread blocks; every load of the per-surfel record is a float4.
 #include <math.h>
 #include "gsl_common.cuh"
+#include <cstdlib>
 #include "gsl_math.cuh"
 
 namespace gsl {
@@ -1088,9 +1089,110 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
 }
 
 
+// EXPERIMENTAL (off unless GSL_EXPAND_COMPACT=1 in the environment; not yet measured on 8 GPUs): the same expansion with
+// the tile's touched surfels compacted first.  About half of the surfels have no factor on any rank, so in the kernel
+// above half of the lanes idle through up to 8 x ~150 instructions; here a CTA (= one 256-surfel tile) builds the list of
+// rows with a factor on some rank (OR of the ranks' bit words, prefix over 8 words) and only ceil(n / 32) dense warps do
+// the work.  Needs a zero-filled dL_dsh (only listed rows are written).
+__global__ void __launch_bounds__(256) k_peer_sh_expand_compact(const PeerView pv, const PeerLayout pl, int row0, int row1,
+                                                                int D, int M, const float* __restrict__ means3D,
+                                                                float* __restrict__ dL_dsh) {
+  __shared__ uint2 s_meta[PEER_MAX][8];
+  __shared__ uint32_t s_union[8];
+  __shared__ int s_pref[9];
+  __shared__ uint16_t s_list[256];
+  __shared__ float4 s_t[8][32][9];
+  const int tile = (row0 >> 8) + blockIdx.x;
+  const int base_row = tile * 256;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint2* fmeta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta);
+  const float4* factor = reinterpret_cast<const float4*>(pv.own + pl.off_factor);
+  if (threadIdx.x < 8 * PEER_MAX) {
+    const int g = threadIdx.x >> 3, w = threadIdx.x & 7;
+    uint2 m = make_uint2(0u, 0u);
+    if (g < pv.world && base_row + 32 * w < row1) m = fmeta[((size_t)(pv.parity * pv.world + g) * pl.tiles + tile) * 8 + w];
+    s_meta[g][w] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    uint32_t u = 0u;
+#pragma unroll
+    for (int g = 0; g < PEER_MAX; ++g) u |= s_meta[g][threadIdx.x].x;
+    s_union[threadIdx.x] = u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int w = 0; w < 8; ++w) { s_pref[w] = acc; acc += __popc(s_union[w]); }
+    s_pref[8] = acc;
+  }
+  __syncthreads();
+  {
+    const uint32_t u = s_union[warp];
+    if ((u >> lane) & 1u) s_list[s_pref[warp] + __popc(u & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+  }
+  __syncthreads();
+  const int n = s_pref[8];
+  if (warp * 32 >= n) return;  // whole warps only: the listed rows fill the first ceil(n / 32) warps
+  const bool valid = (int)threadIdx.x < n;
+  const int r = valid ? (int)s_list[threadIdx.x] : 0;
+  const size_t row = (size_t)base_row + r;
+  float4 d[PEER_MAX];
+#pragma unroll
+  for (int g = 0; g < PEER_MAX; ++g) {
+    d[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < pv.world) {
+      const uint2 m = s_meta[g][r >> 5];
+      if (valid && ((m.x >> (r & 31)) & 1u))
+        d[g] = factor[((size_t)(pv.parity * pv.world + g) * pl.tiles + tile) * 256 + m.y + __popc(m.x & ((1u << (r & 31)) - 1u))];
+    }
+  }
+  float4 acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float mx = means3D[3 * row], my = means3D[3 * row + 1], mz = means3D[3 * row + 2];
+  const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF) + pv.parity * PEER_MAX;
+#pragma unroll
+  for (int g = 0; g < PEER_MAX; ++g) {
+    const float4 dg = d[g];
+    if (g >= pv.world || (dg.x == 0.f && dg.y == 0.f && dg.z == 0.f && dg.w == 0.f)) continue;
+    const float4 cpos = campos_all[g];
+    sh_basis_accumulate(acc, D, mx - cpos.x, my - cpos.y, mz - cpos.z, dg);
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_t[warp][lane][k] = acc[8 * half + k];
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane;
+      const int rr = idx >> 3, q = idx & 7;
+      const int cid = warp * 32 + rr, k = 8 * half + q;
+      if (cid < n && k < M)
+        reinterpret_cast<float4*>(dL_dsh)[((size_t)base_row + s_list[cid]) * M + k] = s_t[warp][rr][q];
+    }
+  }
+}
+
+static bool expand_compact_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GSL_EXPAND_COMPACT");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
                           const float* means3D, float* dL_dsh, cudaStream_t st) {
   if (row1 <= row0 || M == 0) return 0;
+  if (prezeroed && M <= 16 && expand_compact_enabled()) {
+    k_peer_sh_expand_compact<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0,
+                                                                       row1, D, M, means3D, dL_dsh);
+    return check_cuda(cudaGetLastError(), "k_peer_sh_expand_compact launch");
+  }
   k_peer_sh_expand<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0, row1, D,
                                                              M, prezeroed ? 1 : 0, means3D, dL_dsh);
   return check_cuda(cudaGetLastError(), "k_peer_sh_expand launch");
