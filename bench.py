@@ -417,7 +417,6 @@ def run_ours(args, rank, world, local):
 
 def cpu_baseline(args, full=True):
     """CPU oracle (plain-C port of the reference algorithm) timed on the host cores on a bounded sample."""
-    import numpy as np
     import oracle
     from gs_lidar_b200 import synth
     o = oracle.CpuOracle()

@@ -15,7 +15,6 @@ Host-side mirrors in plain PyTorch, same names, arguments and results:
 
 Nothing here touches the CUDA library directly; `renderFunc` is `gs_lidar_b200.renderer.render` (or the reference's).
 """
-import math
 
 import torch
 import torch.nn.functional as F
