@@ -369,6 +369,20 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   if ((rc = check_cuda(cudaMemcpyAsync((char*)ctx.buf[ctx.rank] + GSL_PEER_CAMPOS_OFFSET, in->campos, 12,
                                        cudaMemcpyDeviceToDevice, st), "camera centre copy"))) return rc;
   const int P = p->P;
+  // EXPERIMENTAL, GSL_PEER_EARLY_FACTORS=1: the SH factors are extracted here (before k_preprocess_bwd re-zeroes the
+  // accumulators) and pushed from the side stream; push -> barrier (slot 3) -> expansion of all rows then run beside the
+  // row exchange instead of behind the first barrier of this stream.
+  static const bool early = [] { const char* e = getenv("GSL_PEER_EARLY_FACTORS"); return e && e[0] == '1'; }();
+  if (early) {
+    if ((rc = launch_peer_factor_extract(&ctx, *p, g, st))) return rc;
+    cudaEventRecord(aux->chunk[SIDE_CHUNK_EVENTS - 1], st);
+    cudaStreamWaitEvent(aux->stream, aux->chunk[SIDE_CHUNK_EVENTS - 1], 0);
+    if ((rc = launch_peer_factor_push(&ctx, *p, aux->stream))) return rc;
+    ctx.epoch = step;
+    if ((rc = launch_peer_barrier(&ctx, 3, 3, aux->stream))) return rc;
+    if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
+    if (chunks > SIDE_CHUNK_EVENTS - 1) chunks = SIDE_CHUNK_EVENTS - 1;
+  }
   const int rows_per = (((P + chunks - 1) / chunks) + 255) / 256 * 256;
   int c = 0;
   for (int rb = 0; rb < P; rb += rows_per, ++c) {
@@ -376,12 +390,14 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
     // main stream: VJP of the range (results pushed to the ranks), barrier, sum of the tiles this rank owns (pushed to the
     // ranks); side stream, behind the barrier: dL_dsh of the range from the local factor tables -- it overlaps the
     // reduce / unpack and the next range
-    if ((rc = launch_preprocess_backward(*p, *in, *fwd, go, g, false, rb, re, st))) return rc;
+    if ((rc = launch_preprocess_backward(*p, *in, *fwd, go, g, false, rb, re, st, !early))) return rc;
     ctx.epoch = c == 0 ? step : step * 64u + (uint32_t)c;
     if ((rc = launch_peer_barrier(&ctx, c == 0 ? 0 : 1, 3, st))) return rc;
-    cudaEventRecord(aux->chunk[c], st);
-    cudaStreamWaitEvent(aux->stream, aux->chunk[c], 0);
-    if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, rb, re, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
+    if (!early) {
+      cudaEventRecord(aux->chunk[c], st);
+      cudaStreamWaitEvent(aux->stream, aux->chunk[c], 0);
+      if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, rb, re, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
+    }
     if ((rc = launch_peer_reduce_rows(&ctx, P, p->S, rb, re, st))) return rc;
   }
   cudaEventRecord(aux->join, aux->stream);

@@ -222,7 +222,7 @@ int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out,
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st);
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
-                               bool prezeroed, int row0, int row1, cudaStream_t st);
+                               bool prezeroed, int row0, int row1, cudaStream_t st, bool push_factors = true);
 int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
                      size_t drgb_stride, float* dL_dsh, cudaStream_t st);
 int launch_glue_forward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& out, cudaStream_t st);
@@ -270,6 +270,8 @@ PeerLayout peer_layout(size_t P, int S, int world);
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
                           const float* means3D, float* dL_dsh, cudaStream_t st);
+int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st);
+int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st);
 int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st);
 int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st);
 

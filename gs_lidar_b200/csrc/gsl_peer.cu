@@ -64,7 +64,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 __global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long long timeout_ns, int* error) {
   const int g = threadIdx.x;
   if (g >= pv.world) return;
-  if (phase == 0 && (mode & 1)) {  // publish this rank's camera centre into rank g's table: k_peer_sh_expand then reads it locally
+  if ((phase == 0 || phase == 3) && (mode & 1)) {  // publish this rank's camera centre into rank g's table: k_peer_sh_expand then reads it locally
     const float* own = reinterpret_cast<const float*>(pv.own + PEER_CAMPOS_OFF);
     float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * (pv.parity * PEER_MAX + pv.rank);
     dst[0] = own[0]; dst[1] = own[1]; dst[2] = own[2];

@@ -10,6 +10,7 @@
 #include <math.h>
 #include "gsl_common.cuh"
 #include <cstdlib>
+#include <algorithm>
 #include "gsl_math.cuh"
 
 namespace gsl {
@@ -475,6 +476,7 @@ struct PreBwdParams {
                  // only non-zero values are written here
   int row0, row1; // surfel range of this launch (chunked launches pipeline the peer exchange behind the kernel)
   int rw;         // > 0: GSL_FLAG_BWD_PEER_ROWS -- floats per packed exchange row (peer_row_width(S))
+  int push_factors;  // peer mode: this kernel also pushes the SH factors (0: k_peer_factor_extract/_push did it earlier)
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -745,7 +747,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     if (lane == 0 && live) reinterpret_cast<uint32_t*>(obuf + pl.off_stagebits)[(slot0 >> 5) + warp] = bits;
     if (lane == 0) s_any[warp] = bits;
     // SH factors: block-local compaction, pushed to every rank
-    const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
+    const bool nz = pp.push_factors && (fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f);
     const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
     if (lane == 0) s_warp[warp] = __popc(fbits);
     __syncthreads();
@@ -758,7 +760,8 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     for (int g = 0; g < PEER_MAX; ++g) {
       if (g < pv.world) {
         if (nz) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[fpos] = fac;
-        if (lane == 0 && live) reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[mpos] = make_uint2(fbits, (uint32_t)before);
+        if (lane == 0 && live && pp.push_factors)
+          reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[mpos] = make_uint2(fbits, (uint32_t)before);
       }
     }
     const int count = s_count;
@@ -915,7 +918,7 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
 
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
                                gsl_bwd_outputs& gout, const GeomView& g, bool prezeroed, int row0, int row1,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool push_factors) {
   if (p.P == 0 || row1 <= row0) return 0;
   PreBwdParams pp;
   pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.S = p.S;
@@ -936,6 +939,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   pp.rw = (p.flags & GSL_FLAG_BWD_PEER_ROWS) ? peer_row_width(p.S) : 0;
   PeerView pv = {};
   PeerLayout pl = {};
+  pp.push_factors = push_factors ? 1 : 0;
   if (pp.rw > 0) {
     pp.factored = 1;
     pv = make_view(gout.peer);
@@ -1088,6 +1092,73 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
   }
 }
 
+
+// EXPERIMENTAL (GSL_PEER_EARLY_FACTORS=1, see gsl_backward_surfels_exchange): the SH factors leave BEFORE the per-surfel
+// backward kernel.  k_peer_factor_extract packs this rank's non-zero factors of every tile into its OWN table (local
+// stores, right after the backward compositor and before k_preprocess_bwd re-zeroes the accumulators);
+// k_peer_factor_push then copies the used front of every tile segment + its 8 meta words to the other ranks from a
+// side stream, so that push -> barrier -> expansion runs beside k_preprocess_bwd -> barrier -> reduce -> unpack.
+__global__ void __launch_bounds__(256) k_peer_factor_extract(const PeerView pv, const PeerLayout pl, int P, int gstride,
+                                                             const float* __restrict__ grad,
+                                                             const uint8_t* __restrict__ clamped) {
+  __shared__ int s_warp[8];
+  const int tile = blockIdx.x;
+  const int i = tile * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 fac = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < P) {
+    const float4 gc = reinterpret_cast<const float4*>(grad + (size_t)i * gstride)[3];
+    if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
+      const uint8_t cl = clamped[i];
+      fac = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
+    }
+  }
+  const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
+  const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
+  if (lane == 0) s_warp[warp] = __popc(fbits);
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += s_warp[w];
+  const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;
+  if (nz) reinterpret_cast<float4*>(pv.own + pl.off_factor)[table * 256 + before + __popc(fbits & ((1u << lane) - 1u))] = fac;
+  if (lane == 0 && tile * 256 + warp * 32 < P)
+    reinterpret_cast<uint2*>(pv.own + pl.off_fmeta)[table * 8 + warp] = make_uint2(fbits, (uint32_t)before);
+}
+
+__global__ void __launch_bounds__(256) k_peer_factor_push(const PeerView pv, const PeerLayout pl, int P) {
+  for (int tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x) {
+    const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;
+    const uint2* meta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta) + table * 8;
+    const int words = min(8, (P - tile * 256 + 31) / 32);
+    const uint2 last = meta[words - 1];
+    const int count = (int)last.y + __popc(last.x);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 m = make_uint2(0u, 0u);
+    if ((int)threadIdx.x < count) v = reinterpret_cast<const float4*>(pv.own + pl.off_factor)[table * 256 + threadIdx.x];
+    if ((int)threadIdx.x < words) m = meta[threadIdx.x];
+#pragma unroll
+    for (int g = 0; g < PEER_MAX; ++g) {
+      if (g < pv.world && g != pv.rank) {
+        if ((int)threadIdx.x < count) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[table * 256 + threadIdx.x] = v;
+        if ((int)threadIdx.x < words) reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[table * 8 + threadIdx.x] = m;
+      }
+    }
+  }
+}
+
+int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
+  k_peer_factor_extract<<<pl.tiles, 256, 0, st>>>(make_view(c), pl, p.P, grad_stride(p.S), g.grad, g.clamped);
+  return check_cuda(cudaGetLastError(), "k_peer_factor_extract launch");
+}
+
+int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st) {
+  if (p.P == 0 || c->world < 2) return 0;
+  const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
+  k_peer_factor_push<<<std::min(pl.tiles, 148 * 8), 256, 0, st>>>(make_view(c), pl, p.P);
+  return check_cuda(cudaGetLastError(), "k_peer_factor_push launch");
+}
 
 // EXPERIMENTAL (off unless GSL_EXPAND_COMPACT=1 in the environment; not yet measured on 8 GPUs): the same expansion with
 // the tile's touched surfels compacted first.  About half of the surfels have no factor on any rank, so in the kernel
