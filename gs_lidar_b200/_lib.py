@@ -136,6 +136,9 @@ SYMBOLS = {
                                                 C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), C.c_uint32, C.c_int32, vp]),
     "gsl_backward_surfels_rows": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
                                             C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), C.c_int32, C.c_int32, vp]),
+    "gsl_chamfer_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "gsl_chamfer_forward": (C.c_int, [C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "gsl_chamfer_backward": (C.c_int, [C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
                                    C.POINTER(gsl_state_export), vp]),
     "gsl_profile_enable": (C.c_int, [C.c_int]),

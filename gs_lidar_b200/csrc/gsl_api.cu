@@ -517,6 +517,41 @@ GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const
   return launch_peer_unpack(ctx, P, S, false, *out, (cudaStream_t)stream);
 }
 
+// ---- Chamfer distance (gsl_chamfer.cu) ------------------------------------------------------------------------------
+static int validate_chamfer(int32_t b, int32_t n, int32_t m, const void* xyz1, const void* xyz2) {
+  if (b < 0 || n < 0 || m < 0 || b > 65535) return set_error(GSL_EINVAL, "chamfer: bad sizes b=%d n=%d m=%d", b, n, m);
+  if ((size_t)b * (size_t)n > 0x7fffffffull || (size_t)b * (size_t)m > 0x7fffffffull)
+    return set_error(GSL_EINVAL, "chamfer: b * n and b * m must fit 31 bits");
+  if (b > 0 && ((n > 0 && !xyz1) || (m > 0 && !xyz2))) return set_error(GSL_EINVAL, "chamfer: a point set pointer is NULL");
+  return 0;
+}
+
+GSL_API size_t gsl_chamfer_scratch_bytes(int32_t b, int32_t n, int32_t m) {
+  if (b < 0 || n < 0 || m < 0) return 0;
+  return 8 * (size_t)b * ((size_t)n + (size_t)m);
+}
+
+GSL_API int gsl_chamfer_forward(int32_t b, int32_t n, const float* xyz1, int32_t m, const float* xyz2, float* dist1,
+                                int32_t* idx1, float* dist2, int32_t* idx2, void* scratch, void* stream) {
+  int rc = validate_chamfer(b, n, m, xyz1, xyz2);
+  if (rc) return rc;
+  if (b == 0 || (n == 0 && m == 0)) return 0;
+  if ((n > 0 && (!dist1 || !idx1)) || (m > 0 && (!dist2 || !idx2)) || !scratch)
+    return set_error(GSL_EINVAL, "chamfer_forward: an output / scratch pointer is NULL");
+  return launch_chamfer_forward(b, n, xyz1, m, xyz2, dist1, idx1, dist2, idx2, scratch, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_chamfer_backward(int32_t b, int32_t n, const float* xyz1, int32_t m, const float* xyz2,
+                                 const float* gdist1, const int32_t* idx1, const float* gdist2, const int32_t* idx2,
+                                 float* gxyz1, float* gxyz2, void* stream) {
+  int rc = validate_chamfer(b, n, m, xyz1, xyz2);
+  if (rc) return rc;
+  if (b == 0 || (n == 0 && m == 0)) return 0;
+  if ((n > 0 && (!gdist1 || !idx1 || !gxyz1)) || (m > 0 && (!gdist2 || !idx2 || !gxyz2)))
+    return set_error(GSL_EINVAL, "chamfer_backward: a pointer is NULL");
+  return launch_chamfer_backward(b, n, xyz1, m, xyz2, gdist1, idx1, gdist2, idx2, gxyz1, gxyz2, (cudaStream_t)stream);
+}
+
 static int validate_glue(const gsl_glue_params* p, const gsl_glue_inputs* in) {
   if (!p || !in) return set_error(GSL_EINVAL, "glue: params / inputs is NULL");
   if (p->P < 0) return set_error(GSL_EINVAL, "glue: P must be >= 0");

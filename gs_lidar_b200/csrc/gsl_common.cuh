@@ -270,6 +270,10 @@ PeerLayout peer_layout(size_t P, int S, int world);
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
                           const float* means3D, float* dL_dsh, cudaStream_t st);
+int launch_chamfer_forward(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
+                           int* idx2, void* scratch, cudaStream_t st);
+int launch_chamfer_backward(int b, int n, const float* xyz1, int m, const float* xyz2, const float* gdist1, const int* idx1,
+                            const float* gdist2, const int* idx2, float* gxyz1, float* gxyz2, cudaStream_t st);
 int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st);
 int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st);
 int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st);

@@ -317,6 +317,19 @@ GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs*
 GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                                   gsl_bwd_outputs* gout, gsl_workspace* ws, uint32_t step, int32_t chunks, void* stream);
 
+/* ---- Chamfer distance of two point sets.  Replaces chamfer_cuda_forward / chamfer_cuda_backward
+ * of chamfer/chamfer3D/chamfer3D.cu:142-165,199-230 (pybind names `forward` / `backward`, chamfer_cuda.cpp) of the
+ * reference: xyz1 (b,n,3), xyz2 (b,m,3) float32 -> dist1 (b,n) / dist2 (b,m) squared distance to the nearest neighbour
+ * in the other set, idx1 / idx2 int32 its index (lowest index among equal minima, like the reference's scan).
+ * scratch: 8 * b * (n + m) bytes of device memory.  The backward zero-fills and then accumulates gxyz1 (b,n,3), gxyz2
+ * (b,m,3) (the reference's Python wrapper passes torch.zeros). */
+GSL_API size_t gsl_chamfer_scratch_bytes(int32_t b, int32_t n, int32_t m);
+GSL_API int gsl_chamfer_forward(int32_t b, int32_t n, const float* xyz1, int32_t m, const float* xyz2, float* dist1,
+                                int32_t* idx1, float* dist2, int32_t* idx2, void* scratch, void* stream);
+GSL_API int gsl_chamfer_backward(int32_t b, int32_t n, const float* xyz1, int32_t m, const float* xyz2,
+                                 const float* gdist1, const int32_t* idx1, const float* gdist2, const int32_t* idx2,
+                                 float* gxyz1, float* gxyz2, void* stream);
+
 /* Per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline block.
  * Kernel ids index the arrays of gsl_profile_read. */
 enum {
