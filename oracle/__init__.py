@@ -7,6 +7,8 @@ Two checkers for the panoramic surfel rasterizer:
   * RefCuda    -- ctypes front-end of oracle/_ref/libgslidar_ref.so, the UNMODIFIED reference CUDA
                   rasterizer compiled from /root/reference by oracle/build_ref.sh (torch CUDA tensors
                   in/out; needs a GPU).  This is the parity reference and the GPU baseline.
+  * RefChamfer -- the same for the reference's Chamfer kernels (oracle/_ref/libchamfer_ref.so, the unmodified
+                  chamfer/chamfer3D/chamfer3D.cu compiled against oracle/ref_stub/ATen/ATen.h).
 
 Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference / the parity
 gate) may import this package; gs_lidar_b200 never does.
@@ -20,6 +22,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libgsl_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libgslidar_ref.so")
+REF_CHAMFER_SO = os.path.join(HERE, "_ref", "libchamfer_ref.so")
 
 
 def build_oracle(force=False):
@@ -291,3 +294,41 @@ class RefCuda:
             out[name] = t
         assert N > 0
         return out
+
+
+class RefChamfer:
+    """torch front-end of the UNMODIFIED reference Chamfer kernels (oracle/_ref/libchamfer_ref.so): same call sequence as
+    chamfer/chamfer3D/dist_chamfer_3D.py:40-85 (zero-filled outputs, forward, zero-filled gradients, backward).  Legacy
+    default stream, like the reference."""
+
+    def __init__(self):
+        if not os.path.exists(REF_CHAMFER_SO):
+            raise FileNotFoundError(REF_CHAMFER_SO + " missing: run oracle/build_ref.sh where /root/reference exists")
+        self.lib = C.CDLL(REF_CHAMFER_SO)
+
+    def forward(self, xyz1, xyz2, outs=None):
+        import torch
+        B, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+        dev = xyz1.device
+        if outs is None:
+            outs = (torch.zeros((B, n), device=dev), torch.zeros((B, m), device=dev),
+                    torch.zeros((B, n), dtype=torch.int32, device=dev), torch.zeros((B, m), dtype=torch.int32, device=dev))
+        else:
+            for t in outs:
+                t.zero_()
+        d1, d2, i1, i2 = outs
+        p = lambda t: C.c_void_p(t.data_ptr())
+        ok = self.lib.chamferref_forward(B, n, p(xyz1), m, p(xyz2), p(d1), p(d2), p(i1), p(i2))
+        if ok != 1:
+            raise RuntimeError("reference chamfer forward failed")
+        return d1, d2, i1, i2
+
+    def backward(self, xyz1, xyz2, g1, g2, i1, i2):
+        import torch
+        B, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+        gx1, gx2 = torch.zeros_like(xyz1), torch.zeros_like(xyz2)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        ok = self.lib.chamferref_backward(B, n, p(xyz1), m, p(xyz2), p(gx1), p(gx2), p(g1), p(g2), p(i1), p(i2))
+        if ok != 1:
+            raise RuntimeError("reference chamfer backward failed")
+        return gx1, gx2

@@ -18,11 +18,32 @@ mkdir -p "$OUT"
 SO="$OUT/libgslidar_ref.so"
 STAMP="$OUT/.stamp"
 NEW_STAMP="$(cat "$HERE/ref_shim.cu" "$HERE/build_ref.sh" "$REF"/cuda_rasterizer/*.cu "$REF"/cuda_rasterizer/*.h | sha1sum | cut -d' ' -f1)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+
+# ---- the reference's Chamfer kernels (chamfer/chamfer3D/chamfer3D.cu), unmodified, against the stub ATen header ----
+CH_SRC="${GSL_REFERENCE_DIR:-/root/reference}/chamfer/chamfer3D/chamfer3D.cu"
+CH_SO="$OUT/libchamfer_ref.so"
+CH_STAMP="$OUT/.stamp_chamfer"
+if [ -f "$CH_SRC" ]; then
+  CH_NEW="$(cat "$CH_SRC" "$HERE/ref_chamfer_shim.cu" "$HERE/ref_stub/ATen/ATen.h" "$HERE/build_ref.sh" | sha1sum | cut -d' ' -f1)"
+  if [ -f "$CH_SO" ] && [ -f "$CH_STAMP" ] && [ "$(cat "$CH_STAMP")" = "$CH_NEW" ]; then
+    echo "[build_ref] up to date: $CH_SO"
+  else
+    CH_TMP="$(mktemp -d)"
+    CH_FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -I"$HERE/ref_stub")
+    "$NVCC" "${CH_FLAGS[@]}" -c "$CH_SRC" -o "$CH_TMP/chamfer3D.o"
+    "$NVCC" "${CH_FLAGS[@]}" -c "$HERE/ref_chamfer_shim.cu" -o "$CH_TMP/shim.o"
+    "$NVCC" -shared -o "$CH_SO" "$CH_TMP/chamfer3D.o" "$CH_TMP/shim.o" -lcudart
+    rm -rf "$CH_TMP"
+    echo "$CH_NEW" > "$CH_STAMP"
+    echo "[build_ref] built $CH_SO"
+  fi
+fi
+
 if [ -f "$SO" ] && [ -f "$STAMP" ] && [ "$(cat "$STAMP")" = "$NEW_STAMP" ]; then
   echo "[build_ref] up to date: $SO"
   exit 0
 fi
-NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --expt-relaxed-constexpr
        -include cstdint -Xcompiler -fPIC -I"$REF/third_party/glm" -I"$REF" -I"$REF/cuda_rasterizer")
 TMP="$(mktemp -d)"
