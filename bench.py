@@ -6,8 +6,11 @@ panorama (BASELINE.json metric; workload = configs[2], the config the metric is 
 
 One process per GPU.  For N > 1 launch with torchrun (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* from the
 env): every rank renders its own LiDAR frame (camera pose) of the replicated surfel set, and the
-per-surfel gradients are summed with one NCCL all-reduce inside the timed step ("weak" scaling:
-per-GPU work is fixed, value = frames of all ranks / max-over-ranks time).
+per-surfel gradients are summed inside the timed step by this repo's peer-memory exchange (own kernels
+storing over NVLink, gs_lidar_b200.parallel.PeerExchange; `--exchange nccl` selects the NCCL baseline)
+-- "weak" scaling: per-GPU work is fixed, value = frames of all ranks / max-over-ranks time.  Before
+anything is timed at N > 1 the exchanged gradients are checked against a torch.distributed all-reduce
+of the dense per-rank gradients (`exchange_parity`); a failed check prints no `value`.
 
 A "step" is one forward+backward pass of the rasterizer op for one frame through the public
 GaussianRasterizer API.  Rank 0 prints ONE JSON line (see the module-level keys at the end).
@@ -55,6 +58,9 @@ def parse_args():
     ap.add_argument("--wrap-azimuth", action="store_true",
                     help="opt-in extension, NOT the reference's semantics and not the headline: periodic panorama")
     ap.add_argument("--cpu-sample-surfels", type=int, default=0, help="0 = pick from a quick calibration")
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="CUDA-graph replay of the forward / backward pass (gs_lidar_b200.set_cuda_graphs); the line always "
+                         "carries the other mode's device-timed number as well")
     return ap.parse_args()
 
 
@@ -145,10 +151,77 @@ def render_bwd_algorithmic_bytes(V, N, S):
     return N * per_px + V * per_surfel
 
 
+def shared_config(P, H, W, S, M, D, V, R, world):
+    """The `config` object of the JSON line: identical keys and values in both arms (ours / reference) for the same run."""
+    return {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "sh_degree": D, "sh_coefficients": M,
+            "feature_channels": S, "visible_surfels": V, "tile_instances": R,
+            "parallelism": "frame-parallel dp%d, 1 frame/rank/step" % world,
+            "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % (
+                (45 * P + 16 * M * P + 4 * S * P) / 1e6)}
+
+
 def make_frame_pose(rank):
     # frame k of a drive: yaw N(0, 0.5 deg)-like fixed offsets and +0.1*sf*k along x (SURVEY.md 8d, C4)
     yaw = [0.0, 0.4, -0.3, 0.7, -0.6, 0.2, -0.1, 0.5][rank % 8]
     return dict(view_yaw_deg=yaw, view_shift=(0.01 * rank, 0.0, 0.0))
+
+
+def check_exchange_parity(step, leaves, names, exchange, dev, tol=1e-4):
+    """N > 1, outside the timed region: one step with the fused exchange against the same step without it followed by a
+    torch.distributed all-reduce (sum) of every dense gradient tensor."""
+    step()
+    torch.cuda.synchronize(dev)
+    got = {k: leaves[k].grad.detach().clone() for k in names}
+    exchange.disable()
+    step()
+    torch.cuda.synchronize(dev)
+    want = {k: leaves[k].grad.detach().clone() for k in names}
+    exchange.enable()
+    max_err, worst, identical = 0.0, None, True
+    for k in names:
+        dist.all_reduce(want[k], op=dist.ReduceOp.SUM)
+        err = float((got[k].double() - want[k].double()).norm() / (want[k].double().norm() + 1e-30))
+        if not (err <= max_err):  # also catches NaN
+            max_err, worst = err, k
+        ref0 = got[k].clone()
+        dist.broadcast(ref0, src=0)
+        identical = identical and bool(torch.equal(ref0.view(torch.int32), got[k].view(torch.int32)))
+    flags = torch.tensor([max_err if max_err == max_err else float("inf"), 0.0 if identical else 1.0],
+                         dtype=torch.float64, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+    max_err, identical = float(flags[0]), float(flags[1]) == 0.0
+    return {"max_err": max_err, "worst_tensor": worst, "bit_identical": identical, "tol": tol,
+            "against": "torch.distributed all-reduce (sum) of the dense per-rank gradients, norm-wise per tensor",
+            "ok": bool(max_err <= tol and identical)}
+
+
+def ncu_traffic_from_profiles():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of this repo's kernels from the newest
+    profiles/rNN_*ncu_full*.md (written by scripts/ncu_summary.py from an `ncu --set full` capture of this workload)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.md")))
+    out, src = {}, None
+    for f in files:  # later rounds overwrite earlier ones
+        try:
+            lines = open(f).read().splitlines()
+        except OSError:
+            continue
+        hdr = None
+        for ln in lines:
+            cells = [c.strip() for c in ln.strip().strip("|").split("|")]
+            if "kernel" in cells and "dram_rd" in cells:
+                hdr = cells
+                continue
+            if hdr and len(cells) == len(hdr) and cells[0].startswith("k_"):
+                row = dict(zip(hdr, cells))
+                try:
+                    mb = float(row["dram_rd"].split()[0]) + float(row["dram_wr"].split()[0])
+                except (ValueError, IndexError):
+                    continue
+                out[re.sub(r"<.*", "", row["kernel"])] = mb * 1e6
+                src = os.path.basename(f)
+    return out, src
 
 
 def run_ours(args, rank, world, local):
@@ -175,9 +248,8 @@ def run_ours(args, rank, world, local):
                   rotations=scene.rotations.clone())
     for v in leaves.values():
         v.requires_grad_(True)
-    # N > 1: the gradient exchange is fused into the backward pass (parallel.GradientExchange): flat non-SH
-    # gradients all-reduced, 16-byte SH factors all-gathered, SH gradient rebuilt on the device.
-    bucket = None
+    # N > 1: the gradient exchange is fused into the backward pass (parallel.PeerExchange: packed rows + SH factors pushed
+    # over NVLink peer memory by this repo's kernels; parallel.GradientExchange is the NCCL baseline)
     exchange = None
     if world > 1:
         exchange = (parallel.PeerExchange(chunks=args.exchange_chunks) if args.exchange == "peer"
@@ -192,9 +264,6 @@ def run_ours(args, rank, world, local):
             features=leaves["features"], scales=leaves["scales"], rotations=leaves["rotations"], mask=scene.mask)
         torch.autograd.backward([color, feature, depth, alpha],
                                 [cots["color"], cots["feature"], cots["depth"], cots["alpha"]])
-        if bucket is not None:
-            bucket.load({k: leaves[k].grad for k in names})
-            bucket.all_reduce()
         last.update(color=color, feature=feature, depth=depth, alpha=alpha, radii=radii, contrib=contrib)
 
     def barrier():
@@ -214,27 +283,97 @@ def run_ours(args, rank, world, local):
     V = int((last["radii"] > 0).sum())
     R = int(last["color"].grad_fn.num_rendered) if last["color"].grad_fn is not None else 0
 
-    # ---- timed region: device-resident inputs --------------------------------------------------
+    # ---- N > 1: parity gate, outside the timed region.  The gradients the fused exchange returned must equal a
+    # torch.distributed all-reduce (sum) of the dense gradients each rank computes alone, norm-wise to 1e-4 per tensor, and
+    # must be bit-identical on all ranks.  A timing without this check is void, so a failure prints no value.
+    exchange_parity = None
+    if world > 1:
+        exchange_parity = check_exchange_parity(step, leaves, names, exchange, dev)
+        if not exchange_parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "impl": "ours", "n_gpus": world, "error": "exchange parity check failed",
+                                  "exchange_parity": exchange_parity}))
+            dist.barrier()
+            dist.destroy_process_group()
+            sys.exit(1)
+        for _ in range(2):
+            step()
+        barrier()
+
+    # ---- N > 1 diagnostic, outside the timed region: every rank alone (exchange off, no barrier between the ranks inside
+    # the loop) -- the spread of these times is the rank skew the in-step barriers turn into waiting
+    per_rank_alone = None
+    if world > 1:
+        exchange.disable()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(args.steps):
+            step()
+        eb.record()
+        torch.cuda.synchronize(dev)
+        mine = torch.tensor([ea.elapsed_time(eb) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_alone = [float(x) for x in allr]
+        exchange.enable()
+        for _ in range(2):
+            step()
+        barrier()
+
+    # ---- timed region: device-resident inputs, per-kernel profiling OFF ---------------------------
+    L.load().gsl_profile_enable(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(graph_on):
+        G.set_cuda_graphs(graph_on)
+        for _ in range(4):  # a new call signature runs once un-graphed, is captured on its second call
+            step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    use_graph = args.graph == "on"
+    ms_other = timed(not use_graph)
+    ms = timed(use_graph)  # the headline mode runs last and stays on for the e2e leg
+    clocks = sampler.stop() if rank == 0 else {}
+    G.set_cuda_graphs(False)  # the per-kernel pass below needs individual launches
+
+    # ---- separate pass: per-kernel CUDA-event times (two event records per kernel, so NOT part of the timed region)
+    # and the per-step spread (one event per step boundary)
     L.load().gsl_profile_read(None, None, 1)
     L.load().gsl_profile_enable(1)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    prof_steps = min(args.steps, 20)
+    for _ in range(prof_steps):
         step()
-    e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else {}
     L.load().gsl_profile_enable(0)
     kms = (C.c_double * L.GSL_K_COUNT)()
     kn = (C.c_int64 * L.GSL_K_COUNT)()
     L.load().gsl_profile_read(kms, kn, 1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    spread = None
+    if args.steps >= 50:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        evs[0].record()
+        for i in range(args.steps):
+            step()
+            evs[i + 1].record()
+        barrier()
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+        q = lambda f: per[min(len(per) - 1, int(f * len(per)))]
+        spread = {"p10_ms": q(0.10), "median_ms": q(0.50), "p90_ms": q(0.90), "steps": args.steps,
+                  "note": "per-step device time between step-boundary events on rank 0, separate pass"}
 
+    G.set_cuda_graphs(use_graph)
     # ---- e2e: per-step host->device copy of the frame's inputs, device->host read of the result --
     # Per-step inputs of the op are the camera (view matrix, camera centre) and the cotangent maps the
     # loss produced from the host-side ground-truth panoramas; the surfel parameters are resident model
@@ -279,9 +418,6 @@ def run_ours(args, rank, world, local):
         main.wait_event(ev_in)
         torch.autograd.backward([color, feature, depth, alpha],
                                 [d_cot["color"], d_cot["feature"], d_cot["depth"], d_cot["alpha"]])
-        if bucket is not None:
-            bucket.load({k: leaves[k].grad for k in names})
-            bucket.all_reduce()
         h_out["gradsum"].copy_(leaves["means3D"].grad.sum(0), non_blocking=True)
         s_out.synchronize()
         main.synchronize()
@@ -359,6 +495,7 @@ def run_ours(args, rank, world, local):
         0: 45 * P + V * (16 * K) + P * (64 + 16 + 8 + 8 + 4 + 4 + 8),                 # k_preprocess_fwd
         1: 12 * P + 3 * 4 * (((W + 15) // 16) * ((H + 15) // 16)) * ((P + 255) // 256),   # k_bin_count/scan/bases (order + rect in, hist out/in/out)
         2: 12 * P + 4 * R,                                                             # k_bin_scatter
+        3: 16 * P,                                                                     # depth keys + surfel sort: means3D in, order out (side stream)
         4: 12 * R,                                                                     # k_tile_blists (id + box in, entry out)
         5: N * (8 + 16 + 4 * (S + 3) + 16 + 4 + 12) + V * (64 + 16 + 4 * S),           # k_render_fwd
         6: render_bwd_algorithmic_bytes(V, N, S),                                      # k_render_bwd
@@ -366,8 +503,14 @@ def run_ours(args, rank, world, local):
         # the surfels that contributed (measured: half of the visible ones); the zero rows are a memset on the side stream
         7: P * (96 + 4) + (V // 2) * (48 + 45 + 16 * M) + (V // 2) * (12 + 16 + 16 + 4 * S + 4 + 16 * M + 12 + 16),
     }
-    ncu_traffic = {0: 401.2e6, 1: 17.1e6, 2: 17.1e6, 4: 19.4e6, 5: 114.5e6, 6: 129.7e6, 7: 519.9e6}  # profiles/r01_v9_ncu_full.md
-    dom_id = max(kern_bytes, key=lambda i: kms[i])
+    # DRAM traffic per launch as ncu measured it (read from the newest profiles/*ncu_full*.md, not hard-coded)
+    md, traffic_src = ncu_traffic_from_profiles()
+    groups = {0: ["k_preprocess_fwd"], 1: ["k_bin_count", "k_bin_scan", "k_bin_bases"], 2: ["k_bin_scatter"],
+              3: ["k_depth_keys", "k_sort_hist", "k_sort_scan", "k_sort_scatter", "k_sort_buckets", "k_sort_rank", "k_sort_big"],
+              4: ["k_tile_blists"], 5: ["k_render_fwd"], 6: ["k_render_bwd"], 7: ["k_preprocess_bwd"]}
+    ncu_traffic = {i: sum(md[k] for k in ks if k in md) for i, ks in groups.items() if any(k in md for k in ks)}
+    # the dominant kernel = the largest share of the step among ALL of this repo's kernel groups
+    dom_id = max((i for i in kern_bytes if kn[i] > 0), key=lambda i: kms[i])
     dom_ms = kms[dom_id] / max(kn[dom_id], 1)
     dom_name = L.load().gsl_kernel_name(dom_id).decode()
     dom_bytes = kern_bytes[dom_id]
@@ -386,15 +529,21 @@ def run_ours(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W, "visible_surfels": V, "tile_instances": R,
-                   "azimuth_wrap_around": bool(args.wrap_azimuth),
-                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step%s" % (world, "" if world == 1 else (
-                       ", fp32 gradient exchange in the step: packed rows + SH factors pushed over NVLink peer memory by the backward kernel, "
-                       "summed by the tile owners (own kernels, no collective library)" if args.exchange == "peer" else
-                       ", fp32 gradient exchange (NCCL all-reduce of the non-SH gradients + all-gather of the SH factors) in the step")),
-                   "l2": "inputs (%.0f MB of surfel parameters per step) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6),
-                   "grad_exchange": None if exchange is None else args.exchange,
-                   "grad_exchange_bytes": 0 if exchange is None else (exchange.flat_nbytes + (0 if exchange.packed else exchange.local.numel() * 4))},
+        "config": shared_config(P, H, W, S, M, scene.sh_degree, V, R, world),
+        "run": {"azimuth_wrap_around": bool(args.wrap_azimuth),
+                "grad_exchange": None if exchange is None else (
+                    "fp32, inside the step: packed rows + SH factors pushed over NVLink peer memory by the backward kernel, summed by "
+                    "the tile owners (own kernels, no collective library)" if args.exchange == "peer" else
+                    "fp32, inside the step: NCCL all-reduce of the non-SH gradients + all-gather of the SH factors"),
+                "grad_exchange_bytes": 0 if exchange is None else (exchange.flat_nbytes + (0 if exchange.packed else exchange.local.numel() * 4)),
+                "profiling": "timed region runs with per-kernel events OFF; `kernels` come from a separate pass"},
+        "cuda_graph": {"mode": args.graph, "ms_per_step_graph_on": (ms if use_graph else ms_other) / args.steps,
+                       "ms_per_step_graph_off": (ms_other if use_graph else ms) / args.steps,
+                       "note": "value / e2e are measured in `mode`; graph replay = one launch per pass into static buffers "
+                               "(gs_lidar_b200.set_cuda_graphs)"},
+        "exchange_parity": exchange_parity,
+        "per_rank_ms_without_exchange": per_rank_alone,
+        "step_spread": spread,
         "clocks": clocks,
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -402,7 +551,7 @@ def run_ours(args, rank, world, local):
         "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD +
                          (0 if exchange is None or not exchange.packed else L.OWN_LAUNCHES_PEER(len(exchange.ranges(P))))) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                      "note": "the two compositors are FP32-issue / L2-reduction bound at this shape, not HBM-bound (ncu: profiles/); "
                              "the streaming kernels' fractions are in kernel_rooflines"},
@@ -478,13 +627,15 @@ def cpu_toy_baseline(args, budget_s=15.0):
 
 
 def run_reference(args, rank, world, local):
-    """Reference arm: the UNMODIFIED reference CUDA rasterizer (oracle/_ref) on the same GPU, same scene,
-    same cotangents; falls back to the CPU oracle port when the compiled reference is absent."""
-    if rank != 0:
-        return None
+    """Reference arm: the UNMODIFIED reference CUDA rasterizer (oracle/_ref) on the same GPU(s), same scene, same
+    cotangents.  The reference has no multi-GPU code, so at N > 1 this arm runs N independent replicas, one frame per
+    rank and step, with NO gradient exchange (the most favourable reading for the reference); value = frames of all
+    ranks / max-over-ranks time.  Falls back to the CPU oracle port (rank 0) when the compiled reference is absent."""
     import oracle
     from gs_lidar_b200 import synth
     if not os.path.exists(oracle.REF_SO):
+        if rank != 0:
+            return None
         cb = cpu_baseline(args)
         return {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 1, "steps": 1, "warmup": 0,
                 "ms_per_step": cb["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -495,36 +646,53 @@ def run_reference(args, rank, world, local):
     import common
     dev = torch.device("cuda", local)
     P, H, W, S = args.surfels, args.height, args.width, 4
-    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(0)).to(dev)
+    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0, **make_frame_pose(0))
+    if rank != 0:
+        cam = synth.make_scene(16, H=H, W=W, S=S, seed=0, **make_frame_pose(rank))
+        scene = scene._replace(viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, campos=cam.campos)
+    scene = scene.to(dev)
     cot = {k: v.to(dev) for k, v in synth.make_cotangents(H, W, S, seed=1).items()}
     ref = oracle.RefCuda()
     a = common.ref_args(scene)
     bufs = {}
+    last = {}
 
     def step():
         f = ref.forward(a, zero_fill=True, outs=bufs.get("o"))
+        last["R"] = f["R"]
         bufs["o"] = {k: v for k, v in f.items() if k != "R"}
         bufs["g"] = ref.backward(a, f, cot, zero_fill=True, grads=bufs.get("g"))
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
-    torch.cuda.synchronize()
+    barrier()
+    V, R = int((bufs["o"]["radii"][:P] > 0).sum()), int(last["R"])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = max(e0.elapsed_time(e1), 0.0)
     wall = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
-    value = args.steps / (ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else {}
+    t = torch.tensor([ms, max(ms, wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * args.steps / (ms * 1e-3)
     # M2: the pair of half panoramas the reference's own render_range_map issues (see run_ours)
     m2 = None
-    if W % 2 == 0:
+    if W % 2 == 0 and world == 1:
         flip = torch.diag(torch.tensor([-1.0, 1.0, -1.0, 1.0], device=dev))
         vm_back = (flip @ scene.viewmatrix.t()).t().contiguous()
         a_f = dict(a, W=W // 2, hfov=(-90.0, 90.0))
@@ -549,17 +717,21 @@ def run_reference(args, rank, world, local):
         m2_ms = e0.elapsed_time(e1) / max(3, args.steps // 2)
         m2 = {"value": 1e3 / m2_ms, "unit": UNIT, "ms_per_panorama": m2_ms,
               "what": "M2: two half panoramas %dx%d (hfov +-90, front + back camera), fwd+bwd each" % (H, W // 2)}
-    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "surfels": P, "height": H, "width": W,
-                       "what": "unmodified reference CUDA rasterizer (diff-gaussian-rasterization-2d) compiled for sm_100a by oracle/build_ref.sh, "
-                               "buffers pre-allocated, outputs/gradients zero-filled per step like its torch binding"},
+            "config": shared_config(P, H, W, S, scene.shs.shape[1], scene.sh_degree, V, R, world),
+            "run": {"what": "unmodified reference CUDA rasterizer (diff-gaussian-rasterization-2d) compiled for sm_100a by oracle/build_ref.sh, "
+                            "buffers pre-allocated, outputs/gradients zero-filled per step like its torch binding"
+                            + ("" if world == 1 else "; %d independent replicas (the reference is single-GPU), one frame per rank and "
+                                                     "step, no gradient exchange" % world)},
             "clocks": clocks,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                              "sample": "full workload on the GPU (the reference path is CUDA; it has no CPU implementation)"},
             "m2_half_panorama_pair": m2,
-            "e2e": {"value": args.steps / (max(ms, wall) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def main():

@@ -7,7 +7,7 @@ it is missing or stale: there is no CPU or PyTorch fallback.  (The names are res
 `python -m gs_lidar_b200.build` can rebuild the library when the one on disk is out of date.)
 """
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians",
-           "set_keep_workspace_after_backward"]
+           "set_keep_workspace_after_backward", "set_cuda_graphs", "set_wrap_azimuth"]
 
 
 def __getattr__(name):

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GSL_B200_LIB", os.path.join(HERE, "libgsl_b200.so"))  # override: dev builds only
 
-GSL_ABI_VERSION = 3
+GSL_ABI_VERSION = 4
 GSL_EINVAL, GSL_ENOSPACE, GSL_ESTATE = -1, -2, -3
 GSL_FLAG_DEBUG_SYNC = 1
 GSL_FLAG_BWD_SH_FACTORED = 2
@@ -124,12 +124,15 @@ SYMBOLS = {
     "gsl_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.POINTER(gsl_peer_handle)]),
     "gsl_peer_open": (C.c_int, [C.POINTER(gsl_peer_handle), C.POINTER(vp)]),
     "gsl_peer_close": (C.c_int, [vp]),
+    "gsl_peer_set_timeout_ms": (C.c_int, [C.c_uint32]),
     "gsl_peer_free": (C.c_int, [vp]),
     "gsl_peer_barrier": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
     "gsl_peer_signal": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
     "gsl_peer_wait": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
     "gsl_peer_sh_expand": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, vp, vp, vp]),
+    "gsl_peer_sh_expand_sparse": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, vp, vp, vp]),
     "gsl_peer_reduce": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "gsl_peer_unpack": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, C.c_int32, C.POINTER(gsl_bwd_outputs), vp]),
     "gsl_backward_surfels_exchange": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
@@ -141,11 +144,16 @@ SYMBOLS = {
     "gsl_chamfer_backward": (C.c_int, [C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gsl_export_state": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_workspace), C.c_int64,
                                    C.POINTER(gsl_state_export), vp]),
+    "gsl_graph_begin": (C.c_int, [C.POINTER(vp)]),
+    "gsl_graph_end": (C.c_int, [vp, C.POINTER(vp)]),
+    "gsl_graph_launch": (C.c_int, [vp, vp]),
+    "gsl_graph_destroy": (C.c_int, [vp]),
+    "gsl_stage_camera": (C.c_int, [vp, vp, vp, vp, vp]),
     "gsl_profile_enable": (C.c_int, [C.c_int]),
     "gsl_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "gsl_kernel_name": (C.c_char_p, [C.c_int]),
 }
-GSL_K_COUNT = 10
+GSL_K_COUNT = 13
 # kernels of THIS repo launched per forward / backward call on the fast binning path (<= 1024 tiles; no library
 # kernel is launched there): used by bench.py for "gpu_launches".
 OWN_LAUNCHES_FWD = 1 + 4 + 1 + 3 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan/bases,
@@ -154,10 +162,10 @@ OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
 
 
 
-def OWN_LAUNCHES_PEER(ranges):
-    """extra launches of a backward with the peer-memory exchange: per row range the per-surfel kernel (one is already
-    counted in OWN_LAUNCHES_BWD), a barrier, the reduce and the expand; then the last barrier and the unpack."""
-    return 4 * ranges - 1 + 2
+def OWN_LAUNCHES_PEER(ranges=1):
+    """extra launches of a backward with the fused peer-memory exchange: k_peer_begin, k_peer_signal, k_peer_reduce_rows,
+    k_peer_sh_expand_tiles, k_peer_unpack (the waiting halves of the barriers live inside the last three)."""
+    return 5
 
 
 _lib = None

@@ -137,6 +137,9 @@ static SideStream* side_stream() {
   return &aux[dev];
 }
 
+static unsigned long long g_peer_timeout_ns = 20000000000ull;
+unsigned long long peer_timeout_ns() { return g_peer_timeout_ns; }
+
 static int debug_sync(const gsl_params* p, cudaStream_t st, const char* stage) {
   if (!(p->flags & GSL_FLAG_DEBUG_SYNC)) return 0;
   return check_cuda(cudaStreamSynchronize(st), stage);
@@ -289,6 +292,15 @@ GSL_API int gsl_backward_composite(const gsl_params* p, const gsl_fwd_inputs* in
 #ifdef GSL_NO_PREZERO
   aux = nullptr;
 #endif
+  {
+    // Captured into a CUDA graph the fork costs more than it hides (measured at 1M surfels: 0.925 ms / step with the
+    // forked fill against 0.895 ms with the per-surfel kernel writing its own zeros; on plain streams 0.884 against 0.888),
+    // so a captured single-GPU backward skips it.  The fused exchange keeps it: its kernels write non-zero rows only.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive &&
+        !(p->flags & GSL_FLAG_BWD_PEER_ROWS))
+      aux = nullptr;
+  }
   if (p->flags & GSL_FLAG_BWD_PEER_ROWS) {
     // the dense outputs given here (the targets of gsl_backward_surfels_exchange) are zero-filled on the side stream;
     // without them (the piecewise calls) there is nothing to fill
@@ -348,62 +360,50 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dopacity || !gout->dL_dscales || !gout->dL_drotations ||
       (p->S > 0 && !gout->dL_dfeatures) || !gout->dL_dsh)
     return set_error(GSL_EINVAL, "backward_surfels_exchange: a dense gradient output pointer is NULL");
-  if (chunks < 1) chunks = 1;
-  if (chunks > SIDE_CHUNK_EVENTS) chunks = SIDE_CHUNK_EVENTS;
+  (void)step; (void)chunks;  // see include/gsl_b200.h: the ticket is a device-side step counter, one row range
   SideStream* aux = side_stream();
   if (!aux) return set_error(GSL_ESTATE, "no side stream");
-  // zero-fill forked by gsl_backward_composite onto the same side stream the exchange runs on: ordered before every
-  // kernel below that writes the dense outputs (expand on the side stream, unpack after the join)
-  const bool prezeroed = g_prezero_pending;
-  g_prezero_pending = false;
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
-  // the zero-fill of the dense outputs (side stream, forked by gsl_backward_composite) precedes the expand kernels on
-  // that stream; the unpack on this stream waits for its event here (long complete)
-  if (prezeroed) cudaStreamWaitEvent(st, aux->join, 0);
-  gsl_peer_ctx ctx = *gout->peer;  // tickets are set per barrier below
-  ctx.parity = step & 1u;
-  gsl_bwd_outputs go = *gout;
-  go.peer = &ctx;
-  // this rank's camera centre: pushed to every rank's table by the first barrier
-  if ((rc = check_cuda(cudaMemcpyAsync((char*)ctx.buf[ctx.rank] + GSL_PEER_CAMPOS_OFFSET, in->campos, 12,
-                                       cudaMemcpyDeviceToDevice, st), "camera centre copy"))) return rc;
-  const int P = p->P;
-  // EXPERIMENTAL, GSL_PEER_EARLY_FACTORS=1: the SH factors are extracted here (before k_preprocess_bwd re-zeroes the
-  // accumulators) and pushed from the side stream; push -> barrier (slot 3) -> expansion of all rows then run beside the
-  // row exchange instead of behind the first barrier of this stream.
-  static const bool early = [] { const char* e = getenv("GSL_PEER_EARLY_FACTORS"); return e && e[0] == '1'; }();
-  if (early) {
-    if ((rc = launch_peer_factor_extract(&ctx, *p, g, st))) return rc;
-    cudaEventRecord(aux->chunk[SIDE_CHUNK_EVENTS - 1], st);
-    cudaStreamWaitEvent(aux->stream, aux->chunk[SIDE_CHUNK_EVENTS - 1], 0);
-    if ((rc = launch_peer_factor_push(&ctx, *p, aux->stream))) return rc;
-    ctx.epoch = step;
-    if ((rc = launch_peer_barrier(&ctx, 3, 3, aux->stream))) return rc;
-    if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
-    if (chunks > SIDE_CHUNK_EVENTS - 1) chunks = SIDE_CHUNK_EVENTS - 1;
+  // The dense outputs are zero-filled on the side stream under the backward compositor (gsl_backward_composite); the
+  // expansion below runs on that stream behind the fill, the unpack on this stream waits for its event here.
+  bool prezeroed = g_prezero_pending;
+  g_prezero_pending = false;
+  if (prezeroed) {
+    cudaStreamWaitEvent(st, aux->join, 0);
+  } else {
+    if ((rc = launch_zero_outputs(*p, *in, *gout, st))) return rc;
+    prezeroed = true;
   }
-  const int rows_per = (((P + chunks - 1) / chunks) + 255) / 256 * 256;
-  int c = 0;
-  for (int rb = 0; rb < P; rb += rows_per, ++c) {
-    const int re = rb + rows_per < P ? rb + rows_per : P;
-    // main stream: VJP of the range (results pushed to the ranks), barrier, sum of the tiles this rank owns (pushed to the
-    // ranks); side stream, behind the barrier: dL_dsh of the range from the local factor tables -- it overlaps the
-    // reduce / unpack and the next range
-    if ((rc = launch_preprocess_backward(*p, *in, *fwd, go, g, false, rb, re, st, !early))) return rc;
-    ctx.epoch = c == 0 ? step : step * 64u + (uint32_t)c;
-    if ((rc = launch_peer_barrier(&ctx, c == 0 ? 0 : 1, 3, st))) return rc;
-    if (!early) {
-      cudaEventRecord(aux->chunk[c], st);
-      cudaStreamWaitEvent(aux->stream, aux->chunk[c], 0);
-      if ((rc = launch_peer_sh_expand(&ctx, P, p->S, p->D, p->M, rb, re, prezeroed, in->means3D, gout->dL_dsh, aux->stream))) return rc;
-    }
-    if ((rc = launch_peer_reduce_rows(&ctx, P, p->S, rb, re, st))) return rc;
+  const gsl_peer_ctx* ctx = gout->peer;
+  const int P = p->P;
+  // One step (gsl_peer.cuh); no kernel of it blocks the stream waiting for other ranks before it has launched:
+  //   k_peer_begin            (one warp) step counter++, camera centre -> every rank
+  //   k_preprocess_bwd        VJP; packed rows -> tile owners, SH factors -> every rank
+  //   k_peer_signal           (one warp) publishes "pushed"
+  //   k_peer_reduce_rows      every CTA waits for "pushed" of all ranks; sums of my tiles -> every rank; last CTA publishes
+  //                           "summed"                                      | side stream, behind an event:
+  //   k_peer_unpack           every CTA waits for "summed"; dense tensors   | k_peer_sh_expand_tiles: waits for "pushed",
+  //                                                                         | dL_dsh from the local factor tables
+  if ((rc = launch_peer_begin(ctx, in->campos, st))) return rc;
+  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, false, 0, P, st, true))) return rc;
+  if ((rc = launch_peer_signal_fused(ctx, PEER_SLOT_PUSHED, st))) return rc;
+  cudaEventRecord(aux->chunk[0], st);
+  cudaStreamWaitEvent(aux->stream, aux->chunk[0], 0);
+  {
+    ProfScope prof(GSL_K_PEER_EXPAND, aux->stream);
+    if ((rc = launch_peer_sh_expand(ctx, P, p->S, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, aux->stream, true)))
+      return rc;
   }
   cudaEventRecord(aux->join, aux->stream);
-  ctx.epoch = step;
-  if ((rc = launch_peer_barrier(&ctx, 2, 3, st))) return rc;  // every tile's sum arrived; staging may be rewritten
-  if ((rc = launch_peer_unpack(&ctx, P, p->S, prezeroed, *gout, st))) return rc;
+  {
+    ProfScope prof(GSL_K_PEER_REDUCE, st);
+    if ((rc = launch_peer_reduce_rows(ctx, P, p->S, 0, P, st, true))) return rc;
+  }
+  {
+    ProfScope prof(GSL_K_PEER_UNPACK, st);
+    if ((rc = launch_peer_unpack(ctx, P, p->S, prezeroed, *gout, st, true))) return rc;
+  }
   cudaStreamWaitEvent(st, aux->join, 0);  // dL_dsh complete
   return debug_sync(p, st, "backward_surfels_exchange");
 }
@@ -469,6 +469,11 @@ GSL_API int gsl_peer_open(const gsl_peer_handle* handle, void** dptr) {
   return check_cuda(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
 }
 
+GSL_API int gsl_peer_set_timeout_ms(uint32_t ms) {
+  g_peer_timeout_ns = (unsigned long long)(ms ? ms : 1u) * 1000000ull;
+  return 0;
+}
+
 GSL_API int gsl_peer_close(void* dptr) { return dptr ? check_cuda(cudaIpcCloseMemHandle(dptr), "cudaIpcCloseMemHandle") : 0; }
 GSL_API int gsl_peer_free(void* dptr) { return dptr ? check_cuda(cudaFree(dptr), "peer_free") : 0; }
 
@@ -489,15 +494,26 @@ static int validate_rows(const char* what, int32_t P, int32_t S, int32_t row_beg
   return 0;
 }
 
+static int peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
+                          int32_t row_end, const float* means3D, float* dL_dsh, void* stream, bool sparse);
 GSL_API int gsl_peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
                                int32_t row_end, const float* means3D, float* dL_dsh, void* stream) {
+  return peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, means3D, dL_dsh, stream, false);
+}
+GSL_API int gsl_peer_sh_expand_sparse(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
+                                      int32_t row_end, const float* means3D, float* dL_dsh, void* stream) {
+  if (M > 16) return set_error(GSL_EINVAL, "peer_sh_expand_sparse: at most 16 SH coefficients");
+  return peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, means3D, dL_dsh, stream, true);
+}
+static int peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
+                          int32_t row_end, const float* means3D, float* dL_dsh, void* stream, bool sparse) {
   int rc = validate_peer(ctx);
   if (rc) return rc;
   if ((rc = validate_rows("peer_sh_expand", P, S, row_begin, row_end))) return rc;
   if (D < 0 || D > 3 || M < 0) return set_error(GSL_EINVAL, "peer_sh_expand: bad sizes");
   if (M > 0 && (D + 1) * (D + 1) > M) return set_error(GSL_EINVAL, "peer_sh_expand: degree %d needs %d coefficients", D, (D + 1) * (D + 1));
   if (P > 0 && M > 0 && (!means3D || !dL_dsh)) return set_error(GSL_EINVAL, "peer_sh_expand: NULL pointer");
-  return launch_peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, false, means3D, dL_dsh, (cudaStream_t)stream);
+  return launch_peer_sh_expand(ctx, P, S, D, M, row_begin, row_end, sparse, means3D, dL_dsh, (cudaStream_t)stream);
 }
 
 GSL_API int gsl_peer_reduce(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t row_begin, int32_t row_end, void* stream) {
@@ -579,6 +595,104 @@ GSL_API int gsl_glue_backward(const gsl_glue_params* p, const gsl_glue_inputs* i
   return launch_glue_backward(*p, *in, *gout, *gin, (cudaStream_t)stream);
 }
 
+// ---- CUDA-graph capture of a step -----------------------------------------------------------
+// The forward's instance count is polled AFTER all launches and every kernel argument of a step is constant once the
+// workspace, the outputs and the inputs keep their addresses, so a forward (gsl_forward_preprocess + gsl_forward_render)
+// and a backward (gsl_backward, or gsl_backward_composite + gsl_backward_surfels_exchange) can each be captured once and
+// replayed: one launch per pass instead of ~14 / ~4-9, no per-launch host cost, no launch jitter between the ranks.
+__global__ void k_stage_camera(const float* __restrict__ vm, const float* __restrict__ campos, const float* __restrict__ bg,
+                               float* __restrict__ dst) {
+  const int t = threadIdx.x;
+  if (t < 16) dst[t] = vm[t];
+  else if (t < 19) dst[t] = campos[t - 16];
+  else if (t >= 20 && t < 24) dst[t] = bg[t - 20];
+}
+
+GSL_API int gsl_stage_camera(const float* viewmatrix, const float* campos, const float* background, float* dst, void* stream) {
+  if (!viewmatrix || !campos || !background || !dst) return set_error(GSL_EINVAL, "stage_camera: NULL pointer");
+  k_stage_camera<<<1, 32, 0, (cudaStream_t)stream>>>(viewmatrix, campos, background, dst);
+  return check_cuda(cudaGetLastError(), "k_stage_camera launch");
+}
+
+// The legacy default stream (what torch uses unless told otherwise) cannot be captured, so the capture runs on a stream the
+// library owns (one per host thread and device); the instantiated graph can be launched on any stream, the default included.
+static cudaStream_t capture_stream() {
+  static thread_local cudaStream_t cap[64];
+  static thread_local bool have[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!have[dev]) {
+    if (cudaStreamCreateWithFlags(&cap[dev], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    have[dev] = true;
+  }
+  return cap[dev];
+}
+
+GSL_API int gsl_graph_begin(void** capture_stream_out) {
+  if (!capture_stream_out) return set_error(GSL_EINVAL, "graph_begin: NULL argument");
+  if (g_prof_on) return set_error(GSL_ESTATE, "graph capture: switch per-kernel profiling off first (gsl_profile_enable(0))");
+  if (!side_stream()) return set_error(GSL_ESTATE, "graph capture: could not create the side stream");
+  cudaStream_t cap = capture_stream();
+  if (!cap) return set_error(GSL_ESTATE, "graph capture: could not create the capture stream");
+  int rc = check_cuda(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+  if (rc) return rc;
+  *capture_stream_out = (void*)cap;
+  return 0;
+}
+
+GSL_API int gsl_graph_end(void* stream, void** graph_exec) {
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+  if (e != cudaSuccess || !graph) {
+    cudaGetLastError();
+    return check_cuda(e != cudaSuccess ? e : cudaErrorUnknown, "cudaStreamEndCapture");
+  }
+  if (!graph_exec) {  // abort: the caller only wanted the stream out of capture mode
+    cudaGraphDestroy(graph);
+    return 0;
+  }
+#ifndef GSL_GRAPH_NO_PRIO
+  {  // the side stream's priority is not captured with its kernels: re-apply it to the surfel sort's nodes
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0) {
+      std::vector<cudaGraphNode_t> nodes(n);
+      if (cudaGraphGetNodes(graph, nodes.data(), &n) == cudaSuccess) {
+        for (size_t i = 0; i < n; ++i) {
+          cudaGraphNodeType type;
+          if (cudaGraphNodeGetType(nodes[i], &type) != cudaSuccess || type != cudaGraphNodeTypeKernel) continue;
+          cudaKernelNodeParams kp;
+          if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) continue;
+          if (is_sort_kernel(kp.func) || is_depth_keys_kernel(kp.func)) {
+            cudaLaunchAttributeValue v;
+            memset(&v, 0, sizeof(v));
+            v.priority = prio_hi;
+            cudaGraphKernelNodeSetAttribute(nodes[i], cudaLaunchAttributePriority, &v);
+          }
+        }
+      }
+    }
+    cudaGetLastError();
+  }
+#endif
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return check_cuda(e, "cudaGraphInstantiate");
+  *graph_exec = (void*)exec;
+  return 0;
+}
+
+GSL_API int gsl_graph_launch(void* graph_exec, void* stream) {
+  if (!graph_exec) return set_error(GSL_EINVAL, "graph_launch: NULL graph");
+  return check_cuda(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream), "cudaGraphLaunch");
+}
+
+GSL_API int gsl_graph_destroy(void* graph_exec) {
+  return graph_exec ? check_cuda(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec), "cudaGraphExecDestroy") : 0;
+}
+
 GSL_API int gsl_profile_enable(int on) { g_prof_on = on != 0; return 0; }
 
 GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
@@ -601,7 +715,8 @@ GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
 GSL_API const char* gsl_kernel_name(int id) {
   static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan|bases)", "k_bin_scatter",
                                            "k_sort_(hist|scan|scatter|buckets)", "k_tile_blists", "k_render_fwd",
-                                           "k_render_bwd", "k_preprocess_bwd", "k_glue_fwd", "k_glue_bwd"};
+                                           "k_render_bwd", "k_preprocess_bwd", "k_glue_fwd", "k_glue_bwd",
+                                           "k_peer_reduce_rows", "k_peer_sh_expand", "k_peer_unpack"};
   return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
 }
 

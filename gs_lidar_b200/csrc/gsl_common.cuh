@@ -207,6 +207,8 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
 int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st);
 int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st);
 int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st);
+bool is_sort_kernel(const void* func);        // kernels that run with the side stream's (high) priority
+bool is_depth_keys_kernel(const void* func);
 int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,
                    int64_t r_capacity, int32_t* r_host, cudaStream_t st);
 int launch_export_keys(const gsl_params& p, const GeomView& g, const ImageView& im, const uint32_t* point_list,
@@ -222,7 +224,7 @@ int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out,
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st);
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
-                               bool prezeroed, int row0, int row1, cudaStream_t st, bool push_factors = true);
+                               bool prezeroed, int row0, int row1, cudaStream_t st, bool fused = false);
 int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
                      size_t drgb_stride, float* dL_dsh, cudaStream_t st);
 int launch_glue_forward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& out, cudaStream_t st);
@@ -233,18 +235,34 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
 
 // ---- peer-memory gradient exchange (gsl_peer.cu) -------------------------------------------------------------
 constexpr int PEER_MAX = GSL_PEER_MAX;
-constexpr size_t PEER_HEADER = 4096;      // flags: u32[4 phases][PEER_MAX]; camera centre at PEER_CAMPOS_OFF
+// Header of an exchange buffer (first PEER_HEADER bytes):
+//   [0, 256)      flags u32[8 slots][PEER_MAX]: slot s, word g = the last ticket rank g published on slot s.
+//                 slots 0..3: host-ticketed barriers (gsl_peer_barrier / _signal / _wait); slot 4: "rows + factors of
+//                 this step pushed", slot 5: "sums of my tiles pushed" -- the two in-kernel barriers of the fused step
+//   [512, 516)    step counter of the fused step (device side: incremented by k_peer_begin, identical on all ranks)
+//   [516, 520)    error word: != 0 after a barrier time-out; the kernels that write gradients then write NaN
+//   [520, 552)    finished-CTA counters (one per signalling kernel) for "last CTA publishes the flag"
+//   [1024, 1036)  this rank's camera centre;  [1280, 1536) float4[2 parities][PEER_MAX] camera centres of all ranks
+constexpr size_t PEER_HEADER = 4096;
+constexpr int PEER_SLOT_PUSHED = 4, PEER_SLOT_SUMMED = 5, PEER_SLOTS = 8;
+constexpr size_t PEER_STEP_OFF = 512, PEER_ERROR_OFF = 516, PEER_DONE_OFF = 520;
 constexpr size_t PEER_CAMPOS_OFF = GSL_PEER_CAMPOS_OFFSET;
-constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[2 parities][PEER_MAX]: camera centres of all ranks, pushed by barrier 0
+constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[2 parities][PEER_MAX]: camera centres of all ranks
+static_assert(PEER_SLOTS * PEER_MAX * 4 <= PEER_STEP_OFF && PEER_DONE_OFF + 32 <= PEER_CAMPOS_OFF, "header layout");
 static_assert(PEER_CAMPOS_ALL_OFF + 2 * PEER_MAX * 16 <= PEER_HEADER, "header too small");
 struct PeerView {  // gsl_peer_ctx by value, as the kernels take it
   int rank, world;
   uint32_t epoch;
   int parity;  // which factor table (step & 1)
+  int dev_step;  // 1: epoch / parity come from the device-side step counter (fused step; constant kernel arguments,
+                 // so the step can be replayed from a CUDA graph)
   char* own;  // buf[rank]
   char* buf[PEER_MAX];
+  int* error_host;  // pinned host flag (may be null)
+  unsigned long long timeout_ns;  // a rank that never arrives at a barrier: report (error word + host flag), do not hang
 };
-inline PeerView make_view(const gsl_peer_ctx* c) {
+unsigned long long peer_timeout_ns();  // gsl_peer_set_timeout_ms (gsl_api.cu), 20 s by default
+inline PeerView make_view(const gsl_peer_ctx* c, bool dev_step = false) {
   PeerView v;
   v.rank = c->rank;
   v.world = c->world;
@@ -252,6 +270,9 @@ inline PeerView make_view(const gsl_peer_ctx* c) {
   for (int g = 0; g < PEER_MAX; ++g) v.buf[g] = g < c->world ? (char*)c->buf[g] : nullptr;
   v.own = (char*)c->buf[c->rank];
   v.parity = (int)(c->parity & 1u);
+  v.dev_step = dev_step ? 1 : 0;
+  v.error_host = (int*)c->error_flag;
+  v.timeout_ns = peer_timeout_ns();
   return v;
 }
 // Byte offsets inside an exchange buffer for P surfels (tiles of 256), S feature channels and `world` ranks.
@@ -268,15 +289,17 @@ struct PeerLayout {
 int peer_row_width(int S);
 PeerLayout peer_layout(size_t P, int S, int world);
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
+int launch_peer_begin(const gsl_peer_ctx* c, const float* campos, cudaStream_t st);
+int launch_peer_signal_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st);
+// fused: true = one step of gsl_backward_surfels_exchange (device-side step counter, in-kernel flag waits / signals)
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
-                          const float* means3D, float* dL_dsh, cudaStream_t st);
+                          const float* means3D, float* dL_dsh, cudaStream_t st, bool fused = false);
 int launch_chamfer_forward(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
                            int* idx2, void* scratch, cudaStream_t st);
 int launch_chamfer_backward(int b, int n, const float* xyz1, int m, const float* xyz2, const float* gdist1, const int* idx1,
                             const float* gdist2, const int* idx2, float* gxyz1, float* gxyz2, cudaStream_t st);
-int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st);
-int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st);
-int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st);
-int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st);
+int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st, bool fused = false);
+int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st,
+                       bool fused = false);
 
 }  // namespace gsl

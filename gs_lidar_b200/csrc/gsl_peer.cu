@@ -10,9 +10,13 @@
 //     gradient rows of the surfels a pixel touched (~half of them) + their row bits into the staging area of the rank
 //     that owns the tile (tile % world), and the non-zero 16-byte SH factors (packed to the front of the tile's
 //     segment, + bits / prefix words) into every rank's factor table;
-//   * k_peer_barrier   -- one warp: release-store of a ticket into the flag slot this rank owns in every peer's buffer,
-//                         then acquire-spin on the own slots (with a time-out that reports instead of hanging).  A few
-//                         microseconds instead of a collective's launch + protocol latency;
+//   * barriers         -- a ticket release-stored into the flag slot this rank owns in every peer's buffer and an
+//                         acquire-spin on the own slots (with a time-out that reports instead of hanging).  In the fused
+//                         step (gsl_backward_surfels_exchange) the two halves live INSIDE the kernels: the last CTA of the
+//                         producing kernel publishes the flag, every CTA of the consuming kernel waits for it
+//                         (gsl_peer.cuh) -- no barrier kernel, no launch gap on the critical path, and the ticket is a
+//                         device-side step counter, so every kernel argument is constant (CUDA-graph replayable).
+//                         k_peer_barrier (one warp) remains for callers that schedule the pieces themselves;
 //   * k_peer_reduce_rows -- the owner sums the staged rows of its tiles (local reads, fixed rank order) and pushes the
 //                         sums + OR-ed bits into every rank's result area: every rank ends up with bit-identical sums;
 //   * k_peer_sh_expand (gsl_preprocess.cu) -- gsl_sh_expand over the local factor tables;
@@ -20,6 +24,7 @@
 // All of it works on row ranges, so the exchange of one range runs (on a side stream) while k_preprocess_bwd computes
 // the next.  Layout of an exchange buffer: PeerLayout (gsl_common.cuh).
 #include "gsl_common.cuh"
+#include "gsl_peer.cuh"
 #include <algorithm>
 
 namespace gsl {
@@ -44,20 +49,6 @@ PeerLayout peer_layout(size_t P, int S, int world) {
 }
 
 // ---- barrier ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
 // Lane g tells rank g "rank `rank` reached `phase` of step `epoch`" and waits for the same news from rank g.  Everything
 // this rank's stream did before (kernel boundary) is visible to a peer that has seen the flag; a peer that never
 // arrives makes the wait give up after timeout_ns and raise *error (the results of the step are then undefined).
@@ -79,15 +70,56 @@ __global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long l
   while ((int32_t)(ld_acquire_sys(mine) - pv.epoch) < 0) {
     if (global_timer_ns() - t0 > timeout_ns) {
       if (error) *error = 1 + phase;
+      *reinterpret_cast<volatile uint32_t*>(pv.own + PEER_ERROR_OFF) = 1u + (uint32_t)phase;  // gradients become NaN
       break;
     }
     __nanosleep(64);
   }
 }
 
+// First kernel of a fused step (one warp): advances the device-side step counter (same value on every rank: every rank
+// runs the same number of steps), publishes this rank's camera centre in its own header and pushes it into every rank's
+// table of the step's parity.  The pushes are ordered before the "pushed" flag of this step, which the last CTA of the
+// per-surfel kernel (a later kernel of this stream) releases.
+__global__ void k_peer_begin(PeerView pv, const float* __restrict__ campos) {
+  const int g = threadIdx.x;
+  uint32_t* step = reinterpret_cast<uint32_t*>(pv.own + PEER_STEP_OFF);
+  const uint32_t s = *step + 1u;
+  __syncwarp();
+  if (g == 0) *step = s;
+  if (g < 3) reinterpret_cast<float*>(pv.own + PEER_CAMPOS_OFF)[g] = campos[g];
+  if (g < pv.world) {
+    float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * ((int)(s & 1u) * PEER_MAX + pv.rank);
+    dst[0] = campos[0]; dst[1] = campos[1]; dst[2] = campos[2];
+    __threadfence_system();
+  }
+}
+
+// Publishing half of an in-kernel barrier as its own one-warp kernel: everything this stream's earlier kernels stored (to any
+// rank) is complete at the kernel boundary; lane g then release-stores the step's ticket into slot `slot` of rank g.  Used
+// behind k_preprocess_bwd, whose ~4000 short-lived CTAs must not each stall on a system-scope fence (measured: +0.1 ms);
+// k_peer_reduce_rows, one wave of persistent CTAs, publishes its flag itself (peer_signal_when_last).
+__global__ void k_peer_signal(PeerView pv, int slot) {
+  peer_resolve_step(pv);
+  const int g = threadIdx.x;
+  if (g >= pv.world) return;
+  __threadfence_system();
+  st_release_sys(reinterpret_cast<uint32_t*>(pv.buf[g]) + slot * PEER_MAX + pv.rank, pv.epoch);
+}
+
+int launch_peer_signal_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st) {
+  k_peer_signal<<<1, 32, 0, st>>>(make_view(c, true), slot);
+  return check_cuda(cudaGetLastError(), "k_peer_signal launch");
+}
+
+int launch_peer_begin(const gsl_peer_ctx* c, const float* campos, cudaStream_t st) {
+  k_peer_begin<<<1, 32, 0, st>>>(make_view(c, true), campos);
+  return check_cuda(cudaGetLastError(), "k_peer_begin launch");
+}
+
 // mode: 1 = signal, 2 = wait, 3 = both (the barrier)
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st) {
-  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, 20000000000ull, c->error_flag);
+  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, peer_timeout_ns(), c->error_flag);
   return check_cuda(cudaGetLastError(), "k_peer_barrier launch");
 }
 
@@ -96,10 +128,14 @@ int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t
 // staging area.  The owner reads the staged rows whose bit is set (local memory), sums them in rank order and pushes the
 // sum row and the OR of the bits into every rank's result area -- remote STORES only, every rank gets the same bits.
 // Rows nobody touched are neither read nor written (k_peer_unpack looks at the OR-ed bits).
-__global__ void __launch_bounds__(256) k_peer_reduce_rows(const PeerView pv, const PeerLayout pl, int rw4, int tile0,
-                                                          int tile1) {
+__global__ void __launch_bounds__(256) k_peer_reduce_rows(PeerView pv, const PeerLayout pl, int rw4, int tile0,
+                                                          int tile1, int fused) {
   __shared__ uint32_t s_bits[PEER_MAX][8];
   __shared__ uint32_t s_union[8];
+  if (fused) {  // in-kernel barrier: every rank's rows of this step have arrived in my staging area
+    peer_resolve_step(pv);
+    peer_wait_flags(pv, PEER_SLOT_PUSHED);
+  }
   const uint32_t* stagebits = reinterpret_cast<const uint32_t*>(pv.own + pl.off_stagebits);
   const float4* stage = reinterpret_cast<const float4*>(pv.own + pl.off_stage);
   // my tiles in [tile0, tile1): the first one is tile0 rounded up to rank (mod world)
@@ -142,31 +178,41 @@ __global__ void __launch_bounds__(256) k_peer_reduce_rows(const PeerView pv, con
         if (g < pv.world) reinterpret_cast<float4*>(pv.buf[g] + pl.off_rows)[at] = acc;
     }
   }
+  if (fused) peer_signal_when_last(pv, PEER_SLOT_SUMMED, 1);  // the sums of my tiles are on their way to every rank
 }
 
-int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st) {
+int launch_peer_reduce_rows(const gsl_peer_ctx* c, int P, int S, int row_begin, int row_end, cudaStream_t st, bool fused) {
   if (row_end <= row_begin) return 0;
   const int tile0 = row_begin / 256, tile1 = (row_end + 255) / 256;
   const int per_rank = (tile1 - tile0 + c->world - 1) / c->world;
   const int blocks = std::max(1, std::min(per_rank, 148 * 8));
-  k_peer_reduce_rows<<<blocks, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), peer_row_width(S) / 4, tile0,
-                                             tile1);
+  k_peer_reduce_rows<<<blocks, 256, 0, st>>>(make_view(c, fused), peer_layout((size_t)P, S, c->world), peer_row_width(S) / 4,
+                                             tile0, tile1, fused ? 1 : 0);
   return check_cuda(cudaGetLastError(), "k_peer_reduce_rows launch");
 }
 
 // ---- summed packed rows -> the dense gradient tensors autograd returns (local) ------------------------------------------
-__global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, int prezeroed, const float* __restrict__ rows,
-                                                     const uint32_t* __restrict__ bits, float* __restrict__ d_means3D,
+__global__ void __launch_bounds__(256) k_peer_unpack(PeerView pv, int fused, int P, int S, int rw, int prezeroed,
+                                                     const float* rows, const uint32_t* bits, float* __restrict__ d_means3D,
                                                      float* __restrict__ d_means2D, float* __restrict__ d_scales,
                                                      float* __restrict__ d_rot, float* __restrict__ d_opacity,
                                                      float* __restrict__ d_features) {
+  if (fused) {  // in-kernel barrier: every owner's sums of this step have arrived in my result area
+    peer_resolve_step(pv);
+    peer_wait_flags(pv, PEER_SLOT_SUMMED);
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 r0 = zero4, r1 = zero4, r2 = zero4, f[3] = {zero4, zero4, zero4};
-  const bool set = (bits[i >> 5] >> (i & 31)) & 1u;
+  bool set = (bits[i >> 5] >> (i & 31)) & 1u;
+  const bool failed = peer_error(pv);  // a rank missed a barrier: the sums are undefined -> NaN, never silently wrong
+  if (failed) set = true;
   if (!set && prezeroed) return;  // the dense outputs were zero-filled under the backward compositor
-  if (set) {
+  if (failed) {
+    const float qnan = __int_as_float(0x7fc00000);
+    r0 = r1 = r2 = f[0] = f[1] = f[2] = make_float4(qnan, qnan, qnan, qnan);
+  } else if (set) {
     const float4* r = reinterpret_cast<const float4*>(rows + (size_t)i * rw);
     r0 = r[0]; r1 = r[1]; r2 = r[2];
     for (int k = 0; k < rw / 4 - 3; ++k) f[k] = r[3 + k];
@@ -182,11 +228,12 @@ __global__ void __launch_bounds__(256) k_peer_unpack(int P, int S, int rw, int p
   }
 }
 
-int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st) {
+int launch_peer_unpack(const gsl_peer_ctx* c, int P, int S, bool prezeroed, const gsl_bwd_outputs& out, cudaStream_t st,
+                       bool fused) {
   if (P == 0) return 0;
   const char* own = (const char*)c->buf[c->rank];
   const PeerLayout pl = peer_layout((size_t)P, S, c->world);
-  k_peer_unpack<<<(P + 255) / 256, 256, 0, st>>>(P, S, peer_row_width(S), prezeroed ? 1 : 0,
+  k_peer_unpack<<<(P + 255) / 256, 256, 0, st>>>(make_view(c, fused), fused ? 1 : 0, P, S, peer_row_width(S), prezeroed ? 1 : 0,
                                                  reinterpret_cast<const float*>(own + pl.off_rows),
                                                  reinterpret_cast<const uint32_t*>(own + pl.off_rowbits), out.dL_dmeans3D,
                                                  out.dL_dmeans2D, out.dL_dscales, out.dL_drotations, out.dL_dopacity,

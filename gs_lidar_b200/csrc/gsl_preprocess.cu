@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include "gsl_math.cuh"
+#include "gsl_peer.cuh"
 
 namespace gsl {
 
@@ -438,6 +439,8 @@ __device__ __forceinline__ void depth_key_of(int idx, const float* __restrict__ 
   skey[idx] = key;
 }
 
+bool is_depth_keys_kernel(const void* func) { return func == (const void*)k_depth_keys; }
+
 int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st) {
   if (p.P == 0) return 0;
   cudaMemsetAsync(g.ctrl + 8, 0, 2 * sizeof(uint32_t), st);
@@ -476,7 +479,7 @@ struct PreBwdParams {
                  // only non-zero values are written here
   int row0, row1; // surfel range of this launch (chunked launches pipeline the peer exchange behind the kernel)
   int rw;         // > 0: GSL_FLAG_BWD_PEER_ROWS -- floats per packed exchange row (peer_row_width(S))
-  int push_factors;  // peer mode: this kernel also pushes the SH factors (0: k_peer_factor_extract/_push did it earlier)
+  int fused;      // peer mode: part of a fused step -- step / parity come from the device-side counter (gsl_peer.cuh)
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dcolors,
     float* __restrict__ dL_dfeatures,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
-    float* __restrict__ dL_dcov3D, const PeerView pv, const PeerLayout pl) {
+    float* __restrict__ dL_dcov3D, PeerView pv, const PeerLayout pl) {
   __shared__ float4 s_g[5][256];  // queued accumulator records (dT, mean2D, opacity, colour, normal)
   __shared__ uint16_t s_who[256];
   __shared__ int s_count;
@@ -695,6 +698,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     __shared__ int s_warp[8];
     __shared__ uint32_t s_any[8];
     __shared__ float4 s_rows[256][4];  // the tile's 64-byte rows, flushed with 64 contiguous bytes per 4 lanes at the end
+    if (pp.fused) peer_resolve_step(pv);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = cta0 >> 8;
     const int owner = tile % pv.world;
@@ -747,7 +751,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     if (lane == 0 && live) reinterpret_cast<uint32_t*>(obuf + pl.off_stagebits)[(slot0 >> 5) + warp] = bits;
     if (lane == 0) s_any[warp] = bits;
     // SH factors: block-local compaction, pushed to every rank
-    const bool nz = pp.push_factors && (fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f);
+    const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
     const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
     if (lane == 0) s_warp[warp] = __popc(fbits);
     __syncthreads();
@@ -760,7 +764,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     for (int g = 0; g < PEER_MAX; ++g) {
       if (g < pv.world) {
         if (nz) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[fpos] = fac;
-        if (lane == 0 && live && pp.push_factors)
+        if (lane == 0 && live)
           reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[mpos] = make_uint2(fbits, (uint32_t)before);
       }
     }
@@ -779,7 +783,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
         if ((s_any[r >> 5] >> (r & 31)) & 1u) dst[(size_t)r * 4 + q] = s_rows[r][q];
       }
     }
-    return;
+    return;  // fused step: the "pushed" flag is published by k_peer_signal, the next kernel of the stream
   }
   if (idx < pp.row1) {
     float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
@@ -910,7 +914,7 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
     size_t bytes = r[i].bytes;
     int j = i + 1;
     while (j < n && r[j].ptr == start + bytes) { bytes += r[j].bytes; ++j; }
-    cudaMemsetAsync(start, 0, bytes, st);
+    cudaMemsetAsync(start, 0, bytes, st);  // (an own 16-byte-store kernel measured 0.02 ms / step slower)
     i = j;
   }
   return check_cuda(cudaGetLastError(), "zero-fill of the gradient outputs");
@@ -918,7 +922,7 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
 
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
                                gsl_bwd_outputs& gout, const GeomView& g, bool prezeroed, int row0, int row1,
-                               cudaStream_t st, bool push_factors) {
+                               cudaStream_t st, bool fused) {
   if (p.P == 0 || row1 <= row0) return 0;
   PreBwdParams pp;
   pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.S = p.S;
@@ -939,10 +943,10 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   pp.rw = (p.flags & GSL_FLAG_BWD_PEER_ROWS) ? peer_row_width(p.S) : 0;
   PeerView pv = {};
   PeerLayout pl = {};
-  pp.push_factors = push_factors ? 1 : 0;
+  pp.fused = (fused && pp.rw > 0) ? 1 : 0;
   if (pp.rw > 0) {
     pp.factored = 1;
-    pv = make_view(gout.peer);
+    pv = make_view(gout.peer, fused);
     pl = peer_layout((size_t)p.P, p.S, gout.peer->world);
   }
   Fov f = make_fov(p);
@@ -967,7 +971,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
 // ------------------------------------------------------------------------------------------------
 // acc[k] += basis_k(normalize(x, y, z)) * d for the coefficients of degree <= D (the dL_dsh rows of backward.cu:17-134)
 __device__ __forceinline__ void sh_basis_accumulate(float4 (&acc)[16], int D, float x, float y, float z, const float4 d) {
-  const float inv = 1.f / sqrtf(x * x + y * y + z * z);
+  const float inv = rsqrtf(x * x + y * y + z * z);  // 2 ulp: the sum is compared with the dense gradients to 1e-4
   x *= inv; y *= inv; z *= inv;
   acc[0] += kSH_C0 * d;
   if (D > 0) {
@@ -1093,87 +1097,24 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
 }
 
 
-// EXPERIMENTAL (GSL_PEER_EARLY_FACTORS=1, see gsl_backward_surfels_exchange): the SH factors leave BEFORE the per-surfel
-// backward kernel.  k_peer_factor_extract packs this rank's non-zero factors of every tile into its OWN table (local
-// stores, right after the backward compositor and before k_preprocess_bwd re-zeroes the accumulators);
-// k_peer_factor_push then copies the used front of every tile segment + its 8 meta words to the other ranks from a
-// side stream, so that push -> barrier -> expansion runs beside k_preprocess_bwd -> barrier -> reduce -> unpack.
-__global__ void __launch_bounds__(256) k_peer_factor_extract(const PeerView pv, const PeerLayout pl, int P, int gstride,
-                                                             const float* __restrict__ grad,
-                                                             const uint8_t* __restrict__ clamped) {
-  __shared__ int s_warp[8];
-  const int tile = blockIdx.x;
-  const int i = tile * 256 + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 fac = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < P) {
-    const float4 gc = reinterpret_cast<const float4*>(grad + (size_t)i * gstride)[3];
-    if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
-      const uint8_t cl = clamped[i];
-      fac = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
-    }
-  }
-  const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
-  const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
-  if (lane == 0) s_warp[warp] = __popc(fbits);
-  __syncthreads();
-  int before = 0;
-  for (int w = 0; w < warp; ++w) before += s_warp[w];
-  const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;
-  if (nz) reinterpret_cast<float4*>(pv.own + pl.off_factor)[table * 256 + before + __popc(fbits & ((1u << lane) - 1u))] = fac;
-  if (lane == 0 && tile * 256 + warp * 32 < P)
-    reinterpret_cast<uint2*>(pv.own + pl.off_fmeta)[table * 8 + warp] = make_uint2(fbits, (uint32_t)before);
-}
-
-__global__ void __launch_bounds__(256) k_peer_factor_push(const PeerView pv, const PeerLayout pl, int P) {
-  for (int tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x) {
-    const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;
-    const uint2* meta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta) + table * 8;
-    const int words = min(8, (P - tile * 256 + 31) / 32);
-    const uint2 last = meta[words - 1];
-    const int count = (int)last.y + __popc(last.x);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint2 m = make_uint2(0u, 0u);
-    if ((int)threadIdx.x < count) v = reinterpret_cast<const float4*>(pv.own + pl.off_factor)[table * 256 + threadIdx.x];
-    if ((int)threadIdx.x < words) m = meta[threadIdx.x];
-#pragma unroll
-    for (int g = 0; g < PEER_MAX; ++g) {
-      if (g < pv.world && g != pv.rank) {
-        if ((int)threadIdx.x < count) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[table * 256 + threadIdx.x] = v;
-        if ((int)threadIdx.x < words) reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[table * 8 + threadIdx.x] = m;
-      }
-    }
-  }
-}
-
-int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st) {
-  if (p.P == 0) return 0;
-  const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
-  k_peer_factor_extract<<<pl.tiles, 256, 0, st>>>(make_view(c), pl, p.P, grad_stride(p.S), g.grad, g.clamped);
-  return check_cuda(cudaGetLastError(), "k_peer_factor_extract launch");
-}
-
-int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st) {
-  if (p.P == 0 || c->world < 2) return 0;
-  const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
-  k_peer_factor_push<<<std::min(pl.tiles, 148 * 8), 256, 0, st>>>(make_view(c), pl, p.P);
-  return check_cuda(cudaGetLastError(), "k_peer_factor_push launch");
-}
-
-// EXPERIMENTAL (off unless GSL_EXPAND_COMPACT=1 in the environment; not yet measured on 8 GPUs): the same expansion with
-// the tile's touched surfels compacted first.  About half of the surfels have no factor on any rank, so in the kernel
-// above half of the lanes idle through up to 8 x ~150 instructions; here a CTA (= one 256-surfel tile) builds the list of
-// rows with a factor on some rank (OR of the ranks' bit words, prefix over 8 words) and only ceil(n / 32) dense warps do
-// the work.  Needs a zero-filled dL_dsh (only listed rows are written).
-__global__ void __launch_bounds__(256) k_peer_sh_expand_compact(const PeerView pv, const PeerLayout pl, int row0, int row1,
-                                                                int D, int M, const float* __restrict__ means3D,
-                                                                float* __restrict__ dL_dsh) {
+// The same expansion for a fused step (dL_dsh was zero-filled under the backward compositor, so only rows with a factor are
+// written).  About half of the surfels have no factor on any rank and most of the others on only some ranks, so the kernel
+// above idles half of its lanes through up to 8 x ~150 instructions.  Here a CTA (= one 256-surfel tile) first waits for the
+// "pushed" flags of the step (in-kernel barrier), builds the list of rows with a factor on SOME rank (OR of the ranks' bit
+// words, prefix over the 8 words) and only ceil(n / 32) dense warps do the work.
+__global__ void __launch_bounds__(256, 2) k_peer_sh_expand_tiles(PeerView pv, const PeerLayout pl, int tile0, int row1, int D,
+                                                                 int M, int fused, const float* __restrict__ means3D,
+                                                                 float* __restrict__ dL_dsh) {
   __shared__ uint2 s_meta[PEER_MAX][8];
   __shared__ uint32_t s_union[8];
   __shared__ int s_pref[9];
   __shared__ uint16_t s_list[256];
   __shared__ float4 s_t[8][32][9];
-  const int tile = (row0 >> 8) + blockIdx.x;
+  if (fused) {
+    peer_resolve_step(pv);
+    peer_wait_flags(pv, PEER_SLOT_PUSHED);
+  }
+  const int tile = tile0 + blockIdx.x;
   const int base_row = tile * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint2* fmeta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta);
@@ -1185,17 +1126,21 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand_compact(const PeerView p
     s_meta[g][w] = m;
   }
   __syncthreads();
-  if (threadIdx.x < 8) {
+  if (threadIdx.x < 32) {  // union of the ranks' bit words + exclusive prefix of their populations (one warp)
     uint32_t u = 0u;
+    if (lane < 8) {
 #pragma unroll
-    for (int g = 0; g < PEER_MAX; ++g) u |= s_meta[g][threadIdx.x].x;
-    s_union[threadIdx.x] = u;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int w = 0; w < 8; ++w) { s_pref[w] = acc; acc += __popc(s_union[w]); }
-    s_pref[8] = acc;
+      for (int g = 0; g < PEER_MAX; ++g) u |= s_meta[g][lane].x;
+    }
+    const int c = __popc(u);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane < 8) { s_union[lane] = u; s_pref[lane] = inc - c; }
+    if (lane == 7) s_pref[8] = inc;
   }
   __syncthreads();
   {
@@ -1208,6 +1153,7 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand_compact(const PeerView p
   const bool valid = (int)threadIdx.x < n;
   const int r = valid ? (int)s_list[threadIdx.x] : 0;
   const size_t row = (size_t)base_row + r;
+  const bool failed = peer_error(pv);
   float4 d[PEER_MAX];
 #pragma unroll
   for (int g = 0; g < PEER_MAX; ++g) {
@@ -1230,6 +1176,11 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand_compact(const PeerView p
     const float4 cpos = campos_all[g];
     sh_basis_accumulate(acc, D, mx - cpos.x, my - cpos.y, mz - cpos.z, dg);
   }
+  if (failed) {  // a rank missed a barrier of this step: never return silently wrong gradients
+    const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = make_float4(qnan, qnan, qnan, qnan);
+  }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     __syncwarp();
@@ -1247,23 +1198,15 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand_compact(const PeerView p
   }
 }
 
-static bool expand_compact_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("GSL_EXPAND_COMPACT");
-    on = (e && e[0] == '1') ? 1 : 0;
-  }
-  return on == 1;
-}
-
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
-                          const float* means3D, float* dL_dsh, cudaStream_t st) {
+                          const float* means3D, float* dL_dsh, cudaStream_t st, bool fused) {
   if (row1 <= row0 || M == 0) return 0;
-  if (prezeroed && M <= 16 && expand_compact_enabled()) {
-    k_peer_sh_expand_compact<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0,
-                                                                       row1, D, M, means3D, dL_dsh);
-    return check_cuda(cudaGetLastError(), "k_peer_sh_expand_compact launch");
+  if (prezeroed && M <= 16) {
+    k_peer_sh_expand_tiles<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c, fused), peer_layout((size_t)P, S, c->world),
+                                                                     row0 >> 8, row1, D, M, fused ? 1 : 0, means3D, dL_dsh);
+    return check_cuda(cudaGetLastError(), "k_peer_sh_expand_tiles launch");
   }
+  if (fused) return set_error(GSL_EINVAL, "peer_sh_expand: the fused step needs zero-filled outputs and M <= 16");
   k_peer_sh_expand<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0, row1, D,
                                                              M, prezeroed ? 1 : 0, means3D, dL_dsh);
   return check_cuda(cudaGetLastError(), "k_peer_sh_expand launch");

@@ -207,6 +207,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_buckets(uint32_t nb, cons
   }
 }
 
+// CUDA-graph capture does not carry the side stream's priority over to the kernel nodes; gsl_graph_end re-applies it to
+// the nodes of these kernels (they must slip in between the CTAs of k_preprocess_fwd, not queue behind them).
+bool is_sort_kernel(const void* func) {
+  return func == (const void*)k_sort_hist || func == (const void*)k_sort_scan || func == (const void*)k_sort_scatter ||
+         func == (const void*)k_sort_buckets;
+}
+
 // surfel ids in (depth bits, id) order -> g.sval_b.  g.skey_a holds the keys, g.ctrl[8..9] their (~min, max).
 int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st) {
   if (p.P == 0) return 0;

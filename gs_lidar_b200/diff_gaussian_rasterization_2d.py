@@ -113,15 +113,106 @@ def set_wrap_azimuth(flag: bool):
     _wrap_azimuth = bool(flag)
 
 
+# Opt-in: CUDA-graph replay of the forward and backward pass.  A call signature -- device, stream,
+# sizes / fov / flags and the addresses of the surfel tensors -- that is seen a second time gets its own workspace, its own
+# STATIC output and gradient buffers and one captured graph per pass; from then on a pass is one graph launch (plus one
+# one-warp kernel that gathers the per-frame view matrix / camera centre / background, which may live in different tensors
+# every call).  Consequences the caller accepts by switching this on (as with torch.cuda.graphs):
+#   * the tensors a call returns (maps, radii, and the gradients of its backward) are views of the static buffers of its
+#     signature and are OVERWRITTEN by the next call with the same signature -- clone what must outlive a step;
+#   * zero gradients with set_to_none=True (the PyTorch default): an optimizer that zeroes `.grad` in place keeps an alias of
+#     the static gradient buffer alive; the backward detects that and returns copies instead (correct, but slower);
+#   * a second forward with the same signature before the backward of the first one runs un-graphed.
+_cuda_graphs = False
+_GRAPH_CACHE_MAX = 4
+_graph_cache = {}      # signature -> _GraphEntry (insertion order = LRU order)
+_graph_seen = {}       # signature -> number of eager calls so far
+
+
+def set_cuda_graphs(flag: bool):
+    """Switches CUDA-graph replay on or off (see the comment above); switching off frees the captured graphs."""
+    global _cuda_graphs
+    _cuda_graphs = bool(flag)
+    if not _cuda_graphs:
+        for e in list(_graph_cache.values()):
+            e.destroy()
+        _graph_cache.clear()
+        _graph_seen.clear()
+
+
+class _GraphEntry:
+    """Static buffers + captured graphs of one call signature."""
+
+    def __init__(self, device):
+        self.device = device
+        self.ws = _Workspace(device)
+        self.cam = torch.zeros(24, dtype=torch.float32, device=device)  # view matrix [0,16), camera centre [16,19), bg [20,24)
+        self.maps = None
+        self.radii = None
+        self.fin = None
+        self.fout = None
+        self.wss = None
+        self.fwd_graph = None
+        self.bwd = {}            # mode key -> dict(graph=..., keep=...)
+        self.pending = False     # a forward with grad is waiting for its backward
+        self.generation = 0
+        self.flat = None         # static gradient buffer (+ views)
+        self.views = None
+        self.d_cov3D = None
+        self.cot = None          # static cotangent planes of the staged backward graph
+        self.ex_out = None       # static outputs of the fused exchange
+        self.R = 0
+
+    def drop_graphs(self, backward_only=False):
+        if not backward_only and self.fwd_graph is not None:
+            _lib.gsl_graph_destroy(self.fwd_graph)
+            self.fwd_graph = None
+        for b in self.bwd.values():
+            _lib.gsl_graph_destroy(b["graph"])
+        self.bwd = {}
+
+    def destroy(self):
+        try:
+            torch.cuda.synchronize(self.device)
+            self.drop_graphs()
+        except Exception:
+            pass
+
+
+_capture_stream = None  # set while a pass is being captured: the library-owned stream the launches must go to
+
+
+def _capture(dev, fn):
+    """Captures the launches fn() makes (on the stream _stream_ptr hands out) into an instantiated graph; returns its handle."""
+    global _capture_stream
+    cs = C.c_void_p()
+    L.check(_lib.gsl_graph_begin(C.byref(cs)), "gsl_graph_begin")
+    _capture_stream = cs
+    try:
+        fn()
+    except Exception:
+        _lib.gsl_graph_end(cs, None)  # leave capture mode
+        raise
+    finally:
+        _capture_stream = None
+    handle = C.c_void_p()
+    L.check(_lib.gsl_graph_end(cs, C.byref(handle)), "gsl_graph_end")
+    return handle
+
+
 class _Holder:
     """Keeps a workspace attached to one forward call until its backward ran (or it is dropped)."""
 
-    def __init__(self, ws):
+    def __init__(self, ws, entry=None):
         self.ws = ws
+        self.entry = entry  # graph mode: the workspace belongs to a _GraphEntry, not to the pool
 
     def release(self):
         if self.ws is not None:
-            _pool.release(self.ws)
+            if self.entry is None:
+                _pool.release(self.ws)
+            else:
+                self.entry.pending = False
             self.ws = None
 
     def __del__(self):
@@ -160,6 +251,8 @@ def _make_params(settings, P, S, M):
 
 
 def _stream_ptr(device):
+    if _capture_stream is not None:
+        return _capture_stream
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -200,6 +293,10 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
         mask=mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous(),
         viewmatrix=_f32c(settings.viewmatrix), projmatrix=_f32c(settings.projmatrix), campos=_f32c(settings.campos))
     params = _make_params(settings, P, S, M)
+
+    entry = _graph_entry_for(dev, params, inputs, settings) if (_cuda_graphs and P > 0 and not settings.debug) else None
+    if entry is not None:
+        return _forward_graph(entry, dev, params, inputs, P, S, H, W)
 
     with torch.cuda.device(dev):
         # one allocation for all maps (planes of H*W 4-byte elements), one for radii
@@ -250,6 +347,105 @@ def _forward_impl(means3D, sh, colors_precomp, features, opacities, scales, rota
     return outs, holder, params, inputs, R
 
 
+_BIG_INPUTS = ("means3D", "shs", "shs_rest", "colors_precomp", "features", "opacities", "scales", "rotations", "mask")
+
+
+def _graph_entry_for(dev, params, inputs, settings):
+    """The _GraphEntry of this call's signature, or None while the signature is new (the first call runs un-graphed and
+    leaves the instance-count hint the entry's workspace is sized with) or its entry is busy."""
+    sig = (dev.index, torch.cuda.current_stream(dev).cuda_stream, bytes(params),
+           tuple(inputs[k].data_ptr() if inputs[k].numel() else 0 for k in _BIG_INPUTS))
+    entry = _graph_cache.get(sig)
+    if entry is None:
+        n = _graph_seen.get(sig, 0)
+        _graph_seen[sig] = n + 1
+        if n == 0:
+            if len(_graph_seen) > 64:
+                _graph_seen.clear()
+            return None
+        while len(_graph_cache) >= _GRAPH_CACHE_MAX:  # least recently used signature goes
+            old = next(iter(_graph_cache))
+            _graph_cache.pop(old).destroy()
+        entry = _GraphEntry(dev)
+        _graph_cache[sig] = entry
+    else:
+        _graph_cache[sig] = _graph_cache.pop(sig)  # most recently used
+    if entry.pending:
+        return None
+    return entry
+
+
+def _forward_graph(entry, dev, params, inputs, P, S, H, W):
+    """Forward pass by graph replay into the entry's static buffers (see the comment at `_cuda_graphs`)."""
+    with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        L.check(_lib.gsl_stage_camera(inputs["viewmatrix"].data_ptr(), inputs["campos"].data_ptr(),
+                                      inputs["background"].data_ptr(), entry.cam.data_ptr(), st), "gsl_stage_camera")
+        if entry.maps is None:
+            n_planes = 2 + NUM_CHANNELS + (S + 3) + 4 + 1
+            entry.maps = torch.empty((n_planes, H, W), dtype=torch.float32, device=dev)
+            entry.radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            fin = L.gsl_fwd_inputs()
+            for k, t in inputs.items():
+                setattr(fin, k, _ptr(t))
+            fin.cov3D_precomp = None
+            cam = entry.cam.data_ptr()
+            fin.viewmatrix, fin.campos, fin.background = cam, cam + 16 * 4, cam + 20 * 4
+            fin.projmatrix = cam  # only gsl_mark_visible reads it
+            entry.fin = fin  # holds ADDRESSES only: the graph is replayed only for calls whose tensors sit at them
+        maps, n_planes = entry.maps, entry.maps.shape[0]
+        out_contrib = maps[0:2].view(torch.int32)
+        out_color = maps[2:2 + NUM_CHANNELS]
+        out_feature = maps[2 + NUM_CHANNELS:2 + NUM_CHANNELS + S + 3]
+        out_depth = maps[n_planes - 5:n_planes - 1]
+        out_alpha = maps[n_planes - 1:n_planes]
+        if entry.fout is None:
+            fout = L.gsl_fwd_outputs()
+            fout.out_contrib, fout.out_color, fout.out_feature = out_contrib.data_ptr(), out_color.data_ptr(), out_feature.data_ptr()
+            fout.out_depth, fout.out_alpha, fout.radii = out_depth.data_ptr(), out_alpha.data_ptr(), _ptr(entry.radii)
+            entry.fout = fout
+        ws = entry.ws
+        r_host = C.c_int32(0)
+        R = 0
+        for attempt in range(3):
+            if entry.fwd_graph is None:
+                hint = _pool.r_hint.get((dev, P, W, H), max(4 * P, 1024))
+                ws.ensure(params, max(ws.r_capacity, hint))
+                entry.wss = ws.as_struct()
+                entry.params = params
+
+                def launches():
+                    cs = _stream_ptr(dev)  # the capture stream
+                    L.check(_lib.gsl_forward_preprocess(C.byref(params), C.byref(entry.fin), C.byref(entry.fout),
+                                                        C.byref(entry.wss), cs), "gsl_forward_preprocess")
+                    L.check(_lib.gsl_forward_render(C.byref(params), C.byref(entry.fin), C.byref(entry.fout),
+                                                    C.byref(entry.wss), cs), "gsl_forward_render")
+
+                entry.fwd_graph = _capture(dev, launches)
+            ws.host[0] = -1  # the sentinel gsl_wait_num_rendered polls; the graph's copy node overwrites it
+            L.check(_lib.gsl_graph_launch(entry.fwd_graph, st), "gsl_graph_launch (forward)")
+            L.check(_lib.gsl_wait_num_rendered(C.byref(entry.wss), C.byref(r_host), st), "gsl_wait_num_rendered")
+            R = int(r_host.value)
+            if R <= ws.r_capacity:
+                break
+            # the binning chunk was too small (nothing was written): grow it, capture again
+            torch.cuda.current_stream(dev).synchronize()
+            entry.drop_graphs()
+            _pool.r_hint[(dev, P, W, H)] = max(R + R // 4, 1024)
+            ws.r_capacity = 0
+        else:
+            raise RuntimeError("gs_lidar_b200: could not size the binning workspace for %d instances" % R)
+        if R + R // 8 > _pool.r_hint.get((dev, P, W, H), 0):
+            _pool.r_hint[(dev, P, W, H)] = max(R + R // 4, 1024)
+        entry.R = R
+        entry.generation += 1
+    holder = _Holder(ws, entry)
+    outs = (out_contrib, out_color, out_feature, out_depth, out_alpha, entry.radii)
+    ins = dict(inputs)
+    ins["_fin"] = entry.fin
+    return outs, holder, params, ins, R
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
@@ -273,10 +469,17 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.means2D_shape = tuple(means2D.shape)
         ctx.cov_shape = tuple(cov3Ds_precomp.shape)
         needs_grad = any(ctx.needs_input_grad)  # all False under torch.no_grad()
+        ctx.graph_generation = holder.entry.generation if holder.entry is not None else 0
+        if needs_grad and holder.entry is not None:
+            holder.entry.pending = True
         if needs_grad:
             ctx.holder = holder
-            ctx.inputs = inputs  # contiguous fp32 views the kernels read again in backward
-            ctx.save_for_backward(contrib, radii)
+            # the contiguous fp32 tensors the kernels read again in backward go through save_for_backward like in the
+            # reference (diff_gaussian_rasterization_2d.py:122), so an in-place change between forward and backward is
+            # detected by autograd's version counters; `_fin` is the pointer struct over exactly these tensors
+            ctx.input_names = [k for k, v in inputs.items() if isinstance(v, torch.Tensor)]
+            ctx.fin = inputs["_fin"]
+            ctx.save_for_backward(contrib, radii, *[inputs[k] for k in ctx.input_names])
         else:
             holder.release()
             ctx.holder = None
@@ -289,8 +492,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         if holder is None or holder.ws is None:
             raise RuntimeError("gs_lidar_b200: the workspace of this forward call was already released "
                                "(backward called twice, or forward ran without grad)")
-        params, inputs, settings = ctx.gsl_params, ctx.inputs, ctx.raster_settings
-        contrib, radii = ctx.saved_tensors
+        params, settings = ctx.gsl_params, ctx.raster_settings
+        saved = ctx.saved_tensors
+        contrib, radii = saved[0], saved[1]
+        inputs = dict(zip(ctx.input_names, saved[2:]))
+        inputs["_fin"] = ctx.fin
         dev = contrib.device
         P, S, M = params.P, params.S, params.M
         H, W = params.H, params.W
@@ -304,21 +510,53 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_feature = cot(grad_out_feature, (S + 3, H, W))
         g_depth = cot(grad_depth, (4, H, W))
         g_alpha = cot(grad_alpha, (1, H, W))
+        entry = holder.entry  # graph mode: static buffers + captured graphs of this call signature
+        if entry is not None and ctx.graph_generation != entry.generation:
+            raise RuntimeError("gs_lidar_b200 (CUDA-graph mode): the state of this forward call was overwritten by a later "
+                               "forward with the same signature; run backward before the next forward or switch "
+                               "set_cuda_graphs(False)")
+        if entry is not None:
+            # The replayed backward writes the entry's STATIC gradient buffers.  If a leaf still holds one of them as its
+            # .grad (a second backward that accumulates, or gradients zeroed in place instead of set to None) replaying would
+            # overwrite what autograd is about to accumulate into: this backward then runs un-graphed into fresh tensors.
+            spans = [(t.data_ptr(), t.data_ptr() + t.numel() * 4) for t in (entry.flat, entry.d_cov3D) if t is not None]
+            if entry.ex_out is not None:
+                spans += [(t.data_ptr(), t.data_ptr() + t.numel() * 4) for t in entry.ex_out.values()]
+            for t in saved[2:]:
+                g = t.grad if t.is_leaf else None
+                if g is not None and any(lo <= g.data_ptr() < hi for lo, hi in spans):
+                    entry = None
+                    break
 
         split = inputs["shs_rest"].numel() != 0  # never together with the exchange (GaussianRasterizer.forward)
-        ex = _exchange if (_exchange is not None and M > 0 and P > 0 and
+        ex = _exchange if (_exchange is not None and P > 0 and
                            (_exchange.world_size() > 1 or getattr(_exchange, "force", False))) else None
+        if ex is not None and M == 0:
+            # the fused exchange rides on the SH-factor algebra; returning local-only gradients here would let the replicas
+            # diverge without any error
+            raise RuntimeError("gs_lidar_b200: a gradient exchange is active but this call uses colors_precomp (no SH): "
+                               "disable the exchange for this backward and all-reduce the gradients yourself")
         with torch.cuda.device(dev):
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
             # dL_dcov3D is all-zero (forward.cu never reads cov3D_precomp); only materialised when the caller passed one
-            d_cov3D = e(P, 6) if ctx.cov_shape == (P, 6) else None
+            if entry is not None and ctx.cov_shape == (P, 6):
+                if entry.d_cov3D is None:
+                    entry.d_cov3D = e(P, 6)
+                d_cov3D = entry.d_cov3D
+            else:
+                d_cov3D = e(P, 6) if ctx.cov_shape == (P, 6) else None
             fused = False
             if ex is None:
                 # one allocation for all dense gradients; the returned tensors are contiguous views of it
                 # 16-byte-stored tensors first (their sizes are multiples of 16 B), scalar-stored ones after: every
                 # tensor is aligned for its stores and the buffer has no gaps (the C side zero-fills it as one range)
                 widths = (4, NUM_CHANNELS, 4, M * NUM_CHANNELS, 3, 3, 1, S)
-                flat = e(P * sum(widths))
+                if entry is not None:
+                    if entry.flat is None:
+                        entry.flat = e(P * sum(widths))
+                    flat = entry.flat
+                else:
+                    flat = e(P * sum(widths))
                 views, off = [], 0
                 for w in widths:
                     views.append(flat[off:off + P * w].view(P, w))
@@ -335,8 +573,15 @@ class _RasterizeGaussians(torch.autograd.Function):
                 ex.prepare(P, S, M, dev)
                 d_sh = d_sh_rest = None
                 fused = ex.packed and ex.sync  # the whole exchange is one C call writing the summed dense gradients
+                if not fused:
+                    entry = None  # the piecewise / NCCL exchanges are host-driven: not capturable
                 if fused:
-                    v = ex.alloc_outputs(P, S, M, dev)
+                    if entry is not None:
+                        if entry.ex_out is None:
+                            entry.ex_out = ex.alloc_outputs(P, S, M, dev)
+                        v = dict(entry.ex_out)
+                    else:
+                        v = ex.alloc_outputs(P, S, M, dev)
                     d_means3D, d_means2D, d_opacity = v["means3D"], v["means2D"], v["opacities"]
                     d_scales, d_rot, d_features, d_sh = v["scales"], v["rotations"], v["features"], v["shs"]
                     d_colors = None
@@ -385,17 +630,51 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _lib.gsl_backward_surfels_rows(C.byref(params), C.byref(fin), C.byref(ffwd), C.byref(gout),
                                                    C.byref(wss), rb, re, _stream_ptr(dev)), "gsl_backward_surfels_rows"))
 
-            if settings.debug:
-                cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) +
-                                               tuple(v for k, v in inputs.items() if k != "_fin"))
-                try:
+            if entry is not None:
+                # cotangents: the graph captured at the first backward reads them where they were then ("direct"); when
+                # autograd hands over other tensors they are copied into static planes first ("staged")
+                eager_run = run
+                ptrs = (g_color.data_ptr(), g_depth.data_ptr(), g_alpha.data_ptr(), g_feature.data_ptr())
+                exkey = None if ex is None else id(ex)
+                direct = entry.bwd.get(("direct", exkey))
+                if direct is None or direct["ptrs"] == ptrs:
+                    mode, keep = ("direct", exkey), (g_color, g_depth, g_alpha, g_feature)
+                else:
+                    mode = ("staged", exkey)
+                    if entry.cot is None:
+                        entry.cot = e(4 + 4 + 1 + S + 3, H, W)
+                    c = entry.cot
+                    st_c, st_d, st_a, st_f = c[0:4], c[4:8], c[8:9], c[9:]
+                    st_c.copy_(g_color); st_d.copy_(g_depth); st_a.copy_(g_alpha); st_f.copy_(g_feature)
+                    gin.dL_dout_color, gin.dL_dout_depth = st_c.data_ptr(), st_d.data_ptr()
+                    gin.dL_dout_alpha, gin.dL_dout_feature = st_a.data_ptr(), st_f.data_ptr()
+                    keep = None
+
+                def run():  # noqa: F811 -- replay (capture first) instead of the individual launches
+                    b = entry.bwd.get(mode)
+                    if b is None:
+                        b = dict(graph=_capture(dev, eager_run), ptrs=ptrs, keep=keep, gin=gin, gout=gout, ffwd=ffwd,
+                                 params=params, wss=wss)
+                        entry.bwd[mode] = b
+                    L.check(_lib.gsl_graph_launch(b["graph"], _stream_ptr(dev)), "gsl_graph_launch (backward)")
+
+            try:
+                if settings.debug:
+                    cpu_args = cpu_deep_copy_tuple((g_color, g_depth, g_alpha, g_feature, contrib, radii) +
+                                                   tuple(v for k, v in inputs.items() if k != "_fin"))
+                    try:
+                        run()
+                    except Exception as ex_:
+                        torch.save(cpu_args, "snapshot_bw.dump")
+                        print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                        raise ex_
+                else:
                     run()
-                except Exception as ex_:
-                    torch.save(cpu_args, "snapshot_bw.dump")
-                    print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
-                    raise ex_
-            else:
-                run()
+            except Exception:
+                # the packed gradient accumulators may be left dirty (the per-surfel kernel re-zeroes what it consumed,
+                # and it may not have run): force a re-zero before this workspace is used again
+                holder.ws.key = None
+                raise
             if ex is not None and not fused:
                 g = ex.finish(P, params.D, M, inputs["means3D"])
                 d_means3D, d_means2D, d_opacity = g["means3D"], g["means2D"], g["opacities"]
@@ -406,6 +685,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_cov = d_cov3D
         grads = (d_means3D, d_means2D, d_sh if M > 0 else None, d_colors if inputs["colors_precomp"].numel() else None,
                  d_features, d_opacity, d_scales, d_rot, grad_cov, None, None, d_sh_rest)
+        if entry is not None:
+            # fresh view objects of the static buffers: autograd adopts them as .grad without a copy
+            grads = tuple(None if g is None else g.view(g.shape) for g in grads)
         return grads
 
 

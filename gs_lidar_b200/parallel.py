@@ -13,10 +13,17 @@ import torch
 import torch.distributed as dist
 
 
-def shard_frames(num_frames: int, rank: int, world_size: int) -> List[int]:
-    """Frame ids rendered by `rank`: round-robin, frame_id % world_size == rank."""
+def shard_frames(num_frames: int, rank: int, world_size: int, equal_steps: bool = False) -> List[int]:
+    """Frame ids rendered by `rank`: round-robin, frame_id % world_size == rank.
+
+    Inference needs nothing more (no collective).  TRAINING with a gradient exchange (GradientExchange / PeerExchange)
+    requires every rank to run the SAME number of backward passes -- each one is a barrier among the ranks -- so pass
+    equal_steps=True there: the last num_frames % world_size frames are dropped and all shards have equal length
+    (with an uneven shard the ranks that finish early leave the others waiting at a barrier until its time-out)."""
     if world_size <= 0 or not (0 <= rank < world_size):
         raise ValueError("bad rank/world_size %d/%d" % (rank, world_size))
+    if equal_steps:
+        num_frames -= num_frames % world_size
     return list(range(rank, num_frames, world_size))
 
 
@@ -301,13 +308,25 @@ class PeerExchange(GradientExchange):
         self.pkey = None
 
     # -- per backward ---------------------------------------------------------------------------------------------
+    def check(self, synchronize=True):
+        """Raises if a rank missed a barrier of a step enqueued so far (its gradients are NaN on the ranks that noticed:
+        the kernels that write them poison them on a time-out, so a failed step can never be applied silently).  With
+        synchronize=True the current stream is drained first, which makes the check exact for the step just enqueued --
+        call it before optimizer.step() when a late error report (at the next backward) is not good enough."""
+        if self.ctx is None:
+            return
+        if synchronize:
+            torch.cuda.current_stream(self._campos.device).synchronize()
+        if int(self._err[0]) != 0:
+            raise RuntimeError("PeerExchange: a rank did not reach a barrier (flag slot %d) within the time-out; the "
+                               "gradients of that step are NaN / invalid (every rank must run the same number of steps, "
+                               "see shard_frames(equal_steps=True))" % (int(self._err[0]) - 1))
+
     def prepare(self, P, S, M, device):
         G = self.world_size()
         if self.pkey != (P, S, G, str(device)):
             self.setup(P, S, device)
-        if int(self._err[0]) != 0:
-            raise RuntimeError("PeerExchange: a rank did not reach a barrier (flag slot %d) of an earlier step within the "
-                               "time-out; the gradients of that step are invalid" % (int(self._err[0]) - 1))
+        self.check(synchronize=False)
         self.epoch += 1
         self.ctx.parity = self.epoch & 1
         self._S = S
@@ -328,11 +347,13 @@ class PeerExchange(GradientExchange):
             self.ctx.epoch = ticket & 0xFFFFFFFF
             L.check(L.load().gsl_peer_barrier(C.byref(self.ctx), slot, self._sp(stream)), "gsl_peer_barrier")
 
-    def launch_expand(self, P, D, M, means3D, d_sh, row_begin, row_end, stream):
+    def launch_expand(self, P, D, M, means3D, d_sh, row_begin, row_end, stream, sparse=False):
+        """sparse=True: d_sh is zero-filled by the caller and only rows with a factor are written (the fused step's kernel)."""
         from . import _lib as L
         import ctypes as C
-        L.check(L.load().gsl_peer_sh_expand(C.byref(self.ctx), P, self._S, D, M, row_begin, row_end, means3D.data_ptr(),
-                                            d_sh.data_ptr(), self._sp(stream)), "gsl_peer_sh_expand")
+        fn = L.load().gsl_peer_sh_expand_sparse if sparse else L.load().gsl_peer_sh_expand
+        L.check(fn(C.byref(self.ctx), P, self._S, D, M, row_begin, row_end, means3D.data_ptr(), d_sh.data_ptr(),
+                   self._sp(stream)), "gsl_peer_sh_expand")
 
     def launch_reduce(self, P, row_begin, row_end, stream):
         from . import _lib as L

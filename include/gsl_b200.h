@@ -37,7 +37,7 @@ extern "C" {
 #define GSL_API
 #endif
 
-#define GSL_ABI_VERSION 3
+#define GSL_ABI_VERSION 4
 #define GSL_NUM_CHANNELS 4 /* cuda_rasterizer/config.h:12 */
 #define GSL_TILE 16        /* cuda_rasterizer/config.h:13-14 */
 #define GSL_MAX_FEATURES 10 /* forward.cu:348: F[13] holds S features + 3 normal channels */
@@ -289,6 +289,9 @@ GSL_API int32_t gsl_peer_row_width(int32_t S);
 GSL_API int gsl_peer_alloc(size_t bytes, void** dptr, gsl_peer_handle* handle); /* cudaMalloc, zero, export */
 GSL_API int gsl_peer_open(const gsl_peer_handle* handle, void** dptr);          /* map a peer's buffer (other process) */
 GSL_API int gsl_peer_close(void* dptr);
+/* How long a barrier (kernel or in-kernel wait) waits for a rank that does not arrive before it raises the error flag and
+ * lets the step finish with NaN gradients; process-wide, 20000 ms by default. */
+GSL_API int gsl_peer_set_timeout_ms(uint32_t ms);
 GSL_API int gsl_peer_free(void* dptr);
 /* Signal "this rank reached ticket ctx->epoch on flag slot `slot` (0..3)" to all ranks and wait for all of them. */
 GSL_API int gsl_peer_barrier(const gsl_peer_ctx* ctx, int32_t slot, void* stream);
@@ -300,6 +303,11 @@ GSL_API int gsl_peer_wait(const gsl_peer_ctx* ctx, int32_t slot, void* stream);
  * the own buffer (local reads); dL_dsh is the full (P,M,4) tensor. */
 GSL_API int gsl_peer_sh_expand(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
                                int32_t row_end, const float* means3D, float* dL_dsh, void* stream);
+/* The same over a dL_dsh the caller has ZERO-FILLED: only the rows some rank has a factor for are written (about half of
+ * the surfels have none), by dense warps over the compacted rows of each 256-surfel tile.  M <= 16.  This is the kernel
+ * the fused step (gsl_backward_surfels_exchange) runs. */
+GSL_API int gsl_peer_sh_expand_sparse(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32_t D, int32_t M, int32_t row_begin,
+                                      int32_t row_end, const float* means3D, float* dL_dsh, void* stream);
 /* Sum of the staged packed rows [row_begin, row_end) (multiples of 256, or row_end = P): this rank sums the tiles it
  * owns (every world-th) in rank order and pushes sums + OR-ed row bits into every rank's result area; complete after
  * the next barrier. */
@@ -310,10 +318,15 @@ GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const
 /* gsl_backward_surfels for the surfels [row_begin, row_end) only (GSL_FLAG_BWD_PEER_ROWS; row_begin a multiple of 256). */
 GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                               gsl_bwd_outputs* gout, gsl_workspace* ws, int32_t row_begin, int32_t row_end, void* stream);
-/* The sequence above from "for each row range" to gsl_peer_unpack in one call (after gsl_backward_composite): `chunks`
- * row ranges, their exchange on the library's side stream, `step` = the step counter the tickets derive from (same on
- * all ranks, > 0, growing).  gout: peer = the mapped exchange buffers, the dense non-SH pointers and dL_dsh receive
- * the gradients summed over the ranks. */
+/* The whole second half of a frame-parallel backward pass in one call (after gsl_backward_composite), as ONE fused step:
+ * per-surfel VJP with its pushes, sum of the owned tiles, SH expansion (library side stream) and unpack, with both
+ * barriers INSIDE the kernels (the last CTA of a producing kernel publishes a flag in every rank's buffer, every CTA of
+ * a consuming kernel waits for the flags of all ranks) and the ticket taken from a device-side step counter in the
+ * exchange buffer -- every kernel argument is constant from step to step, so the call can be captured in a CUDA graph.
+ * Every rank must make the same sequence of calls on the same exchange buffers.  `step` and `chunks` are accepted for
+ * ABI compatibility and ignored (one row range measured best).  gout: peer = the mapped exchange buffers; the dense
+ * non-SH pointers and dL_dsh receive the gradients summed over the ranks.  If a rank misses a barrier (20 s), the error
+ * flag is raised and the gradients of the step are NaN on the ranks that noticed -- never silently wrong. */
 GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                                   gsl_bwd_outputs* gout, gsl_workspace* ws, uint32_t step, int32_t chunks, void* stream);
 
@@ -330,6 +343,26 @@ GSL_API int gsl_chamfer_backward(int32_t b, int32_t n, const float* xyz1, int32_
                                  const float* gdist1, const int32_t* idx1, const float* gdist2, const int32_t* idx2,
                                  float* gxyz1, float* gxyz2, void* stream);
 
+/* ---- CUDA-graph replay of a pass (the reference re-allocates, zero-fills and synchronises in every
+ * step, rasterize_points.cu:77-91,186-197, train.py:379).  Every kernel argument of a pass is constant once the
+ * workspace, the output / gradient buffers and the inputs keep their addresses, and the forward's instance count is
+ * polled after all launches, so a caller can capture a pass once and replay it with one launch:
+ *     gsl_graph_begin(&cs);  gsl_forward_preprocess(..., cs); gsl_forward_render(..., cs);  gsl_graph_end(cs, &g);
+ *     per step:  ws.num_rendered_host[0] = -1;  gsl_graph_launch(g, stream);  gsl_wait_num_rendered(..., stream);
+ * gsl_graph_begin hands out a library-owned stream in capture mode (`cs`; the legacy default stream cannot be captured) on
+ * which the pass is issued; the instantiated graph runs on any stream.
+ * (same for gsl_backward, or gsl_backward_composite + gsl_backward_surfels_exchange: the fused exchange takes its tickets
+ * from a device-side step counter).  If the instance count exceeds ws.r_capacity after a replay nothing was written: grow
+ * the binning chunk, capture again.  Capture is thread-local; per-kernel profiling must be off; GSL_FLAG_DEBUG_SYNC is not
+ * capturable.  gsl_graph_end(stream, NULL) aborts a capture.  gsl_stage_camera gathers the three small per-frame inputs
+ * (view matrix 16 floats, camera centre 3, background 4) into one 24-float device buffer -- [0,16) [16,19) [20,24) -- so
+ * that a captured pass can read them from fixed addresses whatever tensors the caller holds them in. */
+GSL_API int gsl_graph_begin(void** capture_stream);
+GSL_API int gsl_graph_end(void* stream, void** graph_exec);
+GSL_API int gsl_graph_launch(void* graph_exec, void* stream);
+GSL_API int gsl_graph_destroy(void* graph_exec);
+GSL_API int gsl_stage_camera(const float* viewmatrix, const float* campos, const float* background, float* dst, void* stream);
+
 /* Per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline block.
  * Kernel ids index the arrays of gsl_profile_read. */
 enum {
@@ -344,7 +377,10 @@ enum {
   GSL_K_PREPROCESS_BWD = 7,
   GSL_K_GLUE_FWD = 8,  /* k_glue_fwd (render() glue, next-1) */
   GSL_K_GLUE_BWD = 9,  /* k_glue_bwd */
-  GSL_K_COUNT = 10
+  GSL_K_PEER_REDUCE = 10, /* k_peer_reduce_rows (includes its in-kernel wait for the ranks' "pushed" flags) */
+  GSL_K_PEER_EXPAND = 11, /* k_peer_sh_expand_tiles, side stream */
+  GSL_K_PEER_UNPACK = 12, /* k_peer_unpack (includes its in-kernel wait for the owners' "summed" flags) */
+  GSL_K_COUNT = 13
 };
 GSL_API int gsl_profile_enable(int on);
 /* Waits for all recorded events, then returns accumulated milliseconds and launch counts per id. */

@@ -54,8 +54,8 @@ def test_barrier_of_one_rank_returns_and_bad_contexts_are_refused():
         lib.gsl_peer_free(ptr)
 
 
-@pytest.mark.parametrize("P,split", [(20000, None), (5003, 2048)])
-def test_emulated_two_ranks_equal_the_sum_of_dense_gradients(P, split):
+@pytest.mark.parametrize("P,split,sparse", [(20000, None, False), (5003, 2048, False), (20000, None, True), (5003, 2048, True)])
+def test_emulated_two_ranks_equal_the_sum_of_dense_gradients(P, split, sparse):
     from gs_lidar_b200 import parallel
     from gs_lidar_b200 import _lib as L
     lib = L.load()
@@ -95,7 +95,8 @@ def test_emulated_two_ranks_equal_the_sum_of_dense_gradients(P, split):
                 common.run_ours(scenes[r], cot, export=False)
         st = torch.cuda.current_stream()
         sp = C.c_void_p(st.cuda_stream)
-        d_sh = [torch.empty((P, 16, 4), device="cuda") for _ in range(2)]
+        # sparse: the fused step's expansion kernel, which writes only rows with a factor into a zero-filled tensor
+        d_sh = [(torch.zeros if sparse else torch.empty)((P, 16, 4), device="cuda") for _ in range(2)]
 
         def barrier(phase):  # all ranks signal, then all wait: nothing ever spins in this single-stream emulation
             for r in (0, 1):
@@ -109,7 +110,7 @@ def test_emulated_two_ranks_equal_the_sum_of_dense_gradients(P, split):
                 barrier(1)
             for r in (0, 1):
                 ranks[r].launch_reduce(P, rb, re, st)  # rank r sums the tiles it owns and pushes the sums to both
-                ranks[r].launch_expand(P, 3, 16, scenes[0].means3D, d_sh[r], rb, re, st)
+                ranks[r].launch_expand(P, 3, 16, scenes[0].means3D, d_sh[r], rb, re, st, sparse=sparse)
         barrier(2)
         got = [ranks[r].unpack(P) for r in (0, 1)]
         torch.cuda.synchronize()
@@ -149,6 +150,58 @@ def test_single_rank_exchange_equals_the_plain_backward(P, chunks):
         assert float(got["shs"][culled].abs().sum()) == 0.0  # untouched surfels: exact zeros from the zero-fill
     finally:
         ex.close()
+
+
+def test_a_rank_that_never_arrives_gives_nan_gradients_and_an_error_not_a_hang():
+    """Fused step of rank 0 of 2 while rank 1 never runs: the in-kernel waits time out (100 ms here), the error flag is
+    raised, every gradient the step returns is NaN (never silently wrong) and check() / the next backward raise."""
+    from gs_lidar_b200 import parallel
+    from gs_lidar_b200 import _lib as L
+    lib = L.load()
+    P = 5003
+    scene = synth.make_scene(P, seed=77).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=78).items()}
+    nbytes = lib.gsl_peer_buffer_bytes(P, 4, 2)
+    bufs = []
+    for _ in range(2):
+        q = C.c_void_p()
+        L.check(lib.gsl_peer_alloc(nbytes, C.byref(q), None), "gsl_peer_alloc")
+        bufs.append(q.value)
+
+    class Lonely(parallel.PeerExchange):
+        def world_size(self):
+            return 2
+
+        def rank(self):
+            return 0
+
+        def prepare(self, P_, S, M, device):
+            if self.pkey is None:
+                self.setup(P_, S, device, buffers=bufs)
+            return super().prepare(P_, S, M, device)
+
+    ex = Lonely()
+    lib.gsl_peer_set_timeout_ms(100)
+    try:
+        with ex:
+            got = common.run_ours(scene, cot, export=False)[2]
+        torch.cuda.synchronize()
+        assert int(ex._err[0]) != 0
+        touched = got["opacities"].isnan().any() or got["shs"].isnan().any()
+        assert bool(touched)
+        for k in ("means3D", "opacities", "scales", "rotations"):
+            assert not bool(torch.isfinite(got[k]).all()), k
+        with pytest.raises(RuntimeError, match="did not reach a barrier"):
+            ex.check()
+        with pytest.raises(RuntimeError, match="did not reach a barrier"):
+            with ex:
+                common.run_ours(scene, cot, export=False)
+    finally:
+        lib.gsl_peer_set_timeout_ms(20000)
+        torch.cuda.synchronize()
+        ex.ctx = None  # the buffers are this test's, not the exchange's
+        for q in bufs:
+            lib.gsl_peer_free(q)
 
 
 def _free_port():
