@@ -55,9 +55,15 @@ def parse_args():
                     help="N > 1: gradient exchange by this repo's own kernels over NVLink peer memory (default) or by "
                          "NCCL collectives (all-reduce + all-gather)")
     ap.add_argument("--exchange-chunks", type=int, default=1)
+    ap.add_argument("--exchange-schedule", default="default", choices=["default", "early-low", "early-high", "late"],
+                    help="N > 1, peer exchange: when the SH factors leave and at which priority the SH expansion runs "
+                         "(gs_lidar_b200.parallel.PeerExchange.set_schedule); default = the library's")
     ap.add_argument("--wrap-azimuth", action="store_true",
                     help="opt-in extension, NOT the reference's semantics and not the headline: periodic panorama")
     ap.add_argument("--cpu-sample-surfels", type=int, default=0, help="0 = pick from a quick calibration")
+    ap.add_argument("--clock-sample-ms", type=int, default=20, help="period of the clock sampler on rank 0 (0 = off)")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "off"],
+                    help="nvml: a side process polling two NVML queries (default); smi: an `nvidia-smi --query-gpu -lms` loop")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="CUDA-graph replay of the forward / backward pass (gs_lidar_b200.set_cuda_graphs); the line always "
                          "carries the other mode's device-timed number as well")
@@ -78,27 +84,59 @@ def init_dist(args):
     return rank, world, local
 
 
+_NVML_SAMPLER = r"""
+import sys, time
+import pynvml as N
+idx, period = int(sys.argv[1]), float(sys.argv[2]) / 1e3
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(idx)
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+while True:
+    sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+    try:
+        r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    sys.stdout.write("%d,%d,%d\n" % (sm, mx, r))
+    sys.stdout.flush()
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / clock-event reasons sampled DURING the timed region, on rank 0, by a separate process: two NVML queries per
+    sample (`nvidia-smi --query-gpu=... -lms 20` was measured to cost 2-4 % of the step it samples, and at N > 1 every rank
+    waits for rank 0 at the exchange barriers; the NVML loop was measured at no visible cost).  `--clock-sampler smi` keeps
+    the nvidia-smi loop."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML clock-event reason bits (nvml.h)
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20, kind="nvml"):
         self.index = index
+        self.period_ms = int(period_ms)
+        self.kind = kind
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
     def start(self):
+        if self.period_ms <= 0 or self.kind == "off":
+            return
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            if self.kind == "nvml":
+                self.p = subprocess.Popen([sys.executable, "-c", _NVML_SAMPLER, str(self.index), str(self.period_ms)],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+            else:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                           "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=self.f,
+                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], sampler=self.kind, period_ms=self.period_ms)
         if self.p is None:
             return out
         self.p.terminate()
@@ -111,17 +149,27 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for line in self.f.read().strip().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                if self.kind == "nvml":
+                    if len(parts) < 3:
+                        continue
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                    bits = int(parts[2])
+                    for nme, b in self.BITS.items():
+                        if bits & b:
+                            reasons.add(nme)
+                else:
+                    if len(parts) < 9:
+                        continue
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                    for nme, v in zip(names, parts[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nme)
             except ValueError:
                 continue
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for nme, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
         if sm:
             sm.sort()
             out["sm_mhz"] = sm[len(sm) // 2]
@@ -251,6 +299,9 @@ def run_ours(args, rank, world, local):
     # N > 1: the gradient exchange is fused into the backward pass (parallel.PeerExchange: packed rows + SH factors pushed
     # over NVLink peer memory by this repo's kernels; parallel.GradientExchange is the NCCL baseline)
     exchange = None
+    if world > 1 and args.exchange_schedule != "default":
+        parallel.PeerExchange.set_schedule(early_factors=args.exchange_schedule != "late",
+                                           expand_low_priority=args.exchange_schedule == "early-low")
     if world > 1:
         exchange = (parallel.PeerExchange(chunks=args.exchange_chunks) if args.exchange == "peer"
                     else parallel.GradientExchange()).enable()
@@ -273,7 +324,7 @@ def run_ours(args, rank, world, local):
 
     # ---- warm-up (the clock sampler starts here: the timed region alone is tens of milliseconds, shorter than
     # nvidia-smi's sampling period, so the record covers warm-up + timed region, all under the same load)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_sample_ms, args.clock_sampler)
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
@@ -535,6 +586,7 @@ def run_ours(args, rank, world, local):
                     "fp32, inside the step: packed rows + SH factors pushed over NVLink peer memory by the backward kernel, summed by "
                     "the tile owners (own kernels, no collective library)" if args.exchange == "peer" else
                     "fp32, inside the step: NCCL all-reduce of the non-SH gradients + all-gather of the SH factors"),
+                "exchange_schedule": args.exchange_schedule if world > 1 else None,
                 "grad_exchange_bytes": 0 if exchange is None else (exchange.flat_nbytes + (0 if exchange.packed else exchange.local.numel() * 4)),
                 "profiling": "timed region runs with per-kernel events OFF; `kernels` come from a separate pass"},
         "cuda_graph": {"mode": args.graph, "ms_per_step_graph_on": (ms if use_graph else ms_other) / args.steps,
@@ -549,7 +601,7 @@ def run_ours(args, rank, world, local):
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "note": "per-step camera + cotangent maps from pinned host memory, rendered maps + a gradient checksum read back; surfel parameters stay resident like model weights"},
         "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD +
-                         (0 if exchange is None or not exchange.packed else L.OWN_LAUNCHES_PEER(len(exchange.ranges(P))))) * args.steps,
+                         (0 if exchange is None or not exchange.packed else L.OWN_LAUNCHES_PEER(len(exchange.ranges(P)), args.exchange_schedule))) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
@@ -668,7 +720,7 @@ def run_reference(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_sample_ms, args.clock_sampler)
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):

@@ -125,6 +125,7 @@ SYMBOLS = {
     "gsl_peer_open": (C.c_int, [C.POINTER(gsl_peer_handle), C.POINTER(vp)]),
     "gsl_peer_close": (C.c_int, [vp]),
     "gsl_peer_set_timeout_ms": (C.c_int, [C.c_uint32]),
+    "gsl_peer_set_option": (C.c_int, [C.c_int32, C.c_int32]),
     "gsl_peer_free": (C.c_int, [vp]),
     "gsl_peer_barrier": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
     "gsl_peer_signal": (C.c_int, [C.POINTER(gsl_peer_ctx), C.c_int32, vp]),
@@ -153,7 +154,8 @@ SYMBOLS = {
     "gsl_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "gsl_kernel_name": (C.c_char_p, [C.c_int]),
 }
-GSL_K_COUNT = 13
+GSL_K_COUNT = 14
+GSL_PEER_OPT_EARLY_FACTORS, GSL_PEER_OPT_EXPAND_LOW_PRIORITY = 0, 1
 # kernels of THIS repo launched per forward / backward call on the fast binning path (<= 1024 tiles; no library
 # kernel is launched there): used by bench.py for "gpu_launches".
 OWN_LAUNCHES_FWD = 1 + 4 + 1 + 3 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan/bases,
@@ -162,10 +164,12 @@ OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
 
 
 
-def OWN_LAUNCHES_PEER(ranges=1):
+def OWN_LAUNCHES_PEER(ranges=1, schedule="default"):
     """extra launches of a backward with the fused peer-memory exchange: k_peer_begin, k_peer_signal, k_peer_reduce_rows,
-    k_peer_sh_expand_tiles, k_peer_unpack (the waiting halves of the barriers live inside the last three)."""
-    return 5
+    k_peer_sh_expand_tiles, k_peer_unpack (the waiting halves of the barriers live inside the last three); with early factors
+    also k_peer_factor_extract, k_peer_factor_push and a second k_peer_signal; with the low-priority expansion three
+    one-warp k_peer_wait."""
+    return 5 + (3 if schedule.startswith("early") else 0) + (3 if schedule == "early-low" else 0)
 
 
 _lib = None

@@ -117,7 +117,12 @@ static int validate_ws(const gsl_params* p, const gsl_workspace* ws, bool need_b
 
 // One side stream + fork/join events per host thread and device (the surfel sort runs on it).
 constexpr int SIDE_CHUNK_EVENTS = 32;
-struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; cudaEvent_t chunk[SIDE_CHUNK_EVENTS]; };
+struct SideStream {
+  cudaStream_t stream;  // highest priority: few CTAs that must slip in between the main stream's (sort, NVLink pushes)
+  cudaStream_t low;     // lowest priority: bulk work that should only fill what the main stream leaves idle
+  cudaEvent_t fork, join, join_low;
+  cudaEvent_t chunk[SIDE_CHUNK_EVENTS];
+};
 static SideStream* side_stream() {
   static thread_local SideStream aux[64];
   static thread_local bool have[64] = {false};
@@ -128,6 +133,8 @@ static SideStream* side_stream() {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&aux[dev].stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&aux[dev].low, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&aux[dev].join_low, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&aux[dev].fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&aux[dev].join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     for (int k = 0; k < SIDE_CHUNK_EVENTS; ++k)
@@ -138,6 +145,9 @@ static SideStream* side_stream() {
 }
 
 static unsigned long long g_peer_timeout_ns = 20000000000ull;
+// schedule of the fused exchange step (gsl_peer_set_option; defaults = what measured best, profiles/r02_exchange_schedules.md)
+static int g_peer_early_factors = 0;  // GSL_PEER_OPT_EARLY_FACTORS
+static int g_peer_expand_low = 0;     // GSL_PEER_OPT_EXPAND_LOW_PRIORITY
 unsigned long long peer_timeout_ns() { return g_peer_timeout_ns; }
 
 static int debug_sync(const gsl_params* p, cudaStream_t st, const char* stage) {
@@ -379,32 +389,68 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   const int P = p->P;
   // One step (gsl_peer.cuh); no kernel of it blocks the stream waiting for other ranks before it has launched:
   //   k_peer_begin            (one warp) step counter++, camera centre -> every rank
-  //   k_preprocess_bwd        VJP; packed rows -> tile owners, SH factors -> every rank
-  //   k_peer_signal           (one warp) publishes "pushed"
-  //   k_peer_reduce_rows      every CTA waits for "pushed" of all ranks; sums of my tiles -> every rank; last CTA publishes
-  //                           "summed"                                      | side stream, behind an event:
-  //   k_peer_unpack           every CTA waits for "summed"; dense tensors   | k_peer_sh_expand_tiles: waits for "pushed",
-  //                                                                         | dL_dsh from the local factor tables
+  //   k_peer_factor_extract   SH factors of this rank -> own factor table (before the accumulators are re-zeroed)
+  //   k_preprocess_bwd        VJP; packed rows -> tile owners        | side stream, behind an event:
+  //   k_peer_signal           (one warp) publishes "pushed"          | k_peer_factor_push: own factors -> every rank
+  //   k_peer_reduce_rows      every CTA waits for "pushed" of all    | k_peer_signal: publishes "factors"
+  //                           ranks; sums of my tiles -> every rank; | k_peer_sh_expand_tiles: waits for "factors",
+  //                           last CTA publishes "summed"            | dL_dsh from the local factor tables
+  //   k_peer_unpack           every CTA waits for "summed"; dense tensors
+  // The factor tables are half of the step's NVLink bytes and are complete before the per-surfel kernel starts: pushed
+  // from the side stream they cross the links UNDER that kernel, and the expansion no longer waits for anybody's rows.
+  const bool early = g_peer_early_factors != 0;
   if ((rc = launch_peer_begin(ctx, in->campos, st))) return rc;
-  if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, false, 0, P, st, true))) return rc;
-  if ((rc = launch_peer_signal_fused(ctx, PEER_SLOT_PUSHED, st))) return rc;
+  if (early) {
+    if ((rc = launch_peer_factor_extract(ctx, *p, g, st))) return rc;
+  } else {
+    if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, false, 0, P, st, true, false))) return rc;
+    if ((rc = launch_peer_signal_fused(ctx, PEER_SLOT_PUSHED, st))) return rc;
+  }
   cudaEventRecord(aux->chunk[0], st);
-  cudaStreamWaitEvent(aux->stream, aux->chunk[0], 0);
+  cudaStream_t xs = aux->stream;  // the stream of the expansion
+  const bool low = early && g_peer_expand_low;
+  if (early) {
+    cudaStreamWaitEvent(aux->stream, aux->chunk[0], 0);
+    {
+      ProfScope prof(GSL_K_PEER_FACTORS, aux->stream);
+      if ((rc = launch_peer_factor_push(ctx, *p, aux->stream))) return rc;
+      if ((rc = launch_peer_signal_fused(ctx, PEER_SLOT_FACTORS, aux->stream))) return rc;
+    }
+    cudaEventRecord(aux->join, aux->stream);
+    if (low) {
+      // The expansion must not be resident before this rank's own "factors" flag is out (its CTAs would spin on a flag
+      // that a kernel of this very GPU has yet to publish), and it should not hold SMs while it waits for the other ranks:
+      // behind the signal's event, one warp waits for everybody's factors, then the bulk kernel starts.
+      xs = aux->low;
+      cudaStreamWaitEvent(xs, aux->join, 0);
+      if ((rc = launch_peer_wait_fused(ctx, PEER_SLOT_FACTORS, xs))) return rc;
+    }
+  } else {
+    cudaStreamWaitEvent(xs, aux->chunk[0], 0);
+  }
   {
-    ProfScope prof(GSL_K_PEER_EXPAND, aux->stream);
-    if ((rc = launch_peer_sh_expand(ctx, P, p->S, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, aux->stream, true)))
+    ProfScope prof(GSL_K_PEER_EXPAND, xs);
+    if ((rc = launch_peer_sh_expand(ctx, P, p->S, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, xs, true,
+                                    early ? PEER_SLOT_FACTORS : PEER_SLOT_PUSHED)))
       return rc;
   }
-  cudaEventRecord(aux->join, aux->stream);
+  cudaEventRecord(aux->join_low, xs);
+  if (early) {
+    if ((rc = launch_preprocess_backward(*p, *in, *fwd, *gout, g, false, 0, P, st, true, true))) return rc;
+    if ((rc = launch_peer_signal_fused(ctx, PEER_SLOT_PUSHED, st))) return rc;
+  }
   {
     ProfScope prof(GSL_K_PEER_REDUCE, st);
+    if (low && (rc = launch_peer_wait_fused(ctx, PEER_SLOT_PUSHED, st))) return rc;
     if ((rc = launch_peer_reduce_rows(ctx, P, p->S, 0, P, st, true))) return rc;
   }
   {
     ProfScope prof(GSL_K_PEER_UNPACK, st);
+    if (low && (rc = launch_peer_wait_fused(ctx, PEER_SLOT_SUMMED, st))) return rc;
     if ((rc = launch_peer_unpack(ctx, P, p->S, prezeroed, *gout, st, true))) return rc;
   }
-  cudaStreamWaitEvent(st, aux->join, 0);  // dL_dsh complete
+  if (early) cudaStreamWaitEvent(st, aux->join, 0);  // the factor pushes of this rank have left
+  cudaStreamWaitEvent(st, aux->join_low, 0);         // dL_dsh complete
   return debug_sync(p, st, "backward_surfels_exchange");
 }
 
@@ -467,6 +513,14 @@ GSL_API int gsl_peer_open(const gsl_peer_handle* handle, void** dptr) {
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, sizeof(h));
   return check_cuda(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+GSL_API int gsl_peer_set_option(int32_t option, int32_t value) {
+  switch (option) {
+    case GSL_PEER_OPT_EARLY_FACTORS: g_peer_early_factors = value ? 1 : 0; return 0;
+    case GSL_PEER_OPT_EXPAND_LOW_PRIORITY: g_peer_expand_low = value ? 1 : 0; return 0;
+    default: return set_error(GSL_EINVAL, "peer_set_option: unknown option %d", option);
+  }
 }
 
 GSL_API int gsl_peer_set_timeout_ms(uint32_t ms) {
@@ -622,7 +676,11 @@ static cudaStream_t capture_stream() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!have[dev]) {
-    if (cudaStreamCreateWithFlags(&cap[dev], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // middle priority: the captured "main stream" kernels then rank above the low side stream (bulk work that should only fill
+    // idle SMs) and below the high one (torch's own streams have the lowest priority, so on plain streams low == main)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&cap[dev], cudaStreamNonBlocking, (prio_lo + prio_hi) / 2) != cudaSuccess) return nullptr;
     have[dev] = true;
   }
   return cap[dev];
@@ -716,7 +774,7 @@ GSL_API const char* gsl_kernel_name(int id) {
   static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan|bases)", "k_bin_scatter",
                                            "k_sort_(hist|scan|scatter|buckets)", "k_tile_blists", "k_render_fwd",
                                            "k_render_bwd", "k_preprocess_bwd", "k_glue_fwd", "k_glue_bwd",
-                                           "k_peer_reduce_rows", "k_peer_sh_expand", "k_peer_unpack"};
+                                           "k_peer_reduce_rows", "k_peer_sh_expand", "k_peer_unpack", "k_peer_factor_push"};
   return (id >= 0 && id < GSL_K_COUNT) ? names[id] : "?";
 }
 

@@ -224,7 +224,8 @@ int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out,
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st);
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in,
                                const gsl_fwd_outputs& fwd, gsl_bwd_outputs& gout, const GeomView& g,
-                               bool prezeroed, int row0, int row1, cudaStream_t st, bool fused = false);
+                               bool prezeroed, int row0, int row1, cudaStream_t st, bool fused = false,
+                               bool factors_done = false);
 int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const float* campos_all, const float* drgb_all,
                      size_t drgb_stride, float* dL_dsh, cudaStream_t st);
 int launch_glue_forward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& out, cudaStream_t st);
@@ -238,13 +239,14 @@ constexpr int PEER_MAX = GSL_PEER_MAX;
 // Header of an exchange buffer (first PEER_HEADER bytes):
 //   [0, 256)      flags u32[8 slots][PEER_MAX]: slot s, word g = the last ticket rank g published on slot s.
 //                 slots 0..3: host-ticketed barriers (gsl_peer_barrier / _signal / _wait); slot 4: "rows + factors of
-//                 this step pushed", slot 5: "sums of my tiles pushed" -- the two in-kernel barriers of the fused step
+//                 this step pushed", slot 5: "sums of my tiles pushed", slot 6: "SH factors of this step pushed" (side stream,
+//                 under the per-surfel kernel) -- the in-kernel barriers of the fused step
 //   [512, 516)    step counter of the fused step (device side: incremented by k_peer_begin, identical on all ranks)
 //   [516, 520)    error word: != 0 after a barrier time-out; the kernels that write gradients then write NaN
 //   [520, 552)    finished-CTA counters (one per signalling kernel) for "last CTA publishes the flag"
 //   [1024, 1036)  this rank's camera centre;  [1280, 1536) float4[2 parities][PEER_MAX] camera centres of all ranks
 constexpr size_t PEER_HEADER = 4096;
-constexpr int PEER_SLOT_PUSHED = 4, PEER_SLOT_SUMMED = 5, PEER_SLOTS = 8;
+constexpr int PEER_SLOT_PUSHED = 4, PEER_SLOT_SUMMED = 5, PEER_SLOT_FACTORS = 6, PEER_SLOTS = 8;
 constexpr size_t PEER_STEP_OFF = 512, PEER_ERROR_OFF = 516, PEER_DONE_OFF = 520;
 constexpr size_t PEER_CAMPOS_OFF = GSL_PEER_CAMPOS_OFFSET;
 constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[2 parities][PEER_MAX]: camera centres of all ranks
@@ -291,9 +293,15 @@ PeerLayout peer_layout(size_t P, int S, int world);
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
 int launch_peer_begin(const gsl_peer_ctx* c, const float* campos, cudaStream_t st);
 int launch_peer_signal_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st);
+int launch_peer_wait_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st);
 // fused: true = one step of gsl_backward_surfels_exchange (device-side step counter, in-kernel flag waits / signals)
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
-                          const float* means3D, float* dL_dsh, cudaStream_t st, bool fused = false);
+                          const float* means3D, float* dL_dsh, cudaStream_t st, bool fused = false,
+                          int wait_slot = PEER_SLOT_PUSHED);
+// fused step: SH factors of this rank out of the packed accumulators into the own factor table (main stream, before the
+// per-surfel kernel re-zeroes them), then from there into every other rank's table (side stream, under that kernel)
+int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st);
+int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st);
 int launch_chamfer_forward(int b, int n, const float* xyz1, int m, const float* xyz2, float* dist1, int* idx1, float* dist2,
                            int* idx2, void* scratch, cudaStream_t st);
 int launch_chamfer_backward(int b, int n, const float* xyz1, int m, const float* xyz2, const float* gdist1, const int* idx1,

@@ -107,6 +107,20 @@ __global__ void k_peer_signal(PeerView pv, int slot) {
   st_release_sys(reinterpret_cast<uint32_t*>(pv.buf[g]) + slot * PEER_MAX + pv.rank, pv.epoch);
 }
 
+// Waiting half as its own one-warp kernel: the stream goes on once every rank has published the step's ticket on `slot`.
+// The consuming kernels wait in-kernel as well (peer_wait_flags), which is free once the flags are there; parking the wait
+// in ONE warp instead of in every resident CTA of a 4000-CTA kernel leaves the SMs to the other streams of the step (the
+// low-priority SH expansion fills exactly these waits).
+__global__ void k_peer_wait(PeerView pv, int slot) {
+  peer_resolve_step(pv);
+  peer_wait_flags(pv, slot);
+}
+
+int launch_peer_wait_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st) {
+  k_peer_wait<<<1, 32, 0, st>>>(make_view(c, true), slot);
+  return check_cuda(cudaGetLastError(), "k_peer_wait launch");
+}
+
 int launch_peer_signal_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st) {
   k_peer_signal<<<1, 32, 0, st>>>(make_view(c, true), slot);
   return check_cuda(cudaGetLastError(), "k_peer_signal launch");

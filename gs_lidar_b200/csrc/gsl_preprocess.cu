@@ -480,6 +480,7 @@ struct PreBwdParams {
   int row0, row1; // surfel range of this launch (chunked launches pipeline the peer exchange behind the kernel)
   int rw;         // > 0: GSL_FLAG_BWD_PEER_ROWS -- floats per packed exchange row (peer_row_width(S))
   int fused;      // peer mode: part of a fused step -- step / parity come from the device-side counter (gsl_peer.cuh)
+  int factors_done; // peer mode: the SH factors were pushed already (k_peer_factor_extract / _push), rows only here
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -720,7 +721,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
             (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f) | (g2.z != 0.f) | (g2.w != 0.f) |
             (gc.x != 0.f) | (gc.y != 0.f) | (gc.z != 0.f) | (gc.w != 0.f) | (gn.x != 0.f) | (gn.y != 0.f) |
             (gn.z != 0.f);
-      if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
+      if (!pp.factors_done && (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f)) {
         const uint8_t cl = clamped[idx];
         fac = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
       }
@@ -750,22 +751,26 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     const uint32_t bits = __ballot_sync(0xffffffffu, any);
     if (lane == 0 && live) reinterpret_cast<uint32_t*>(obuf + pl.off_stagebits)[(slot0 >> 5) + warp] = bits;
     if (lane == 0) s_any[warp] = bits;
-    // SH factors: block-local compaction, pushed to every rank
-    const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
-    const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
-    if (lane == 0) s_warp[warp] = __popc(fbits);
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += s_warp[w];
-    const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;  // [parity][source rank][tile]
-    const size_t fpos = table * 256 + before + __popc(fbits & ((1u << lane) - 1u));
-    const size_t mpos = table * 8 + warp;
+    if (pp.factors_done) {
+      __syncthreads();  // s_count, the queued records and s_any are complete
+    } else {
+      // SH factors: block-local compaction, pushed to every rank
+      const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
+      const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
+      if (lane == 0) s_warp[warp] = __popc(fbits);
+      __syncthreads();
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += s_warp[w];
+      const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;  // [parity][source rank][tile]
+      const size_t fpos = table * 256 + before + __popc(fbits & ((1u << lane) - 1u));
+      const size_t mpos = table * 8 + warp;
 #pragma unroll
-    for (int g = 0; g < PEER_MAX; ++g) {
-      if (g < pv.world) {
-        if (nz) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[fpos] = fac;
-        if (lane == 0 && live)
-          reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[mpos] = make_uint2(fbits, (uint32_t)before);
+      for (int g = 0; g < PEER_MAX; ++g) {
+        if (g < pv.world) {
+          if (nz) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[fpos] = fac;
+          if (lane == 0 && live)
+            reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[mpos] = make_uint2(fbits, (uint32_t)before);
+        }
       }
     }
     const int count = s_count;
@@ -884,6 +889,76 @@ int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out,
   return check_cuda(cudaGetLastError(), "k_extract_sh_factor launch");
 }
 
+// ---- fused exchange step: the SH factors leave EARLY ----------------------------------------------------------------------
+// A factor (clamp-masked dL_dRGB) is complete when the backward compositor has finished, 0.15 ms before the packed rows
+// k_preprocess_bwd produces, and the factor tables are half of the step's NVLink traffic (16 B x touched surfels into every
+// rank).  k_peer_factor_extract (main stream, ~10 us: one 32-byte sector per accumulator record) packs this rank's non-zero
+// factors tile by tile into its OWN factor table (+ bits / prefix words), before k_preprocess_bwd re-zeroes the accumulators;
+// k_peer_factor_push (side stream) copies the packed part of every tile into the other ranks' tables while k_preprocess_bwd
+// runs, and the "factors" flag behind it lets every rank start its expansion without waiting for anybody's rows.
+__global__ void __launch_bounds__(256) k_peer_factor_extract(PeerView pv, const PeerLayout pl, int P, int gstride,
+                                                             const float* __restrict__ grad,
+                                                             const uint8_t* __restrict__ clamped) {
+  __shared__ int s_warp[8];
+  peer_resolve_step(pv);
+  const int tile = blockIdx.x;
+  const int idx = tile * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 fac = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < P) {
+    const float4 gc = reinterpret_cast<const float4*>(grad + (size_t)idx * gstride)[3];
+    if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
+      const uint8_t cl = clamped[idx];
+      fac = make_float4((cl & 1) ? 0.f : gc.x, (cl & 2) ? 0.f : gc.y, (cl & 4) ? 0.f : gc.z, (cl & 8) ? 0.f : gc.w);
+    }
+  }
+  const bool nz = fac.x != 0.f || fac.y != 0.f || fac.z != 0.f || fac.w != 0.f;
+  const uint32_t fbits = __ballot_sync(0xffffffffu, nz);
+  if (lane == 0) s_warp[warp] = __popc(fbits);
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += s_warp[w];
+  const size_t table = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles + tile;  // [parity][source rank][tile]
+  if (nz) reinterpret_cast<float4*>(pv.own + pl.off_factor)[table * 256 + before + __popc(fbits & ((1u << lane) - 1u))] = fac;
+  if (lane == 0) reinterpret_cast<uint2*>(pv.own + pl.off_fmeta)[table * 8 + warp] = make_uint2(fbits, (uint32_t)before);
+}
+
+__global__ void __launch_bounds__(256) k_peer_factor_push(PeerView pv, const PeerLayout pl) {
+  peer_resolve_step(pv);
+  const size_t slab = (size_t)(pv.parity * pv.world + pv.rank) * pl.tiles;
+  for (int tile = blockIdx.x; tile < pl.tiles; tile += gridDim.x) {
+    const size_t table = slab + tile;
+    const uint2* meta = reinterpret_cast<const uint2*>(pv.own + pl.off_fmeta) + table * 8;
+    const uint2 last = meta[7];
+    const int count = (int)last.y + __popc(last.x);
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 m = make_uint2(0u, 0u);
+    if ((int)threadIdx.x < count) f = reinterpret_cast<const float4*>(pv.own + pl.off_factor)[table * 256 + threadIdx.x];
+    if (threadIdx.x < 8) m = meta[threadIdx.x];
+#pragma unroll
+    for (int g = 0; g < PEER_MAX; ++g) {
+      if (g < pv.world && g != pv.rank) {
+        if ((int)threadIdx.x < count) reinterpret_cast<float4*>(pv.buf[g] + pl.off_factor)[table * 256 + threadIdx.x] = f;
+        if (threadIdx.x < 8) reinterpret_cast<uint2*>(pv.buf[g] + pl.off_fmeta)[table * 8 + threadIdx.x] = m;
+      }
+    }
+  }
+}
+
+int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st) {
+  if (p.P == 0) return 0;
+  const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
+  k_peer_factor_extract<<<pl.tiles, 256, 0, st>>>(make_view(c, true), pl, p.P, grad_stride(p.S), g.grad, g.clamped);
+  return check_cuda(cudaGetLastError(), "k_peer_factor_extract launch");
+}
+
+int launch_peer_factor_push(const gsl_peer_ctx* c, const gsl_params& p, cudaStream_t st) {
+  if (p.P == 0 || c->world < 2) return 0;
+  const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
+  k_peer_factor_push<<<std::min(pl.tiles, 148 * 8), 256, 0, st>>>(make_view(c, true), pl);
+  return check_cuda(cudaGetLastError(), "k_peer_factor_push launch");
+}
+
 // zero-fill of every dense gradient output (enqueued on a side stream under the backward compositor)
 int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_outputs& gout, cudaStream_t st) {
   const size_t P = (size_t)p.P;
@@ -922,7 +997,7 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
 
 int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, const gsl_fwd_outputs& fwd,
                                gsl_bwd_outputs& gout, const GeomView& g, bool prezeroed, int row0, int row1,
-                               cudaStream_t st, bool fused) {
+                               cudaStream_t st, bool fused, bool factors_done) {
   if (p.P == 0 || row1 <= row0) return 0;
   PreBwdParams pp;
   pp.P = p.P; pp.D = p.D; pp.M = p.M; pp.S = p.S;
@@ -944,6 +1019,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   PeerView pv = {};
   PeerLayout pl = {};
   pp.fused = (fused && pp.rw > 0) ? 1 : 0;
+  pp.factors_done = (factors_done && pp.rw > 0) ? 1 : 0;
   if (pp.rw > 0) {
     pp.factored = 1;
     pv = make_view(gout.peer, fused);
@@ -1103,7 +1179,8 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
 // "pushed" flags of the step (in-kernel barrier), builds the list of rows with a factor on SOME rank (OR of the ranks' bit
 // words, prefix over the 8 words) and only ceil(n / 32) dense warps do the work.
 __global__ void __launch_bounds__(256, 2) k_peer_sh_expand_tiles(PeerView pv, const PeerLayout pl, int tile0, int row1, int D,
-                                                                 int M, int fused, const float* __restrict__ means3D,
+                                                                 int M, int fused, int wait_slot,
+                                                                 const float* __restrict__ means3D,
                                                                  float* __restrict__ dL_dsh) {
   __shared__ uint2 s_meta[PEER_MAX][8];
   __shared__ uint32_t s_union[8];
@@ -1112,7 +1189,7 @@ __global__ void __launch_bounds__(256, 2) k_peer_sh_expand_tiles(PeerView pv, co
   __shared__ float4 s_t[8][32][9];
   if (fused) {
     peer_resolve_step(pv);
-    peer_wait_flags(pv, PEER_SLOT_PUSHED);
+    peer_wait_flags(pv, wait_slot);
   }
   const int tile = tile0 + blockIdx.x;
   const int base_row = tile * 256;
@@ -1199,11 +1276,11 @@ __global__ void __launch_bounds__(256, 2) k_peer_sh_expand_tiles(PeerView pv, co
 }
 
 int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int row0, int row1, bool prezeroed,
-                          const float* means3D, float* dL_dsh, cudaStream_t st, bool fused) {
+                          const float* means3D, float* dL_dsh, cudaStream_t st, bool fused, int wait_slot) {
   if (row1 <= row0 || M == 0) return 0;
   if (prezeroed && M <= 16) {
     k_peer_sh_expand_tiles<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c, fused), peer_layout((size_t)P, S, c->world),
-                                                                     row0 >> 8, row1, D, M, fused ? 1 : 0, means3D, dL_dsh);
+                                                                     row0 >> 8, row1, D, M, fused ? 1 : 0, wait_slot, means3D, dL_dsh);
     return check_cuda(cudaGetLastError(), "k_peer_sh_expand_tiles launch");
   }
   if (fused) return set_error(GSL_EINVAL, "peer_sh_expand: the fused step needs zero-filled outputs and M <= 16");

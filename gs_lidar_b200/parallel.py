@@ -235,6 +235,17 @@ class PeerExchange(GradientExchange):
         self._opened = []
         self.side = None
 
+    @staticmethod
+    def set_schedule(early_factors=False, expand_low_priority=False):
+        """Schedule of the fused step (process-wide, same on every rank; see gsl_peer_set_option in include/gsl_b200.h):
+        early_factors -- SH factors pushed from a side stream under the per-surfel kernel instead of by that kernel;
+        expand_low_priority -- the SH expansion on a lowest-priority stream.  Off by default (measured slower)."""
+        from . import _lib as L
+        lib = L.load()
+        L.check(lib.gsl_peer_set_option(L.GSL_PEER_OPT_EARLY_FACTORS, int(bool(early_factors))), "gsl_peer_set_option")
+        L.check(lib.gsl_peer_set_option(L.GSL_PEER_OPT_EXPAND_LOW_PRIORITY, int(bool(expand_low_priority))),
+                "gsl_peer_set_option")
+
     def rank(self):
         return dist.get_rank(self.group) if (dist.is_available() and dist.is_initialized()) else 0
 

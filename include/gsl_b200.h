@@ -292,6 +292,17 @@ GSL_API int gsl_peer_close(void* dptr);
 /* How long a barrier (kernel or in-kernel wait) waits for a rank that does not arrive before it raises the error flag and
  * lets the step finish with NaN gradients; process-wide, 20000 ms by default. */
 GSL_API int gsl_peer_set_timeout_ms(uint32_t ms);
+/* Schedule of the fused step (gsl_backward_surfels_exchange), process-wide.  Both options are OFF by default: after the
+ * backward compositor every kernel of the step is HBM- or NVLink-bound and the GPU is busy until the step ends, so moving
+ * work between streams re-orders it without shortening it (measured on 2 B200s, profiles/r02_exchange_schedules.md:
+ * 1.03 ms / step by default, 1.06 with early factors, 1.07 with the low-priority expansion as well).
+ *   GSL_PEER_OPT_EARLY_FACTORS: the SH factors are extracted right after the backward compositor and pushed from the
+ *     library's high-priority side stream UNDER the per-surfel kernel; 0: that kernel pushes them together with its rows.
+ *   GSL_PEER_OPT_EXPAND_LOW_PRIORITY (only with early factors): the SH expansion runs on a lowest-priority stream behind
+ *     a one-warp wait for every rank's factors; the waits of the sum and unpack kernels are parked in one-warp kernels too.
+ * Every rank must use the same options. */
+enum { GSL_PEER_OPT_EARLY_FACTORS = 0, GSL_PEER_OPT_EXPAND_LOW_PRIORITY = 1 };
+GSL_API int gsl_peer_set_option(int32_t option, int32_t value);
 GSL_API int gsl_peer_free(void* dptr);
 /* Signal "this rank reached ticket ctx->epoch on flag slot `slot` (0..3)" to all ranks and wait for all of them. */
 GSL_API int gsl_peer_barrier(const gsl_peer_ctx* ctx, int32_t slot, void* stream);
@@ -319,8 +330,8 @@ GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const
 GSL_API int gsl_backward_surfels_rows(const gsl_params* p, const gsl_fwd_inputs* in, const gsl_fwd_outputs* fwd,
                               gsl_bwd_outputs* gout, gsl_workspace* ws, int32_t row_begin, int32_t row_end, void* stream);
 /* The whole second half of a frame-parallel backward pass in one call (after gsl_backward_composite), as ONE fused step:
- * per-surfel VJP with its pushes, sum of the owned tiles, SH expansion (library side stream) and unpack, with both
- * barriers INSIDE the kernels (the last CTA of a producing kernel publishes a flag in every rank's buffer, every CTA of
+ * per-surfel VJP with its pushes, sum of the owned tiles, SH expansion (library side stream) and unpack (other schedules:
+ * gsl_peer_set_option), with the barriers INSIDE the kernels (the last CTA of a producing kernel publishes a flag in every rank's buffer, every CTA of
  * a consuming kernel waits for the flags of all ranks) and the ticket taken from a device-side step counter in the
  * exchange buffer -- every kernel argument is constant from step to step, so the call can be captured in a CUDA graph.
  * Every rank must make the same sequence of calls on the same exchange buffers.  `step` and `chunks` are accepted for
@@ -378,9 +389,10 @@ enum {
   GSL_K_GLUE_FWD = 8,  /* k_glue_fwd (render() glue, next-1) */
   GSL_K_GLUE_BWD = 9,  /* k_glue_bwd */
   GSL_K_PEER_REDUCE = 10, /* k_peer_reduce_rows (includes its in-kernel wait for the ranks' "pushed" flags) */
-  GSL_K_PEER_EXPAND = 11, /* k_peer_sh_expand_tiles, side stream */
+  GSL_K_PEER_EXPAND = 11, /* k_peer_sh_expand_tiles, side stream (includes its in-kernel wait for the ranks' "factors" flags) */
   GSL_K_PEER_UNPACK = 12, /* k_peer_unpack (includes its in-kernel wait for the owners' "summed" flags) */
-  GSL_K_COUNT = 13
+  GSL_K_PEER_FACTORS = 13, /* k_peer_factor_push + its k_peer_signal, side stream, under k_preprocess_bwd */
+  GSL_K_COUNT = 14
 };
 GSL_API int gsl_profile_enable(int on);
 /* Waits for all recorded events, then returns accumulated milliseconds and launch counts per id. */

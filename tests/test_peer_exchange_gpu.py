@@ -127,8 +127,9 @@ def test_emulated_two_ranks_equal_the_sum_of_dense_gradients(P, split, sparse):
             lib.gsl_peer_free(q)
 
 
-@pytest.mark.parametrize("P,chunks", [(20000, 1), (5003, 3), (70000, 4)])
-def test_single_rank_exchange_equals_the_plain_backward(P, chunks):
+@pytest.mark.parametrize("P,chunks,early,low", [(20000, 1, True, True), (5003, 3, True, False), (70000, 4, False, False),
+                                                (5003, 1, True, True)])
+def test_single_rank_exchange_equals_the_plain_backward(P, chunks, early, low):
     """The complete fused path (gsl_backward_surfels_exchange: pushes, barriers, reduce, expand, unpack, zero-fill under
     the compositor, row ranges on the side stream) with one rank: the 'sum' must be the plain backward's gradients."""
     from gs_lidar_b200 import parallel
@@ -136,6 +137,7 @@ def test_single_rank_exchange_equals_the_plain_backward(P, chunks):
     cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=76).items()}
     dense = common.run_ours(scene, cot, export=False)[2]
     ex = parallel.PeerExchange(force=True, chunks=chunks)
+    parallel.PeerExchange.set_schedule(early_factors=early, expand_low_priority=low)
     try:
         for it in range(3):  # the buffers are reused: stale rows / factors of earlier steps must never leak
             sc = scene if it != 1 else scene._replace(opacities=scene.opacities * 0.5)
@@ -149,6 +151,7 @@ def test_single_rank_exchange_equals_the_plain_backward(P, chunks):
         culled = dense["shs"].abs().sum(dim=(1, 2)) == 0
         assert float(got["shs"][culled].abs().sum()) == 0.0  # untouched surfels: exact zeros from the zero-fill
     finally:
+        parallel.PeerExchange.set_schedule()
         ex.close()
 
 
