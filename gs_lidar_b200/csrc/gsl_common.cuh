@@ -72,6 +72,8 @@ struct GeomView {
   uint32_t* sval_a;
   uint32_t* sval_b;      //   surfel ids in (depth, id) order
   uint32_t* sort_buckets;  // count / start / cursor arrays of the bucket sort, 3 x (16384 + 64)
+  uint8_t* touched;      // 1 = some pixel composited this surfel (set by k_render_fwd, consumed and cleared by the backward):
+                         // the per-surfel backward reads the 128-byte accumulator of a surfel only when it is set
   size_t bytes;
 };
 
@@ -124,6 +126,7 @@ inline GeomView geom_view(void* base, int P, int S) {
   carve(p, g.sval_a, Pp);
   carve(p, g.sval_b, Pp);
   carve(p, g.sort_buckets, 3 * (16384 + 64));
+  carve(p, g.touched, Pp);
   g.bytes = (size_t)(p - (char*)base) + 256;
   return g;
 }

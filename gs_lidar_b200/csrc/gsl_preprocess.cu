@@ -138,6 +138,78 @@ __device__ __forceinline__ float4 eval_sh(int deg, const ShView sh, float x, flo
   return make_float4(r[0] + 0.5f, r[1] + 0.5f, r[2] + 0.5f, r[3] + 0.5f);
 }
 
+// One sample of the 12-point AABB (forward.cu:139-171): pixel coordinates of the point (vx, vy) of the splat plane,
+// with exactly the reference's rounding sequence.
+__device__ __forceinline__ float2 aabb_sample_ref(const Splat& s, float vx, float vy, float hfov_min, float vfov_min,
+                                                  float Wf, float Hf, float dH, float dV) {
+  float X = GSL_FA(s.Tuz, GSL_FF(s.Tux, vx, GSL_FM(s.Tuy, vy)));
+  float Y = GSL_FA(s.Tvz, GSL_FF(s.Tvx, vx, GSL_FM(s.Tvy, vy)));
+  float Z = GSL_FA(s.Twz, GSL_FF(s.Twx, vx, GSL_FM(s.Twy, vy)));
+  float ph = atan2f(X, Z);
+  float th = atan2f(sqrtf(GSL_FF(X, X, GSL_FM(Z, Z))), -Y);
+  return make_float2(GSL_FD(GSL_FM(GSL_FS(ph, hfov_min), Wf), dH), GSL_FD(GSL_FM(GSL_FS(th, vfov_min), Hf), dV));
+}
+
+// atan(t) for 0 <= t <= 0.25 (odd series to t^11: truncation 5e-9 relative)
+__device__ __forceinline__ float atan_small(float t) {
+  const float q = t * t;
+  float p = fmaf(q, -0.09090909f, 0.11111111f);
+  p = fmaf(q, p, -0.14285714f);
+  p = fmaf(q, p, 0.2f);
+  p = fmaf(q, p, -0.33333333f);
+  return fmaf(t * q, p, t);
+}
+
+// Filtered AABB radius.  Only ceil(rad) and the test rad < 0.3 consume the 24 atan2f of the reference's 12-sample AABB
+// (forward.cu:139-171, :243-264), so the radius is first computed in a form that needs two short arctangent series:
+// the azimuth / elevation offsets of a sample RELATIVE to the splat centre are atan(c / d) with
+//     azimuth:   c = dX tz - dZ tx,          d = rxz^2 + dX tx + dZ tz           (dX, dY, dZ = sample - centre)
+//     elevation: c = dY rxz - drho ty,       d = Y ty + rho rxz,                 drho = rho - rxz without cancellation
+// atan is odd and monotone, so max(max_i atan(t_i), -min_i atan(t_i)) = atan(max(t_max, -t_min)): ONE series per axis.
+// The result differs from the reference's float value by at most `eps` pixels -- the reference's own rounding (atan2f
+// 2 ulp of pi, the subtraction of the fov origin, one multiplication and one division at magnitude <= W: 2.4e-4 px at
+// W = 1030 for each of the two coordinates it subtracts) plus 2e-4 for this form -- so whenever [rad - eps, rad + eps]
+// contains neither an integer nor 0.3 the radius and the culling decision ARE the reference's.  Returns false when that
+// cannot be certified (band hit, splat wider than atan(0.25) = 14 degrees, sample behind the centre's meridian plane,
+// azimuth range touching the +-pi seam, non-finite values): the caller then evaluates the reference sequence itself.
+__device__ __forceinline__ bool aabb_radius_filtered(const Splat& s, float cutoff, const float* s_sin, const float* s_cos,
+                                                     float rxz, float phi, float kx, float ky, float eps,
+                                                     int& radius_out, bool& small_out) {
+  const float tx = s.Tuz, ty = s.Tvz, tz = s.Twz;
+  const float rxz2 = rxz * rxz;
+  float tmax = -1e30f, tmin = 1e30f, umax = -1e30f, umin = 1e30f;
+  float slack = 1e30f;  // min over the samples of (d - 4|c|) of both axes, and of rho^2: all must be > 1e-30
+#pragma unroll 4
+  for (int i = 0; i < 12; ++i) {
+    const float vx = s_sin[i] * cutoff, vy = s_cos[i] * cutoff;
+    const float dX = fmaf(s.Tux, vx, s.Tuy * vy), dY = fmaf(s.Tvx, vx, s.Tvy * vy), dZ = fmaf(s.Twx, vx, s.Twy * vy);
+    const float X = tx + dX, Y = ty + dY, Z = tz + dZ;
+    const float c = fmaf(dX, tz, -dZ * tx);
+    const float along = fmaf(dX, tx, dZ * tz);
+    const float d = rxz2 + along;
+    const float t = c * fast_rcp(d);
+    tmax = fmaxf(tmax, t); tmin = fminf(tmin, t);
+    const float rho2 = fmaf(X, X, Z * Z);
+    const float rho = rho2 * rsqrtf(rho2);
+    const float drho = fmaf(2.f, along, fmaf(dX, dX, dZ * dZ)) * fast_rcp(rho + rxz);
+    const float c2 = fmaf(dY, rxz, -drho * ty);
+    const float d2 = fmaf(Y, ty, rho * rxz);
+    const float u = c2 * fast_rcp(d2);
+    umax = fmaxf(umax, u); umin = fminf(umin, u);
+    slack = fminf(slack, fminf(fmaf(-4.f, fabsf(c), d), fmaf(-4.f, fabsf(c2), d2)));
+    slack = fminf(slack, rho2);
+  }
+  const float ax = atan_small(fmaxf(tmax, -tmin)), ay = atan_small(fmaxf(umax, -umin));
+  const float rad = fmaxf(ax * kx, ay * ky);
+  const float lo = rad - eps, hi = rad + eps;
+  // NaN anywhere makes a comparison false -> not certified
+  const bool base = (slack > 1e-30f) && (fabsf(phi) + ax < 3.1414f) && (rad < 1e6f);  // (denominators are normal numbers)
+  small_out = hi < 0.2999f;                                         // certainly culled by `radii < 0.3`
+  const bool big = (lo > 0.3001f) && (ceilf(lo) == ceilf(hi));     // certainly kept, with a certain ceil
+  radius_out = (int)ceilf(hi);
+  return base && (small_out || big);
+}
+
 __global__ void __launch_bounds__(256) k_preprocess_fwd(
     PreParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ opacities,
@@ -152,8 +224,9 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     s_cos[threadIdx.x] = cosf(pp.samp[threadIdx.x]);
   }
   __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= pp.P) return;
+  const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gidx < pp.P;          // the whole warp stays: the exact AABB fallback below is warp-cooperative
+  const int idx = live ? gidx : pp.P - 1;  // (loads of a dead lane read the last surfel; nothing is stored for it)
 
   // Invisible unless proven otherwise (forward.cu:214-215).
   int out_radius = 0;
@@ -179,7 +252,7 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
   const float theta = atan2f(rxz, -ty);
   const float r = sqrtf(GSL_FA(GSL_FF(ty, ty, tx2), tz2));
 
-  bool visible = mask[idx] != 0;
+  bool visible = live && mask[idx] != 0;
   const float dV = GSL_FS(pp.VFOV_max, pp.VFOV_min);
   const float dH = GSL_FS(pp.HFOV_max, pp.HFOV_min);
   if (visible) {
@@ -192,6 +265,12 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     if (r <= near_ || (double)ratio_v > 1.3 || (double)ratio_h > 1.3) visible = false;
   }
 
+  // state of a visible surfel that survives the (warp-uniform) AABB stage below
+  Splat s;
+  float nx = 0.f, ny = 0.f, nz = 0.f, cutoff = 0.f, cx = 0.f, cy = 0.f;
+  float4* my = rec + 4 * (size_t)idx;
+  const float Wf = (float)pp.W, Hf = (float)pp.H;
+  s.Tux = s.Tuy = s.Tuz = s.Tvx = s.Tvy = s.Tvz = s.Twx = s.Twy = s.Twz = 0.f;
   if (visible) {
     const float sx = scales[3 * idx], sy = scales[3 * idx + 1];
     const float4 q = reinterpret_cast<const float4*>(rotations)[idx];
@@ -200,7 +279,6 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     const float l0x = GSL_FM(sx, R.r00), l0y = GSL_FM(sx, R.r01), l0z = GSL_FM(sx, R.r02);
     const float l1x = GSL_FM(sy, R.r10), l1y = GSL_FM(sy, R.r11), l1z = GSL_FM(sy, R.r12);
     // T rows (forward.cu:84-105): Tu = x-coefficients, Tv = y, Tw = z over splat coords (u,v,1)
-    Splat s;
     s.Tux = dot3_ref(l0x, vm0, l0y, vm4, l0z, vm8);
     s.Tuy = dot3_ref(l1x, vm0, l1y, vm4, l1z, vm8);
     s.Tuz = tx;
@@ -211,45 +289,95 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
     s.Twy = dot3_ref(l1x, vm2, l1y, vm6, l1z, vm10);
     s.Twz = tz;
     // view-space normal, flipped towards the sensor (forward.cu:106-112)
-    float nx = dot3_ref(vm0, R.r20, vm4, R.r21, vm8, R.r22);
-    float ny = dot3_ref(vm1, R.r20, vm5, R.r21, vm9, R.r22);
-    float nz = dot3_ref(vm2, R.r20, vm6, R.r21, vm10, R.r22);
+    nx = dot3_ref(vm0, R.r20, vm4, R.r21, vm8, R.r22);
+    ny = dot3_ref(vm1, R.r20, vm5, R.r21, vm9, R.r22);
+    nz = dot3_ref(vm2, R.r20, vm6, R.r21, vm10, R.r22);
     float ndot = dot3_ref(nx, tx, ny, ty, nz, tz);
     float mult = ndot < 0.f ? 1.f : -1.f;
     nx = GSL_FM(nx, mult); ny = GSL_FM(ny, mult); nz = GSL_FM(nz, mult);
 
     // The reference stores T before any further culling (forward.cu:238-241).
-    float4* my = rec + 4 * (size_t)idx;
     my[0] = make_float4(s.Tux, s.Tuy, s.Tuz, s.Tvx);
     my[1] = make_float4(s.Tvy, s.Tvz, s.Twx, s.Twy);
 
-    const float cutoff = sqrtf((float)fmax((double)GSL_FF(logf(opacity), 2.f, 9.f), 0.000001));
-    float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
-    const float Wf = (float)pp.W, Hf = (float)pp.H;
-    const float cx = GSL_FD(GSL_FM(GSL_FS(phi, pp.HFOV_min), Wf), dH);
-    const float cy = GSL_FD(GSL_FM(GSL_FS(theta, pp.VFOV_min), Hf), dV);
+    cutoff = sqrtf((float)fmax((double)GSL_FF(logf(opacity), 2.f, 9.f), 0.000001));
+    cx = GSL_FD(GSL_FM(GSL_FS(phi, pp.HFOV_min), Wf), dH);
+    cy = GSL_FD(GSL_FM(GSL_FS(theta, pp.VFOV_min), Hf), dV);
+  }
+
+  // ---- AABB radius (forward.cu:139-171, :243-257): my_radius = ceil(rad), culled if rad < 0.3
+  int my_radius = 0;
+  bool keep = false;
+  if (pp.wrap) {
+    // wrap-around mode (opt-in, not the reference's semantics): azimuth of a sample RELATIVE to the centre
+    if (visible) {
+      float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
 #pragma unroll 1
-    for (int i = 0; i < 12; ++i) {
-      float vx = GSL_FM(s_sin[i], cutoff), vy = GSL_FM(s_cos[i], cutoff);
-      float X = GSL_FA(s.Tuz, GSL_FF(s.Tux, vx, GSL_FM(s.Tuy, vy)));
-      float Y = GSL_FA(s.Tvz, GSL_FF(s.Tvx, vx, GSL_FM(s.Tvy, vy)));
-      float Z = GSL_FA(s.Twz, GSL_FF(s.Twx, vx, GSL_FM(s.Twy, vy)));
-      float ph = atan2f(X, Z);
-      float th = atan2f(sqrtf(GSL_FF(X, X, GSL_FM(Z, Z))), -Y);
-      float ppx = GSL_FD(GSL_FM(GSL_FS(ph, pp.HFOV_min), Wf), dH);
-      if (pp.wrap) {  // azimuth of the sample RELATIVE to the centre, so that a splat on the seam keeps its true extent
-        float dphi = ph - phi;
+      for (int i = 0; i < 12; ++i) {
+        const float vx = GSL_FM(s_sin[i], cutoff), vy = GSL_FM(s_cos[i], cutoff);
+        const float X = GSL_FA(s.Tuz, GSL_FF(s.Tux, vx, GSL_FM(s.Tuy, vy)));
+        const float Z = GSL_FA(s.Twz, GSL_FF(s.Twx, vx, GSL_FM(s.Twy, vy)));
+        const float2 pxy = aabb_sample_ref(s, vx, vy, pp.HFOV_min, pp.VFOV_min, Wf, Hf, dH, dV);
+        float dphi = atan2f(X, Z) - phi;
         if (dphi > 3.14159265f) dphi -= 6.2831853f;
         else if (dphi < -3.14159265f) dphi += 6.2831853f;
-        ppx = cx + dphi * Wf / dH;
+        const float ppx = cx + dphi * Wf / dH;
+        minx = fminf(minx, ppx); maxx = fmaxf(maxx, ppx);
+        miny = fminf(miny, pxy.y); maxy = fmaxf(maxy, pxy.y);
       }
-      float ppy = GSL_FD(GSL_FM(GSL_FS(th, pp.VFOV_min), Hf), dV);
-      minx = fminf(minx, ppx); maxx = fmaxf(maxx, ppx);
-      miny = fminf(miny, ppy); maxy = fmaxf(maxy, ppy);
+      const float rad = fmaxf(fmaxf(GSL_FS(maxx, cx), GSL_FS(cx, minx)), fmaxf(GSL_FS(maxy, cy), GSL_FS(cy, miny)));
+      keep = !((double)rad < 0.3);
+      my_radius = (int)ceilf(rad);
     }
-    const float rad = fmaxf(fmaxf(GSL_FS(maxx, cx), GSL_FS(cx, minx)), fmaxf(GSL_FS(maxy, cy), GSL_FS(cy, miny)));
-    if (!((double)rad < 0.3)) {
-      const int my_radius = (int)ceilf(rad);
+  } else {
+    // 1. filtered form (two short arctangent series); certified for all but ~1 % of the surfels
+    bool exact = false;
+    if (visible) {
+      bool small = false;
+      const float kx = Wf / dH, ky = Hf / dV;
+      const float eps = 3.0f * (7.2e-7f * fmaxf(kx, ky) + 1.2e-7f * fmaxf(Wf, Hf)) + 2e-4f;
+      if (aabb_radius_filtered(s, cutoff, s_sin, s_cos, rxz, phi, kx, ky, eps, my_radius, small)) keep = !small;
+      else exact = true;
+    }
+    // 2. the rest (band hits, splats on the +-pi seam, very large or degenerate ones): the reference sequence itself, one
+    //    surfel at a time with its 12 samples spread over 12 lanes; min / max are order-independent (fminf / fmaxf drop NaN
+    //    operands exactly like the reference's running min / max, seeded with +-infinity)
+    uint32_t todo = __ballot_sync(0xffffffffu, exact);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      Splat q;
+      q.Tux = __shfl_sync(0xffffffffu, s.Tux, src); q.Tuy = __shfl_sync(0xffffffffu, s.Tuy, src);
+      q.Tuz = __shfl_sync(0xffffffffu, s.Tuz, src); q.Tvx = __shfl_sync(0xffffffffu, s.Tvx, src);
+      q.Tvy = __shfl_sync(0xffffffffu, s.Tvy, src); q.Tvz = __shfl_sync(0xffffffffu, s.Tvz, src);
+      q.Twx = __shfl_sync(0xffffffffu, s.Twx, src); q.Twy = __shfl_sync(0xffffffffu, s.Twy, src);
+      q.Twz = __shfl_sync(0xffffffffu, s.Twz, src);
+      const float qcut = __shfl_sync(0xffffffffu, cutoff, src);
+      float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+      if (lane < 12) {
+        const float2 pxy = aabb_sample_ref(q, GSL_FM(s_sin[lane], qcut), GSL_FM(s_cos[lane], qcut), pp.HFOV_min, pp.VFOV_min,
+                                           Wf, Hf, dH, dV);
+        minx = fminf(minx, pxy.x); maxx = fmaxf(maxx, pxy.x);
+        miny = fminf(miny, pxy.y); maxy = fmaxf(maxy, pxy.y);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {  // lanes 0..15 hold the samples (12..15: the seeds)
+        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+      }
+      minx = __shfl_sync(0xffffffffu, minx, 0); maxx = __shfl_sync(0xffffffffu, maxx, 0);
+      miny = __shfl_sync(0xffffffffu, miny, 0); maxy = __shfl_sync(0xffffffffu, maxy, 0);
+      if (lane == src) {
+        const float rad = fmaxf(fmaxf(GSL_FS(maxx, cx), GSL_FS(cx, minx)), fmaxf(GSL_FS(maxy, cy), GSL_FS(cy, miny)));
+        keep = !((double)rad < 0.3);
+        my_radius = (int)ceilf(rad);
+      }
+    }
+  }
+
+  if (visible && keep) {
+    {
       const float rf = (float)my_radius;
       // getRect (auxiliary.h:47-55)
       int rminx = min(pp.gx, max(0, (int)(GSL_FM(GSL_FS(cx, rf), 0.0625f))));
@@ -389,10 +517,12 @@ __global__ void __launch_bounds__(256) k_preprocess_fwd(
       }
     }
   }
-  radii[idx] = out_radius;
-  tiles[idx] = out_tiles;
-  rect[idx] = out_rect;
-  pixbox[idx] = out_box;
+  if (live) {
+    radii[idx] = out_radius;
+    tiles[idx] = out_tiles;
+    rect[idx] = out_rect;
+    pixbox[idx] = out_box;
+  }
 }
 
 // Keys of the surfel depth sort (fast binning): bits of the view-space range r, computed with exactly the
@@ -553,6 +683,26 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const ShView sh, f
   return dnormvdv3(dir_orig, dL_ddir);
 }
 
+// The 16 real SH basis values of a unit direction, as sh_backward scales dL_dRGB with them (backward.cu:17-134).
+__device__ __forceinline__ void sh_basis16(int deg, float x, float y, float z, float (&b)[16]) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) b[k] = 0.f;
+  b[0] = kSH_C0;
+  if (deg > 0) {
+    b[1] = -kSH_C1 * y; b[2] = kSH_C1 * z; b[3] = -kSH_C1 * x;
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      b[4] = kSH_C2[0] * xy; b[5] = kSH_C2[1] * yz; b[6] = kSH_C2[2] * (2.f * zz - xx - yy);
+      b[7] = kSH_C2[3] * xz; b[8] = kSH_C2[4] * (xx - yy);
+      if (deg > 2) {
+        b[9] = kSH_C3[0] * y * (3.f * xx - yy); b[10] = kSH_C3[1] * xy * z; b[11] = kSH_C3[2] * y * (4.f * zz - xx - yy);
+        b[12] = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); b[13] = kSH_C3[4] * x * (4.f * zz - xx - yy);
+        b[14] = kSH_C3[5] * z * (xx - yy); b[15] = kSH_C3[6] * x * (xx - 3.f * yy);
+      }
+    }
+  }
+}
+
 // (k_preprocess_bwd is defined after preprocess_vjp_one)
 // VJP of k_preprocess_fwd and of the SH evaluation for one surfel with accumulator record (g0, g1, g2, dcol, gn).
 __device__ __forceinline__ void preprocess_vjp_one(
@@ -562,7 +712,7 @@ __device__ __forceinline__ void preprocess_vjp_one(
     const float* __restrict__ campos, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
     float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh,
     float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
-    float* __restrict__ rows) {
+    float* __restrict__ rows, bool write_sh = true) {
   {
     const float vm0 = viewmatrix[0], vm1 = viewmatrix[1], vm2 = viewmatrix[2];
     const float vm4 = viewmatrix[4], vm5 = viewmatrix[5], vm6 = viewmatrix[6];
@@ -633,8 +783,8 @@ __device__ __forceinline__ void preprocess_vjp_one(
                                      means3D[3 * (size_t)i + 2] - campos[2]);
       const ShOut out_sh = sh_out(dL_dsh, dL_dsh_rest, (size_t)i, pp.M);
       const ShView sh_i = sh_view(shs, shs_rest, (size_t)i, pp.M);
-      const float3 dm = pp.factored ? sh_backward<false>(pp.D, pp.M, sh_i, dRGB, dir, out_sh)
-                                    : sh_backward<true>(pp.D, pp.M, sh_i, dRGB, dir, out_sh);
+      const float3 dm = (pp.factored || !write_sh) ? sh_backward<false>(pp.D, pp.M, sh_i, dRGB, dir, out_sh)
+                                                   : sh_backward<true>(pp.D, pp.M, sh_i, dRGB, dir, out_sh);
       // coefficients >= (D+1)^2 keep the zeros of the sweep
       dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
     }
@@ -676,7 +826,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     const float* __restrict__ rotations, const float* __restrict__ shs, const float* __restrict__ shs_rest,
     const float* __restrict__ viewmatrix, const float* __restrict__ campos,
     const int* __restrict__ radii, const float4* __restrict__ rec, const uint8_t* __restrict__ clamped,
-    float* __restrict__ grad, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
+    uint8_t* __restrict__ touched, float* __restrict__ grad, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D,
     float* __restrict__ dL_dsh, float* __restrict__ dL_dsh_rest, float* __restrict__ dL_dcolors,
     float* __restrict__ dL_dfeatures,
     float* __restrict__ dL_dopacity, float* __restrict__ dL_dscales, float* __restrict__ dL_drot,
@@ -714,7 +864,8 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     float* rows = staged ? reinterpret_cast<float*>(&s_rows[0][0]) - (ptrdiff_t)cta0 * 16 : rows_remote;
     bool any = false;
     float4 fac = zero4;
-    if (idx < pp.row1) {
+    if (idx < pp.row1 && touched[idx]) {  // no pixel composited the others: their accumulators are all-zero, never read
+      touched[idx] = 0;
       float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
       const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
       any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
@@ -790,16 +941,20 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     }
     return;  // fused step: the "pushed" flag is published by k_peer_signal, the next kernel of the stream
   }
-  if (idx < pp.row1) {
+  const bool was_touched = idx < pp.row1 && touched[idx] != 0;
+  if (was_touched) touched[idx] = 0;
+  if (idx < pp.row1 && (was_touched || !pp.prezeroed)) {
+    // a surfel no pixel composited has an all-zero accumulator: it is not read (prezeroed outputs: nothing to do at all)
     float4* gq = reinterpret_cast<float4*>(grad + (size_t)idx * pp.gstride);
-    const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], gc = gq[3], gn = gq[4];
+    float4 g0 = zero4, g1 = zero4, g2 = zero4, gc = zero4, gn = zero4;
+    if (was_touched) { g0 = gq[0]; g1 = gq[1]; g2 = gq[2]; gc = gq[3]; gn = gq[4]; }
     const bool any = (g0.x != 0.f) | (g0.y != 0.f) | (g0.z != 0.f) | (g0.w != 0.f) | (g1.x != 0.f) | (g1.y != 0.f) |
                      (g1.z != 0.f) | (g1.w != 0.f) | (g2.x != 0.f) | (g2.y != 0.f) | (g2.z != 0.f) | (g2.w != 0.f) |
                      (gc.x != 0.f) | (gc.y != 0.f) | (gc.z != 0.f) | (gc.w != 0.f) | (gn.x != 0.f) | (gn.y != 0.f) |
                      (gn.z != 0.f);
     const int nf4 = (S + 3) / 4;
     for (int k = 0; k < nf4; ++k) {
-      const float4 f = gq[5 + k];
+      const float4 f = was_touched ? gq[5 + k] : zero4;
       const float fv[4] = {f.x, f.y, f.z, f.w};
       bool fany = false;
 #pragma unroll
@@ -858,12 +1013,55 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     }
   }
   __syncthreads();
-  // ---- phase 2: the queued surfels, densely packed over the CTA's threads
+  // ---- phase 2: the queued surfels, densely packed over the CTA's threads (count <= 256: one per thread)
   const int count = s_count;
-  for (int slot = threadIdx.x; slot < count; slot += 256)
-    preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
-                       s_g[4][slot], means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec, clamped,
-                       dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, nullptr);
+  const int slot = threadIdx.x;
+  const bool valid = slot < count;
+  const int row = cta0 + (int)s_who[valid ? slot : 0];
+  const float4 q0 = s_g[0][slot], q1 = s_g[1][slot], q2 = s_g[2][slot], q3 = s_g[3][slot], q4 = s_g[4][slot];
+  const bool sh_rows = have_sh && !pp.factored;  // dL_dsh is written here, through shared memory (below)
+  if (valid)
+    preprocess_vjp_one(pp, row, q0, q1, q2, q3, q4, means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec,
+                       clamped, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, nullptr, !sh_rows);
+  if (!sh_rows) return;
+  // dL_dsh rows (backward.cu:17-134: basis_k(view direction) x dL_dRGB).  A thread storing its own 16 float4 writes 16-byte
+  // pieces 256 bytes apart -- half sectors, read-modify-written in DRAM (ncu: 1.18x the algorithmic traffic).  The rows go
+  // through shared memory instead, four coefficients at a time (the queue's storage is free by now), so that a store
+  // instruction writes 8 rows x 64 contiguous bytes = whole sectors.
+  __syncthreads();  // every thread holds its queue entry in registers: s_g becomes the staging area
+  float4 (*stage)[5] = reinterpret_cast<float4 (*)[5]>(&s_g[0][0]) + (threadIdx.x & ~31);  // [32 rows][4 + 1 pad] per warp
+  const int lane = threadIdx.x & 31;
+  const int wbase = threadIdx.x & ~31;
+  if (wbase >= count) return;  // whole warp without queue entries
+  float b[16];
+  float4 dRGB = zero4;
+  {
+    const size_t rr = (size_t)row;
+    const uint8_t cl = clamped[rr];
+    dRGB = make_float4((cl & 1) ? 0.f : q3.x, (cl & 2) ? 0.f : q3.y, (cl & 4) ? 0.f : q3.z, (cl & 8) ? 0.f : q3.w);
+    const float dx = means3D[3 * rr] - campos[0], dy = means3D[3 * rr + 1] - campos[1], dz = means3D[3 * rr + 2] - campos[2];
+    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    sh_basis16(pp.D, dx / len, dy / len, dz / len, b);
+  }
+  const int ncoef = (pp.D + 1) * (pp.D + 1);  // coefficients >= (D+1)^2 keep the zeros of the sweep
+#pragma unroll
+  for (int quarter = 0; quarter < 4; ++quarter) {
+    if (4 * quarter < ncoef) {  // warp-uniform
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) stage[lane][c] = b[4 * quarter + c] * dRGB;
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2), c = lane & 3;  // 8 rows x 4 coefficients per store instruction
+        const int k = 4 * quarter + c;
+        if (wbase + r < count && k < ncoef) {
+          const int rw = cta0 + (int)s_who[wbase + r];
+          sh_out(dL_dsh, dL_dsh_rest, (size_t)rw, pp.M).set(k, stage[r][c]);
+        }
+      }
+    }
+  }
 }
 
 
@@ -898,14 +1096,15 @@ int launch_extract_sh_factor(const gsl_params& p, const GeomView& g, float* out,
 // runs, and the "factors" flag behind it lets every rank start its expansion without waiting for anybody's rows.
 __global__ void __launch_bounds__(256) k_peer_factor_extract(PeerView pv, const PeerLayout pl, int P, int gstride,
                                                              const float* __restrict__ grad,
-                                                             const uint8_t* __restrict__ clamped) {
+                                                             const uint8_t* __restrict__ clamped,
+                                                             const uint8_t* __restrict__ touched) {
   __shared__ int s_warp[8];
   peer_resolve_step(pv);
   const int tile = blockIdx.x;
   const int idx = tile * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 fac = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (idx < P) {
+  if (idx < P && touched[idx]) {
     const float4 gc = reinterpret_cast<const float4*>(grad + (size_t)idx * gstride)[3];
     if (gc.x != 0.f || gc.y != 0.f || gc.z != 0.f || gc.w != 0.f) {
       const uint8_t cl = clamped[idx];
@@ -948,7 +1147,8 @@ __global__ void __launch_bounds__(256) k_peer_factor_push(PeerView pv, const Pee
 int launch_peer_factor_extract(const gsl_peer_ctx* c, const gsl_params& p, const GeomView& g, cudaStream_t st) {
   if (p.P == 0) return 0;
   const PeerLayout pl = peer_layout((size_t)p.P, p.S, c->world);
-  k_peer_factor_extract<<<pl.tiles, 256, 0, st>>>(make_view(c, true), pl, p.P, grad_stride(p.S), g.grad, g.clamped);
+  k_peer_factor_extract<<<pl.tiles, 256, 0, st>>>(make_view(c, true), pl, p.P, grad_stride(p.S), g.grad, g.clamped,
+                                                  g.touched);
   return check_cuda(cudaGetLastError(), "k_peer_factor_extract launch");
 }
 
@@ -1030,7 +1230,7 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   int blocks = (row1 - row0 + 255) / 256;
   ProfScope prof(GSL_K_PREPROCESS_BWD, st);
   k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.shs_rest, in.viewmatrix,
-                                          in.campos, fwd.radii, g.rec, g.clamped, g.grad, gout.dL_dmeans3D,
+                                          in.campos, fwd.radii, g.rec, g.clamped, g.touched, g.grad, gout.dL_dmeans3D,
                                           gout.dL_dmeans2D, gout.dL_dsh, in.shs_rest ? gout.dL_dsh_rest : nullptr,
                                           gout.dL_dcolors, gout.dL_dfeatures,
                                           gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D,

@@ -21,8 +21,8 @@ __global__ void __launch_bounds__(32) k_render_fwd(
     RenderParams rp, const uint2* __restrict__ ranges, uint4* __restrict__ bdesc, const uint2* __restrict__ blist,
     uint32_t* __restrict__ pairmask, size_t plane_stride, const float4* __restrict__ rec,
     const float4* __restrict__ colors, const float* __restrict__ features, const short4* __restrict__ pixbox,
-    const float* __restrict__ bg, const uint32_t* __restrict__ ctrl, float* __restrict__ final_T,
-    int32_t* __restrict__ out_contrib, float* __restrict__ out_color, float* __restrict__ out_feature,
+    const float* __restrict__ bg, const uint32_t* __restrict__ ctrl, uint8_t* __restrict__ touched,
+    float* __restrict__ final_T, int32_t* __restrict__ out_contrib, float* __restrict__ out_color, float* __restrict__ out_feature,
     float* __restrict__ out_depth, float* __restrict__ out_alpha) {
   constexpr bool FEAT4 = (S_T == 4);
   const int S = (S_T >= 0) ? S_T : rp.S;
@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(32) k_render_fwd(
       }
       // ---- per-entry masks of the pixels it contributed to
       const uint32_t pm = transpose32(contributed, lane);
-      if (lane < n) pmk[c0 + lane] = pm;
+      if (lane < n) {
+        pmk[c0 + lane] = pm;
+        if (pm != 0u) touched[sb.ent[lane].x] = 1;  // idempotent byte store: the backward skips every other surfel's accumulator
+      }
       const uint32_t nz = __ballot_sync(0xffffffffu, pm != 0u);
       if (nz) walk = (c0 - bs) + (32u - (uint32_t)__clz(nz));
 #ifdef GSL_STATS
@@ -242,7 +245,7 @@ int launch_render_forward(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd
   ProfScope prof(GSL_K_RENDER_FWD, st);
 #define GSL_LAUNCH_FWD(ST)                                                                                  \
   k_render_fwd<ST><<<nblocks, 32, 0, st>>>(rp, im.ranges, im.bdesc, b.blist, b.pairmask, b.plane_stride, g.rec, \
-                                           colors, in.features, g.pixbox, in.background, g.ctrl, im.final_T,  \
+                                           colors, in.features, g.pixbox, in.background, g.ctrl, g.touched, im.final_T,  \
                                            out.out_contrib, out.out_color, out.out_feature, out.out_depth,   \
                                            out.out_alpha)
   if (p.S == 4) GSL_LAUNCH_FWD(4);

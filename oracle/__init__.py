@@ -41,6 +41,9 @@ def build_ref():
     r = subprocess.run(["bash", os.path.join(HERE, "build_ref.sh")], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("oracle/build_ref.sh failed:\n" + r.stdout + r.stderr)
+    # the reference's Python callers of the rasterizer (render(), GaussianModel, ...), staged unmodified for the drop-in tests
+    from . import ref_python
+    ref_python.stage()
     return REF_SO if os.path.exists(REF_SO) else None
 
 

@@ -187,3 +187,21 @@ def grad_err(a, b):
     if a.numel() == 0:
         return 0.0, 0.0
     return rel_err(a, b, floor_frac=1e-2), float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def report(name, measured):
+    """Appends the measured error maxima of a parity check to gpurun_out/parity_measured.jsonl (when that directory exists or
+    GSL_REPORT names a file) and prints them -- visible with `pytest -s` and in the captured output of a failure."""
+    import json
+    line = json.dumps({"check": name, "measured": measured}, default=float)
+    print(line)
+    path = os.environ.get("GSL_REPORT")
+    if not path:
+        d = os.path.join(ROOT, "gpurun_out")
+        path = os.path.join(d, "parity_measured.jsonl") if os.path.isdir(d) else None
+    if path:
+        try:
+            with open(path, "a") as f:
+                f.write(line + "\n")
+        except OSError:
+            pass

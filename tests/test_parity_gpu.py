@@ -55,14 +55,19 @@ def scene_from_golden(g):
     return sc, cp, cot
 
 
-def check_against(out, state, grads, r_out, r_state, r_grads, precomp, r_grads_again=None, grads_again=None):
-    """Shared assertions: `r_*` are the reference's outputs as torch tensors (any device).  `r_grads_again` = the
-    gradients of a second run of the reference on the same inputs: its atomicAdd order is not reproducible, and the
-    product cannot be asked to match the reference more closely than the reference matches itself, so the
-    element-wise bound is max(1e-4, 4 x the reference's own run-to-run error) (measured: 1e-6 ... 5e-5).
-    `grads_again` = a second run of the product: both implementations sum signed fp32 terms per surfel in
-    scheduling order (thousands of them for big splats), so the element-wise bound also admits 4 x the product's own
-    run-to-run error (same order as the reference's).  The norm-wise bound stays 1e-4 (measured ~2e-6) everywhere."""
+def check_against(out, state, grads, r_out, r_state, r_grads, precomp, r_grads_again=None, grads_again=None, label=""):
+    """Shared assertions: `r_*` are the reference's outputs as torch tensors (any device).
+
+    Gradients.  Contract (BASELINE.json north_star): 1e-4 relative.  The norm-wise reading, |g - g_ref| / |g_ref| per
+    tensor, is asserted at 1e-4 everywhere (measured ~1e-6).  The element-wise reading (floored at 1 % of the tensor's
+    scale, common.grad_err) cannot be asked to be tighter than the reference is against ITSELF: its atomicAdd order is
+    not reproducible, and the maximum over a tensor of the run-to-run difference is a heavy-tailed number (measured on
+    the big-splat case over six runs: reference vs. reference 1.6e-5 ... 7.5e-5, product vs. reference 3e-5 ... 1.2e-4,
+    product vs. product 1e-5 ... 5e-5 -- scripts/grad_case_noise.py).  `r_grads_again` is therefore a LIST of further
+    runs of the reference on the same inputs, and the element-wise bound is max(1e-4, 4 x the largest reference-vs-
+    reference error among them).  The product's own run-to-run noise does not enter the bound when a live reference is
+    there; for the stored goldens (one reference run, `r_grads_again` None) it enters capped at 3e-4.  Every measured
+    maximum is recorded (common.report) so that a drift shows up before it fails."""
     dev = out["radii"].device
     to = lambda x: x.to(dev)
     # --- integer state: bit exact
@@ -81,22 +86,33 @@ def check_against(out, state, grads, r_out, r_state, r_grads, precomp, r_grads_a
         assert common.rel_err(state["rgb"][vis], to(r_state["rgb"])[vis]) < TOL_MAP
         assert torch.equal(state["clamped"][vis], to(r_state["clamped"])[vis])
     # --- rendered maps
+    measured = {}
     for k in ("out_color", "out_feature", "out_depth", "out_alpha"):
-        assert common.rel_err(out[k], to(r_out[k])) < TOL_MAP, k
+        e = common.rel_err(out[k], to(r_out[k]))
+        measured[k] = e
+        assert e < TOL_MAP, k
     assert torch.equal(out["out_contrib"], to(r_out["out_contrib"]).int())
     # --- gradients
     if grads is not None:
+        if r_grads_again is not None and not isinstance(r_grads_again, (list, tuple)):
+            r_grads_again = [r_grads_again]
         for k, rk in GRAD_KEYS.items():
             if grads.get(k) is None or rk not in r_grads:
                 continue
             ref_k = to(r_grads[rk]).reshape(grads[k].shape)
             elem, norm = common.grad_err(grads[k], ref_k)
+            ref_noise = own_noise = None
             tol_elem = TOL_GRAD
-            if r_grads_again is not None and rk in r_grads_again:
-                tol_elem = max(TOL_GRAD, 4.0 * common.grad_err(to(r_grads_again[rk]).reshape(grads[k].shape), ref_k)[0])
+            if r_grads_again:
+                ref_noise = max(common.grad_err(to(rg[rk]).reshape(grads[k].shape), ref_k)[0] for rg in r_grads_again if rk in rg)
+                tol_elem = max(TOL_GRAD, 4.0 * ref_noise)
             if grads_again is not None and grads_again.get(k) is not None:
-                tol_elem = max(tol_elem, 4.0 * common.grad_err(grads_again[k], grads[k])[0])
+                own_noise = common.grad_err(grads_again[k], grads[k])[0]
+                if not r_grads_again:
+                    tol_elem = max(tol_elem, min(4.0 * own_noise, 3e-4))
+            measured["grad_" + k] = dict(elem=elem, norm=norm, tol_elem=tol_elem, ref_noise=ref_noise, own_noise=own_noise)
             assert elem < tol_elem and norm < TOL_GRAD, (k, elem, norm, tol_elem)
+    common.report("parity" + (":" + label if label else ""), measured)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -117,7 +133,8 @@ def test_matches_golden_reference_outputs(path):
         r_grads["dL_dfeatures"] = r_grads["dL_dfeatures"][:, :S]
     if cp is not None:
         r_grads.pop("dL_dsh", None)
-    check_against(out, state, grads, r_out, r_state, r_grads, cp is not None, None, grads_again)
+    check_against(out, state, grads, r_out, r_state, r_grads, cp is not None, None, grads_again,
+                  label="golden " + os.path.basename(path)[:-4])
 
 
 CASES = [
@@ -135,6 +152,7 @@ CASES = [
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libgslidar_ref.so not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
 def test_matches_reference_cuda(kw):
+    kw0 = kw
     kw = dict(kw)
     P = kw.pop("P")
     scene = synth.make_scene(P, **kw).to("cuda")
@@ -143,14 +161,14 @@ def test_matches_reference_cuda(kw):
     out, state, grads = common.run_ours(scene, cot)
     r_out, r_state, r_grads, ref = common.run_ref(scene, cot)
     r_grads = {k: v.clone() for k, v in r_grads.items()}
-    r_again = {k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()}
-    for rg in (r_grads, r_again):
+    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()} for _ in range(3)]
+    for rg in [r_grads] + r_again:
         if S > 0:
             rg["dL_dfeatures"] = rg["dL_dfeatures"][:, :S]
         else:
             rg.pop("dL_dfeatures", None)
     grads_again = common.run_ours(scene, cot, export=False)[2]
-    check_against(out, state, grads, r_out, r_state, r_grads, False, r_again, grads_again)
+    check_against(out, state, grads, r_out, r_state, r_grads, False, r_again, grads_again, label="case %s" % (CASES.index(kw0),))
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
@@ -166,10 +184,10 @@ def test_matches_reference_cuda_colors_precomp_and_close_range():
     out, state, grads = common.run_ours(scene, cot, colors_precomp=cp)
     r_out, r_state, r_grads, ref = common.run_ref(scene, cot, colors_precomp=cp)
     r_grads = {k: v.clone() for k, v in r_grads.items()}
-    r_again = {k: v.clone() for k, v in common.run_ref(scene, cot, colors_precomp=cp, ref=ref)[2].items()}
+    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, colors_precomp=cp, ref=ref)[2].items()} for _ in range(3)]
     r_grads.pop("dL_dsh", None)
     grads_again = common.run_ours(scene, cot, colors_precomp=cp, export=False)[2]
-    check_against(out, state, grads, r_out, r_state, r_grads, True, r_again, grads_again)
+    check_against(out, state, grads, r_out, r_state, r_grads, True, r_again, grads_again, label="precomp close range")
 
 
 def test_matches_cpu_oracle_small():
@@ -504,9 +522,9 @@ def test_full_size_matches_reference_cuda(full_run):
     scene, cot, out, state, grads = full_run
     r_out, r_state, r_grads, ref = common.run_ref(scene, cot)
     r_grads = {k: v.clone() for k, v in r_grads.items()}
-    r_again = {k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()}
+    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()} for _ in range(2)]
     grads_again = common.run_ours(scene, cot, export=False)[2]
-    check_against(out, state, grads, r_out, r_state, r_grads, False, r_again, grads_again)
+    check_against(out, state, grads, r_out, r_state, r_grads, False, r_again, grads_again, label="1M surfels 66x1030")
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference CUDA not built")
