@@ -64,6 +64,11 @@ def parse_args():
     ap.add_argument("--clock-sample-ms", type=int, default=20, help="period of the clock sampler on rank 0 (0 = off)")
     ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "off"],
                     help="nvml: a side process polling two NVML queries (default); smi: an `nvidia-smi --query-gpu -lms` loop")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"],
+                    help="c3 (default, the headline): fwd+bwd, 1M surfels, 66x1030.  c2: forward-only render of 100k surfels, 66x1030, "
+                         "one GPU.  c5: stress inference, 4M surfels, 128x2048 OPV2V-style panoramas, --frames frames sharded by "
+                         "frame over the GPUs (BASELINE.json configs[1] / configs[4]); both forward only")
+    ap.add_argument("--frames", type=int, default=512, help="c5: frames of the batch (all ranks together)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="CUDA-graph replay of the forward / backward pass (gs_lidar_b200.set_cuda_graphs); the line always "
                          "carries the other mode's device-timed number as well")
@@ -616,6 +621,144 @@ def run_ours(args, rank, world, local):
     return res
 
 
+INFER = {
+    "c2": dict(P=100000, H=66, W=1030, vfov=None, metric="panoramas/sec forward-only at 100k surfels 66x1030",
+               workload="forward-only render: 100k synthetic surfels -> 66x1030 KITTI-360 range/intensity/raydrop panorama, 1 B200"),
+    "c5": dict(P=4000000, H=128, W=2048, vfov="opv2v", metric="panoramas/sec forward-only at 4M surfels 128x2048, frames sharded over the GPUs",
+               workload="stress inference: 4M surfels, 128x2048 OPV2V-style panoramas, 512-frame batch sharded by frame across 8 B200"),
+}
+
+
+def run_inference(args, rank, world, local):
+    """--config c2 / c5: forward-only frames through the public API (gs_lidar_b200.batch.render_frames: frames on two
+    alternating streams), one camera pose per frame, frames sharded frame_id % world, no collective on the data path."""
+    from gs_lidar_b200 import synth, parallel, batch
+    import gs_lidar_b200.diff_gaussian_rasterization_2d as G
+    cfg = INFER[args.config]
+    dev = torch.device("cuda", local)
+    P, H, W, S = cfg["P"], cfg["H"], cfg["W"], 4
+    if args.surfels != 1000000:
+        P = args.surfels
+    vfov = synth.OPV2V_VFOV if cfg["vfov"] == "opv2v" else synth.KITTI_VFOV
+    scene = synth.make_scene(P, H=H, W=W, S=S, vfov=vfov, seed=0).to(dev)
+    total = args.frames if args.config == "c5" else max(args.steps, 1) * world
+    mine = parallel.shard_frames(total, rank, world, equal_steps=True)
+    # frame k of a drive: +0.1 sf k along x, small yaw (SURVEY.md 8d); only the 4x4 view matrix and camera centre differ
+    base = synth.settings_for(scene)
+    cams = []
+    for k in mine:
+        c = synth.make_scene(16, H=H, W=W, S=S, vfov=vfov, seed=0, view_yaw_deg=0.5 * math.sin(0.7 * k),
+                             view_shift=(0.1 * scene.scale_factor * (k % 64), 0.0, 0.0))
+        cams.append(base._replace(viewmatrix=c.viewmatrix.to(dev), projmatrix=c.projmatrix.to(dev), campos=c.campos.to(dev)))
+    surfels = dict(means3D=scene.means3D, opacities=scene.opacities, shs=scene.shs, features=scene.features,
+                   scales=scene.scales, rotations=scene.rotations, mask=scene.mask)
+    stats = {}
+
+    def consume(i, out):
+        stats["V"] = out[5]
+        stats["last"] = out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local, args.clock_sample_ms, args.clock_sampler)
+    if rank == 0:
+        sampler.start()
+    warm = cams[:max(args.warmup, 3)] if len(cams) >= 3 else cams
+    batch.render_frames(warm, consume=consume, **surfels)
+    batch.render_frames(warm, consume=consume, **surfels)
+    barrier()
+    V = int((stats["V"] > 0).sum())
+    r_hint = max([v for k, v in G._pool.r_hint.items() if k[1] == P] + [0])
+    R = int(r_hint / 1.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    batch.render_frames(cams, consume=consume, **surfels)
+    e1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = e0.elapsed_time(e1)
+    # single-stream, frame after frame (what a caller without render_frames gets), same frames
+    e0.record()
+    batch.render_frames(cams, consume=consume, streams=1, **surfels)
+    e1.record()
+    barrier()
+    ms_1s = e0.elapsed_time(e1)
+    # e2e: camera matrices from pinned host memory per frame, rendered maps back to pinned host memory per frame
+    n_e2e = min(len(cams), 64)
+    h_cam = [(c.viewmatrix.cpu().pin_memory(), c.campos.cpu().pin_memory()) for c in cams[:n_e2e]]
+    h_out = [torch.empty((4 + S + 3 + 4 + 1, H, W)).pin_memory() for _ in range(2)]
+    d_cam = [(torch.empty(4, 4, device=dev), torch.empty(3, device=dev)) for _ in range(n_e2e)]
+    h2d = 16 * 4 + 3 * 4
+    d2h = h_out[0].numel() * 4
+
+    def e2e_pass():
+        sets = []
+        for i in range(n_e2e):
+            d_cam[i][0].copy_(h_cam[i][0], non_blocking=True)
+            d_cam[i][1].copy_(h_cam[i][1], non_blocking=True)
+            sets.append(base._replace(viewmatrix=d_cam[i][0], projmatrix=d_cam[i][0], campos=d_cam[i][1]))
+
+        def to_host(i, out):
+            buf = h_out[i % 2]
+            o = 0
+            for t in (out[1], out[2], out[3], out[4]):
+                n = t.shape[0]
+                buf[o:o + n].copy_(t, non_blocking=True)
+                o += n
+
+        batch.render_frames(sets, consume=to_host, **surfels)
+        torch.cuda.synchronize(dev)
+
+    e2e_pass()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else {}
+    t = torch.tensor([ms, max(ms, wall), ms_1s, e2e_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, _, ms_1s, e2e_wall = [float(x) for x in t]
+    if rank != 0:
+        return None
+    frames = len(cams)
+    N, K, M = H * W, (scene.sh_degree + 1) ** 2, scene.shs.shape[1]
+    fwd_b, _, bin_b = algorithmic_bytes(P, V, R, N, S, K, M)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ms_frame = ms / frames
+    gbs = (fwd_b + bin_b) / (ms_frame * 1e-3) / 1e9
+    from gs_lidar_b200 import _lib as L
+    return {
+        "metric": cfg["metric"], "value": world * frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": frames,
+        "warmup": 2 * len(warm), "ms_per_step": ms_frame, "higher_is_better": True, "scaling": "weak" if args.config == "c2" else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+        "config": {"workload": cfg["workload"], "surfels": P, "height": H, "width": W, "sh_degree": scene.sh_degree,
+                   "feature_channels": S, "visible_surfels": V, "tile_instances": R, "frames_total": frames * world,
+                   "parallelism": "frames sharded frame_id %% %d, no collective" % world,
+                   "l2": "inputs (%.0f MB of surfel parameters per frame) exceed the 126 MB L2; no explicit flush" % ((45 * P + 16 * M * P + 4 * S * P) / 1e6)},
+        "run": {"streams": "auto (2 from 500k surfels, else 1)", "ms_per_frame_one_stream": ms_1s / frames,
+                "note": "gs_lidar_b200.batch.render_frames: frames on alternating streams for large scenes; ms_per_frame_one_stream = the same frames issued one after the other on one stream"},
+        "clocks": clocks,
+        "e2e": {"value": world * n_e2e / (e2e_wall * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                "note": "per frame: view matrix + camera centre from pinned host memory, all rendered maps back to pinned host memory; wall clock incl. the final synchronisation"},
+        "gpu_launches": L.OWN_LAUNCHES_FWD * frames,
+        "roofline": {"bound": "hbm", "kernel": "whole forward frame", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                     "traffic": None, "algorithmic_bytes_per_launch": int(fwd_b + bin_b), "ms_per_launch": ms_frame,
+                     "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
+                     "note": "SURVEY.md 8(d) forward bytes (FWD_IO + BIN) of one frame over the frame time"},
+    }
+
+
 def cpu_baseline(args, full=True):
     """CPU oracle (plain-C port of the reference algorithm) timed on the host cores on a bounded sample."""
     import oracle
@@ -797,6 +940,8 @@ def main():
     rank, world, local = init_dist(args)
     if args.impl == "reference":
         res = run_reference(args, rank, world, local)
+    elif args.config != "c3":
+        res = run_inference(args, rank, world, local)
     else:
         res = run_ours(args, rank, world, local)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -69,6 +69,11 @@ class gsl_glue_params(C.Structure):
                 ("velocity_decay", C.c_float), ("dynamic", C.c_int32)]
 
 
+class gsl_pano_params(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("vfov_min", C.c_float), ("vfov_max", C.c_float),
+                ("hfov_min", C.c_float), ("hfov_max", C.c_float)]
+
+
 class gsl_glue_inputs(C.Structure):
     _fields_ = [(n, vp) for n in ("xyz", "velocity", "t", "scaling_t", "opacity", "scaling", "rotation", "mask")]
 
@@ -114,6 +119,9 @@ SYMBOLS = {
                                          C.POINTER(gsl_workspace), vp, vp]),
     "gsl_backward_surfels": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs), C.POINTER(gsl_fwd_outputs),
                                        C.POINTER(gsl_bwd_outputs), C.POINTER(gsl_workspace), vp]),
+    "gsl_pano_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "gsl_pano_forward": (C.c_int, [C.POINTER(gsl_pano_params), vp, vp, vp, vp, vp, vp, vp]),
+    "gsl_pano_backward": (C.c_int, [C.POINTER(gsl_pano_params), vp, C.c_int32, vp, vp, vp, vp, vp]),
     "gsl_glue_forward": (C.c_int, [C.POINTER(gsl_glue_params), C.POINTER(gsl_glue_inputs), C.POINTER(gsl_glue_outputs), vp]),
     "gsl_glue_backward": (C.c_int, [C.POINTER(gsl_glue_params), C.POINTER(gsl_glue_inputs), C.POINTER(gsl_glue_outputs),
                                     C.POINTER(gsl_glue_inputs_grad), vp]),

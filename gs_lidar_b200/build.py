@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libgsl_b200.so")
-SOURCES = ["gsl_api.cu", "gsl_preprocess.cu", "gsl_binning.cu", "gsl_sort.cu", "gsl_glue.cu", "gsl_peer.cu", "gsl_chamfer.cu", "gsl_render_fwd.cu", "gsl_render_bwd.cu"]
+SOURCES = ["gsl_api.cu", "gsl_preprocess.cu", "gsl_binning.cu", "gsl_sort.cu", "gsl_glue.cu", "gsl_peer.cu", "gsl_chamfer.cu", "gsl_postops.cu", "gsl_render_fwd.cu", "gsl_render_bwd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", INCLUDE,

@@ -649,6 +649,37 @@ GSL_API int gsl_glue_backward(const gsl_glue_params* p, const gsl_glue_inputs* i
   return launch_glue_backward(*p, *in, *gout, *gin, (cudaStream_t)stream);
 }
 
+// ---- panorama post-ops (gsl_postops.cu) ---------------------------------------------------------------------------------
+GSL_API size_t gsl_pano_scratch_bytes(int32_t H, int32_t W) {
+  const long long n = (long long)(H > 0 ? H : 0) * (W > 0 ? W : 0);
+  return (size_t)((n + 255) / 256 + 1) * sizeof(int32_t);
+}
+
+static int validate_pano(const gsl_pano_params* p, const float* range) {
+  if (!p) return set_error(GSL_EINVAL, "pano: params is NULL");
+  if (p->H < 0 || p->W < 0 || (long long)p->H * p->W > 0x7fffffffLL) return set_error(GSL_EINVAL, "pano: bad image size %d x %d", p->H, p->W);
+  if ((long long)p->H * p->W > 0 && !range) return set_error(GSL_EINVAL, "pano: range is NULL");
+  return 0;
+}
+
+GSL_API int gsl_pano_forward(const gsl_pano_params* p, const float* range, float* points, int32_t* index, int32_t* count,
+                             float* normals, void* scratch, void* stream) {
+  int rc = validate_pano(p, range);
+  if (rc) return rc;
+  if (!points && !normals) return set_error(GSL_EINVAL, "pano_forward: no output requested");
+  if (points && (!count || !scratch)) return set_error(GSL_EINVAL, "pano_forward: points need count and scratch");
+  return launch_pano_forward(*p, range, points, index, count, normals, scratch, (cudaStream_t)stream);
+}
+
+GSL_API int gsl_pano_backward(const gsl_pano_params* p, const float* range, int32_t K, const float* g_points,
+                              const int32_t* index, const float* g_normals, float* g_range, void* stream) {
+  int rc = validate_pano(p, range);
+  if (rc) return rc;
+  if (!g_range && (long long)p->H * p->W > 0) return set_error(GSL_EINVAL, "pano_backward: g_range is NULL");
+  if (K < 0 || (K > 0 && g_points && !index)) return set_error(GSL_EINVAL, "pano_backward: g_points need the point index");
+  return launch_pano_backward(*p, range, K, g_points, index, g_normals, g_range, (cudaStream_t)stream);
+}
+
 // ---- CUDA-graph capture of a step -----------------------------------------------------------
 // The forward's instance count is polled AFTER all launches and every kernel argument of a step is constant once the
 // workspace, the outputs and the inputs keep their addresses, so a forward (gsl_forward_preprocess + gsl_forward_render)

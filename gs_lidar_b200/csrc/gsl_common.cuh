@@ -234,6 +234,10 @@ int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const flo
 int launch_glue_forward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& out, cudaStream_t st);
 int launch_glue_backward(const gsl_glue_params& p, const gsl_glue_inputs& in, const gsl_glue_outputs& gout,
                          const gsl_glue_inputs_grad& gin, cudaStream_t st);
+int launch_pano_forward(const gsl_pano_params& p, const float* range, float* points, int32_t* index, int32_t* count,
+                        float* normals, void* scratch, cudaStream_t st);
+int launch_pano_backward(const gsl_pano_params& p, const float* range, int K, const float* g_points, const int32_t* index,
+                         const float* g_normals, float* g_range, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         const float* projmatrix, uint8_t* present, cudaStream_t st);
 

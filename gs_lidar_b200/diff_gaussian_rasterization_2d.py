@@ -79,21 +79,27 @@ class _Workspace:
 
 
 class _Pool:
+    """Free workspaces per (device, stream): a workspace is handed back while the GPU work of its call may still be queued,
+    so it may only be reused by a later call on the SAME stream (stream order then protects it)."""
+
     def __init__(self):
         self.free = {}
         self.lock = threading.Lock()
         self.r_hint = {}
 
     def acquire(self, device):
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
         with self.lock:
-            lst = self.free.setdefault(device, [])
+            lst = self.free.setdefault(key, [])
             if lst:
                 return lst.pop()
-        return _Workspace(device)
+        ws = _Workspace(device)
+        ws.pool_key = key
+        return ws
 
     def release(self, ws):
         with self.lock:
-            self.free.setdefault(ws.device, []).append(ws)
+            self.free.setdefault(getattr(ws, "pool_key", (ws.device, 0)), []).append(ws)
 
 
 _pool = _Pool()

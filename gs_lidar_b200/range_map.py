@@ -2,61 +2,101 @@
 `render_range_map` (gaussian_renderer/__init__.py:158-227 of the reference) and the two panorama post-ops the training
 loop runs on every rendered range image, `pano_to_lidar` and `depth_to_normal` (utils/graphics_utils.py:96-149).
 
-Host-side mirrors in plain PyTorch, same names, arguments and results:
+Same names, arguments and results as the reference's:
 
-  * the ray directions of a (H, W, vfov, hfov) panorama are built once per shape and device and reused (the reference
-    rebuilds meshgrid / sin / cos / normalize -- about ten element-wise kernels -- on every call, three times per
-    training step, train.py:261-262,306);
+  * `pano_to_lidar` / `depth_to_normal` (and `pano_post_ops`, both from one pass) are CUDA ops of this package's library
+    (csrc/gsl_postops.cu, C-ABI gsl_pano_forward / gsl_pano_backward) with autograd: 2 launches instead of the ~15
+    element-wise PyTorch kernels each of them is in the reference (meshgrid, sin, cos, stack, normalize, mask, cross ...
+    rebuilt on every call, three times per training step, train.py:261-262,306).  CUDA tensors only, like the rest of the
+    package;
   * `render_range_map` stitches the two half panoramas with one concatenation per map instead of fifteen slice
     assignments into zero-filled buffers;
   * `render_range_map_360` renders the same maps in ONE rasterizer call with the azimuth wrap-around mode
     (GSL_FLAG_WRAP_AZIMUTH): the stitched panorama's columns are azimuth -180..180 deg of the front
     camera, which is exactly a 360-degree camera with the front camera's pose.
 
-Nothing here touches the CUDA library directly; `renderFunc` is `gs_lidar_b200.renderer.render` (or the reference's).
+`renderFunc` is `gs_lidar_b200.renderer.render` (or the reference's).
 """
+import ctypes as C
 
 import torch
-import torch.nn.functional as F
 
-_dir_cache = {}
+from . import _lib as L
+from .diff_gaussian_rasterization_2d import _f32c, _stream_ptr
+
+_lib = L.load()
 
 
-def ray_directions(height, width, vfov, hfov, device, dtype=torch.float32):
-    """(3, H, W) unit ray directions of the panorama pixels, x right / y down / z forward, as both reference post-ops
-    compute them (graphics_utils.py:99-116): theta = (90 - vfov[1] + row / H * (vfov[1] - vfov[0])) deg,
-    phi = (hfov[0] + col / W * (hfov[1] - hfov[0])) deg.  Cached per shape, field of view, device and dtype."""
-    key = (int(height), int(width), float(vfov[0]), float(vfov[1]), float(hfov[0]), float(hfov[1]), str(device), dtype)
-    d = _dir_cache.get(key)
-    if d is None:
-        rows, cols = torch.meshgrid(torch.arange(height, device=device), torch.arange(width, device=device), indexing="ij")
-        theta = (90 - vfov[1] + rows / height * (vfov[1] - vfov[0])) * torch.pi / 180
-        phi = (hfov[0] + cols / width * (hfov[1] - hfov[0])) * torch.pi / 180
-        d = torch.stack([torch.sin(theta) * torch.sin(phi), -torch.cos(theta), torch.sin(theta) * torch.cos(phi)], dim=0)
-        d = F.normalize(d, dim=0).to(dtype)
-        if len(_dir_cache) > 32:
-            _dir_cache.clear()
-        _dir_cache[key] = d
-    return d
+def _pano_params(h, w, vfov, hfov):
+    return L.gsl_pano_params(int(h), int(w), float(vfov[0]), float(vfov[1]), float(hfov[0]), float(hfov[1]))
+
+
+class _PanoPostOps(torch.autograd.Function):
+    """(points (K,3), normals (3,H,W)) of a (1,H,W) range image; either output can be switched off."""
+
+    @staticmethod
+    def forward(ctx, range_image, vfov, hfov, want_points, want_normals):
+        if not range_image.is_cuda:
+            raise RuntimeError("gs_lidar_b200 runs on CUDA tensors only (no CPU fallback)")
+        h, w = range_image.shape[-2:]
+        if range_image.numel() != h * w:
+            raise RuntimeError("range image must be (1, H, W)")
+        dev = range_image.device
+        rng = _f32c(range_image)
+        p = _pano_params(h, w, vfov, hfov)
+        n = h * w
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            points = index = count = scratch = normals = None
+            if want_points:
+                points = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
+                index = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+                count = torch.zeros((1,), dtype=torch.int32, device=dev)
+                scratch = torch.empty((int(_lib.gsl_pano_scratch_bytes(h, w)),), dtype=torch.uint8, device=dev)
+            if want_normals:
+                normals = torch.empty((3, h, w), dtype=torch.float32, device=dev)
+            ptr = lambda t: None if t is None else t.data_ptr()
+            if n > 0:
+                L.check(_lib.gsl_pano_forward(C.byref(p), rng.data_ptr(), ptr(points), ptr(index), ptr(count), ptr(normals),
+                                              ptr(scratch), st), "gsl_pano_forward")
+            k = int(count.item()) if want_points else 0  # the one host read the (K, 3) result shape needs (the reference's
+            #                                              boolean-mask indexing synchronises in the same place)
+        ctx.pano = (p, rng, index, k, want_points, want_normals)
+        out_points = points[:k] if want_points else torch.empty((0, 3), dtype=torch.float32, device=dev)
+        out_normals = normals if want_normals else torch.empty((3, 0, 0), dtype=torch.float32, device=dev)
+        return out_points.to(range_image.dtype), out_normals.to(range_image.dtype)
+
+    @staticmethod
+    def backward(ctx, g_points, g_normals):
+        p, rng, index, k, want_points, want_normals = ctx.pano
+        dev = rng.device
+        gp = _f32c(g_points) if (want_points and g_points is not None and k > 0) else None
+        gn = _f32c(g_normals) if (want_normals and g_normals is not None) else None
+        with torch.cuda.device(dev):
+            g_range = torch.empty_like(rng)
+            if rng.numel() > 0:
+                L.check(_lib.gsl_pano_backward(C.byref(p), rng.data_ptr(), k if gp is not None else 0,
+                                               None if gp is None else gp.data_ptr(),
+                                               None if index is None else index.data_ptr(),
+                                               None if gn is None else gn.data_ptr(), g_range.data_ptr(), _stream_ptr(dev)),
+                        "gsl_pano_backward")
+        return g_range, None, None, None, None
+
+
+def pano_post_ops(range_image, vfov, hfov):
+    """(pano_to_lidar(range_image), depth_to_normal(range_image)) from one pass over the range image."""
+    return _PanoPostOps.apply(range_image, tuple(vfov), tuple(hfov), True, True)
 
 
 def pano_to_lidar(range_image, vfov, hfov):
     """(1, H, W) range image -> (K, 3) points of the pixels with range > 0, row-major (graphics_utils.py:96-118)."""
-    h, w = range_image.shape[-2:]
-    d = ray_directions(h, w, vfov, hfov, range_image.device, range_image.dtype)
-    return (d * range_image)[:, range_image[0] > 0].permute(1, 0)
+    return _PanoPostOps.apply(range_image, tuple(vfov), tuple(hfov), True, False)[0]
 
 
 def depth_to_normal(range_image, vfov, hfov):
     """(1, H, W) range image -> (3, H, W) surface normals from central differences of the back-projected points, zero on
     the one-pixel border (graphics_utils.py:121-149)."""
-    h, w = range_image.shape[-2:]
-    pts = ray_directions(h, w, vfov, hfov, range_image.device, range_image.dtype) * range_image
-    out = torch.zeros_like(pts)
-    down = pts[:, 2:, 1:-1] - pts[:, :-2, 1:-1]
-    right = pts[:, 1:-1, 2:] - pts[:, 1:-1, :-2]
-    out[:, 1:-1, 1:-1] = F.normalize(torch.cross(down, right, dim=0), dim=0)
-    return out
+    return _PanoPostOps.apply(range_image, tuple(vfov), tuple(hfov), False, True)[1]
 
 
 def stitch_half_panoramas(front, back):

@@ -234,6 +234,26 @@ GSL_API int gsl_glue_forward(const gsl_glue_params* p, const gsl_glue_inputs* in
 GSL_API int gsl_glue_backward(const gsl_glue_params* p, const gsl_glue_inputs* in, const gsl_glue_outputs* gout,
                       const gsl_glue_inputs_grad* gin, void* stream);
 
+/* ---- panorama post-ops: utils/graphics_utils.py:96-118 pano_to_lidar and :121-149 depth_to_normal of
+ * the reference (called on every rendered range image, train.py:261-262,306), as one pass over the (H, W) range image.
+ * Pixel (row, col) looks along normalize(sin th sin ph, -cos th, sin th cos ph), th = (90 - vfov_max + row / H * (vfov_max -
+ * vfov_min)) deg, ph = (hfov_min + col / W * (hfov_max - hfov_min)) deg. ---- */
+typedef struct gsl_pano_params {
+  int32_t H, W;
+  float vfov_min, vfov_max, hfov_min, hfov_max; /* degrees, as args.vfov / args.hfov */
+} gsl_pano_params;
+/* scratch bytes for gsl_pano_forward */
+GSL_API size_t gsl_pano_scratch_bytes(int32_t H, int32_t W);
+/* range (H*W) -> points (capacity H*W x 3): direction * range of the pixels with range > 0 in row-major order, index (H*W):
+ * the pixel of every point (needed by the backward pass; may be NULL), *count (device int32): how many; normals (3,H,W):
+ * normalize(cross(p[y+1,x] - p[y-1,x], p[y,x+1] - p[y,x-1])), zero on the one-pixel border.  points (with index, count) or
+ * normals may be NULL to compute only the other. */
+GSL_API int gsl_pano_forward(const gsl_pano_params* p, const float* range, float* points, int32_t* index, int32_t* count,
+                             float* normals, void* scratch, void* stream);
+/* g_range (H*W, overwritten) = d/d range of <g_points, points> + <g_normals, normals>; either cotangent may be NULL. */
+GSL_API int gsl_pano_backward(const gsl_pano_params* p, const float* range, int32_t K, const float* g_points,
+                              const int32_t* index, const float* g_normals, float* g_range, void* stream);
+
 /* Pinhole frustum test, present[i] = in_frustum(means3D[i]) (auxiliary.h:157-180). */
 GSL_API int gsl_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);

@@ -1,6 +1,8 @@
 """gs_lidar_b200/range_map.py (the callers / post-ops either side of the rasterizer) on CPU:
-the post-ops against outputs of the reference's own functions (tests/golden/postop_*.npz, made by
-tests/golden/make_postop_golden.py), the stitching against a restatement of the reference's slice assignments."""
+the stitching against a restatement of the reference's slice assignments, and the CHECKER of the CUDA post-ops
+(tests/postop_oracle.py, a PyTorch restatement) against outputs of the reference's own functions
+(tests/golden/postop_*.npz, made by tests/golden/make_postop_golden.py).  The CUDA post-ops themselves are compared with
+that checker, the stored outputs and the live reference functions in tests/test_postops_gpu.py."""
 import glob
 import os
 from types import SimpleNamespace
@@ -10,6 +12,7 @@ import pytest
 import torch
 
 from gs_lidar_b200 import range_map
+import postop_oracle
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postop_*.npz")))
 
@@ -19,21 +22,21 @@ def test_fixtures_exist():
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-def test_post_ops_match_the_reference_functions(path):
+def test_post_op_checker_matches_the_reference_functions(path):
     g = np.load(path)
     rng = torch.from_numpy(g["range_image"])
     vfov, hfov = tuple(g["vfov"].tolist()), tuple(g["hfov"].tolist())
-    for _ in range(2):  # second round: directions come from the cache
-        pts = range_map.pano_to_lidar(rng, vfov, hfov)
-        nrm = range_map.depth_to_normal(rng, vfov, hfov)
-        assert pts.shape == g["points"].shape
-        np.testing.assert_allclose(pts.numpy(), g["points"], rtol=0, atol=1e-6)
-        np.testing.assert_allclose(nrm.numpy(), g["normals"], rtol=0, atol=1e-5)
+    pts = postop_oracle.pano_to_lidar(rng, vfov, hfov)
+    nrm = postop_oracle.depth_to_normal(rng, vfov, hfov)
+    assert pts.shape == g["points"].shape
+    np.testing.assert_allclose(pts.numpy(), g["points"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(nrm.numpy(), g["normals"], rtol=0, atol=1e-5)
     assert float(nrm[:, 0].abs().sum()) == 0 and float(nrm[:, :, -1].abs().sum()) == 0   # zero border
-    # gradients flow to the range image (the normal-consistency and chamfer losses back-propagate through these)
-    r = rng.clone().requires_grad_(True)
-    (range_map.depth_to_normal(r, vfov, hfov).sum() + range_map.pano_to_lidar(r, vfov, hfov).sum()).backward()
-    assert torch.isfinite(r.grad).all() and float(r.grad.abs().sum()) > 0
+
+
+def test_the_cuda_post_ops_refuse_cpu_tensors():
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        range_map.pano_to_lidar(torch.ones(1, 4, 6), (-24.9, 2.0), (-180.0, 180.0))
 
 
 def _reference_stitch(front, back):
