@@ -50,7 +50,7 @@ def build_ref():
 class orc_params(C.Structure):
     _fields_ = [("P", C.c_int), ("S", C.c_int), ("D", C.c_int), ("M", C.c_int), ("W", C.c_int), ("H", C.c_int),
                 ("vfov_min", C.c_float), ("vfov_max", C.c_float), ("hfov_min", C.c_float), ("hfov_max", C.c_float),
-                ("scale_factor", C.c_float), ("tanfovx", C.c_float), ("tanfovy", C.c_float)]
+                ("scale_factor", C.c_float), ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("wrap", C.c_int)]
 
 
 def _np(a, dtype):
@@ -76,8 +76,9 @@ class CpuOracle:
         return int(self.lib.orc_num_threads())
 
     @staticmethod
-    def params(P, S, D, M, W, H, vfov, hfov, scale_factor, tanfovx=-0.5463024898437905, tanfovy=-0.5463024898437905):
-        return orc_params(P, S, D, M, W, H, vfov[0], vfov[1], hfov[0], hfov[1], scale_factor, tanfovx, tanfovy)
+    def params(P, S, D, M, W, H, vfov, hfov, scale_factor, tanfovx=-0.5463024898437905, tanfovy=-0.5463024898437905, wrap=False):
+        """wrap: the azimuth wrap-around mode of this repo (GSL_FLAG_WRAP_AZIMUTH), restated in gsl_oracle.c"""
+        return orc_params(P, S, D, M, W, H, vfov[0], vfov[1], hfov[0], hfov[1], scale_factor, tanfovx, tanfovy, int(bool(wrap)))
 
     def preprocess(self, p, means3D, scales, rotations, opacities, shs, colors_precomp, mask, viewmatrix, campos):
         P = p.P

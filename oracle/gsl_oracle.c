@@ -40,6 +40,10 @@ typedef struct {
   float vfov_min, vfov_max, hfov_min, hfov_max; /* degrees */
   float scale_factor;
   float tanfovx, tanfovy;
+  int wrap; /* != 0: azimuth wrap-around mode (this repo's opt-in extension, NOT the reference's semantics): the
+               reference has getRect_panorama (auxiliary.h:67-75) but never calls it; the mode restated here is the
+               periodic panorama of DESIGN.md 5b -- AABB samples measured relative to the centre azimuth, modular
+               tile-column ranges, low-pass distance to the nearest periodic image */
 } orc_params;
 
 typedef struct { float VFOV_min, VFOV_max, HFOV_min, HFOV_max; } orc_fov;
@@ -86,6 +90,32 @@ static void get_rect(float px, float py, int radius, int gx, int gy, int* rect /
   v = (int)((py - radius) / BLOCK_Y); rect[1] = v < 0 ? 0 : (v > gy ? gy : v);
   v = (int)((px + radius + BLOCK_X - 1) / BLOCK_X); rect[2] = v < 0 ? 0 : (v > gx ? gx : v);
   v = (int)((py + radius + BLOCK_Y - 1) / BLOCK_Y); rect[3] = v < 0 ? 0 : (v > gy ? gy : v);
+}
+
+/* wrap-around mode: tile columns [rect[0], rect[2]) as a modular range over gx columns (rect[2] may exceed gx: column
+   = x mod gx); the part of the footprint left of pixel 0 continues at pixel W, the part right of pixel W-1 at pixel 0;
+   rows as in get_rect. */
+static void get_rect_wrap(float px, float py, int radius, int gx, int gy, int W, int* rect) {
+  get_rect(px, py, radius, gx, gy, rect);
+  const float rf = (float)radius, Wf = (float)W;
+  const int tx0 = (int)floorf((px - rf) * 0.0625f), tx1 = (int)floorf((px + rf + 15.f) * 0.0625f);
+  const int left = (px - rf) < 0.f, right = (px + rf) >= Wf;
+  int start = tx0 > 0 ? tx0 : 0;
+  int len = (tx1 < gx ? tx1 : gx) - start;
+  if (left) {
+    int a0 = (int)floorf((Wf + px - rf) * 0.0625f);
+    a0 = a0 < 0 ? 0 : (a0 > gx ? gx : a0);
+    start = a0;
+    len += gx - a0;
+  }
+  if (right) {
+    int b1 = (int)floorf((px + rf - Wf + 15.f) * 0.0625f);
+    b1 = b1 < 0 ? 0 : (b1 > gx ? gx : b1);
+    len += b1;
+  }
+  if ((left && right) || len >= gx) { start = 0; len = gx; }
+  rect[0] = start;
+  rect[2] = start + (len > 0 ? len : 0);
 }
 
 /* forward.cu:17-69 computeColorFromSH (4 channels) */
@@ -173,6 +203,7 @@ void orc_preprocess(const orc_params* p, const float* means3D, const float* scal
 
     float cutoff = sqrtf((float)fmax((double)(9.f + 2.f * logf(opacity)), 0.000001)); /* forward.cu:243 */
     float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+    const float cx0 = (phi - f.HFOV_min) * W / (f.HFOV_max - f.HFOV_min);
     for (int k = 0; k < 12; ++k) { /* forward.cu:153-168 */
       float a = (float)(2 * ORC_PI * k / 12);
       float vx = cutoff * sinf(a), vy = cutoff * cosf(a);
@@ -182,6 +213,12 @@ void orc_preprocess(const orc_params* p, const float* means3D, const float* scal
       float ph = atan2f(X, Z);
       float th = atan2f(sqrtf(X * X + Z * Z), -Y);
       float ppx = (ph - f.HFOV_min) * W / (f.HFOV_max - f.HFOV_min);
+      if (p->wrap) { /* azimuth of the sample relative to the centre: a splat on the seam keeps its true extent */
+        float dphi = ph - phi;
+        if (dphi > 3.14159265f) dphi -= 6.2831853f;
+        else if (dphi < -3.14159265f) dphi += 6.2831853f;
+        ppx = cx0 + dphi * (float)W / (f.HFOV_max - f.HFOV_min);
+      }
       float ppy = (th - f.VFOV_min) * H / (f.VFOV_max - f.VFOV_min);
       minx = fminf(minx, ppx); maxx = fmaxf(maxx, ppx);
       miny = fminf(miny, ppy); maxy = fmaxf(maxy, ppy);
@@ -192,7 +229,8 @@ void orc_preprocess(const orc_params* p, const float* means3D, const float* scal
     if ((double)rad < 0.3) continue;
     int my_radius = (int)ceilf(rad);
     int rect[4];
-    get_rect(cx, cy, my_radius, gx, gy, rect);
+    if (p->wrap) get_rect_wrap(cx, cy, my_radius, gx, gy, W, rect);
+    else get_rect(cx, cy, my_radius, gx, gy, rect);
     int area = (rect[2] - rect[0]) * (rect[3] - rect[1]);
     if (area == 0) continue;
     if (colors_precomp == NULL) sh_to_color(p->D, shs + (size_t)i * p->M * 4, po, campos, rgb + 4 * (size_t)i, clamped + 4 * (size_t)i);
@@ -233,12 +271,13 @@ int64_t orc_binning(const orc_params* p, const int* radii, const float* means2D,
     if (radii[i] <= 0) continue;
     uint32_t off = i == 0 ? 0 : point_offsets[i - 1];
     int rect[4];
-    get_rect(means2D[2 * i], means2D[2 * i + 1], radii[i], gx, gy, rect);
+    if (p->wrap) get_rect_wrap(means2D[2 * i], means2D[2 * i + 1], radii[i], gx, gy, p->W, rect);
+    else get_rect(means2D[2 * i], means2D[2 * i + 1], radii[i], gx, gy, rect);
     uint32_t dbits;
     memcpy(&dbits, depths + i, 4);
     for (int y = rect[1]; y < rect[3]; ++y)
       for (int x = rect[0]; x < rect[2]; ++x) {
-        keys[off] = ((uint64_t)(y * gx + x) << 32) | dbits;
+        keys[off] = ((uint64_t)(y * gx + (x >= gx ? x - gx : x)) << 32) | dbits;
         vals[off] = (uint32_t)i;
         off++;
       }
@@ -286,7 +325,7 @@ typedef struct {
 
 /* forward.cu:397-441 == backward.cu:296-339: ray-splat intersection, low-pass, depth, alpha + skips */
 static void eval_pair(const float* T, const float* xy, float opa, float sdepth, float pxf, float pyf, float cph,
-                      float sph, float cth, float sth, float near_, float far_, pair_eval* e) {
+                      float sph, float cth, float sth, float near_, float far_, float wrapW, pair_eval* e) {
   const float* Tu = T; const float* Tv = T + 3; const float* Tw = T + 6;
   e->valid = 0;
   for (int c = 0; c < 3; ++c) {
@@ -301,6 +340,10 @@ static void eval_pair(const float* T, const float* xy, float opa, float sdepth, 
   float sx = px / pz, sy = py / pz;
   float rho3d = sx * sx + sy * sy;
   float dx = xy[0] - pxf, dy = xy[1] - pyf;
+  if (wrapW > 0.f) { /* wrap-around mode: distance to the nearest periodic image of the projected centre */
+    if (dx > 0.5f * wrapW) dx -= wrapW;
+    else if (dx < -0.5f * wrapW) dx += wrapW;
+  }
   float rho2d = 2.0f * (dx * dx + dy * dy);
   float rho = fminf(rho3d, rho2d);
   float sTu = sx * Tu[0] + sy * Tu[1] + Tu[2];
@@ -348,7 +391,7 @@ void orc_render_forward(const orc_params* p, const uint32_t* ranges, const uint3
       const uint32_t id = point_list[q];
       pair_eval e;
       eval_pair(transMat + 9 * (size_t)id, means2D + 2 * (size_t)id, normal_opacity[4 * (size_t)id + 3], depths[id], pxf,
-                pyf, cph, sph, cth, sth, near_, far_, &e);
+                pyf, cph, sph, cth, sth, near_, far_, p->wrap ? (float)p->W : 0.f, &e);
       if (!e.valid) continue;
       float alpha = e.alpha, depth = e.depth;
       float test_T = T * (1 - alpha);
@@ -422,7 +465,7 @@ void orc_render_backward(const orc_params* p, const uint32_t* ranges, const uint
       const float* Tm = transMat + 9 * (size_t)id;
       pair_eval e;
       eval_pair(Tm, means2D + 2 * (size_t)id, normal_opacity[4 * (size_t)id + 3], depths[id], pxf, pyf, cph, sph, cth, sth,
-                near_, far_, &e);
+                near_, far_, p->wrap ? (float)p->W : 0.f, &e);
       if (!e.valid) continue;
       const float alpha = e.alpha, G = e.G, depth = e.depth;
       T = T / (1.f - alpha);

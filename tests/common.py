@@ -132,14 +132,14 @@ def run_ref(scene, cot=None, colors_precomp=None, ref=None):
     return out, state, grads, ref
 
 
-def run_oracle(scene, cot=None, colors_precomp=None, threads=None):
+def run_oracle(scene, cot=None, colors_precomp=None, threads=None, wrap=False):
     """CPU oracle on a CPU copy of the scene; returns (state dict incl. outputs, grads)."""
     import oracle
     o = oracle.CpuOracle(threads)
     s = scene.to("cpu")
     P, S = s.means3D.shape[0], s.features.shape[1]
     M = s.shs.shape[1] if colors_precomp is None else 0
-    p = o.params(P, S, s.sh_degree, M, s.W, s.H, s.vfov, s.hfov, s.scale_factor, TANFOV, TANFOV)
+    p = o.params(P, S, s.sh_degree, M, s.W, s.H, s.vfov, s.hfov, s.scale_factor, TANFOV, TANFOV, wrap=wrap)
     shs = s.shs.numpy() if colors_precomp is None else None
     cp = None if colors_precomp is None else colors_precomp.cpu().numpy()
     st = o.forward(p, s.means3D.numpy(), s.scales.numpy(), s.rotations.numpy(), s.opacities.numpy(), shs, cp,

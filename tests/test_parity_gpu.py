@@ -59,15 +59,17 @@ def check_against(out, state, grads, r_out, r_state, r_grads, precomp, r_grads_a
     """Shared assertions: `r_*` are the reference's outputs as torch tensors (any device).
 
     Gradients.  Contract (BASELINE.json north_star): 1e-4 relative.  The norm-wise reading, |g - g_ref| / |g_ref| per
-    tensor, is asserted at 1e-4 everywhere (measured ~1e-6).  The element-wise reading (floored at 1 % of the tensor's
-    scale, common.grad_err) cannot be asked to be tighter than the reference is against ITSELF: its atomicAdd order is
-    not reproducible, and the maximum over a tensor of the run-to-run difference is a heavy-tailed number (measured on
-    the big-splat case over six runs: reference vs. reference 1.6e-5 ... 7.5e-5, product vs. reference 3e-5 ... 1.2e-4,
-    product vs. product 1e-5 ... 5e-5 -- scripts/grad_case_noise.py).  `r_grads_again` is therefore a LIST of further
-    runs of the reference on the same inputs, and the element-wise bound is max(1e-4, 4 x the largest reference-vs-
-    reference error among them).  The product's own run-to-run noise does not enter the bound when a live reference is
-    there; for the stored goldens (one reference run, `r_grads_again` None) it enters capped at 3e-4.  Every measured
-    maximum is recorded (common.report) so that a drift shows up before it fails."""
+    tensor, is asserted at 1e-4 for every single run (measured ~1e-6).  The element-wise reading (floored at 1 % of the
+    tensor's scale, common.grad_err) is a statement about the gradients the two implementations COMPUTE, not about the
+    order in which their atomics happen to land: both sum signed fp32 terms per surfel in scheduling order, and the
+    maximum over a tensor of the run-to-run difference is a heavy-tailed number (measured over six runs of the big-splat
+    case: reference vs. reference 1.6e-5 ... 7.5e-5, product vs. reference 3e-5 ... 1.2e-4, product vs. product
+    1e-5 ... 5e-5 -- scripts/grad_case_noise.py).  So where a live reference is available `r_grads_again` / `grads_again`
+    are LISTS of further runs of the reference / of the product on the same inputs, the element-wise comparison is made
+    between the MEANS over the runs, and the bound is max(1e-4, 4 x the element-wise difference between the means of the
+    two halves of the reference's runs) -- the reference's own noise at that averaging depth; the product's noise does
+    not enter the bound.  For the stored goldens (one reference run, `r_grads_again` None) a single run is compared and
+    the product's own run-to-run error enters capped at 3e-4.  Every measured maximum is recorded (common.report)."""
     dev = out["radii"].device
     to = lambda x: x.to(dev)
     # --- integer state: bit exact
@@ -96,22 +98,34 @@ def check_against(out, state, grads, r_out, r_state, r_grads, precomp, r_grads_a
     if grads is not None:
         if r_grads_again is not None and not isinstance(r_grads_again, (list, tuple)):
             r_grads_again = [r_grads_again]
+        if grads_again is not None and not isinstance(grads_again, (list, tuple)):
+            grads_again = [grads_again]
         for k, rk in GRAD_KEYS.items():
             if grads.get(k) is None or rk not in r_grads:
                 continue
-            ref_k = to(r_grads[rk]).reshape(grads[k].shape)
+            shape = grads[k].shape
+            ref_k = to(r_grads[rk]).reshape(shape)
             elem, norm = common.grad_err(grads[k], ref_k)
             ref_noise = own_noise = None
             tol_elem = TOL_GRAD
+            elem_means = None
             if r_grads_again:
-                ref_noise = max(common.grad_err(to(rg[rk]).reshape(grads[k].shape), ref_k)[0] for rg in r_grads_again if rk in rg)
+                refs = [ref_k.double()] + [to(rg[rk]).reshape(shape).double() for rg in r_grads_again if rk in rg]
+                ours = [grads[k].double()] + [g[k].double() for g in (grads_again or []) if g.get(k) is not None]
+                h = len(refs) // 2
+                ref_noise = common.grad_err(torch.stack(refs[:h]).mean(0), torch.stack(refs[h:]).mean(0))[0] if h else 0.0
+                own_noise = common.grad_err(ours[-1], ours[0])[0] if len(ours) > 1 else None
                 tol_elem = max(TOL_GRAD, 4.0 * ref_noise)
-            if grads_again is not None and grads_again.get(k) is not None:
-                own_noise = common.grad_err(grads_again[k], grads[k])[0]
-                if not r_grads_again:
+                elem_means = common.grad_err(torch.stack(ours).mean(0), torch.stack(refs).mean(0))[0]
+                ok_elem = elem_means < tol_elem
+            else:
+                if grads_again:
+                    own_noise = common.grad_err(grads_again[0][k], grads[k])[0]
                     tol_elem = max(tol_elem, min(4.0 * own_noise, 3e-4))
-            measured["grad_" + k] = dict(elem=elem, norm=norm, tol_elem=tol_elem, ref_noise=ref_noise, own_noise=own_noise)
-            assert elem < tol_elem and norm < TOL_GRAD, (k, elem, norm, tol_elem)
+                ok_elem = elem < tol_elem
+            measured["grad_" + k] = dict(elem_single_run=elem, elem_of_means=elem_means, norm=norm, tol_elem=tol_elem,
+                                         ref_noise=ref_noise, own_noise=own_noise)
+            assert ok_elem and norm < TOL_GRAD, (k, elem, elem_means, norm, tol_elem)
     common.report("parity" + (":" + label if label else ""), measured)
 
 
@@ -161,13 +175,13 @@ def test_matches_reference_cuda(kw):
     out, state, grads = common.run_ours(scene, cot)
     r_out, r_state, r_grads, ref = common.run_ref(scene, cot)
     r_grads = {k: v.clone() for k, v in r_grads.items()}
-    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()} for _ in range(3)]
+    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()} for _ in range(7)]
     for rg in [r_grads] + r_again:
         if S > 0:
             rg["dL_dfeatures"] = rg["dL_dfeatures"][:, :S]
         else:
             rg.pop("dL_dfeatures", None)
-    grads_again = common.run_ours(scene, cot, export=False)[2]
+    grads_again = [common.run_ours(scene, cot, export=False)[2] for _ in range(7)]
     check_against(out, state, grads, r_out, r_state, r_grads, False, r_again, grads_again, label="case %s" % (CASES.index(kw0),))
 
 
@@ -184,9 +198,9 @@ def test_matches_reference_cuda_colors_precomp_and_close_range():
     out, state, grads = common.run_ours(scene, cot, colors_precomp=cp)
     r_out, r_state, r_grads, ref = common.run_ref(scene, cot, colors_precomp=cp)
     r_grads = {k: v.clone() for k, v in r_grads.items()}
-    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, colors_precomp=cp, ref=ref)[2].items()} for _ in range(3)]
+    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, colors_precomp=cp, ref=ref)[2].items()} for _ in range(7)]
     r_grads.pop("dL_dsh", None)
-    grads_again = common.run_ours(scene, cot, colors_precomp=cp, export=False)[2]
+    grads_again = [common.run_ours(scene, cot, colors_precomp=cp, export=False)[2] for _ in range(7)]
     check_against(out, state, grads, r_out, r_state, r_grads, True, r_again, grads_again, label="precomp close range")
 
 
@@ -522,8 +536,8 @@ def test_full_size_matches_reference_cuda(full_run):
     scene, cot, out, state, grads = full_run
     r_out, r_state, r_grads, ref = common.run_ref(scene, cot)
     r_grads = {k: v.clone() for k, v in r_grads.items()}
-    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()} for _ in range(2)]
-    grads_again = common.run_ours(scene, cot, export=False)[2]
+    r_again = [{k: v.clone() for k, v in common.run_ref(scene, cot, ref=ref)[2].items()} for _ in range(3)]
+    grads_again = [common.run_ours(scene, cot, export=False)[2] for _ in range(3)]
     check_against(out, state, grads, r_out, r_state, r_grads, False, r_again, grads_again, label="1M surfels 66x1030")
 
 
