@@ -391,7 +391,7 @@ def run_ours(args, rank, world, local):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(graph_on):
-        G.set_cuda_graphs(graph_on)
+        G.set_cuda_graphs(graph_on, deferred_count=True)
         for _ in range(4):  # a new call signature runs once un-graphed, is captured on its second call
             step()
         barrier()
@@ -436,36 +436,56 @@ def run_ours(args, rank, world, local):
         spread = {"p10_ms": q(0.10), "median_ms": q(0.50), "p90_ms": q(0.90), "steps": args.steps,
                   "note": "per-step device time between step-boundary events on rank 0, separate pass"}
 
-    G.set_cuda_graphs(use_graph)
+    G.set_cuda_graphs(use_graph, deferred_count=True)
     # ---- e2e: per-step host->device copy of the frame's inputs, device->host read of the result --
     # Per-step inputs of the op are the camera (view matrix, camera centre) and the cotangent maps the
     # loss produced from the host-side ground-truth panoramas; the surfel parameters are resident model
     # state, exactly as scene/gaussian_model.py keeps them on the GPU in the reference's training loop.
-    pin = lambda x: x.clone().pin_memory()
-    h_cam = dict(viewmatrix=pin(scene.viewmatrix.cpu()), campos=pin(scene.campos.cpu()))
-    h_cot = {k: pin(v) for k, v in cot_cpu.items()}
-    d_cam = {k: torch.empty_like(v, device=dev) for k, v in h_cam.items()}
-    d_cot = {k: torch.empty_like(v, device=dev) for k, v in h_cot.items()}
-    h_out = dict(color=torch.empty((4, H, W)).pin_memory(), feature=torch.empty((S + 3, H, W)).pin_memory(),
-                 depth=torch.empty((4, H, W)).pin_memory(), alpha=torch.empty((1, H, W)).pin_memory(),
-                 gradsum=torch.empty((3,)).pin_memory())
-    h2d = sum(v.numel() * 4 for v in h_cam.values()) + sum(v.numel() * 4 for v in h_cot.values())
+    # One pinned staging buffer per direction (a loader hands over one block per frame; 3 copies per step instead of 11):
+    #   in : [view matrix 16 | camera centre 3 | pad] on the main stream, [cotangent planes color 4, feature S+3, depth 4, alpha 1]
+    #        on a copy stream;   out: the rendered planes in the same order + a gradient checksum
+    n_pl = 4 + (S + 3) + 4 + 1
+    h_cam = torch.zeros(20).pin_memory()
+    h_cam[:16] = scene.viewmatrix.cpu().reshape(-1)
+    h_cam[16:19] = scene.campos.cpu()
+    d_camv = torch.empty(20, device=dev)
+    d_cam = dict(viewmatrix=d_camv[:16].view(4, 4), campos=d_camv[16:19])
+    h_cotv = torch.cat([cot_cpu[k].reshape(-1, H, W) for k in ("color", "feature", "depth", "alpha")]).pin_memory()
+    d_cotv = torch.empty_like(h_cotv, device=dev)
+    d_cot = dict(color=d_cotv[0:4], feature=d_cotv[4:4 + S + 3], depth=d_cotv[4 + S + 3:8 + S + 3], alpha=d_cotv[8 + S + 3:])
+    h_out = dict(maps=torch.empty((n_pl, H, W)).pin_memory(), gradsum=torch.empty((3,)).pin_memory())
+    h2d = (h_cam.numel() + h_cotv.numel()) * 4
     d2h = sum(v.numel() * 4 for v in h_out.values())
 
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_in, ev_fwd = torch.cuda.Event(), torch.cuda.Event()
+    ev_bwd, ev_maps = torch.cuda.Event(), torch.cuda.Event()
+    h_outs = [h_out, {k: torch.empty_like(v).pin_memory() for k, v in h_out.items()}]
+    ev_d2h = [torch.cuda.Event(), torch.cuda.Event()]
+    gsum = torch.empty((3,), device=dev)
+    consumed = []
 
-    def e2e_step():
-        # within ONE step: the cotangent upload rides a copy stream under the forward pass (the backward waits for
-        # it), the rendered maps are read back on a second copy stream under the backward pass; nothing overlaps
-        # across steps (the step ends with a full synchronisation of all three streams).
+    def e2e_step(k, pipelined):
+        """One step with its host traffic inside: camera + cotangent maps from pinned host memory, all rendered maps and a
+        gradient checksum back to pinned host memory.  The cotangent upload rides a copy stream under the forward pass (the
+        backward waits for it), the maps are read back on a second copy stream under the backward pass.
+        pipelined=False: the step ends with a full synchronisation of all three streams (nothing overlaps across steps).
+        pipelined=True : what a training loop with a prefetching loader and asynchronous logging does -- the host never
+        blocks on the step it has just issued; it consumes the results of step k-1 (waits for THEIR device->host event, long
+        complete) before issuing step k, and the pinned result buffers alternate."""
         main = torch.cuda.current_stream(dev)
-        for k in h_cam:
-            d_cam[k].copy_(h_cam[k], non_blocking=True)
-        s_in.wait_stream(main)
+        ho = h_outs[k % 2] if pipelined else h_out
+        if pipelined and k >= 1:
+            ev_d2h[(k - 1) % 2].synchronize()
+            consumed.append(float(h_outs[(k - 1) % 2]["gradsum"][0]))  # the host reads the previous step's result
+        d_camv.copy_(h_cam, non_blocking=True)
+        if pipelined:
+            s_in.wait_event(ev_bwd)    # the previous backward has read the cotangent buffers
+            main.wait_event(ev_maps)   # the previous maps have left the (static, graph-mode) output buffers
+        else:
+            s_in.wait_stream(main)
         with torch.cuda.stream(s_in):
-            for k in h_cot:
-                d_cot[k].copy_(h_cot[k], non_blocking=True)
+            d_cotv.copy_(h_cotv, non_blocking=True)
             ev_in.record(s_in)
         st = settings._replace(viewmatrix=d_cam["viewmatrix"], campos=d_cam["campos"])
         for v in leaves.values():
@@ -476,31 +496,48 @@ def run_ours(args, rank, world, local):
         ev_fwd.record(main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_fwd)
-            for k, t in (("color", color), ("feature", feature), ("depth", depth), ("alpha", alpha)):
-                h_out[k].copy_(t.detach(), non_blocking=True)
+            # colour, feature, depth and alpha planes are consecutive planes of ONE allocation of the op: one copy
+            planes = torch.as_strided(color.detach(), (n_pl, H, W), (H * W, W, 1), color.storage_offset())
+            ho["maps"].copy_(planes, non_blocking=True)
+            ev_maps.record(s_out)
         main.wait_event(ev_in)
         torch.autograd.backward([color, feature, depth, alpha],
                                 [d_cot["color"], d_cot["feature"], d_cot["depth"], d_cot["alpha"]])
-        h_out["gradsum"].copy_(leaves["means3D"].grad.sum(0), non_blocking=True)
-        s_out.synchronize()
-        main.synchronize()
+        torch.sum(leaves["means3D"].grad, dim=0, out=gsum)
+        ev_bwd.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_bwd)
+            ho["gradsum"].copy_(gsum, non_blocking=True)
+            ev_d2h[k % 2].record(s_out)
+        if not pipelined:
+            s_out.synchronize()
+            main.synchronize()
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
+    def e2e_run(pipelined, n):
+        ev_bwd.record(torch.cuda.current_stream(dev))
+        ev_maps.record(torch.cuda.current_stream(dev))
+        for k in range(3):
+            e2e_step(k, pipelined)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(n):
+            e2e_step(k, pipelined)
+        if pipelined:
+            ev_d2h[(n - 1) % 2].synchronize()
+            consumed.append(float(h_outs[(n - 1) % 2]["gradsum"][0]))
+        torch.cuda.current_stream(dev).wait_stream(s_out)
+        e1.record()
+        barrier()
+        ms_ = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        tt = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     e2e_steps = max(5, args.steps // 2)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    e2e_wall = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([max(e2e_ms, e2e_wall)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_sync_ms = e2e_run(False, e2e_steps)
+    e2e_ms = e2e_run(True, e2e_steps)
 
     # ---- M2: the reference-faithful pair of half panoramas, two calls of H x W/2 with hfov +-90 and the
     # front / back view matrices of scene/kitti360_loader.py:215-218, gradients summed; reported next to the headline
@@ -603,15 +640,20 @@ def run_ours(args, rank, world, local):
                 "profiling": "timed region runs with per-kernel events OFF; `kernels` come from a separate pass"},
         "cuda_graph": {"mode": args.graph, "ms_per_step_graph_on": (ms if use_graph else ms_other) / args.steps,
                        "ms_per_step_graph_off": (ms_other if use_graph else ms) / args.steps,
-                       "note": "value / e2e are measured in `mode`; graph replay = one launch per pass into static buffers "
-                               "(gs_lidar_b200.set_cuda_graphs)"},
+                       "note": "value / e2e are measured in `mode`; graph replay = one launch per pass into static buffers, the "
+                               "instance count of a forward read at the next call (gs_lidar_b200.set_cuda_graphs(True, "
+                               "deferred_count=True))"},
         "exchange_parity": exchange_parity,
         "per_rank_ms_without_exchange": per_rank_alone,
         "step_spread": spread,
         "clocks": clocks,
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "note": "per-step camera + cotangent maps from pinned host memory, rendered maps + a gradient checksum read back; surfel parameters stay resident like model weights"},
+                "value_synchronous_steps": world * e2e_steps / (e2e_sync_ms * 1e-3),
+                "note": "per-step camera + cotangent maps from pinned host memory, rendered maps + a gradient checksum read back to pinned "
+                        "host memory; surfel parameters stay resident like model weights.  value: the host consumes the results of step "
+                        "k-1 before issuing step k (prefetching loader, asynchronous logging); value_synchronous_steps: a full "
+                        "synchronisation of all streams at the end of every step"},
         "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD +
                          (0 if exchange is None or not exchange.packed else L.OWN_LAUNCHES_PEER(len(exchange.ranges(P)), args.exchange_schedule))) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -640,6 +682,7 @@ def run_inference(args, rank, world, local):
     """--config c2 / c5: forward-only frames through the public API (gs_lidar_b200.batch.render_frames: frames on two
     alternating streams), one camera pose per frame, frames sharded frame_id % world, no collective on the data path."""
     from gs_lidar_b200 import synth, parallel, batch
+    from gs_lidar_b200 import _lib as L
     import gs_lidar_b200.diff_gaussian_rasterization_2d as G
     cfg = INFER[args.config]
     dev = torch.device("cuda", local)
@@ -694,6 +737,18 @@ def run_inference(args, rank, world, local):
     e1.record()
     barrier()
     ms_1s = e0.elapsed_time(e1)
+    # separate pass: per-kernel CUDA-event times (one stream, profiling on -- not part of any timed region)
+    Lb = L.load()
+    Lb.gsl_profile_read(None, None, 1)
+    Lb.gsl_profile_enable(1)
+    batch.render_frames(cams[:min(len(cams), 16)], consume=consume, streams=1, **surfels)
+    barrier()
+    Lb.gsl_profile_enable(0)
+    kms = (C.c_double * L.GSL_K_COUNT)()
+    kn = (C.c_int64 * L.GSL_K_COUNT)()
+    Lb.gsl_profile_read(kms, kn, 1)
+    per_kernel = {Lb.gsl_kernel_name(i).decode(): dict(ms_per_launch=kms[i] / kn[i], launches=int(kn[i]))
+                  for i in range(L.GSL_K_COUNT) if kn[i] > 0}
     # e2e: camera matrices from pinned host memory per frame, rendered maps back to pinned host memory per frame
     n_e2e = min(len(cams), 64)
     h_cam = [(c.viewmatrix.cpu().pin_memory(), c.campos.cpu().pin_memory()) for c in cams[:n_e2e]]
@@ -744,7 +799,6 @@ def run_inference(args, rank, world, local):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     ms_frame = ms / frames
     gbs = (fwd_b + bin_b) / (ms_frame * 1e-3) / 1e9
-    from gs_lidar_b200 import _lib as L
     return {
         "metric": cfg["metric"], "value": world * frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": frames,
         "warmup": 2 * len(warm), "ms_per_step": ms_frame, "higher_is_better": True, "scaling": "weak" if args.config == "c2" else "strong",
@@ -763,6 +817,7 @@ def run_inference(args, rank, world, local):
                      "traffic": None, "algorithmic_bytes_per_launch": int(fwd_b + bin_b), "ms_per_launch": ms_frame,
                      "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
                      "note": "SURVEY.md 8(d) forward bytes (FWD_IO + BIN) of one frame over the frame time"},
+        "kernels": per_kernel,
     }
 
 

@@ -129,16 +129,23 @@ def set_wrap_azimuth(flag: bool):
 #   * zero gradients with set_to_none=True (the PyTorch default): an optimizer that zeroes `.grad` in place keeps an alias of
 #     the static gradient buffer alive; the backward detects that and returns copies instead (correct, but slower);
 #   * a second forward with the same signature before the backward of the first one runs un-graphed.
+#   * deferred_count=True (off by default): the one host wait a forward has -- the instance count, needed only to detect that
+#     the binning workspace was too small -- is taken at the NEXT call of the signature instead of inside this one, so the host
+#     never blocks on work it has just issued (a loop with a prefetching loader then stays ahead of the GPU).  The workspace
+#     keeps 25 % of headroom over the last count; should a step still exceed it (its kernels then write nothing), the next
+#     backward / forward of the signature raises instead of returning: the results of that one step were invalid.
 _cuda_graphs = False
+_deferred_count = False
 _GRAPH_CACHE_MAX = 4
 _graph_cache = {}      # signature -> _GraphEntry (insertion order = LRU order)
 _graph_seen = {}       # signature -> number of eager calls so far
 
 
-def set_cuda_graphs(flag: bool):
+def set_cuda_graphs(flag: bool, deferred_count: bool = False):
     """Switches CUDA-graph replay on or off (see the comment above); switching off frees the captured graphs."""
-    global _cuda_graphs
+    global _cuda_graphs, _deferred_count
     _cuda_graphs = bool(flag)
+    _deferred_count = bool(flag) and bool(deferred_count)
     if not _cuda_graphs:
         for e in list(_graph_cache.values()):
             e.destroy()
@@ -168,6 +175,8 @@ class _GraphEntry:
         self.cot = None          # static cotangent planes of the staged backward graph
         self.ex_out = None       # static outputs of the fused exchange
         self.R = 0
+        self.count_event = None  # deferred count: recorded behind the replay whose count has not been looked at yet
+        self.count_key = None
 
     def drop_graphs(self, backward_only=False):
         if not backward_only and self.fwd_graph is not None:
@@ -381,6 +390,33 @@ def _graph_entry_for(dev, params, inputs, settings):
     return entry
 
 
+def _check_deferred_count(entry, dev, P, W, H, blocking=True):
+    """Deferred count of the previous replay (set_cuda_graphs(deferred_count=True)): waits for its event (long complete unless
+    the host is a whole step ahead), updates the capacity hint, and raises if that replay did not fit."""
+    ev = entry.count_event
+    if ev is None or entry.count_key is None:
+        return
+    if not blocking and not ev.query():
+        return
+    ev.synchronize()
+    entry.count_key = None
+    R = int(entry.ws.host[0])
+    if R < 0:
+        return
+    if R + R // 8 > _pool.r_hint.get((dev, P, W, H), 0):
+        _pool.r_hint[(dev, P, W, H)] = max(R + R // 4, 1024)
+    if R > entry.ws.r_capacity:
+        torch.cuda.current_stream(dev).synchronize()
+        entry.drop_graphs()
+        entry.ws.r_capacity = 0
+        entry.R = 0
+        raise RuntimeError("gs_lidar_b200 (CUDA-graph mode, deferred count): the previous step of this call signature produced "
+                           "%d tile instances, more than its binning workspace held; its outputs and gradients were "
+                           "invalid.  The workspace has been re-sized; repeat the step (or use set_cuda_graphs(True) without "
+                           "deferred_count, which re-runs such a forward transparently)." % R)
+    entry.R = R
+
+
 def _forward_graph(entry, dev, params, inputs, P, S, H, W):
     """Forward pass by graph replay into the entry's static buffers (see the comment at `_cuda_graphs`)."""
     with torch.cuda.device(dev):
@@ -428,8 +464,17 @@ def _forward_graph(entry, dev, params, inputs, P, S, H, W):
                                                     C.byref(entry.wss), cs), "gsl_forward_render")
 
                 entry.fwd_graph = _capture(dev, launches)
+            _check_deferred_count(entry, dev, P, W, H)  # the previous replay of this signature, if it was not looked at
             ws.host[0] = -1  # the sentinel gsl_wait_num_rendered polls; the graph's copy node overwrites it
             L.check(_lib.gsl_graph_launch(entry.fwd_graph, st), "gsl_graph_launch (forward)")
+            if _deferred_count and entry.R > 0 and entry.R + entry.R // 8 <= ws.r_capacity:
+                # trusted capacity (the last count fits with 12 % to spare): the count of THIS replay is read later
+                if entry.count_event is None:
+                    entry.count_event = torch.cuda.Event()
+                entry.count_event.record(torch.cuda.current_stream(dev))
+                entry.count_key = (dev, P, W, H)
+                R = entry.R
+                break
             L.check(_lib.gsl_wait_num_rendered(C.byref(entry.wss), C.byref(r_host), st), "gsl_wait_num_rendered")
             R = int(r_host.value)
             if R <= ws.r_capacity:
@@ -517,6 +562,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         g_depth = cot(grad_depth, (4, H, W))
         g_alpha = cot(grad_alpha, (1, H, W))
         entry = holder.entry  # graph mode: static buffers + captured graphs of this call signature
+        if entry is not None and entry.count_key is not None:
+            _check_deferred_count(entry, dev, P, W, H, blocking=False)  # raises if this step's forward did not fit
         if entry is not None and ctx.graph_generation != entry.generation:
             raise RuntimeError("gs_lidar_b200 (CUDA-graph mode): the state of this forward call was overwritten by a later "
                                "forward with the same signature; run backward before the next forward or switch "

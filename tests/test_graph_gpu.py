@@ -127,3 +127,41 @@ def test_outputs_are_static_and_a_busy_signature_runs_ungraphed(graphs):
     with torch.no_grad():
         rast(mask=scene.mask, **lv)                           # ... busy entry: this one runs un-graphed
     torch.autograd.backward([o3[1]], [cot["color"]])       # still valid
+
+
+def test_deferred_count_gives_the_same_steps_and_reports_an_overflow_at_the_next_call():
+    """set_cuda_graphs(True, deferred_count=True): the host does not wait for the instance count inside the forward.  Steps
+    must equal the plain path; a step whose instances outgrow the captured workspace (its kernels write nothing) makes
+    the NEXT call of the signature raise, after which the signature works again with a larger workspace."""
+    import gs_lidar_b200.diff_gaussian_rasterization_2d as G
+    P = 20000
+    scene = synth.make_scene(P, seed=13).to("cuda")
+    cot = {k: v.cuda() for k, v in synth.make_cotangents(scene.H, scene.W, 4, seed=14).items()}
+    lv = _leaves(scene)
+    want_maps, want_grads = _step(G, scene, lv, cot)
+    G.set_cuda_graphs(True, deferred_count=True)
+    try:
+        for it in range(5):
+            maps, grads = _step(G, scene, lv, cot)
+            for a, b in zip(maps, want_maps):
+                assert torch.equal(a, b), it
+            for k in NAMES:
+                assert common.grad_err(grads[k], want_grads[k])[1] < 1e-5, (it, k)
+        entry = next(iter(G._graph_cache.values()))
+        assert entry.count_event is not None  # the deferred path was taken
+        cap = entry.ws.r_capacity
+        lv["scales"].data.mul_(6.0)  # same tensors, 6x larger splats: several times the instances
+        with torch.no_grad():
+            rast = G.GaussianRasterizer(synth.settings_for(scene))
+            rast(mask=scene.mask, **lv)  # does not fit; nobody has looked yet
+            with pytest.raises(RuntimeError, match="more than its binning workspace held"):
+                rast(mask=scene.mask, **lv)
+            grown = [o.clone() for o in rast(mask=scene.mask, **lv)]  # re-sized: works again
+            entry = next(iter(G._graph_cache.values()))
+            assert entry.ws.r_capacity > cap
+            G.set_cuda_graphs(False)
+            plain = rast(mask=scene.mask, **lv)
+            for a, b in zip(plain, grown):
+                assert torch.equal(a, b)
+    finally:
+        G.set_cuda_graphs(False)
