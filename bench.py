@@ -599,9 +599,10 @@ def run_ours(args, rank, world, local):
         4: 12 * R,                                                                     # k_tile_blists (id + box in, entry out)
         5: N * (8 + 16 + 4 * (S + 3) + 16 + 4 + 12) + V * (64 + 16 + 4 * S),           # k_render_fwd
         6: render_bwd_algorithmic_bytes(V, N, S),                                      # k_render_bwd
-        # k_preprocess_bwd: accumulator + radii of every surfel; record, parameters and SH in, dense gradient rows out for
-        # the surfels that contributed (measured: half of the visible ones); the zero rows are a memset on the side stream
-        7: P * (96 + 4) + (V // 2) * (48 + 45 + 16 * M) + (V // 2) * (12 + 16 + 16 + 4 * S + 4 + 16 * M + 12 + 16),
+        # k_preprocess_bwd: one `touched` byte per surfel; per surfel a pixel composited (measured: half of the visible ones) the
+        # accumulator read and re-zeroed + radii, record, parameters and SH in, dense gradient rows out; the zero rows are a memset
+        # on the side stream
+        7: P * 1 + (V // 2) * (96 + 96 + 4) + (V // 2) * (48 + 45 + 16 * M) + (V // 2) * (12 + 16 + 16 + 4 * S + 4 + 16 * M + 12 + 16),
     }
     # DRAM traffic per launch as ncu measured it (read from the newest profiles/*ncu_full*.md, not hard-coded)
     md, traffic_src = ncu_traffic_from_profiles()
