@@ -471,13 +471,15 @@ def run_ours(args, rank, world, local):
         backward waits for it), the maps are read back on a second copy stream under the backward pass.
         pipelined=False: the step ends with a full synchronisation of all three streams (nothing overlaps across steps).
         pipelined=True : what a training loop with a prefetching loader and asynchronous logging does -- the host never
-        blocks on the step it has just issued; it consumes the results of step k-1 (waits for THEIR device->host event, long
-        complete) before issuing step k, and the pinned result buffers alternate."""
+        blocks on the step it has just issued; it consumes the results of step k-2 (waits for THEIR device->host event, long
+        complete) before issuing step k, and the two pinned result buffers alternate."""
         main = torch.cuda.current_stream(dev)
         ho = h_outs[k % 2] if pipelined else h_out
-        if pipelined and k >= 1:
-            ev_d2h[(k - 1) % 2].synchronize()
-            consumed.append(float(h_outs[(k - 1) % 2]["gradsum"][0]))  # the host reads the previous step's result
+        if pipelined and k >= 2:
+            # the host reads the results of step k-2 (they sit in the pinned buffers step k is about to reuse) before it issues
+            # step k: it is never more than two steps ahead and never waits for the step it has just issued
+            ev_d2h[k % 2].synchronize()
+            consumed.append(float(h_outs[k % 2]["gradsum"][0]))
         d_camv.copy_(h_cam, non_blocking=True)
         if pipelined:
             s_in.wait_event(ev_bwd)    # the previous backward has read the cotangent buffers
@@ -524,8 +526,10 @@ def run_ours(args, rank, world, local):
         for k in range(n):
             e2e_step(k, pipelined)
         if pipelined:
-            ev_d2h[(n - 1) % 2].synchronize()
-            consumed.append(float(h_outs[(n - 1) % 2]["gradsum"][0]))
+            for k in (n - 2, n - 1):
+                if k >= 0:
+                    ev_d2h[k % 2].synchronize()
+                    consumed.append(float(h_outs[k % 2]["gradsum"][0]))
         torch.cuda.current_stream(dev).wait_stream(s_out)
         e1.record()
         barrier()
@@ -653,7 +657,7 @@ def run_ours(args, rank, world, local):
                 "value_synchronous_steps": world * e2e_steps / (e2e_sync_ms * 1e-3),
                 "note": "per-step camera + cotangent maps from pinned host memory, rendered maps + a gradient checksum read back to pinned "
                         "host memory; surfel parameters stay resident like model weights.  value: the host consumes the results of step "
-                        "k-1 before issuing step k (prefetching loader, asynchronous logging); value_synchronous_steps: a full "
+                        "k-2 before issuing step k (prefetching loader, asynchronous logging); value_synchronous_steps: a full "
                         "synchronisation of all streams at the end of every step"},
         "gpu_launches": (L.OWN_LAUNCHES_FWD + L.OWN_LAUNCHES_BWD +
                          (0 if exchange is None or not exchange.packed else L.OWN_LAUNCHES_PEER(len(exchange.ranges(P)), args.exchange_schedule))) * args.steps,
