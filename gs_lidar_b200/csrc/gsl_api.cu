@@ -72,8 +72,8 @@ static int validate(const gsl_params* p) {
   if (p->flags & GSL_FLAG_WRAP_AZIMUTH) {
     if (fabsf((p->hfov_max - p->hfov_min) - 360.f) > 1e-3f)
       return set_error(GSL_EINVAL, "azimuth wrap-around needs a 360 degree hfov (got %g .. %g)", p->hfov_min, p->hfov_max);
-    if (!fast_binning(p->W, p->H))
-      return set_error(GSL_EINVAL, "azimuth wrap-around supports images of up to %d tiles", GSL_FAST_BIN_MAX_TILES);
+    if (p->W > 16 * GSL_BIN_GROUP_TILES)
+      return set_error(GSL_EINVAL, "azimuth wrap-around supports images of up to %d pixels in width", 16 * GSL_BIN_GROUP_TILES);
   }
   return 0;
 }
@@ -185,7 +185,7 @@ GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in
   if ((rc = validate_ws(p, ws, false))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   GeomView g = geom_view(ws->geom, p->P, p->S);
-  if (fast_binning(p->W, p->H) && p->P > 0) {
+  if (p->P > 0) {
     // fork: depth keys + surfel sort on a side stream UNDER the preprocess kernel; join before binning
     SideStream* aux = side_stream();
     if (!aux) return set_error(GSL_EINVAL, "could not create the side stream");
@@ -199,10 +199,7 @@ GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in
     return debug_sync(p, st, "preprocess + surfel sort");
   }
   if ((rc = launch_preprocess(*p, *in, *out, g, st))) return rc;
-  if ((rc = debug_sync(p, st, "preprocess"))) return rc;
-  if (fast_binning(p->W, p->H)) return 0;
-  if ((rc = launch_scan(*p, g, ws->num_rendered_host, st))) return rc;
-  return debug_sync(p, st, "scan");
+  return debug_sync(p, st, "preprocess");
 }
 
 GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
@@ -847,7 +844,7 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
   GeomView g = geom_view(ws->geom, p->P, p->S);
   ImageView im = image_view(ws->image, p->W, p->H, p->P);
   if (p->P > 0) {
-    if (dst->point_offsets) {  // the fast binning path does not need the scan; run it for the export
+    if (dst->point_offsets) {  // the render path does not need the tiles_touched scan; run it for the export
       if ((rc = launch_scan(*p, g, nullptr, st))) return rc;
     }
     k_export_geom<<<(p->P + 255) / 256, 256, 0, st>>>(p->P, g.rec, g.rgb, g.clamped, g.pixbox, *dst);
@@ -860,11 +857,7 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
     if (R > ws->r_capacity) return set_error(GSL_EINVAL, "R exceeds the binning capacity");
     BinView b = bin_view(ws->binning, ws->r_capacity);
     if (dst->point_list_keys) {
-      if (fast_binning(p->W, p->H)) {
-        if ((rc = launch_export_keys(*p, g, im, b.vals_b, dst->point_list_keys, st))) return rc;
-      } else {
-        cudaMemcpyAsync(dst->point_list_keys, b.keys_b, (size_t)R * 8, cudaMemcpyDeviceToDevice, st);
-      }
+      if ((rc = launch_export_keys(*p, g, im, b.vals_b, dst->point_list_keys, st))) return rc;
     }
     if (dst->point_list) cudaMemcpyAsync(dst->point_list, b.vals_b, (size_t)R * 4, cudaMemcpyDeviceToDevice, st);
   }

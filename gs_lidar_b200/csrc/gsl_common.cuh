@@ -23,9 +23,8 @@
 //   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2),
 //     bdesc uint4[tiles*8]  per 8x4 pixel block (tile, b): (start, end) of its block list inside plane b,
 //                     .z = number of leading entries the backward pass has to walk (written by the forward)
-//     hist u32[tiles][ceil(P/256)], bintotal u32[tiles]  counting pass of the fast binning path
-//   binning chunk (capacity Rcap): vals_b u32 = point_list (sorted surfel ids); keys_a/keys_b u64, vals_a u32 and the
-//     sort scratch of the general path;
+//     hist u32[min(tiles, 1024)][ceil(P/256)], bintotal u32[min(tiles, 1024)]  counting pass of the binning
+//   binning chunk (capacity Rcap): vals_b u32 = point_list (sorted surfel ids);
 //     blist uint2[8][Rcap]  BLOCK LISTS: plane b holds, for tile t at [ranges[t].x, ...), in list order, the
 //                     (surfel id, list position) of every entry of t whose conservative pixel box overlaps
 //                     8x4 pixel block b = (row/4)*2 + col/8 of the tile -- the list of block (t, b)
@@ -48,13 +47,23 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // the record in lane c, so one 32-lane reduction instruction flushes a whole record.
 inline __host__ __device__ int grad_stride(int /*S*/) { return 32; }
 
-// Up to this many 16x16 tiles the binning runs as "depth-sort the surfels once, then one stable counting
-// pass per tile" (gsl_binning.cu); larger images take the 64-bit key sort of the reference.
-#define GSL_FAST_BIN_MAX_TILES 1024
+// The binning is "depth-sort the surfels once, then one stable counting pass per tile" (gsl_binning.cu).  The
+// counting pass keeps a [tile][256 surfels] bitmap in shared memory (36 bytes per tile), so it takes this many
+// consecutive 16x16 tiles at a time; larger images are binned group after group.
+#define GSL_BIN_GROUP_TILES 1024
+// most buckets of the surfel depth sort (gsl_sort.cu): ~32-64 surfels per bucket up to 4M surfels
+#define GSL_SORT_MAX_BUCKETS 65536
 inline __host__ __device__ int tile_count(int W, int H) {
   return ((W + GSL_BLOCK_X - 1) / GSL_BLOCK_X) * ((H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y);
 }
-inline bool fast_binning(int W, int H) { return tile_count(W, H) <= GSL_FAST_BIN_MAX_TILES; }
+// groups of a gx x gy tile grid: whole tile rows, or pieces of one row when a row alone exceeds a group
+inline int bin_group_count(int gx, int gy) {
+  if (gx <= GSL_BIN_GROUP_TILES) {
+    const int rows = GSL_BIN_GROUP_TILES / gx;
+    return (gy + rows - 1) / rows;
+  }
+  return gy * ((gx + GSL_BIN_GROUP_TILES - 1) / GSL_BIN_GROUP_TILES);
+}
 
 struct GeomView {
   float4* rec;
@@ -71,7 +80,7 @@ struct GeomView {
   uint32_t* skey_b;      //   keys / ids scattered into their buckets,
   uint32_t* sval_a;
   uint32_t* sval_b;      //   surfel ids in (depth, id) order
-  uint32_t* sort_buckets;  // count / start / cursor arrays of the bucket sort, 3 x (16384 + 64)
+  uint32_t* sort_buckets;  // count / start arrays of the bucket sort, 2 x (GSL_SORT_MAX_BUCKETS + 64)
   uint8_t* touched;      // 1 = some pixel composited this surfel (set by k_render_fwd, consumed and cleared by the backward):
                          // the per-surfel backward reads the 128-byte accumulator of a surfel only when it is set
   size_t bytes;
@@ -81,19 +90,14 @@ struct ImageView {
   float* final_T;   // 3N
   uint2* ranges;    // tiles
   uint4* bdesc;     // tiles * 8
-  uint32_t* hist;   // [tiles][ncta]: instances of tile t emitted by surfel chunk c, then its exclusive prefix
-  uint32_t* bintotal;  // [tiles]
+  uint32_t* hist;   // [tiles of a group][ncta]: instances of tile t emitted by surfel chunk c, then its exclusive prefix
+  uint32_t* bintotal;  // [tiles of a group]
   size_t ncta;      // surfel chunks of 256 (depth-rank order)
   size_t bytes;
 };
 
 struct BinView {
-  uint64_t* keys_a;
-  uint64_t* keys_b;
-  uint32_t* vals_a;
-  uint32_t* vals_b;
-  void* sort_tmp;
-  size_t sort_tmp_bytes;
+  uint32_t* vals_b;     // point_list
   uint2* blist;
   uint32_t* pairmask;
   size_t plane_stride;  // entries per plane of blist / pairmask
@@ -125,7 +129,7 @@ inline GeomView geom_view(void* base, int P, int S) {
   carve(p, g.skey_b, Pp);
   carve(p, g.sval_a, Pp);
   carve(p, g.sval_b, Pp);
-  carve(p, g.sort_buckets, 3 * (16384 + 64));
+  carve(p, g.sort_buckets, 2 * (GSL_SORT_MAX_BUCKETS + 64));
   carve(p, g.touched, Pp);
   g.bytes = (size_t)(p - (char*)base) + 256;
   return g;
@@ -140,27 +144,18 @@ inline ImageView image_view(void* base, int W, int H, int P) {
   carve(p, v.ranges, tiles + 1);
   carve(p, v.bdesc, 8 * tiles + 8);
   v.ncta = ((size_t)(P > 0 ? P : 1) + 255) / 256;
-  const bool fast = fast_binning(W, H);
-  carve(p, v.hist, fast ? tiles * v.ncta : 1);
-  carve(p, v.bintotal, fast ? tiles + 1 : 1);
+  const size_t group = tiles < (size_t)GSL_BIN_GROUP_TILES ? tiles : (size_t)GSL_BIN_GROUP_TILES;
+  carve(p, v.hist, group * v.ncta);
+  carve(p, v.bintotal, group + 1);
   v.bytes = (size_t)(p - (char*)base) + 256;
   return v;
 }
-
-size_t sort_temp_bytes(int64_t Rcap);
 
 inline BinView bin_view(void* base, int64_t Rcap) {
   BinView b;
   char* p = (char*)base;
   size_t R = (size_t)(Rcap > 0 ? Rcap : 1);
-  carve(p, b.keys_a, R);
-  carve(p, b.keys_b, R);
-  carve(p, b.vals_a, R);
   carve(p, b.vals_b, R);
-  b.sort_tmp_bytes = sort_temp_bytes((int64_t)R);
-  char* tmp;
-  carve(p, tmp, b.sort_tmp_bytes);
-  b.sort_tmp = tmp;
   b.plane_stride = align_up(R, 64) + 64;
   carve(p, b.blist, 8 * b.plane_stride);
   carve(p, b.pairmask, 8 * b.plane_stride);
@@ -210,6 +205,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
 int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st);
 int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st);
 int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st);
+uint32_t sort_num_buckets_host(int P);
 bool is_sort_kernel(const void* func);        // kernels that run with the side stream's (high) priority
 bool is_depth_keys_kernel(const void* func);
 int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,

@@ -210,7 +210,12 @@ __device__ __forceinline__ bool aabb_radius_filtered(const Splat& s, float cutof
   return base && (small_out || big);
 }
 
-__global__ void __launch_bounds__(256) k_preprocess_fwd(
+#ifdef GSL_PFWD_MINB
+#define GSL_PFWD_BOUNDS __launch_bounds__(256, GSL_PFWD_MINB)
+#else
+#define GSL_PFWD_BOUNDS __launch_bounds__(256)
+#endif
+__global__ void GSL_PFWD_BOUNDS k_preprocess_fwd(
     PreParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ opacities,
     const float* __restrict__ shs, const float* __restrict__ shs_rest, const float* __restrict__ colors_precomp,
@@ -534,8 +539,9 @@ __device__ __forceinline__ void depth_key_of(int idx, const float* __restrict__ 
                                              uint32_t* __restrict__ skey, uint32_t& key);
 __global__ void __launch_bounds__(256) k_depth_keys(int P, const float* __restrict__ means3D,
                                                     const float* __restrict__ viewmatrix, uint32_t* __restrict__ skey,
-                                                    uint32_t* __restrict__ ctrl) {
+                                                    uint32_t* __restrict__ ctrl, uint32_t* __restrict__ hist, uint32_t nb) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t b = (uint32_t)idx; b < nb; b += gridDim.x * blockDim.x) hist[b] = 0u;  // the sort's histogram (gsl_sort.cu)
   uint32_t key = 0;
   const bool live = idx < P;
   if (live) depth_key_of(idx, means3D, viewmatrix, skey, key);
@@ -573,8 +579,10 @@ bool is_depth_keys_kernel(const void* func) { return func == (const void*)k_dept
 
 int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st) {
   if (p.P == 0) return 0;
-  cudaMemsetAsync(g.ctrl + 8, 0, 2 * sizeof(uint32_t), st);
-  k_depth_keys<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, in.means3D, in.viewmatrix, g.skey_a, g.ctrl);
+  // ctrl[8..9] (the key range, accumulated with atomicMax) were reset by the previous sort's last kernel; a workspace
+  // is zero-filled before its first use.  A stale range only widens the bucket domain: the sort stays exact.
+  k_depth_keys<<<(p.P + 255) / 256, 256, 0, st>>>(p.P, in.means3D, in.viewmatrix, g.skey_a, g.ctrl, g.sort_buckets,
+                                                  sort_num_buckets_host(p.P));
   return check_cuda(cudaGetLastError(), "k_depth_keys launch");
 }
 
@@ -659,6 +667,9 @@ __device__ __forceinline__ float3 sh_backward(int deg, int M, const ShView sh, f
       dRGBdy += (kSH_C2[0] * x) * s4 + (kSH_C2[1] * z) * s5 + (kSH_C2[2] * 2.f * -y) * s6 + (kSH_C2[4] * 2.f * -y) * s8;
       dRGBdz += (kSH_C2[1] * y) * s5 + (kSH_C2[2] * 2.f * 2.f * z) * s6 + (kSH_C2[3] * x) * s7;
       if (deg > 2) {
+#ifdef GSL_PBWD_FENCE
+        asm volatile("" ::: "memory");  // the seven degree-3 coefficient loads start after the degree-2 terms are consumed
+#endif
         if (WRITE) dL_dsh.set(9, (kSH_C3[0] * y * (3.f * xx - yy)) * dL_dRGB);
         if (WRITE) dL_dsh.set(10, (kSH_C3[1] * xy * z) * dL_dRGB);
         if (WRITE) dL_dsh.set(11, (kSH_C3[2] * y * (4.f * zz - xx - yy)) * dL_dRGB);
@@ -705,6 +716,8 @@ __device__ __forceinline__ void sh_basis16(int deg, float x, float y, float z, f
 
 // (k_preprocess_bwd is defined after preprocess_vjp_one)
 // VJP of k_preprocess_fwd and of the SH evaluation for one surfel with accumulator record (g0, g1, g2, dcol, gn).
+// PEER: the result is a packed exchange row (pp.rw floats) instead of entries of the dense tensors.
+template <bool PEER>
 __device__ __forceinline__ void preprocess_vjp_one(
     const PreBwdParams& pp, int i, float4 g0, float4 g1, float4 g2, float4 dcol, float4 gn,
     const float* __restrict__ means3D, const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -795,7 +808,7 @@ __device__ __forceinline__ void preprocess_vjp_one(
     const float du_dth = -v * sinf(phi), dv_dth = sqrtf(u * u + w * w), dw_dth = -v * cosf(phi);
     dm2.y = (float)((raw_du * du_dth + raw_dv * dv_dth + raw_dw * dw_dth) * 0.5 * dVr * pp.W / pp.H);
 
-    if (pp.rw > 0) {  // packed exchange row: [means2D.xy scales.xy | rot | means3D opacity | features...]
+    if (PEER) {  // packed exchange row: [means2D.xy scales.xy | rot | means3D opacity | features...]
       float4* r = reinterpret_cast<float4*>(rows + (size_t)i * pp.rw);
       r[0] = make_float4(dm2.x, dm2.y, dscale.x, dscale.y);
       r[1] = drot;
@@ -818,10 +831,17 @@ __device__ __forceinline__ void preprocess_vjp_one(
 //     coefficients are never read.
 //  2. the queued surfels, densely packed over the CTA's threads: VJP of k_preprocess_fwd and of the SH
 //     evaluation (preprocess_vjp_one).  Every element of every dense output is written by one of the phases.
+// Three CTAs per SM for the plain kernel (80 registers, no spills): the kernel is bound by the latency of its dependent
+// gathers, and 768 instead of 512 resident threads took it from 0.150 to 0.123 ms at 1M surfels (four CTAs: the same).
+// The peer-exchange variant keeps two (it spills at 80 registers).
 #ifndef GSL_PBWD_MINB
-#define GSL_PBWD_MINB 2
+#define GSL_PBWD_MINB 3
 #endif
-__global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
+#ifndef GSL_PBWD_PEER_MINB
+#define GSL_PBWD_PEER_MINB 2
+#endif
+template <bool PEER>
+__global__ void __launch_bounds__(256, PEER ? GSL_PBWD_PEER_MINB : GSL_PBWD_MINB) k_preprocess_bwd(
     PreBwdParams pp, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ shs, const float* __restrict__ shs_rest,
     const float* __restrict__ viewmatrix, const float* __restrict__ campos,
@@ -841,7 +861,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  if (pp.rw > 0) {
+  if (PEER) {
     // ---- peer-memory gradient exchange: this CTA's 256 surfels are one tile; its packed rows (only those with a
     // non-zero record, + a row bitmap) are PUSHED into the staging area of the rank that owns the tile, its non-zero SH
     // factors (packed to the front of the tile's segment, + bits / prefix words) into every rank's factor table.  Remote
@@ -926,7 +946,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
     }
     const int count = s_count;
     for (int slot = threadIdx.x; slot < count; slot += 256)
-      preprocess_vjp_one(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
+      preprocess_vjp_one<true>(pp, cta0 + (int)s_who[slot], s_g[0][slot], s_g[1][slot], s_g[2][slot], s_g[3][slot],
                          s_g[4][slot], means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec, clamped,
                          dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, rows);
     if (staged) {
@@ -1021,7 +1041,7 @@ __global__ void __launch_bounds__(256, GSL_PBWD_MINB) k_preprocess_bwd(
   const float4 q0 = s_g[0][slot], q1 = s_g[1][slot], q2 = s_g[2][slot], q3 = s_g[3][slot], q4 = s_g[4][slot];
   const bool sh_rows = have_sh && !pp.factored;  // dL_dsh is written here, through shared memory (below)
   if (valid)
-    preprocess_vjp_one(pp, row, q0, q1, q2, q3, q4, means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec,
+    preprocess_vjp_one<false>(pp, row, q0, q1, q2, q3, q4, means3D, scales, rotations, shs, shs_rest, viewmatrix, campos, rec,
                        clamped, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, nullptr, !sh_rows);
   if (!sh_rows) return;
   // dL_dsh rows (backward.cu:17-134: basis_k(view direction) x dL_dRGB).  A thread storing its own 16 float4 writes 16-byte
@@ -1229,12 +1249,16 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
   int blocks = (row1 - row0 + 255) / 256;
   ProfScope prof(GSL_K_PREPROCESS_BWD, st);
-  k_preprocess_bwd<<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.shs_rest, in.viewmatrix,
-                                          in.campos, fwd.radii, g.rec, g.clamped, g.touched, g.grad, gout.dL_dmeans3D,
-                                          gout.dL_dmeans2D, gout.dL_dsh, in.shs_rest ? gout.dL_dsh_rest : nullptr,
-                                          gout.dL_dcolors, gout.dL_dfeatures,
-                                          gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, gout.dL_dcov3D,
-                                          pv, pl);
+#define GSL_LAUNCH_PBWD(PEER)                                                                                         \
+  k_preprocess_bwd<PEER><<<blocks, 256, 0, st>>>(pp, in.means3D, in.scales, in.rotations, in.shs, in.shs_rest,         \
+                                                in.viewmatrix, in.campos, fwd.radii, g.rec, g.clamped, g.touched, g.grad, \
+                                                gout.dL_dmeans3D, gout.dL_dmeans2D, gout.dL_dsh,                         \
+                                                in.shs_rest ? gout.dL_dsh_rest : nullptr, gout.dL_dcolors,               \
+                                                gout.dL_dfeatures, gout.dL_dopacity, gout.dL_dscales, gout.dL_drotations, \
+                                                gout.dL_dcov3D, pv, pl)
+  if (pp.rw > 0) GSL_LAUNCH_PBWD(true);
+  else GSL_LAUNCH_PBWD(false);
+#undef GSL_LAUNCH_PBWD
   return check_cuda(cudaGetLastError(), "k_preprocess_bwd launch");
 }
 

@@ -11,6 +11,10 @@
 
 namespace gsl {
 
+#ifndef GSL_FWD_ILP
+#define GSL_FWD_ILP 1
+#endif
+
 #ifdef GSL_STATS
 __device__ unsigned long long g_stats[16];
 #define STAT_ADD(i, v) do { unsigned long long _s = __reduce_add_sync(0xffffffffu, (unsigned)(v)); if ((threadIdx.x & 31) == 0) atomicAdd(&g_stats[i], _s); } while (0)
@@ -102,11 +106,80 @@ __global__ void __launch_bounds__(32) k_render_fwd(
 #ifdef GSL_STATS
       if (lane == 0) st_cand += n;
 #endif
+      // One composited pair: the reference's blend recursion (forward.cu:449-487) in its rounding sequence.
+      auto blend = [&](const int j, const Splat& sp, const PairEval& e) {
+        const float alpha = e.alpha;
+        const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
+        if (test_T < 0.0001f) {
+          done = true;
+          mine = 0;
+          return;
+        }
+        const int pos = (int)(sb.ent[j].y - r0) + 1;  // 1-based list position (the reference's `contributor`)
+        const float wgt = GSL_FM(T, alpha);
+        const float A = GSL_FS(1.f, T);
+        const float mm1 = GSL_FM(rp.far_over_range, GSL_FS(1.f, GSL_FD(rp.near_, e.depth)));
+        const float mm = GSL_FM(mm1, mm1);
+        const float t0 = GSL_FF(-M1, GSL_FA(mm1, mm1), GSL_FF(A, mm, M2));
+        distortion = GSL_FF(wgt, t0, distortion);
+        M1 = GSL_FF(wgt, mm1, M1);
+        M2 = GSL_FF(wgt, mm, M2);
+        if (T > 0.5f) {
+          median_depth = e.depth;
+          median_contributor = pos;
+        }
+        const float4 col = sb.v[4][j];
+        C[0] = GSL_FF(T, GSL_FM(alpha, col.x), C[0]);
+        C[1] = GSL_FF(T, GSL_FM(alpha, col.y), C[1]);
+        C[2] = GSL_FF(T, GSL_FM(alpha, col.z), C[2]);
+        C[3] = GSL_FF(T, GSL_FM(alpha, col.w), C[3]);
+        if (FEAT4) {
+          const float4 f = sb.v[5][j];
+          F[0] = GSL_FF(T, GSL_FM(alpha, f.x), F[0]);
+          F[1] = GSL_FF(T, GSL_FM(alpha, f.y), F[1]);
+          F[2] = GSL_FF(T, GSL_FM(alpha, f.z), F[2]);
+          F[3] = GSL_FF(T, GSL_FM(alpha, f.w), F[3]);
+        } else if (S > 0) {
+          const float* fp = features + (size_t)sb.ent[j].x * S;
+#pragma unroll
+          for (int ch = 0; ch < GSL_MAX_FEATURES; ++ch)
+            if (ch < S) F[ch] = GSL_FF(T, GSL_FM(alpha, __ldg(fp + ch)), F[ch]);
+        }
+        Nn[0] = GSL_FF(T, GSL_FM(alpha, sp.nx), Nn[0]);
+        Nn[1] = GSL_FF(T, GSL_FM(alpha, sp.ny), Nn[1]);
+        Nn[2] = GSL_FF(T, GSL_FM(alpha, sp.nz), Nn[2]);
+        D = GSL_FF(T, GSL_FM(alpha, e.depth), D);
+        D2 = GSL_FF(T, GSL_FM(alpha, GSL_FM(e.depth, e.depth)), D2);
+        T = test_T;
+        last_contributor = pos;
+        contributed |= 1u << j;
+      };
       while (__any_sync(0xffffffffu, mine != 0)) {
 #ifdef GSL_STATS
         if (lane == 0) st_iter++;
 #endif
         if (mine != 0) {
+#if GSL_FWD_ILP == 2
+          // TWO entries per turn: their pair evaluations are independent and interleave in the pipeline (the warps of
+          // this kernel are few -- one per 8x4 block -- so a lane's own instruction-level parallelism is what hides the
+          // latency of the divisions and the exponential); the blends stay in list order.
+          const int j = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const bool two = mine != 0;
+          const int j2 = two ? __ffs(mine) - 1 : j;
+          mine &= mine - 1;  // 0 stays 0
+          const Splat sp = staged_splat(sb, j);
+          const Splat sp2 = staged_splat(sb, j2);
+          const PairEval e = eval_pair<false>(sp, ray, rp.near_, rp.far_);
+          const PairEval e2 = eval_pair<false>(sp2, ray, rp.near_, rp.far_);
+#ifdef GSL_STATS
+          st_eval += two ? 2 : 1;
+          if (e.valid) st_valid++;
+          if (two && e2.valid) st_valid++;
+#endif
+          if (e.valid) blend(j, sp, e);
+          if (two && !done && e2.valid) blend(j2, sp2, e2);
+#else
           const int j = __ffs(mine) - 1;
           mine &= mine - 1;
           const Splat sp = staged_splat(sb, j);
@@ -115,53 +188,8 @@ __global__ void __launch_bounds__(32) k_render_fwd(
           st_eval++;
           if (e.valid) st_valid++;
 #endif
-          if (e.valid) {
-            const float alpha = e.alpha;
-            const float test_T = GSL_FM(T, GSL_FS(1.f, alpha));
-            if (test_T < 0.0001f) {
-              done = true;
-              mine = 0;
-            } else {
-              const int pos = (int)(sb.ent[j].y - r0) + 1;  // 1-based list position (the reference's `contributor`)
-              const float wgt = GSL_FM(T, alpha);
-              const float A = GSL_FS(1.f, T);
-              const float mm1 = GSL_FM(rp.far_over_range, GSL_FS(1.f, GSL_FD(rp.near_, e.depth)));
-              const float mm = GSL_FM(mm1, mm1);
-              const float t0 = GSL_FF(-M1, GSL_FA(mm1, mm1), GSL_FF(A, mm, M2));
-              distortion = GSL_FF(wgt, t0, distortion);
-              M1 = GSL_FF(wgt, mm1, M1);
-              M2 = GSL_FF(wgt, mm, M2);
-              if (T > 0.5f) {
-                median_depth = e.depth;
-                median_contributor = pos;
-              }
-              const float4 col = sb.v[4][j];
-              C[0] = GSL_FF(T, GSL_FM(alpha, col.x), C[0]);
-              C[1] = GSL_FF(T, GSL_FM(alpha, col.y), C[1]);
-              C[2] = GSL_FF(T, GSL_FM(alpha, col.z), C[2]);
-              C[3] = GSL_FF(T, GSL_FM(alpha, col.w), C[3]);
-              if (FEAT4) {
-                const float4 f = sb.v[5][j];
-                F[0] = GSL_FF(T, GSL_FM(alpha, f.x), F[0]);
-                F[1] = GSL_FF(T, GSL_FM(alpha, f.y), F[1]);
-                F[2] = GSL_FF(T, GSL_FM(alpha, f.z), F[2]);
-                F[3] = GSL_FF(T, GSL_FM(alpha, f.w), F[3]);
-              } else if (S > 0) {
-                const float* fp = features + (size_t)sb.ent[j].x * S;
-#pragma unroll
-                for (int ch = 0; ch < GSL_MAX_FEATURES; ++ch)
-                  if (ch < S) F[ch] = GSL_FF(T, GSL_FM(alpha, __ldg(fp + ch)), F[ch]);
-              }
-              Nn[0] = GSL_FF(T, GSL_FM(alpha, sp.nx), Nn[0]);
-              Nn[1] = GSL_FF(T, GSL_FM(alpha, sp.ny), Nn[1]);
-              Nn[2] = GSL_FF(T, GSL_FM(alpha, sp.nz), Nn[2]);
-              D = GSL_FF(T, GSL_FM(alpha, e.depth), D);
-              D2 = GSL_FF(T, GSL_FM(alpha, GSL_FM(e.depth, e.depth)), D2);
-              T = test_T;
-              last_contributor = pos;
-              contributed |= 1u << j;
-            }
-          }
+          if (e.valid) blend(j, sp, e);
+#endif
         }
       }
       // ---- per-entry masks of the pixels it contributed to

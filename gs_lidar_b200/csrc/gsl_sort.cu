@@ -1,18 +1,21 @@
-// gsl_sort.cu -- depth sort of the surfels (fast binning path), hand-written, no library.
+// gsl_sort.cu -- depth sort of the surfels, hand-written, no library.
 //
 // What is needed is the permutation of the P surfels by (depth bits, id): the instances of a tile then come out in
 // the order of the reference's stable 64-bit (tile | depth) radix sort (rasterizer_impl.cu:338-344; see
 // gsl_binning.cu).  Depth keys are positive floats, i.e. their bit patterns are monotone and smoothly spread, so an
 // MSD bucket sort finishes in two levels:
-//   k_depth_keys (gsl_preprocess.cu)  key[i] = bits(r_i); min / max key by warp reduction + one atomic per warp
-//   k_sort_hist     bucket = (key - kmin) >> shift  (NB <= 16384 buckets of ~128 surfels), global histogram
+//   k_depth_keys (gsl_preprocess.cu)  key[i] = bits(r_i); min / max key by warp reduction + one atomic per warp;
+//                   also zero-fills the histogram
+//   k_sort_hist     bucket = (key - kmin) >> shift  (NB <= 65536 buckets of ~32-64 surfels), global histogram
 //   k_sort_hist     ... and the atomic's return value = the surfel's arrival rank inside its bucket
 //   k_sort_scan     exclusive scan of the histogram -> bucket_start[]
 //   k_sort_scatter  (key, id) -> bucket_start + rank (the order inside a bucket does not matter ...)
-//   k_sort_buckets  ... because every bucket is then sorted by the unique 64-bit value (key << 32 | id): bitonic
-//                   network in shared memory, one CTA per bucket.  A bucket that does not fit (degenerate inputs:
-//                   thousands of surfels at identical range) is sorted by the same network in global memory --
-//                   slow but exact.
+//   k_sort_buckets  ... because every bucket is then sorted by the unique 64-bit value (key << 32 | id).  One WARP per
+//                   bucket of up to 256 surfels: 1, 2, 4 or 8 elements per lane in registers, bitonic network with
+//                   shuffles for partner distances below 32 and register-local exchanges above -- no shared memory,
+//                   no barrier.  Larger buckets (clustered depths) are sorted by the whole CTA in shared memory, and
+//                   buckets that do not fit there (degenerate inputs: thousands of surfels at identical range) by
+//                   the same network in global memory -- slow but exact.
 // The whole sort runs on the side stream under k_preprocess_fwd (gsl_api.cu).
 #include "gsl_common.cuh"
 
@@ -20,10 +23,12 @@ namespace gsl {
 
 constexpr int SORT_CAP = 2048;      // elements a bucket may hold to be sorted in shared memory
 constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARP_MAX = 256;  // largest bucket one warp sorts in registers (8 elements per lane)
+constexpr int SORT_CTA_BUCKETS = 64;  // consecutive buckets one CTA owns at most
 
 __host__ __device__ inline uint32_t sort_num_buckets(int P) {
   uint32_t nb = 256;
-  while (nb < 16384u && (uint64_t)nb * 192u < (uint64_t)(P > 0 ? P : 1)) nb <<= 1;
+  while (nb < (uint32_t)GSL_SORT_MAX_BUCKETS && (uint64_t)nb * 64u < (uint64_t)(P > 0 ? P : 1)) nb <<= 1;
   return nb;
 }
 
@@ -42,27 +47,32 @@ __device__ __forceinline__ SortDomain sort_domain(const uint32_t* __restrict__ c
 }
 
 // histogram; the value the atomic returns is the element's (arbitrary but unique) rank inside its bucket, which
-// saves the scatter pass its own atomics
+// saves the scatter pass its own atomics.  Two elements per turn: the atomics are latency, not issue.
 __global__ void __launch_bounds__(256) k_sort_hist(int P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ctrl,
                                                    uint32_t nb, uint32_t* __restrict__ count, uint32_t* __restrict__ rank) {
   const SortDomain d = sort_domain(ctrl, nb);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
-    rank[i] = atomicAdd(&count[(keys[i] - d.kmin) >> d.shift], 1u);
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += 2 * stride) {
+    const int i2 = i + stride;
+    const uint32_t k1 = keys[i];
+    const uint32_t k2 = i2 < P ? keys[i2] : 0u;
+    const uint32_t r1 = atomicAdd(&count[(k1 - d.kmin) >> d.shift], 1u);
+    uint32_t r2 = 0;
+    if (i2 < P) r2 = atomicAdd(&count[(k2 - d.kmin) >> d.shift], 1u);
+    rank[i] = r1;
+    if (i2 < P) rank[i2] = r2;
+  }
 }
 
 // exclusive scan of count[0..nb) -> start[0..nb]; one CTA, every thread owns nb / 1024 consecutive buckets
 __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t nb, const uint32_t* __restrict__ count, uint32_t* __restrict__ start) {
   __shared__ uint32_t s_w[32];
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const uint32_t per = (nb + 1023u) / 1024u;  // <= 16
+  const uint32_t per = (nb + 1023u) / 1024u;  // <= GSL_SORT_MAX_BUCKETS / 1024
   const uint32_t i0 = threadIdx.x * per;
-  uint32_t v[16];
   uint32_t sum = 0;
-#pragma unroll
-  for (uint32_t k = 0; k < 16; ++k) {
-    v[k] = (k < per && i0 + k < nb) ? count[i0 + k] : 0u;
-    sum += v[k];
-  }
+  for (uint32_t k = 0; k < per; ++k)
+    if (i0 + k < nb) sum += count[i0 + k];
   uint32_t inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -83,10 +93,11 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t nb, const uint32_t*
   }
   __syncthreads();
   uint32_t ex = s_w[wv] + inc - sum;
-#pragma unroll
-  for (uint32_t k = 0; k < 16; ++k) {
-    if (k < per && i0 + k < nb) start[i0 + k] = ex;
-    ex += v[k];
+  for (uint32_t k = 0; k < per; ++k) {
+    if (i0 + k < nb) {
+      start[i0 + k] = ex;
+      ex += count[i0 + k];
+    }
   }
 }
 
@@ -103,57 +114,57 @@ __global__ void __launch_bounds__(256) k_sort_scatter(int P, const uint32_t* __r
   }
 }
 
-// compare-exchange network step of the bitonic sort over m = 2^x virtual elements (indices >= n hold +inf)
-// Bitonic network over M <= SORT_THREADS elements, one per thread (threads >= M idle): partners closer than a warp are
-// exchanged with shuffles, only the steps with j >= 32 go through shared memory.  Fully unrolled: the directions and
-// partner tests fold into constants per step.  Must be called by all threads of the CTA.
-template <int M>
-__device__ __forceinline__ unsigned long long bitonic_one_per_thread(unsigned long long v, unsigned long long* s_v) {
-  const uint32_t i = threadIdx.x;
-  const bool warp_live = (i & ~31u) < (uint32_t)M;
+// One warp sorts a bucket of n <= 32 E elements held E per lane (element i = e * 32 + lane, padding = +inf): bitonic
+// network, ascending.  Partner i ^ j is another lane for j < 32 (one 64-bit shuffle) and another register of the same
+// lane for j >= 32; with the loops unrolled every direction folds into a constant or a test of the lane id.
+template <int E>
+__device__ __forceinline__ void warp_sort_bucket(uint32_t lo, uint32_t n, const uint32_t* __restrict__ tmp_key,
+                                                 const uint32_t* __restrict__ tmp_id, uint32_t* __restrict__ order, int lane) {
+  unsigned long long v[E];
 #pragma unroll
-  for (int k = 2; k <= M; k <<= 1) {
+  for (int e = 0; e < E; ++e) {
+    const uint32_t i = (uint32_t)(e * 32 + lane);
+    v[e] = (i < n) ? (((unsigned long long)tmp_key[lo + i] << 32) | tmp_id[lo + i]) : ~0ull;
+  }
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      unsigned long long o = 0;
       if (j >= 32) {
-        __syncthreads();
-        if (warp_live) s_v[i] = v;
-        __syncthreads();
-        if (warp_live) o = s_v[i ^ j];
-      } else if (warp_live) {
-        o = __shfl_xor_sync(0xffffffffu, v, j);
-      }
-      if (warp_live) {
-        // the lower partner keeps the smaller value when sorting upwards: one 64-bit compare, one select
-        const bool take_min = (((i & j) == 0) == ((i & k) == 0));
-        v = ((v < o) == take_min) ? v : o;
+        const int jj = j >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & jj) == 0) {
+            const unsigned long long a = v[e], b = v[e | jj];
+            const bool up = ((e * 32) & k) == 0;  // k >= 64 here: the lane bits do not matter
+            const bool swap = (a > b) == up;
+            v[e] = swap ? b : a;
+            v[e | jj] = swap ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], j);
+          const int i = e * 32 + lane;
+          const bool take_min = (((i & j) == 0) == ((i & k) == 0));
+          v[e] = ((v[e] < o) == take_min) ? v[e] : o;
+        }
       }
     }
   }
-  return v;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const uint32_t i = (uint32_t)(e * 32 + lane);
+    if (i < n) order[lo + i] = (uint32_t)v[e];
+  }
 }
 
-__device__ void sort_one_bucket(unsigned long long* s_v, uint32_t lo, uint32_t n, uint32_t* __restrict__ tmp_key,
+// A bucket too large for one warp, sorted by the whole CTA (must be called by all its threads).
+__device__ void sort_big_bucket(unsigned long long* s_v, uint32_t lo, uint32_t n, uint32_t* __restrict__ tmp_key,
                                 uint32_t* __restrict__ tmp_id, uint32_t* __restrict__ order) {
-  if (n == 0) return;
-  if (n == 1) {
-    if (threadIdx.x == 0) order[lo] = tmp_id[lo];
-    return;
-  }
   uint32_t m = 2;
   while (m < n) m <<= 1;
-  if (n <= (uint32_t)SORT_THREADS) {
-    // the common case: one element per thread, network fully unrolled for the padded size
-    const uint32_t i = threadIdx.x;
-    unsigned long long v = (i < n) ? (((unsigned long long)tmp_key[lo + i] << 32) | tmp_id[lo + i]) : ~0ull;
-    if (m <= 32) v = bitonic_one_per_thread<32>(v, s_v);
-    else if (m == 64) v = bitonic_one_per_thread<64>(v, s_v);
-    else if (m == 128) v = bitonic_one_per_thread<128>(v, s_v);
-    else v = bitonic_one_per_thread<256>(v, s_v);
-    if (i < n) order[lo + i] = (uint32_t)v;
-    return;
-  }
   if (n <= (uint32_t)SORT_CAP) {
     for (uint32_t i = threadIdx.x; i < m; i += SORT_THREADS)
       s_v[i] = (i < n) ? (((unsigned long long)tmp_key[lo + i] << 32) | tmp_id[lo + i]) : ~0ull;
@@ -195,14 +206,43 @@ __device__ void sort_one_bucket(unsigned long long* s_v, uint32_t lo, uint32_t n
   for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) order[lo + i] = tmp_id[lo + i];
 }
 
-// persistent: a few CTAs per SM walk the buckets, so that the sort leaves room for the kernel it runs under
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_buckets(uint32_t nb, const uint32_t* __restrict__ start,
+// Every CTA owns `per` <= SORT_CTA_BUCKETS consecutive buckets: its warps take them in turn (a few CTAs per SM, so that
+// the sort leaves room for the kernel it runs under); the buckets no warp can hold are queued and sorted by the whole
+// CTA afterwards.  Block 0 also resets the key range for the next sort (k_depth_keys accumulates it with atomicMax).
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_buckets(uint32_t nb, uint32_t per, const uint32_t* __restrict__ start,
                                                                uint32_t* __restrict__ tmp_key, uint32_t* __restrict__ tmp_id,
-                                                               uint32_t* __restrict__ order) {
+                                                               uint32_t* __restrict__ order, uint32_t* __restrict__ ctrl) {
   __shared__ unsigned long long s_v[SORT_CAP];
-  for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+  __shared__ uint32_t s_big[SORT_CTA_BUCKETS];
+  __shared__ uint32_t s_nbig;
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_nbig = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 2) ctrl[8 + threadIdx.x] = 0u;
+  __syncthreads();
+  const uint32_t b0 = blockIdx.x * per, b1 = min(nb, b0 + per);
+  for (uint32_t b = b0 + wv; b < b1; b += SORT_THREADS / 32) {
     const uint32_t lo = start[b], n = start[b + 1] - lo;
-    sort_one_bucket(s_v, lo, n, tmp_key, tmp_id, order);
+    if (n == 0) continue;
+    if (n == 1) {
+      if (lane == 0) order[lo] = tmp_id[lo];
+    } else if (n <= 32) {
+      warp_sort_bucket<1>(lo, n, tmp_key, tmp_id, order, lane);
+    } else if (n <= 64) {
+      warp_sort_bucket<2>(lo, n, tmp_key, tmp_id, order, lane);
+    } else if (n <= 128) {
+      warp_sort_bucket<4>(lo, n, tmp_key, tmp_id, order, lane);
+    } else if (n <= (uint32_t)SORT_WARP_MAX) {
+      warp_sort_bucket<8>(lo, n, tmp_key, tmp_id, order, lane);
+    } else if (lane == 0) {
+      s_big[atomicAdd(&s_nbig, 1u)] = b;
+    }
+  }
+  __syncthreads();
+  const uint32_t nbig = s_nbig;
+  for (uint32_t q = 0; q < nbig; ++q) {
+    const uint32_t b = s_big[q];
+    const uint32_t lo = start[b], n = start[b + 1] - lo;
+    sort_big_bucket(s_v, lo, n, tmp_key, tmp_id, order);
     __syncthreads();  // s_v is reused by the next bucket
   }
 }
@@ -214,15 +254,17 @@ bool is_sort_kernel(const void* func) {
          func == (const void*)k_sort_buckets;
 }
 
-// surfel ids in (depth bits, id) order -> g.sval_b.  g.skey_a holds the keys, g.ctrl[8..9] their (~min, max).
+uint32_t sort_num_buckets_host(int P) { return sort_num_buckets(P); }
+
+// surfel ids in (depth bits, id) order -> g.sval_b.  g.skey_a holds the keys, g.ctrl[8..9] their (~min, max); the
+// histogram was zero-filled by k_depth_keys.
 int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st) {
   if (p.P == 0) return 0;
   const uint32_t nb = sort_num_buckets(p.P);
   uint32_t* count = g.sort_buckets;
-  uint32_t* start = g.sort_buckets + 16384 + 64;
-  uint32_t* rank = g.offs;  // scratch: the tiles_touched scan is not used on the fast binning path
+  uint32_t* start = g.sort_buckets + GSL_SORT_MAX_BUCKETS + 64;
+  uint32_t* rank = g.offs;  // scratch: the tiles_touched scan is only run for state exports
   ProfScope prof(GSL_K_SORT, st);
-  cudaMemsetAsync(count, 0, nb * sizeof(uint32_t), st);
   // small grids (a few CTAs per SM): the sort is atomic / latency bound and shares the GPU with k_preprocess_fwd
 #ifndef GSL_SORT_GRID
 #define GSL_SORT_GRID 12
@@ -231,7 +273,13 @@ int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st) 
   k_sort_hist<<<blocks, 256, 0, st>>>(p.P, g.skey_a, g.ctrl, nb, count, rank);
   k_sort_scan<<<1, 1024, 0, st>>>(nb, count, start);
   k_sort_scatter<<<blocks, 256, 0, st>>>(p.P, g.skey_a, g.ctrl, nb, start, rank, g.skey_b, g.sval_a);
-  k_sort_buckets<<<min((int)nb, 148 * GSL_SORT_GRID), SORT_THREADS, 0, st>>>(nb, start, g.skey_b, g.sval_a, g.sval_b);
+  int bgrid = min((int)nb, 148 * GSL_SORT_GRID);
+  uint32_t per = (nb + (uint32_t)bgrid - 1u) / (uint32_t)bgrid;
+  if (per > (uint32_t)SORT_CTA_BUCKETS) {
+    per = SORT_CTA_BUCKETS;
+    bgrid = (int)((nb + per - 1u) / per);
+  }
+  k_sort_buckets<<<bgrid, SORT_THREADS, 0, st>>>(nb, per, start, g.skey_b, g.sval_a, g.sval_b, g.ctrl);
   return check_cuda(cudaGetLastError(), "surfel sort launch");
 }
 

@@ -51,7 +51,7 @@ extern "C" {
 #define GSL_FLAG_WRAP_AZIMUTH 4u /* opt-in, NOT the reference's semantics (it clamps rects, auxiliary.h:47-55): the
                                     panorama is periodic in azimuth -- a splat on the +-180 deg seam keeps its true
                                     footprint (modular tile columns) and its low-pass distance wraps.  Needs
-                                    hfov_max - hfov_min = 360 and an image of <= 1024 tiles. */
+                                    hfov_max - hfov_min = 360 and an image of <= 16384 pixels in width. */
 #define GSL_FLAG_BWD_SH_FACTORED 2u /* gsl_backward: write the clamp-masked dL_dRGB factor into dL_dcolors and do
                                        not write dL_dsh (frame-parallel training rebuilds it with gsl_sh_expand) */
 
@@ -148,8 +148,8 @@ GSL_API const char* gsl_last_error(void);
 /* Sizes of the scratch chunks for P surfels, r_capacity tile instances and W*H pixels. */
 GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_sizes* out);
 
-/* Stage 1 of the forward pass: per-surfel preprocess, then the depth sort of the surfels (images of up to 1024
- * tiles) or the tile-count scan (larger images).  Never blocks the host. */
+/* Stage 1 of the forward pass: per-surfel preprocess with the depth sort of the surfels on a side stream under
+ * it.  Never blocks the host. */
 GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
                            gsl_workspace* ws, void* stream);
 
@@ -158,8 +158,8 @@ GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in
  * exceeds it the kernels write nothing and the overflow flag is raised; the caller then learns R with
  * gsl_wait_num_rendered(), grows the binning chunk and calls this function again.  An asynchronous copy of
  * (R, overflow) into ws->num_rendered_host is enqueued right after the counting kernels, long before the
- * compositing finishes.  (Images of more than 1024 tiles use a 64-bit key sort that needs R on the host:
- * there this call waits for the count itself and returns GSL_ENOSPACE without launching when R does not fit.) */
+ * compositing finishes.  Images of more than 1024 tiles are binned in groups of 1024 consecutive tiles by the same
+ * kernels (no library sort, no host wait at any size). */
 GSL_API int gsl_forward_render(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
                        gsl_workspace* ws, void* stream);
 
@@ -398,10 +398,9 @@ GSL_API int gsl_stage_camera(const float* viewmatrix, const float* campos, const
  * Kernel ids index the arrays of gsl_profile_read. */
 enum {
   GSL_K_PREPROCESS_FWD = 0,
-  GSL_K_SCAN = 1,      /* k_bin_count + k_bin_scan + k_bin_bases (k_scan_* on the > 1024-tile path) */
-  GSL_K_DUPLICATE = 2, /* k_bin_scatter (k_duplicate on the > 1024-tile path) */
-  GSL_K_SORT = 3,      /* k_depth_keys + k_sort_hist/scan/scatter/buckets: this repo's depth sort of the surfels (the
-                          64-bit cub radix sort only on the > 1024-tile path) */
+  GSL_K_SCAN = 1,      /* k_bin_count + k_bin_scan + k_bin_bases (per group of 1024 tiles) */
+  GSL_K_DUPLICATE = 2, /* k_bin_scatter */
+  GSL_K_SORT = 3,      /* k_depth_keys + k_sort_hist/scan/scatter/buckets: this repo's depth sort of the surfels */
   GSL_K_RANGES = 4,    /* k_tile_blists */
   GSL_K_RENDER_FWD = 5,
   GSL_K_RENDER_BWD = 6,

@@ -159,7 +159,9 @@ CASES = [
     dict(P=5003, H=50, W=70, vfov=(-60.0, 60.0), hfov=(-100.0, 100.0), seed=5, footprint_px=3.0, S=0, sh_degree=0),  # odd P: alignment of packed buffers
     dict(P=8000, H=66, W=515, hfov=(-90.0, 90.0), seed=6, S=10, sh_degree=2),          # S at the cap, generic-S kernels
     dict(P=8000, H=33, W=1030, vfov=(-85.0, 85.0), hfov=(-180.0, 180.0), seed=7, footprint_px=4.0),  # near the poles
-    dict(P=20000, H=272, W=1040, vfov=(-40.0, 20.0), hfov=(-180.0, 180.0), seed=8, footprint_px=2.0),  # 1105 tiles: 64-bit key-sort path
+    dict(P=20000, H=272, W=1040, vfov=(-40.0, 20.0), hfov=(-180.0, 180.0), seed=8, footprint_px=2.0),  # 1105 tiles: two tile groups (15 + 2 tile rows)
+    dict(P=12000, H=500, W=2040, vfov=(-45.0, 45.0), hfov=(-180.0, 180.0), seed=9, footprint_px=1.5),  # 32 x 128 tiles: four groups of 8 tile rows
+    dict(P=6000, H=24, W=16500, vfov=(-0.3, 0.3), hfov=(-180.0, 180.0), seed=10, footprint_px=0.3),   # 1032 tiles per row: a row is split into two groups
 ]
 
 
