@@ -94,9 +94,14 @@ class gsl_peer_handle(C.Structure):
     _fields_ = [("reserved", C.c_ubyte * 64)]
 
 
+class gsl_peer_glue(C.Structure):
+    _fields_ = [("timestamp", C.c_float), ("time_shift", C.c_float), ("cycle", C.c_float), ("velocity_decay", C.c_float),
+                ("dynamic", C.c_int32), ("xyz", vp), ("velocity", vp), ("t", vp), ("scaling_t", vp), ("opacity", vp)]
+
+
 class gsl_peer_ctx(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("parity", C.c_uint32),
-                ("buf", vp * GSL_PEER_MAX), ("error_flag", vp)]
+                ("buf", vp * GSL_PEER_MAX), ("error_flag", vp), ("glue", C.POINTER(gsl_peer_glue))]
 
 
 # name -> (restype, argtypes); every symbol include/gsl_b200.h declares
@@ -129,6 +134,7 @@ SYMBOLS = {
     "gsl_sh_expand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_size_t, vp, vp]),
     "gsl_peer_buffer_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "gsl_peer_row_width": (C.c_int32, [C.c_int32]),
+    "gsl_peer_rows_channels": (C.c_int32, [C.c_int32, C.c_int32]),
     "gsl_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), C.POINTER(gsl_peer_handle)]),
     "gsl_peer_open": (C.c_int, [C.POINTER(gsl_peer_handle), C.POINTER(vp)]),
     "gsl_peer_close": (C.c_int, [vp]),

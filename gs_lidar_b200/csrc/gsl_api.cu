@@ -253,6 +253,8 @@ static int validate_peer(const gsl_peer_ctx* c) {
     return set_error(GSL_EINVAL, "peer: bad rank/world %d/%d (at most %d ranks)", c->rank, c->world, GSL_PEER_MAX);
   for (int g = 0; g < c->world; ++g)
     if (!c->buf[g]) return set_error(GSL_EINVAL, "peer: buffer of rank %d is not mapped", g);
+  if (c->glue && (!c->glue->xyz || !c->glue->velocity || !c->glue->t || !c->glue->scaling_t || !c->glue->opacity || !(c->glue->cycle > 0.f)))
+    return set_error(GSL_EINVAL, "peer: glue needs xyz, velocity, t, scaling_t, opacity and a positive cycle");
   return 0;
 }
 
@@ -266,6 +268,8 @@ static int backward_validate(const gsl_params* p, const gsl_fwd_inputs* in, cons
   if (p->flags & GSL_FLAG_BWD_PEER_ROWS) {
     if (!in->shs) return set_error(GSL_EINVAL, "GSL_FLAG_BWD_PEER_ROWS needs the SH colour path");
     if ((rc = validate_peer(gout->peer))) return rc;
+    if (gout->peer->glue && p->S > 4)
+      return set_error(GSL_EINVAL, "GSL_FLAG_BWD_PEER_ROWS with the glue's VJP folded in supports S <= 4 (got %d)", p->S);
   } else
   if (!gout->dL_dmeans3D || !gout->dL_dmeans2D || !gout->dL_dcolors || !gout->dL_dopacity ||
       !gout->dL_dscales || !gout->dL_drotations || (p->S > 0 && !gout->dL_dfeatures) ||
@@ -384,6 +388,7 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   }
   const gsl_peer_ctx* ctx = gout->peer;
   const int P = p->P;
+  const int S_rows = peer_rows_S(p->S, ctx);  // with the glue folded in: dL_dfeatures is (P, S_rows), see gsl_peer_glue
   // One step (gsl_peer.cuh); no kernel of it blocks the stream waiting for other ranks before it has launched:
   //   k_peer_begin            (one warp) step counter++, camera centre -> every rank
   //   k_peer_factor_extract   SH factors of this rank -> own factor table (before the accumulators are re-zeroed)
@@ -396,6 +401,7 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   // The factor tables are half of the step's NVLink bytes and are complete before the per-surfel kernel starts: pushed
   // from the side stream they cross the links UNDER that kernel, and the expansion no longer waits for anybody's rows.
   const bool early = g_peer_early_factors != 0;
+  if (early && ctx->glue) return set_error(GSL_EINVAL, "backward_surfels_exchange: the early-factor schedule does not carry the glue's VJP");
   if ((rc = launch_peer_begin(ctx, in->campos, st))) return rc;
   if (early) {
     if ((rc = launch_peer_factor_extract(ctx, *p, g, st))) return rc;
@@ -427,7 +433,7 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   }
   {
     ProfScope prof(GSL_K_PEER_EXPAND, xs);
-    if ((rc = launch_peer_sh_expand(ctx, P, p->S, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, xs, true,
+    if ((rc = launch_peer_sh_expand(ctx, P, S_rows, p->D, p->M, 0, P, prezeroed, in->means3D, gout->dL_dsh, xs, true,
                                     early ? PEER_SLOT_FACTORS : PEER_SLOT_PUSHED)))
       return rc;
   }
@@ -439,12 +445,12 @@ GSL_API int gsl_backward_surfels_exchange(const gsl_params* p, const gsl_fwd_inp
   {
     ProfScope prof(GSL_K_PEER_REDUCE, st);
     if (low && (rc = launch_peer_wait_fused(ctx, PEER_SLOT_PUSHED, st))) return rc;
-    if ((rc = launch_peer_reduce_rows(ctx, P, p->S, 0, P, st, true))) return rc;
+    if ((rc = launch_peer_reduce_rows(ctx, P, S_rows, 0, P, st, true))) return rc;
   }
   {
     ProfScope prof(GSL_K_PEER_UNPACK, st);
     if (low && (rc = launch_peer_wait_fused(ctx, PEER_SLOT_SUMMED, st))) return rc;
-    if ((rc = launch_peer_unpack(ctx, P, p->S, prezeroed, *gout, st, true))) return rc;
+    if ((rc = launch_peer_unpack(ctx, P, S_rows, prezeroed, *gout, st, true))) return rc;
   }
   if (early) cudaStreamWaitEvent(st, aux->join, 0);  // the factor pushes of this rank have left
   cudaStreamWaitEvent(st, aux->join_low, 0);         // dL_dsh complete
@@ -481,6 +487,7 @@ GSL_API size_t gsl_peer_buffer_bytes(int64_t P, int32_t S, int32_t world) {
   return peer_layout((size_t)(P < 0 ? 0 : P), S, world).total;
 }
 GSL_API int32_t gsl_peer_row_width(int32_t S) { return peer_row_width(S); }
+GSL_API int32_t gsl_peer_rows_channels(int32_t S, int32_t with_glue) { return with_glue ? 4 * ((S + 3) / 4) + 8 : S; }
 
 GSL_API int gsl_peer_alloc(size_t bytes, void** dptr, gsl_peer_handle* handle) {
   static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(gsl_peer_handle), "handle size");
@@ -539,7 +546,7 @@ GSL_API int gsl_peer_signal(const gsl_peer_ctx* ctx, int32_t phase, void* stream
 GSL_API int gsl_peer_wait(const gsl_peer_ctx* ctx, int32_t phase, void* stream) { return peer_barrier(ctx, phase, 2, stream); }
 
 static int validate_rows(const char* what, int32_t P, int32_t S, int32_t row_begin, int32_t row_end) {
-  if (P < 0 || S < 0 || S > 10 || row_begin < 0 || row_end > P || row_begin > row_end || (row_begin & 255) ||
+  if (P < 0 || S < 0 || S > 12 || row_begin < 0 || row_end > P || row_begin > row_end || (row_begin & 255) ||
       ((row_end & 255) && row_end != P))
     return set_error(GSL_EINVAL, "%s: bad sizes / row range [%d, %d) of %d", what, row_begin, row_end, P);
   return 0;
@@ -577,7 +584,7 @@ GSL_API int gsl_peer_reduce(const gsl_peer_ctx* ctx, int32_t P, int32_t S, int32
 GSL_API int gsl_peer_unpack(const gsl_peer_ctx* ctx, int32_t P, int32_t S, const gsl_bwd_outputs* out, void* stream) {
   int rc = validate_peer(ctx);
   if (rc) return rc;
-  if (P < 0 || S < 0 || S > 10) return set_error(GSL_EINVAL, "peer_unpack: bad sizes");
+  if (P < 0 || S < 0 || S > 12) return set_error(GSL_EINVAL, "peer_unpack: bad sizes");
   if (P > 0 && (!out || !out->dL_dmeans3D || !out->dL_dmeans2D || !out->dL_dscales || !out->dL_drotations ||
                 !out->dL_dopacity || (S > 0 && !out->dL_dfeatures)))
     return set_error(GSL_EINVAL, "peer_unpack: an output pointer is NULL");

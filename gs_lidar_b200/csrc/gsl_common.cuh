@@ -254,7 +254,26 @@ constexpr size_t PEER_STEP_OFF = 512, PEER_ERROR_OFF = 516, PEER_DONE_OFF = 520;
 constexpr size_t PEER_CAMPOS_OFF = GSL_PEER_CAMPOS_OFFSET;
 constexpr size_t PEER_CAMPOS_ALL_OFF = 1280;  // float4[2 parities][PEER_MAX]: camera centres of all ranks
 static_assert(PEER_SLOTS * PEER_MAX * 4 <= PEER_STEP_OFF && PEER_DONE_OFF + 32 <= PEER_CAMPOS_OFF, "header layout");
-static_assert(PEER_CAMPOS_ALL_OFF + 2 * PEER_MAX * 16 <= PEER_HEADER, "header too small");
+constexpr size_t PEER_GLUE_ALL_OFF = 1536;  // float4[2 parities][PEER_MAX]: (timestamp - time_shift, time_shift, 0, 0) of all ranks (gsl_peer_glue)
+static_assert(PEER_CAMPOS_ALL_OFF + 2 * PEER_MAX * 16 <= PEER_GLUE_ALL_OFF && PEER_GLUE_ALL_OFF + 2 * PEER_MAX * 16 <= PEER_HEADER,
+              "header too small");
+// What the SH expansion needs to rebuild the position a rank rasterized: xyz + velocity * coef(that rank's timestamp)
+struct GlueMean {
+  const float* xyz;   // null: no glue, the caller's means3D is used for every rank
+  const float* vel;
+  const float* t0;
+  const float* sigt;
+  float a, inv2T_decay;
+};
+inline GlueMean make_glue_mean(const gsl_peer_ctx* c) {
+  GlueMean m = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f};
+  if (c && c->glue) {
+    m.xyz = c->glue->xyz; m.vel = c->glue->velocity; m.t0 = c->glue->t; m.sigt = c->glue->scaling_t;
+    m.a = (float)(1.0 / (double)c->glue->cycle * 3.141592653589793 * 2.0);
+    m.inv2T_decay = c->glue->velocity_decay / c->glue->cycle / 2.f;
+  }
+  return m;
+}
 struct PeerView {  // gsl_peer_ctx by value, as the kernels take it
   int rank, world;
   uint32_t epoch;
@@ -292,6 +311,8 @@ struct PeerLayout {
   size_t total;
 };
 int peer_row_width(int S);
+// "feature" channels of the packed rows: S, or S rounded up to whole quads + two quads of glue gradients (gsl_peer_glue)
+inline int peer_rows_S(int S, const gsl_peer_ctx* c) { return (c && c->glue) ? 4 * ((S + 3) / 4) + 8 : S; }
 PeerLayout peer_layout(size_t P, int S, int world);
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st);
 int launch_peer_begin(const gsl_peer_ctx* c, const float* campos, cudaStream_t st);

@@ -30,6 +30,7 @@
 namespace gsl {
 
 // floats per packed exchange row: means2D.xy scales.xy | rot | means3D opacity | features (padded to whole 32-B sectors)
+// (with the glue's VJP folded in the "features" are 4 ceil(S/4) + 8 channels, see peer_rows_S: 24 floats for S <= 4)
 int peer_row_width(int S) { return S <= 4 ? 16 : 24; }
 
 PeerLayout peer_layout(size_t P, int S, int world) {
@@ -52,13 +53,16 @@ PeerLayout peer_layout(size_t P, int S, int world) {
 // Lane g tells rank g "rank `rank` reached `phase` of step `epoch`" and waits for the same news from rank g.  Everything
 // this rank's stream did before (kernel boundary) is visible to a peer that has seen the flag; a peer that never
 // arrives makes the wait give up after timeout_ns and raise *error (the results of the step are then undefined).
-__global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long long timeout_ns, int* error) {
+__global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long long timeout_ns, int* error, float glue_ts,
+                               float glue_shift) {
   const int g = threadIdx.x;
   if (g >= pv.world) return;
   if ((phase == 0 || phase == 3) && (mode & 1)) {  // publish this rank's camera centre into rank g's table: k_peer_sh_expand then reads it locally
     const float* own = reinterpret_cast<const float*>(pv.own + PEER_CAMPOS_OFF);
     float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * (pv.parity * PEER_MAX + pv.rank);
     dst[0] = own[0]; dst[1] = own[1]; dst[2] = own[2];
+    float* gdst = reinterpret_cast<float*>(pv.buf[g] + PEER_GLUE_ALL_OFF) + 4 * (pv.parity * PEER_MAX + pv.rank);
+    gdst[0] = glue_ts; gdst[1] = glue_shift;  // (timestamp - time_shift, time_shift) of this rank's frame (gsl_peer_glue)
   }
   if (mode & 1) {
     __threadfence_system();
@@ -81,7 +85,7 @@ __global__ void k_peer_barrier(PeerView pv, int phase, int mode, unsigned long l
 // runs the same number of steps), publishes this rank's camera centre in its own header and pushes it into every rank's
 // table of the step's parity.  The pushes are ordered before the "pushed" flag of this step, which the last CTA of the
 // per-surfel kernel (a later kernel of this stream) releases.
-__global__ void k_peer_begin(PeerView pv, const float* __restrict__ campos) {
+__global__ void k_peer_begin(PeerView pv, const float* __restrict__ campos, float glue_ts, float glue_shift) {
   const int g = threadIdx.x;
   uint32_t* step = reinterpret_cast<uint32_t*>(pv.own + PEER_STEP_OFF);
   const uint32_t s = *step + 1u;
@@ -91,6 +95,8 @@ __global__ void k_peer_begin(PeerView pv, const float* __restrict__ campos) {
   if (g < pv.world) {
     float* dst = reinterpret_cast<float*>(pv.buf[g] + PEER_CAMPOS_ALL_OFF) + 4 * ((int)(s & 1u) * PEER_MAX + pv.rank);
     dst[0] = campos[0]; dst[1] = campos[1]; dst[2] = campos[2];
+    float* gdst = reinterpret_cast<float*>(pv.buf[g] + PEER_GLUE_ALL_OFF) + 4 * ((int)(s & 1u) * PEER_MAX + pv.rank);
+    gdst[0] = glue_ts; gdst[1] = glue_shift;
     __threadfence_system();
   }
 }
@@ -127,13 +133,15 @@ int launch_peer_signal_fused(const gsl_peer_ctx* c, int slot, cudaStream_t st) {
 }
 
 int launch_peer_begin(const gsl_peer_ctx* c, const float* campos, cudaStream_t st) {
-  k_peer_begin<<<1, 32, 0, st>>>(make_view(c, true), campos);
+  const float ts = c->glue ? c->glue->timestamp - c->glue->time_shift : 0.f, sh = c->glue ? c->glue->time_shift : 0.f;
+  k_peer_begin<<<1, 32, 0, st>>>(make_view(c, true), campos, ts, sh);
   return check_cuda(cudaGetLastError(), "k_peer_begin launch");
 }
 
 // mode: 1 = signal, 2 = wait, 3 = both (the barrier)
 int launch_peer_barrier(const gsl_peer_ctx* c, int phase, int mode, cudaStream_t st) {
-  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, peer_timeout_ns(), c->error_flag);
+  const float ts = c->glue ? c->glue->timestamp - c->glue->time_shift : 0.f, sh = c->glue ? c->glue->time_shift : 0.f;
+  k_peer_barrier<<<1, 32, 0, st>>>(make_view(c), phase, mode, peer_timeout_ns(), c->error_flag, ts, sh);
   return check_cuda(cudaGetLastError(), "k_peer_barrier launch");
 }
 

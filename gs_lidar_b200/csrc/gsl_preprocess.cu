@@ -619,6 +619,10 @@ struct PreBwdParams {
   int rw;         // > 0: GSL_FLAG_BWD_PEER_ROWS -- floats per packed exchange row (peer_row_width(S))
   int fused;      // peer mode: part of a fused step -- step / parity come from the device-side counter (gsl_peer.cuh)
   int factors_done; // peer mode: the SH factors were pushed already (k_peer_factor_extract / _push), rows only here
+  // peer mode, gsl_peer_glue: the time-dependent part of render()'s glue VJP is applied to the row before it is pushed
+  int glue, g_dynamic;
+  float g_ts, g_shift, g_a, g_inv2T_decay;  // as GlueParams (gsl_glue.cu)
+  const float* g_vel; const float* g_t0; const float* g_sigt; const float* g_opa;
   float VFOV_min, VFOV_max, HFOV_min, HFOV_max;
 };
 
@@ -712,6 +716,53 @@ __device__ __forceinline__ void sh_basis16(int deg, float x, float y, float z, f
       }
     }
   }
+}
+
+// The frame-dependent part of the VJP of render()'s glue (k_glue_bwd, gsl_glue.cu; gaussian_model.py:151-157,185-186,
+// gaussian_renderer/__init__.py:69-79), applied to one surfel's (dL/dmeans3D, dL/dopacity) of THIS frame before the rows
+// of the frames are summed: gv = (dL/dvelocity.xyz, dL/dt), gs.x = dL/dscaling_t, gop becomes dL/d sigmoid(opacity).
+__device__ __forceinline__ void glue_fold(const PreBwdParams& pp, int i, float3 dmean, float& gop, float4& gv, float4& gs) {
+  const float vx = pp.g_vel[3 * (size_t)i], vy = pp.g_vel[3 * (size_t)i + 1], vz = pp.g_vel[3 * (size_t)i + 2];
+  const float tt = pp.g_t0[i];
+  const float sig = expf(pp.g_sigt[i]);
+  const float ph = (pp.g_ts - tt) * pp.g_a;
+  float sn, cs;
+  sincosf(ph, &sn, &cs);
+  float coef = sn / pp.g_a;
+  float ev = 0.f;
+  if (pp.g_shift != 0.f) { ev = expf(-sig * pp.g_inv2T_decay); coef += ev * pp.g_shift; }
+  const float gvv = dmean.x * vx + dmean.y * vy + dmean.z * vz;
+  float g_tt = -cs * gvv;
+  float g_sig = (pp.g_shift != 0.f) ? gvv * pp.g_shift * ev * (-pp.g_inv2T_decay) : 0.f;
+  if (pp.g_dynamic) {
+    const float d = tt - pp.g_ts;
+    const float mt = expf(-0.5f * d * d / (sig * sig));
+    const float os = 1.f / (1.f + expf(-pp.g_opa[i]));
+    const float g_mt = gop * os;
+    gop = gop * mt;
+    g_tt += g_mt * mt * (-d / (sig * sig));
+    g_sig += g_mt * mt * d * d / (sig * sig * sig);
+  }
+  gv = make_float4(dmean.x * coef, dmean.y * coef, dmean.z * coef, g_tt);
+  gs = make_float4(g_sig * sig, 0.f, 0.f, 0.f);
+}
+
+// Position a rank rasterized surfel `row` at: xyz + velocity * coef(that rank's timestamp) (k_glue_fwd, gsl_glue.cu).
+struct GlueRow {
+  float x, y, z, vx, vy, vz, t0, ev;
+};
+__device__ __forceinline__ GlueRow glue_row(const GlueMean& gm, size_t row) {
+  GlueRow r;
+  r.x = gm.xyz[3 * row]; r.y = gm.xyz[3 * row + 1]; r.z = gm.xyz[3 * row + 2];
+  r.vx = gm.vel[3 * row]; r.vy = gm.vel[3 * row + 1]; r.vz = gm.vel[3 * row + 2];
+  r.t0 = gm.t0[row];
+  r.ev = expf(-expf(gm.sigt[row]) * gm.inv2T_decay);
+  return r;
+}
+__device__ __forceinline__ float3 glue_mean_of(const GlueMean& gm, const GlueRow& r, float4 stamp) {  // stamp = (ts, shift)
+  float coef = sinf((stamp.x - r.t0) * gm.a) / gm.a;
+  if (stamp.y != 0.f) coef += r.ev * stamp.y;
+  return make_float3(r.x + r.vx * coef, r.y + r.vy * coef, r.z + r.vz * coef);
 }
 
 // (k_preprocess_bwd is defined after preprocess_vjp_one)
@@ -808,11 +859,19 @@ __device__ __forceinline__ void preprocess_vjp_one(
     const float du_dth = -v * sinf(phi), dv_dth = sqrtf(u * u + w * w), dw_dth = -v * cosf(phi);
     dm2.y = (float)((raw_du * du_dth + raw_dv * dv_dth + raw_dw * dw_dth) * 0.5 * dVr * pp.W / pp.H);
 
-    if (PEER) {  // packed exchange row: [means2D.xy scales.xy | rot | means3D opacity | features...]
+    if (PEER) {  // packed exchange row: [means2D.xy scales.xy | rot | means3D opacity | features... | glue]
       float4* r = reinterpret_cast<float4*>(rows + (size_t)i * pp.rw);
       r[0] = make_float4(dm2.x, dm2.y, dscale.x, dscale.y);
       r[1] = drot;
-      r[2] = make_float4(dmean.x, dmean.y, dmean.z, g2.w);
+      float gop = g2.w;
+      if (pp.glue) {
+        float4 gv, gs;
+        glue_fold(pp, i, dmean, gop, gv, gs);
+        const int q = 3 + (pp.S + 3) / 4;  // first quad behind the feature quads
+        r[q] = gv;
+        r[q + 1] = gs;
+      }
+      r[2] = make_float4(dmean.x, dmean.y, dmean.z, gop);
       return;
     }
     dL_dmeans3D[3 * (size_t)i] = dmean.x; dL_dmeans3D[3 * (size_t)i + 1] = dmean.y; dL_dmeans3D[3 * (size_t)i + 2] = dmean.z;
@@ -868,7 +927,7 @@ __global__ void __launch_bounds__(256, PEER ? GSL_PBWD_PEER_MINB : GSL_PBWD_MINB
     // stores only: nothing here waits for NVLink.  Nothing is zero-filled (readers look at the bits first).
     __shared__ int s_warp[8];
     __shared__ uint32_t s_any[8];
-    __shared__ float4 s_rows[256][4];  // the tile's 64-byte rows, flushed with 64 contiguous bytes per 4 lanes at the end
+    __shared__ float4 s_rows[256 * 6];  // the tile's 64- or 96-byte rows, flushed as contiguous 16-byte pieces at the end
     if (pp.fused) peer_resolve_step(pv);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = cta0 >> 8;
@@ -880,8 +939,8 @@ __global__ void __launch_bounds__(256, PEER ? GSL_PBWD_PEER_MINB : GSL_PBWD_MINB
     const size_t slot0 = ((size_t)pv.rank * pl.tiles_per_rank + tile / pv.world) * 256;  // staging row of the tile's row 0
     float* rows_remote = reinterpret_cast<float*>(obuf + pl.off_stage) + (ptrdiff_t)(slot0 - (size_t)cta0) * pp.rw;
     // 16-byte stores 64 bytes apart make poor NVLink packets: 64-byte rows are staged in shared memory first
-    const bool staged = pp.rw == 16;
-    float* rows = staged ? reinterpret_cast<float*>(&s_rows[0][0]) - (ptrdiff_t)cta0 * 16 : rows_remote;
+    const bool staged = pp.rw == 16 || pp.rw == 24;
+    float* rows = staged ? reinterpret_cast<float*>(&s_rows[0]) - (ptrdiff_t)cta0 * pp.rw : rows_remote;
     bool any = false;
     float4 fac = zero4;
     if (idx < pp.row1 && touched[idx]) {  // no pixel composited the others: their accumulators are all-zero, never read
@@ -914,7 +973,14 @@ __global__ void __launch_bounds__(256, PEER ? GSL_PBWD_PEER_MINB : GSL_PBWD_MINB
           s_who[slot] = (uint16_t)threadIdx.x;
           s_g[0][slot] = g0; s_g[1][slot] = g1; s_g[2][slot] = g2; s_g[3][slot] = gc; s_g[4][slot] = gn;
         } else {
-          r[0] = zero4; r[1] = zero4; r[2] = make_float4(0.f, 0.f, 0.f, g2.w);
+          float gop = g2.w;
+          if (pp.glue) {  // (a culled surfel's opacity gradient is zero in practice; kept exact all the same)
+            float4 gv, gs;
+            glue_fold(pp, idx, make_float3(0.f, 0.f, 0.f), gop, gv, gs);
+            r[3 + nf4] = gv;
+            r[4 + nf4] = gs;
+          }
+          r[0] = zero4; r[1] = zero4; r[2] = make_float4(0.f, 0.f, 0.f, gop);
         }
       }
     }
@@ -951,12 +1017,11 @@ __global__ void __launch_bounds__(256, PEER ? GSL_PBWD_PEER_MINB : GSL_PBWD_MINB
                          dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dsh_rest, dL_dscales, dL_drot, rows);
     if (staged) {
       __syncthreads();
-      float4* dst = reinterpret_cast<float4*>(obuf + pl.off_stage) + slot0 * 4;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int item = it * 256 + threadIdx.x;
-        const int r = item >> 2, q = item & 3;
-        if ((s_any[r >> 5] >> (r & 31)) & 1u) dst[(size_t)r * 4 + q] = s_rows[r][q];
+      const int rw4 = pp.rw >> 2;  // 4 or 6 sixteen-byte pieces per row; consecutive threads store consecutive pieces
+      float4* dst = reinterpret_cast<float4*>(obuf + pl.off_stage) + slot0 * rw4;
+      for (int item = threadIdx.x; item < 256 * rw4; item += 256) {
+        const int r = rw4 == 4 ? item >> 2 : item / 6;
+        if ((s_any[r >> 5] >> (r & 31)) & 1u) dst[item] = s_rows[item];
       }
     }
     return;  // fused step: the "pushed" flag is published by k_peer_signal, the next kernel of the stream
@@ -1193,7 +1258,8 @@ int launch_zero_outputs(const gsl_params& p, const gsl_fwd_inputs& in, gsl_bwd_o
   add(gout.dL_dopacity, P * 4);
   add(gout.dL_dscales, P * 12);
   add(gout.dL_drotations, P * 16);
-  if (p.S > 0) add(gout.dL_dfeatures, P * 4 * (size_t)p.S);
+  const int S_out = (p.flags & GSL_FLAG_BWD_PEER_ROWS) ? peer_rows_S(p.S, gout.peer) : p.S;
+  if (S_out > 0) add(gout.dL_dfeatures, P * 4 * (size_t)S_out);
   if (in.shs && (p.flags & GSL_FLAG_BWD_PEER_ROWS)) {
     add(gout.dL_dsh, P * 16 * (size_t)p.M);  // summed over the ranks by k_peer_sh_expand, non-zero rows only
   } else if (in.shs && !(p.flags & GSL_FLAG_BWD_SH_FACTORED)) {
@@ -1235,15 +1301,27 @@ int launch_preprocess_backward(const gsl_params& p, const gsl_fwd_inputs& in, co
   pp.factored = (p.flags & GSL_FLAG_BWD_SH_FACTORED) ? 1 : 0;
   pp.prezeroed = prezeroed ? 1 : 0;
   pp.row0 = row0; pp.row1 = row1;
-  pp.rw = (p.flags & GSL_FLAG_BWD_PEER_ROWS) ? peer_row_width(p.S) : 0;
+  pp.rw = (p.flags & GSL_FLAG_BWD_PEER_ROWS) ? peer_row_width(peer_rows_S(p.S, gout.peer)) : 0;
   PeerView pv = {};
   PeerLayout pl = {};
   pp.fused = (fused && pp.rw > 0) ? 1 : 0;
   pp.factors_done = (factors_done && pp.rw > 0) ? 1 : 0;
+  pp.glue = 0; pp.g_dynamic = 0;
+  pp.g_ts = pp.g_shift = pp.g_a = pp.g_inv2T_decay = 0.f;
+  pp.g_vel = pp.g_t0 = pp.g_sigt = pp.g_opa = nullptr;
   if (pp.rw > 0) {
     pp.factored = 1;
     pv = make_view(gout.peer, fused);
-    pl = peer_layout((size_t)p.P, p.S, gout.peer->world);
+    pl = peer_layout((size_t)p.P, peer_rows_S(p.S, gout.peer), gout.peer->world);
+    if (const gsl_peer_glue* gl = gout.peer->glue) {  // same constants as make_glue_params (gsl_glue.cu)
+      pp.glue = 1;
+      pp.g_dynamic = gl->dynamic;
+      pp.g_ts = gl->timestamp - gl->time_shift;
+      pp.g_shift = gl->time_shift;
+      pp.g_a = (float)(1.0 / (double)gl->cycle * 3.141592653589793 * 2.0);
+      pp.g_inv2T_decay = gl->velocity_decay / gl->cycle / 2.f;
+      pp.g_vel = gl->velocity; pp.g_t0 = gl->t; pp.g_sigt = gl->scaling_t; pp.g_opa = gl->opacity;
+    }
   }
   Fov f = make_fov(p);
   pp.VFOV_min = f.VFOV_min; pp.VFOV_max = f.VFOV_max; pp.HFOV_min = f.HFOV_min; pp.HFOV_max = f.HFOV_max;
@@ -1331,7 +1409,7 @@ int launch_sh_expand(int P, int D, int M, int G, const float* means3D, const flo
 // gsl_sh_expand over the factor tables the ranks pushed into this rank's buffer (local reads only), rows [row0, row1).
 __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const PeerLayout pl, int row0, int row1, int D,
                                                         int M, int prezeroed, const float* __restrict__ means3D,
-                                                        float* __restrict__ dL_dsh) {
+                                                        const GlueMean gm, float* __restrict__ dL_dsh) {
   const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int word = i >> 5;  // warp-uniform (row0 is a multiple of 256)
@@ -1362,13 +1440,21 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
   if (rowmask == 0u) return;
   const bool in_range = i < row1;
   const size_t ic = in_range ? (size_t)i : 0;
-  const float mx = means3D[3 * ic], my = means3D[3 * ic + 1], mz = means3D[3 * ic + 2];
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  GlueRow grow = {};
+  if (gm.xyz) grow = glue_row(gm, ic);
+  else { mx = means3D[3 * ic]; my = means3D[3 * ic + 1]; mz = means3D[3 * ic + 2]; }
   const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF) + pv.parity * PEER_MAX;
+  const float4* stamp_all = reinterpret_cast<const float4*>(pv.own + PEER_GLUE_ALL_OFF) + pv.parity * PEER_MAX;
 #pragma unroll
   for (int g = 0; g < PEER_MAX; ++g) {
     const float4 dg = d[g];
     if (g >= pv.world || (dg.x == 0.f && dg.y == 0.f && dg.z == 0.f && dg.w == 0.f)) continue;
     const float4 cpos = campos_all[g];
+    if (gm.xyz) {  // rank g's basis is evaluated where rank g rasterized the surfel (its own timestamp)
+      const float3 m = glue_mean_of(gm, grow, stamp_all[g]);
+      mx = m.x; my = m.y; mz = m.z;
+    }
     sh_basis_accumulate(acc, D, mx - cpos.x, my - cpos.y, mz - cpos.z, dg);
   }
   // coalesced stores: a warp's 32 rows x 16 float4 go through shared memory, 8 coefficients at a time, so that one
@@ -1404,7 +1490,7 @@ __global__ void __launch_bounds__(256) k_peer_sh_expand(const PeerView pv, const
 // words, prefix over the 8 words) and only ceil(n / 32) dense warps do the work.
 __global__ void __launch_bounds__(256, 2) k_peer_sh_expand_tiles(PeerView pv, const PeerLayout pl, int tile0, int row1, int D,
                                                                  int M, int fused, int wait_slot,
-                                                                 const float* __restrict__ means3D,
+                                                                 const float* __restrict__ means3D, const GlueMean gm,
                                                                  float* __restrict__ dL_dsh) {
   __shared__ uint2 s_meta[PEER_MAX][8];
   __shared__ uint32_t s_union[8];
@@ -1468,13 +1554,21 @@ __global__ void __launch_bounds__(256, 2) k_peer_sh_expand_tiles(PeerView pv, co
   float4 acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float mx = means3D[3 * row], my = means3D[3 * row + 1], mz = means3D[3 * row + 2];
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  GlueRow grow = {};
+  if (gm.xyz) grow = glue_row(gm, row);
+  else { mx = means3D[3 * row]; my = means3D[3 * row + 1]; mz = means3D[3 * row + 2]; }
   const float4* campos_all = reinterpret_cast<const float4*>(pv.own + PEER_CAMPOS_ALL_OFF) + pv.parity * PEER_MAX;
+  const float4* stamp_all = reinterpret_cast<const float4*>(pv.own + PEER_GLUE_ALL_OFF) + pv.parity * PEER_MAX;
 #pragma unroll
   for (int g = 0; g < PEER_MAX; ++g) {
     const float4 dg = d[g];
     if (g >= pv.world || (dg.x == 0.f && dg.y == 0.f && dg.z == 0.f && dg.w == 0.f)) continue;
     const float4 cpos = campos_all[g];
+    if (gm.xyz) {  // rank g's basis is evaluated where rank g rasterized the surfel (its own timestamp)
+      const float3 m = glue_mean_of(gm, grow, stamp_all[g]);
+      mx = m.x; my = m.y; mz = m.z;
+    }
     sh_basis_accumulate(acc, D, mx - cpos.x, my - cpos.y, mz - cpos.z, dg);
   }
   if (failed) {  // a rank missed a barrier of this step: never return silently wrong gradients
@@ -1504,12 +1598,12 @@ int launch_peer_sh_expand(const gsl_peer_ctx* c, int P, int S, int D, int M, int
   if (row1 <= row0 || M == 0) return 0;
   if (prezeroed && M <= 16) {
     k_peer_sh_expand_tiles<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c, fused), peer_layout((size_t)P, S, c->world),
-                                                                     row0 >> 8, row1, D, M, fused ? 1 : 0, wait_slot, means3D, dL_dsh);
+                                                                     row0 >> 8, row1, D, M, fused ? 1 : 0, wait_slot, means3D, make_glue_mean(c), dL_dsh);
     return check_cuda(cudaGetLastError(), "k_peer_sh_expand_tiles launch");
   }
   if (fused) return set_error(GSL_EINVAL, "peer_sh_expand: the fused step needs zero-filled outputs and M <= 16");
   k_peer_sh_expand<<<(row1 - row0 + 255) / 256, 256, 0, st>>>(make_view(c), peer_layout((size_t)P, S, c->world), row0, row1, D,
-                                                             M, prezeroed ? 1 : 0, means3D, dL_dsh);
+                                                             M, prezeroed ? 1 : 0, means3D, make_glue_mean(c), dL_dsh);
   return check_cuda(cudaGetLastError(), "k_peer_sh_expand launch");
 }
 

@@ -106,6 +106,9 @@ _pool = _Pool()
 
 # frame-parallel training: a gs_lidar_b200.parallel.GradientExchange that the backward pass feeds directly
 _exchange = None
+# renderer.render() leaves the record of its glue call here right before it calls the rasterizer; the forward below attaches
+# it to its autograd node, so that a fused PeerExchange can fold the glue's frame-dependent VJP into the rows it sums
+_pending_fold = None
 
 # Opt-in extension, OFF by default (= the reference's semantics): treat a 360-degree panorama as periodic in azimuth.
 # The reference clamps tile rects at the image border (auxiliary.h:47-55), so a splat on the +-180 degree seam gets an
@@ -514,6 +517,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             outs, holder, params, inputs, R = _forward_impl(*args)
         contrib, color, feature, depth, alpha, radii = outs
 
+        global _pending_fold
+        ctx.fold, _pending_fold = _pending_fold, None
         ctx.raster_settings = raster_settings
         ctx.num_rendered = R
         ctx.gsl_params = params
@@ -589,6 +594,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             # diverge without any error
             raise RuntimeError("gs_lidar_b200: a gradient exchange is active but this call uses colors_precomp (no SH): "
                                "disable the exchange for this backward and all-reduce the gradients yourself")
+        fold = getattr(ctx, "fold", None) if (ex is not None and ex.packed) else None
+        if ex is not None and ex.packed:
+            ex.set_glue(fold)
+        if fold is not None:
+            entry = None  # the frame's timestamp is a kernel argument of the folded VJP: not replayed from a graph
         with torch.cuda.device(dev):
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
             # dL_dcov3D is all-zero (forward.cu never reads cov3D_precomp); only materialised when the caller passed one
@@ -732,6 +742,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                 g = ex.finish(P, params.D, M, inputs["means3D"])
                 d_means3D, d_means2D, d_opacity = g["means3D"], g["means2D"], g["opacities"]
                 d_scales, d_rot, d_features, d_sh = g["scales"], g["rotations"], g["features"], g["shs"]
+                v = g
+            if fold is not None:
+                # the exchanged rows carried dL/dvelocity, dL/dt, dL/dscaling_t of every rank's own timestamp behind the
+                # features; the glue's backward (renderer._ActivateSurfels) takes them from the record
+                d_features, fold["extras"] = ex.split_glue(v, S)
         if not _KEEP_WORKSPACE_AFTER_BACKWARD:
             holder.release()
 

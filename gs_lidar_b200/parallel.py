@@ -234,6 +234,29 @@ class PeerExchange(GradientExchange):
         self._own = None
         self._opened = []
         self.side = None
+        self._glue = None
+
+    def set_glue(self, fold):
+        """`fold`: the record renderer.activate_surfels keeps of one render() call (glue parameters + raw tensors), or
+        None.  With it the NEXT backward applies the frame-dependent part of the glue's VJP (motion model, marginal) to
+        this rank's rows before they are summed (gsl_peer_glue in include/gsl_b200.h) and exchanges dL/dvelocity, dL/dt,
+        dL/dscaling_t as 8 more row channels; the rasterizer's backward calls this itself for calls that came through
+        gs_lidar_b200.renderer.render().  S <= 4."""
+        from . import _lib as L
+        if fold is None:
+            self._glue = None
+            return
+        p, raw = fold["p"], fold["raw"]  # raw: xyz, velocity, t, scaling_t, opacity, scaling, rotation
+        g = L.gsl_peer_glue()
+        g.timestamp, g.time_shift, g.cycle, g.velocity_decay = p.timestamp, p.time_shift, p.cycle, p.velocity_decay
+        g.dynamic = p.dynamic
+        g.xyz = raw[0].data_ptr()
+        g.velocity, g.t, g.scaling_t, g.opacity = raw[1].data_ptr(), raw[2].data_ptr(), raw[3].data_ptr(), raw[4].data_ptr()
+        self._glue = (g, raw)  # keeps the struct and the tensors alive
+
+    def rows_channels(self, S):
+        """Channels of the exchanged rows' feature part: S, or 4 ceil(S / 4) + 8 with the glue folded in."""
+        return S if self._glue is None else 4 * ((S + 3) // 4) + 8
 
     @staticmethod
     def set_schedule(early_factors=False, expand_low_priority=False):
@@ -334,12 +357,19 @@ class PeerExchange(GradientExchange):
                                "see shard_frames(equal_steps=True))" % (int(self._err[0]) - 1))
 
     def prepare(self, P, S, M, device):
+        """S: the rasterizer's feature channels; the rows carry rows_channels(S) of them (set_glue)."""
+        import ctypes as C
+        from . import _lib as L
         G = self.world_size()
+        if self._glue is not None and S > 4:
+            raise RuntimeError("PeerExchange: the glue's VJP can be folded into the rows for S <= 4 feature channels only")
+        S = self.rows_channels(S)
         if self.pkey != (P, S, G, str(device)):
             self.setup(P, S, device)
         self.check(synchronize=False)
         self.epoch += 1
         self.ctx.parity = self.epoch & 1
+        self.ctx.glue = C.pointer(self._glue[0]) if self._glue is not None else C.POINTER(L.gsl_peer_glue)()
         self._S = S
         self.views = None
         return self
@@ -389,7 +419,9 @@ class PeerExchange(GradientExchange):
         launch(0, P)
 
     def alloc_outputs(self, P, S, M, device):
-        """Fresh dense gradient tensors (one allocation for the non-SH ones, NAMES order, + dL_dsh)."""
+        """Fresh dense gradient tensors (one allocation for the non-SH ones, NAMES order, + dL_dsh).  With the glue folded
+        in, `features` is (P, rows_channels(S)): split_glue() separates the exchanged glue gradients from it."""
+        S = self.rows_channels(S)
         widths = dict(means3D=3, means2D=4, opacities=1, scales=3, rotations=4, features=S)
         flat = torch.empty(P * (15 + S), dtype=torch.float32, device=device)
         out, off = {}, 0
@@ -420,6 +452,16 @@ class PeerExchange(GradientExchange):
                 "gsl_peer_unpack")
         self.flat_nbytes = flat.numel() * 4
         return out
+
+    def split_glue(self, out, S):
+        """(dL_dfeatures (P,S), glue gradients or None) from the `features` tensor the exchange returned: with the glue
+        folded in its columns are [features | padding to whole quads | dL/dvelocity (3), dL/dt, dL/dscaling_t, 0, 0, 0]."""
+        f = out["features"]
+        if self._glue is None:
+            return f, None
+        q = 4 * ((S + 3) // 4)
+        extras = dict(velocity=f[:, q:q + 3], t=f[:, q + 3:q + 4], scaling_t=f[:, q + 4:q + 5])
+        return f[:, :S], extras
 
     def finish(self, P, D, M, means3D):
         out = self.unpack(P)

@@ -17,6 +17,7 @@ import math
 import torch
 
 from . import _lib as L
+from . import diff_gaussian_rasterization_2d as _G
 from .diff_gaussian_rasterization_2d import GaussianRasterizationSettings, GaussianRasterizer, _f32c, _stream_ptr
 
 _lib = L.load()
@@ -43,6 +44,11 @@ class _ActivateSurfels(torch.autograd.Function):
             go = L.gsl_glue_outputs(*[x.data_ptr() if x.numel() else None for x in (means3D, opac, scales, rots, marg, mask_out)])
             L.check(_lib.gsl_glue_forward(C.byref(p), C.byref(gi), C.byref(go), _stream_ptr(dev)), "gsl_glue_forward")
         ctx.glue = (p, raw, gi)
+        # record of this call for a fused PeerExchange (render() hands it to the rasterizer's autograd node): under frame-
+        # parallel training the frame-dependent part of this op's VJP is applied to every rank's rows BEFORE they are summed
+        # (include/gsl_b200.h: gsl_peer_glue) and comes back as fold["extras"]
+        ctx.fold = dict(p=p, raw=raw, extras=None)
+        _ActivateSurfels.last_fold = ctx.fold
         ctx.mark_non_differentiable(marg, mask_out)
         return means3D, opac, scales, rots, marg, mask_out
 
@@ -50,6 +56,11 @@ class _ActivateSurfels(torch.autograd.Function):
     def backward(ctx, g_means3D, g_opacity, g_scales, g_rotations, _gm, _gk):
         p, raw, gi = ctx.glue
         dev, P = raw[0].device, p.P
+        extras, ctx.fold["extras"] = ctx.fold["extras"], None
+        if extras is not None:
+            # summed over the ranks already, each with its own timestamp: g_means3D is dL/dxyz, g_opacity is
+            # dL/d sigmoid(opacity); only the frame-independent Jacobians (sigmoid', exp', normalize') are left
+            p = L.gsl_glue_params(p.P, p.timestamp, p.time_shift, p.cycle, p.velocity_decay, 0)
         cots = [None if g is None else _f32c(g) for g in (g_means3D, g_opacity, g_scales, g_rotations)]
         with torch.cuda.device(dev):
             outs = [torch.empty_like(x) for x in raw]
@@ -57,6 +68,10 @@ class _ActivateSurfels(torch.autograd.Function):
             gin = L.gsl_glue_inputs_grad(*[o.data_ptr() if o.numel() else None for o in outs])
             L.check(_lib.gsl_glue_backward(C.byref(p), C.byref(gi), C.byref(go), C.byref(gin), _stream_ptr(dev)),
                     "gsl_glue_backward")
+        if extras is not None:
+            outs[1] = extras["velocity"].reshape(raw[1].shape).contiguous()
+            outs[2] = extras["t"].reshape(raw[2].shape).contiguous()
+            outs[3] = extras["scaling_t"].reshape(raw[3].shape).contiguous()
         return (*outs, None, None, None, None, None, None)
 
 
@@ -108,6 +123,7 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
         features = torch.zeros_like(means3D[:, :0])
         S_other = 0
 
+    _G._pending_fold, _ActivateSurfels.last_fold = getattr(_ActivateSurfels, "last_fold", None), None  # consumed by the rasterizer forward
     contrib, rendered_image, rendered_feature, rendered_depth, rendered_opacity, radii = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp, features=features,
         opacities=opacity, scales=scales, rotations=rotations, cov3D_precomp=None, mask=pre_mask.view(-1, 1),

@@ -295,6 +295,28 @@ GSL_API int gsl_export_state(const gsl_params* p, const gsl_workspace* ws, int64
 #define GSL_PEER_CAMPOS_OFFSET 1024 /* float[3] at this byte offset of the own buffer: this rank's camera centre
                                        (pushed to every rank's table by a barrier on flag slot 0) */
 typedef struct gsl_peer_handle { unsigned char reserved[64]; } gsl_peer_handle; /* cudaIpcMemHandle_t */
+/* Optional: the per-surfel glue of render() (gsl_glue_forward below) sits IN FRONT of the rasterizer, and the Jacobian of
+ * its motion model depends on the FRAME's timestamp (means3D = xyz + v sin((t - t0) a) / a, opacity * marginal(t)): for
+ * ranks rendering different timestamps sum_g J_g^T G_g != J^T sum_g G_g, so the time-dependent part of the glue's VJP has
+ * to be applied BEFORE the sum.  With `glue` set in the context the per-surfel backward kernel does that: the packed rows
+ * carry 8 more floats after the feature quads -- (dL/dvelocity.xyz, dL/dt | dL/dscaling_t, 0, 0, 0) -- and the opacity
+ * slot holds dL/d sigmoid(opacity) (the marginal already applied); dL_dmeans3D is dL/dxyz as it is.  The exchange then
+ * moves S_rows = 4 ceil(S / 4) + 8 "feature" channels (gsl_peer_rows_channels): pass S_rows wherever a gsl_peer_* call
+ * takes S, and a (P, S_rows) dL_dfeatures to gsl_peer_unpack / gsl_backward_surfels_exchange -- columns [0, S) are
+ * dL_dfeatures, [4 ceil(S/4), +3) dL/dvelocity, then dL/dt and dL/dscaling_t.  S <= 4.  The remaining, frame-independent
+ * part of the glue's VJP (sigmoid', exp', normalize') is applied to the sums (gsl_glue_backward with dynamic = 0; its
+ * velocity / t / scaling_t outputs are then replaced by the exchanged ones).  The SH expansion evaluates rank g's basis at
+ * the position rank g rasterized, xyz + velocity * coef(timestamp_g): every rank's (timestamp - time_shift, time_shift) is
+ * pushed next to its camera centre, and the `means3D` argument of gsl_peer_sh_expand* is ignored when glue is set. */
+typedef struct gsl_peer_glue {
+  float timestamp, time_shift, cycle, velocity_decay; /* as gsl_glue_params */
+  int32_t dynamic;
+  const float* xyz;       /* (P,3) raw parameters, as gsl_glue_inputs */
+  const float* velocity;  /* (P,3) */
+  const float* t;         /* (P,1) */
+  const float* scaling_t; /* (P,1) */
+  const float* opacity;   /* (P,1) */
+} gsl_peer_glue;
 typedef struct gsl_peer_ctx {
   int32_t rank, world;       /* world <= GSL_PEER_MAX */
   uint32_t epoch;            /* the ticket of the next barrier call; barriers wait for flags >= ticket (wrap-safe) */
@@ -302,7 +324,10 @@ typedef struct gsl_peer_ctx {
                                 tables, so that a fast rank's next step never overwrites factors a slow rank still reads) */
   void* buf[GSL_PEER_MAX];   /* exchange buffer of every rank as mapped into THIS process; buf[rank] is the own one */
   int32_t* error_flag;       /* device-visible int (pinned host memory): set to 1 + slot when a barrier timed out */
+  const gsl_peer_glue* glue; /* NULL: rows of rasterizer-input gradients; else see gsl_peer_glue (appended field) */
 } gsl_peer_ctx;
+/* channels the exchange moves for S feature channels: S, or 4 ceil(S / 4) + 8 with the glue's VJP folded in */
+GSL_API int32_t gsl_peer_rows_channels(int32_t S, int32_t with_glue);
 GSL_API size_t gsl_peer_buffer_bytes(int64_t P, int32_t S, int32_t world);
 /* floats per packed row: [means2D.xy scales.xy | rotations | means3D opacity | features (S), zero padded] */
 GSL_API int32_t gsl_peer_row_width(int32_t S);

@@ -75,6 +75,8 @@ int main(void) {
          offsetof(gsl_bwd_outputs, peer), offsetof(gsl_peer_ctx, parity), offsetof(gsl_peer_ctx, buf),
          offsetof(gsl_peer_ctx, error_flag));
   printf("%d %d %u %u\n", GSL_PEER_MAX, GSL_PEER_CAMPOS_OFFSET, GSL_FLAG_BWD_PEER_ROWS, GSL_FLAG_BWD_SH_FACTORED);
+  printf("%zu %zu %zu %zu\n", sizeof(gsl_peer_glue), offsetof(gsl_peer_ctx, glue), offsetof(gsl_peer_glue, xyz),
+         offsetof(gsl_peer_glue, opacity));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -86,7 +88,14 @@ int main(void) {
                                              L.gsl_glue_outputs, L.gsl_glue_inputs_grad)]
     assert out[6:12] == [L.gsl_fwd_inputs.shs_rest.offset, L.gsl_bwd_outputs.dL_dsh_rest.offset, L.gsl_bwd_outputs.peer.offset,
                          L.gsl_peer_ctx.parity.offset, L.gsl_peer_ctx.buf.offset, L.gsl_peer_ctx.error_flag.offset]
-    assert out[12:] == [L.GSL_PEER_MAX, L.GSL_PEER_CAMPOS_OFFSET, L.GSL_FLAG_BWD_PEER_ROWS, L.GSL_FLAG_BWD_SH_FACTORED]
+    assert out[12:16] == [L.GSL_PEER_MAX, L.GSL_PEER_CAMPOS_OFFSET, L.GSL_FLAG_BWD_PEER_ROWS, L.GSL_FLAG_BWD_SH_FACTORED]
+    assert out[16:] == [C.sizeof(L.gsl_peer_glue), L.gsl_peer_ctx.glue.offset, L.gsl_peer_glue.xyz.offset,
+                        L.gsl_peer_glue.opacity.offset]
+    # the exchange moves S feature channels, or whole quads of them + two quads of glue gradients
+    lib = L.load()
+    assert [lib.gsl_peer_rows_channels(s_, 0) for s_ in (0, 3, 4)] == [0, 3, 4]
+    assert [lib.gsl_peer_rows_channels(s_, 1) for s_ in (0, 3, 4)] == [8, 12, 12]
+    assert lib.gsl_peer_row_width(12) == 24
 
 
 def _params(**kw):
