@@ -37,6 +37,7 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "panoramas/sec fwd+bwd at 1M surfels 66x1030"
 UNIT = "panoramas/s"
+METRIC_C4 = "panoramas/sec fwd+bwd, dynamic training step through render() at 1M surfels 66x1030 (C4)"
 WORKLOAD = "KITTI-360 seq 1908-shaped static training step: 1M synthetic surfels, fwd+bwd 66x1030 (hfov +-180, SH deg 3, S=4)"
 
 
@@ -64,8 +65,11 @@ def parse_args():
     ap.add_argument("--clock-sample-ms", type=int, default=20, help="period of the clock sampler on rank 0 (0 = off)")
     ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "off"],
                     help="nvml: a side process polling two NVML queries (default); smi: an `nvidia-smi --query-gpu -lms` loop")
-    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"],
-                    help="c3 (default, the headline): fwd+bwd, 1M surfels, 66x1030.  c2: forward-only render of 100k surfels, 66x1030, "
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
+                    help="c3 (default, the headline): fwd+bwd, 1M surfels, 66x1030.  c4: the DYNAMIC training step (BASELINE.json "
+                         "configs[3]): 51 frames with their own poses and timestamps through gs_lidar_b200.renderer.render() "
+                         "(fused glue: SHM motion model, marginal, activations) + the rasterizer, frame-parallel with the fused "
+                         "exchange carrying the glue's frame-dependent VJP.  c2: forward-only render of 100k surfels, 66x1030, "
                          "one GPU.  c5: stress inference, 4M surfels, 128x2048 OPV2V-style panoramas, --frames frames sharded by "
                          "frame over the GPUs (BASELINE.json configs[1] / configs[4]); both forward only")
     ap.add_argument("--frames", type=int, default=512, help="c5: frames of the batch (all ranks together)")
@@ -610,6 +614,7 @@ def run_ours(args, rank, world, local):
     }
     # DRAM traffic per launch as ncu measured it (read from the newest profiles/*ncu_full*.md, not hard-coded)
     md, traffic_src = ncu_traffic_from_profiles()
+    # (k_bin_bases: a separate kernel in profiles of earlier builds, now the last CTA of k_bin_scan)
     groups = {0: ["k_preprocess_fwd"], 1: ["k_bin_count", "k_bin_scan", "k_bin_bases"], 2: ["k_bin_scatter"],
               3: ["k_depth_keys", "k_sort_hist", "k_sort_scan", "k_sort_scatter", "k_sort_buckets", "k_sort_rank", "k_sort_big"],
               4: ["k_tile_blists"], 5: ["k_render_fwd"], 6: ["k_render_bwd"], 7: ["k_preprocess_bwd"]}
@@ -826,6 +831,144 @@ def run_inference(args, rank, world, local):
     }
 
 
+def run_dynamic(args, rank, world, local):
+    """--config c4: one training step of a DYNAMIC scene per rank and step -- render() (fused glue + rasterizer) forward and
+    backward down to the RAW GaussianModel parameters; frame (step * world + rank) % 51 of a drive with its own pose and
+    timestamp.  N > 1: the fused peer exchange sums the raw-parameter gradients of the ranks' frames, the
+    frame-dependent part of the glue's VJP folded into the rows (parallel.PeerExchange.set_glue); checked, outside the timed
+    region, against an all-reduce of the raw-parameter gradients every rank's own autograd graph gives."""
+    from types import SimpleNamespace
+    from gs_lidar_b200 import synth, parallel, renderer
+    from gs_lidar_b200 import _lib as L
+    import gs_lidar_b200.diff_gaussian_rasterization_2d as G
+    dev = torch.device("cuda", local)
+    P, H, W, S = args.surfels, args.height, args.width, 4
+    NF = 51  # KITTI-360 10750-10800 (scene/kitti360_loader.py:154-156)
+    scene = synth.make_scene(P, H=H, W=W, S=S, seed=0).to(dev)
+    g = torch.Generator().manual_seed(4)
+    n_ = lambda *s_: torch.randn(*s_, generator=g)
+    pc = SimpleNamespace()  # raw GaussianModel parameters (scene/gaussian_model.py:266-298), surfels of the synthetic scene
+    pc._xyz = scene.means3D.clone().requires_grad_(True)
+    pc._velocity = (0.01 * n_(P, 3)).to(dev).requires_grad_(True)
+    pc._t = (torch.rand(P, 1, generator=g) * 1.2 - 0.6).to(dev).requires_grad_(True)
+    pc._scaling_t = (math.log(0.1) + 0.3 * n_(P, 1)).to(dev).requires_grad_(True)
+    pc._opacity = torch.logit(scene.opacities.clamp(1e-4, 1 - 1e-4)).clone().requires_grad_(True)
+    pc._scaling = scene.scales.log().clone().requires_grad_(True)
+    pc._rotation = scene.rotations.clone().requires_grad_(True)
+    pc._features_dc = scene.shs[:, :1].clone().requires_grad_(True)
+    pc._features_rest = scene.shs[:, 1:].clone().requires_grad_(True)
+    pc.T, pc.velocity_decay, pc.active_sh_degree = 0.2, 1.0, scene.sh_degree
+    names = ["_xyz", "_velocity", "_t", "_scaling_t", "_opacity", "_scaling", "_rotation", "_features_dc", "_features_rest"]
+    pipe = SimpleNamespace(neg_fov=True, debug=False, scale_factor=scene.scale_factor, dynamic=True, median_depth=False,
+                           compute_cov3D_python=False, convert_SHs_python=False)
+    cams = []
+    for k in range(NF):
+        c = synth.make_scene(16, H=H, W=W, S=S, seed=0, view_yaw_deg=0.5 * math.sin(0.7 * k),
+                             view_shift=(0.1 * scene.scale_factor * k, 0.0, 0.0))
+        cams.append(SimpleNamespace(image_height=H, image_width=W, world_view_transform=c.viewmatrix.to(dev),
+                                    full_proj_transform=c.projmatrix.to(dev), camera_center=c.campos.to(dev), vfov=scene.vfov,
+                                    hfov=scene.hfov, timestamp=-0.5 + k / (NF - 1.0), towards="forward", FoVx=1.0, FoVy=1.0))
+    cot = {k: v.to(dev) for k, v in synth.make_cotangents(H, W, S, seed=1).items()}
+    exchange = parallel.PeerExchange().enable() if world > 1 else None
+    state = {"k": 0, "last": None}
+
+    def step(frame=None):
+        for nme in names:
+            getattr(pc, nme).grad = None
+        k = state["k"] if frame is None else frame
+        state["k"] = k + 1
+        cam = cams[(k * world + rank) % NF]
+        other = [torch.exp(pc._scaling_t).detach(), pc._velocity.detach()]  # train.py:167-169
+        pkg = renderer.render(cam, pc, pipe, scene.bg, other=other)
+        # fixed cotangents on the maps the loss of train.py reads (depth, intensity, ray-drop, alpha, features, normal),
+        # handed to autograd directly: no loss kernels in the step, like the headline's
+        torch.autograd.backward([pkg["depth"], pkg["intensity_sh"], pkg["raydrop"], pkg["alpha"], pkg["feature"], pkg["normal"]],
+                                [cot["depth"][:1], cot["color"][2:3], cot["color"][3:4], cot["alpha"], cot["feature"][:S],
+                                 cot["feature"][S:]])
+        state["last"] = pkg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local, args.clock_sample_ms, args.clock_sampler)
+    if rank == 0:
+        sampler.start()
+    G.set_cuda_graphs(args.graph == "on", deferred_count=True)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 1.0:
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize(dev)
+    barrier()
+    V = int(state["last"]["visibility_filter"].sum())
+    exchange_parity = None
+    if world > 1:
+        leaves = {nme: getattr(pc, nme) for nme in names}
+        exchange_parity = check_exchange_parity(lambda: step(frame=7), leaves, names, exchange, dev)
+        if not exchange_parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC_C4, "impl": "ours", "n_gpus": world, "error": "exchange parity check failed",
+                                  "exchange_parity": exchange_parity}))
+            dist.barrier()
+            dist.destroy_process_group()
+            sys.exit(1)
+        for _ in range(2):
+            step()
+        barrier()
+    L.load().gsl_profile_enable(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # separate pass: per-kernel CUDA-event times of rank 0
+    G.set_cuda_graphs(False)
+    Lb = L.load()
+    Lb.gsl_profile_read(None, None, 1)
+    Lb.gsl_profile_enable(1)
+    for _ in range(min(args.steps, 10)):
+        step()
+    barrier()
+    Lb.gsl_profile_enable(0)
+    kms = (C.c_double * L.GSL_K_COUNT)()
+    kn = (C.c_int64 * L.GSL_K_COUNT)()
+    Lb.gsl_profile_read(kms, kn, 1)
+    per_kernel = {Lb.gsl_kernel_name(i).decode(): dict(ms_per_launch=kms[i] / kn[i], launches=int(kn[i]))
+                  for i in range(L.GSL_K_COUNT) if kn[i] > 0}
+    clocks = sampler.stop() if rank == 0 else {}
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if exchange is not None:
+        exchange.disable()
+        exchange.close()
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC_C4, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+        "config": {"workload": "C4: dynamic KITTI-360-shaped training step through render(): fused glue (SHM motion model, "
+                               "marginal, activations) + rasterizer, fwd+bwd to the raw GaussianModel parameters, 51 frames with "
+                               "their own poses and timestamps", "surfels": P, "height": H, "width": W,
+                   "sh_degree": scene.sh_degree, "feature_channels": S, "visible_surfels_last_frame": V, "frames": NF,
+                   "parallelism": "frame-parallel dp%d, 1 frame/rank/step" % world,
+                   "l2": "inputs exceed the 126 MB L2; no explicit flush"},
+        "run": {"grad_exchange": None if world == 1 else "peer-memory exchange with the glue's frame-dependent VJP folded into "
+                                                        "the rows (96-byte rows: + dL/dvelocity, dL/dt, dL/dscaling_t)",
+                "cuda_graph": args.graph + " (forward replayed; a backward with the folded glue is issued kernel by kernel)"},
+        "exchange_parity": exchange_parity, "clocks": clocks, "kernels": per_kernel,
+    }
+
+
 def cpu_baseline(args, full=True):
     """CPU oracle (plain-C port of the reference algorithm) timed on the host cores on a bounded sample."""
     import oracle
@@ -1007,6 +1150,8 @@ def main():
     rank, world, local = init_dist(args)
     if args.impl == "reference":
         res = run_reference(args, rank, world, local)
+    elif args.config == "c4":
+        res = run_dynamic(args, rank, world, local)
     elif args.config != "c3":
         res = run_inference(args, rank, world, local)
     else:

@@ -170,9 +170,9 @@ SYMBOLS = {
 }
 GSL_K_COUNT = 14
 GSL_PEER_OPT_EARLY_FACTORS, GSL_PEER_OPT_EXPAND_LOW_PRIORITY = 0, 1
-# kernels of THIS repo launched per forward / backward call on the fast binning path (<= 1024 tiles; no library
-# kernel is launched there): used by bench.py for "gpu_launches".
-OWN_LAUNCHES_FWD = 1 + 4 + 1 + 3 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan/bases,
+# kernels of THIS repo launched per forward / backward call for images of up to 1024 tiles (one tile group; no library
+# kernel is launched at any size): used by bench.py for "gpu_launches".
+OWN_LAUNCHES_FWD = 1 + 4 + 1 + 2 + 1 + 1 + 1   # depth keys, sort hist/scan/scatter/buckets, preprocess, bin count/scan,
                                             # bin scatter, tile block lists, render_fwd
 OWN_LAUNCHES_BWD = 1 + 1               # render_bwd, preprocess_bwd
 

@@ -806,7 +806,7 @@ GSL_API int gsl_profile_read(double* total_ms, int64_t* launches, int reset) {
 }
 
 GSL_API const char* gsl_kernel_name(int id) {
-  static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan|bases)", "k_bin_scatter",
+  static const char* names[GSL_K_COUNT] = {"k_preprocess_fwd", "k_bin_(count|scan)", "k_bin_scatter",
                                            "k_sort_(hist|scan|scatter|buckets)", "k_tile_blists", "k_render_fwd",
                                            "k_render_bwd", "k_preprocess_bwd", "k_glue_fwd", "k_glue_bwd",
                                            "k_peer_reduce_rows", "k_peer_sh_expand", "k_peer_unpack", "k_peer_factor_push"};

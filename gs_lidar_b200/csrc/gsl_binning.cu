@@ -4,7 +4,7 @@
 //   key = (tile_id << 32) | float_bits(depth), value = surfel id, emitted y-major/x-minor per surfel
 //   stable sort over key bits [0, 32 + bits(tiles));  ranges[tile] = [first, last+1)
 // How: the surfels are depth-sorted once (gsl_sort.cu) and a stable counting pass distributes their instances to the
-// tiles (k_bin_count / k_bin_scan / k_bin_bases / k_bin_scatter below) -- no 64-bit keys are materialised and no library
+// tiles (k_bin_count / k_bin_scan / k_bin_scatter below) -- no 64-bit keys are materialised and no library
 // kernel runs.  The counting pass holds a [tile][256 surfels] bitmap in shared memory, so it handles GSL_BIN_GROUP_TILES
 // tiles at a time: images with more tiles (every BASELINE.json config has at most 1,024) are processed as consecutive
 // GROUPS of tile ids -- whole tile rows, or pieces of one row for images wider than 16,384 pixels -- each group
@@ -131,7 +131,7 @@ int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStr
 // ------------------------------------------------------------------------------------------------
 // identifyTileRanges (rasterizer_impl.cu:116-142) + second-level binning into 8x4-pixel BLOCK LISTS,
 // one CTA per 16x16 tile:
-//   * ranges[tile] = [first, last+1) comes from k_bin_bases (empty tiles hold (0,0) like the reference's memset);
+//   * ranges[tile] = [first, last+1) comes from k_bin_scan (empty tiles hold (0,0) like the reference's memset);
 //   * the CTA streams the tile's list; every position computes which of the tile's eight 8x4 blocks
 //     the surfel's conservative pixel box overlaps, and an order-preserving compaction per block (ballot
 //     ranks + running counters) appends (surfel id, list position) to blist[b][first + k].  The region of
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
     if (threadIdx.x < 8) bdesc[tile * 8 + threadIdx.x] = make_uint4(0, 0, 0, 0);
     return;
   }
-  if (threadIdx.x == 0) {  // written by k_bin_bases
+  if (threadIdx.x == 0) {  // written by k_bin_scan
     const uint2 r = ranges[tile];
     s_bounds[0] = r.x;
     s_bounds[1] = r.y;
@@ -209,15 +209,17 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
       }
     }
     __syncthreads();
-    if (threadIdx.x < 8) {  // exclusive prefix over the segments of this plane, seeded with the running total
-      uint32_t run = s_run[threadIdx.x];
-#pragma unroll 8
-      for (int sg = 0; sg < SEGS; ++sg) {
-        const uint32_t c = s_seg[sg][threadIdx.x];
-        s_seg[sg][threadIdx.x] = run;
-        run += c;
-      }
-      s_run[threadIdx.x] = run;
+    if (wv < 8) {  // warp p: exclusive prefix over the segments of plane p, seeded with the running total
+      static_assert(SEGS % 32 == 0, "whole segments per lane");
+      constexpr int PER = SEGS / 32;
+      uint32_t c[PER], sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) { c[k] = s_seg[lane * PER + k][wv]; sum += c[k]; }
+      uint32_t ex = warp_incl_scan(sum) - sum + s_run[wv];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < PER; ++k) { s_seg[lane * PER + k][wv] = ex; ex += c[k]; }
+      if (lane == 31) s_run[wv] = ex;
     }
     __syncthreads();
 #pragma unroll
@@ -246,8 +248,8 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_blists(
 // Step 2 works on chunks of 256 depth-ranked surfels (one CTA each) and on one GROUP of at most
 // GSL_BIN_GROUP_TILES consecutive tile ids at a time (TileGroup; one group for every image of up to 1,024 tiles):
 //   k_bin_count    per chunk, a shared-memory bitmap [tile of the group][256 surfels]; hist[tile][chunk] = popcount
-//   k_bin_scan     per tile, exclusive scan of hist[tile][*] over the chunks + total[tile]
-//   k_bin_bases    exclusive scan of total[], continued from the previous group -> ranges[tile], R, overflow flag
+//   k_bin_scan     per tile, exclusive scan of hist[tile][*] over the chunks + total[tile]; its last CTA: exclusive scan
+//                  of total[], continued from the previous group -> ranges[tile], R, overflow flag
 //   k_bin_scatter  rebuilds the bitmap; instance of surfel thread t in tile b goes to
 //                  ranges[b].x + hist[b][chunk] + popcount(bitmap[b] below t)
 // ------------------------------------------------------------------------------------------------
@@ -314,8 +316,9 @@ __global__ void __launch_bounds__(256) k_bin_count(int P, const uint32_t* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) k_bin_scan(uint32_t* __restrict__ hist, size_t ncta,
-                                                  uint32_t* __restrict__ bintotal) {
+__global__ void __launch_bounds__(256) k_bin_scan(uint32_t* __restrict__ hist, size_t ncta, uint32_t* __restrict__ bintotal,
+                                                  const TileGroup tg, int first, uint2* __restrict__ ranges,
+                                                  uint32_t* __restrict__ ctrl, uint32_t r_capacity) {
   __shared__ uint32_t sm[33];
   uint32_t* row = hist + (size_t)blockIdx.x * ncta;
   uint32_t carry = 0;
@@ -334,27 +337,32 @@ __global__ void __launch_bounds__(256) k_bin_scan(uint32_t* __restrict__ hist, s
     }
     carry += total;
   }
-  if (threadIdx.x == 0) bintotal[blockIdx.x] = carry;
-}
-
-// ranges of the group's tiles, continuing at the instance count the previous groups left in ctrl[0]
-__global__ void __launch_bounds__(1024) k_bin_bases(const uint32_t* __restrict__ bintotal, const TileGroup tg, int first,
-                                                    uint2* __restrict__ ranges, uint32_t* __restrict__ ctrl,
-                                                    uint32_t r_capacity) {
-  __shared__ uint32_t sm[33];
-  uint32_t carry = first ? 0u : ctrl[0];
+  // ---- the CTA that finishes last turns the tile totals into ranges (one launch less on the critical path):
+  // exclusive scan of total[], continued at the instance count the previous groups left in ctrl[0]
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    bintotal[blockIdx.x] = carry;
+    __threadfence();
+    const uint32_t done = atomicAdd(&ctrl[2], 1u);
+    s_last = (done == gridDim.x - 1) ? 1 : 0;
+    if (s_last) ctrl[2] = 0u;  // left at zero for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  uint32_t base_count = first ? 0u : ctrl[0];
   __syncthreads();  // everybody has read ctrl[0] before thread 0 replaces it
-  for (int base = 0; base < tg.nt; base += 1024) {
+  for (int base = 0; base < tg.nt; base += 256) {
     const int i = base + threadIdx.x;
-    const uint32_t v = (i < tg.nt) ? bintotal[i] : 0u;
+    const uint32_t v = (i < tg.nt) ? __ldcg(bintotal + i) : 0u;
     uint32_t total;
-    const uint32_t ex = block_excl_scan(v, sm, &total) + carry;
+    const uint32_t ex = block_excl_scan(v, sm, &total) + base_count;
     if (i < tg.nt) ranges[tg.t0 + i] = v ? make_uint2(ex, ex + v) : make_uint2(0, 0);  // empty tiles: (0,0) like the memset
-    carry += total;
+    base_count += total;
   }
   if (threadIdx.x == 0) {
-    ctrl[0] = carry;                          // R (so far)
-    ctrl[1] = carry > r_capacity ? 1u : 0u;   // overflow: the instance buffers are too small, nothing more is written
+    ctrl[0] = base_count;                          // R (so far)
+    ctrl[1] = base_count > r_capacity ? 1u : 0u;   // overflow: the instance buffers are too small, nothing more is written
   }
 }
 
@@ -373,12 +381,21 @@ __global__ void __launch_bounds__(256) k_bin_scatter(int P, const uint32_t* __re
     id = order[j];
     rc = rect[id];
   }
+  uint8_t* s_pref = reinterpret_cast<uint8_t*>(s_base + tg.nt);  // [tiles][8]: instances of the tile before each 32-surfel word
   for (int b = threadIdx.x; b < tg.nt; b += 256) s_base[b] = ranges[tg.t0 + b].x + hist[(size_t)b * ncta + blockIdx.x];
   chunk_bitmap(s_bits, gx, tg, rc);
+  for (int b = threadIdx.x; b < tg.nt; b += 256) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      s_pref[b * 8 + w] = (uint8_t)run;  // <= 224
+      run += __popc(s_bits[b * 8 + w]);
+    }
+  }
+  __syncthreads();
   for_each_chunk_tile(rc, gx, tg, id, [&](int tile, int t, uint32_t sid) {
     const int w = t >> 5;
-    uint32_t r = __popc(s_bits[tile * 8 + w] & ((1u << (t & 31)) - 1u));
-    for (int k = 0; k < w; ++k) r += __popc(s_bits[tile * 8 + k]);
+    const uint32_t r = (uint32_t)s_pref[tile * 8 + w] + __popc(s_bits[tile * 8 + w] & ((1u << (t & 31)) - 1u));
     point_list[s_base[tile] + r] = sid;
   });
 }
@@ -453,19 +470,20 @@ int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, 
   const int ngroups = bin_group_count(gx, gy);
   for (int gi = 0; gi < ngroups; ++gi) {
     const TileGroup tg = tile_group(gx, gy, gi);
-    const size_t smem = (size_t)tg.nt * 9 * sizeof(uint32_t);
+    const size_t smem = (size_t)tg.nt * 9 * sizeof(uint32_t);         // bitmap [+ first slots]
+    const size_t smem_scatter = smem + (size_t)tg.nt * 8;               // + prefix bytes: 44 KB for a full group
     {
       ProfScope prof(GSL_K_SCAN, st);
       k_bin_count<<<ncta, 256, smem, st>>>(p.P, g.sval_b, g.rect, tg, gx, im.ncta, im.hist);
-      k_bin_scan<<<tg.nt, 256, 0, st>>>(im.hist, im.ncta, im.bintotal);
-      k_bin_bases<<<1, 1024, 0, st>>>(im.bintotal, tg, gi == 0 ? 1 : 0, im.ranges, g.ctrl, (uint32_t)r_capacity);
+      k_bin_scan<<<tg.nt, 256, 0, st>>>(im.hist, im.ncta, im.bintotal, tg, gi == 0 ? 1 : 0, im.ranges, g.ctrl,
+                                        (uint32_t)r_capacity);
     }
     if (r_host && gi == ngroups - 1) {
       r_host[0] = -1;  // sentinel for wait_num_rendered
       cudaMemcpyAsync(r_host, g.ctrl, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     }
     ProfScope prof(GSL_K_DUPLICATE, st);
-    k_bin_scatter<<<ncta, 256, smem, st>>>(p.P, g.sval_b, g.rect, tg, gx, im.ncta, im.hist, im.ranges, g.ctrl,
+    k_bin_scatter<<<ncta, 256, smem_scatter, st>>>(p.P, g.sval_b, g.rect, tg, gx, im.ncta, im.hist, im.ranges, g.ctrl,
                                           (uint32_t)r_capacity, b.vals_b);
   }
   ProfScope prof(GSL_K_RANGES, st);

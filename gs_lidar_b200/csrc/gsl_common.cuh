@@ -19,7 +19,7 @@
 //     grad[i]     float[32] packed gradient accumulators, kept all-zero between steps:
 //         [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity,
 //         [12..15] dL_dcolor, [16..18] dL_dnormal, [19] pad, [20..20+S) dL_dfeature, pad to 32
-//     ctrl        u32[64]  [0]=R, [1]=overflow, [8]=max(~depth key), [9]=max(depth key)
+//     ctrl        u32[64]  [0]=R, [1]=overflow, [2]=finished CTAs of k_bin_scan, [8]=max(~depth key), [9]=max(depth key)
 //   image chunk: final_T (3N f32: T, M1, M2), ranges (tiles x uint2),
 //     bdesc uint4[tiles*8]  per 8x4 pixel block (tile, b): (start, end) of its block list inside plane b,
 //                     .z = number of leading entries the backward pass has to walk (written by the forward)

@@ -12,7 +12,7 @@
 namespace gsl {
 
 #ifndef GSL_FWD_ILP
-#define GSL_FWD_ILP 1
+#define GSL_FWD_ILP 2
 #endif
 
 #ifdef GSL_STATS

@@ -423,7 +423,7 @@ GSL_API int gsl_stage_camera(const float* viewmatrix, const float* campos, const
  * Kernel ids index the arrays of gsl_profile_read. */
 enum {
   GSL_K_PREPROCESS_FWD = 0,
-  GSL_K_SCAN = 1,      /* k_bin_count + k_bin_scan + k_bin_bases (per group of 1024 tiles) */
+  GSL_K_SCAN = 1,      /* k_bin_count + k_bin_scan (per group of 1024 tiles) */
   GSL_K_DUPLICATE = 2, /* k_bin_scatter */
   GSL_K_SORT = 3,      /* k_depth_keys + k_sort_hist/scan/scatter/buckets: this repo's depth sort of the surfels */
   GSL_K_RANGES = 4,    /* k_tile_blists */
