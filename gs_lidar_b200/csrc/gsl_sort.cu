@@ -64,15 +64,28 @@ __global__ void __launch_bounds__(256) k_sort_hist(int P, const uint32_t* __rest
   }
 }
 
-// exclusive scan of count[0..nb) -> start[0..nb]; one CTA, every thread owns nb / 1024 consecutive buckets
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t nb, const uint32_t* __restrict__ count, uint32_t* __restrict__ start) {
-  __shared__ uint32_t s_w[32];
+// exclusive scan of count[0..nb) -> start[0..nb]; one CTA, every thread owns PER = nb / 1024 consecutive buckets (nb is a
+// power of two >= 256).  PER <= 16: the counts stay in registers between the two halves (16-byte loads / stores); the
+// single CTA is a latency chain on the sort's critical path, so every dependent round trip counts.
+template <int PER>
+__device__ __forceinline__ void sort_scan_body(uint32_t nb, const uint32_t* __restrict__ count, uint32_t* __restrict__ start,
+                                               uint32_t* s_w) {
   const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  const uint32_t per = (nb + 1023u) / 1024u;  // <= GSL_SORT_MAX_BUCKETS / 1024
-  const uint32_t i0 = threadIdx.x * per;
+  const uint32_t i0 = threadIdx.x * PER;
+  uint32_t v[PER];
   uint32_t sum = 0;
-  for (uint32_t k = 0; k < per; ++k)
-    if (i0 + k < nb) sum += count[i0 + k];
+  if (PER >= 4) {
+#pragma unroll
+    for (int k = 0; k < PER; k += 4) {
+      const uint4 q = (i0 + k < nb) ? *reinterpret_cast<const uint4*>(count + i0 + k) : make_uint4(0u, 0u, 0u, 0u);
+      v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) v[k] = (i0 + k < nb) ? count[i0 + k] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) sum += v[k];
   uint32_t inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -93,12 +106,33 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t nb, const uint32_t*
   }
   __syncthreads();
   uint32_t ex = s_w[wv] + inc - sum;
-  for (uint32_t k = 0; k < per; ++k) {
-    if (i0 + k < nb) {
-      start[i0 + k] = ex;
-      ex += count[i0 + k];
+  if (i0 >= nb) return;
+  if (PER >= 4) {
+#pragma unroll
+    for (int k = 0; k < PER; k += 4) {
+      uint4 q;
+      q.x = ex; ex += v[k];
+      q.y = ex; ex += v[k + 1];
+      q.z = ex; ex += v[k + 2];
+      q.w = ex; ex += v[k + 3];
+      *reinterpret_cast<uint4*>(start + i0 + k) = q;
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { start[i0 + k] = ex; ex += v[k]; }
   }
+}
+
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t nb, const uint32_t* __restrict__ count, uint32_t* __restrict__ start) {
+  __shared__ uint32_t s_w[32];
+  const uint32_t per = (nb + 1023u) / 1024u;  // 1 (nb <= 1024), 2, 4, ..., GSL_SORT_MAX_BUCKETS / 1024
+  if (per <= 1) { sort_scan_body<1>(nb, count, start, s_w); return; }
+  if (per == 2) { sort_scan_body<2>(nb, count, start, s_w); return; }
+  if (per == 4) { sort_scan_body<4>(nb, count, start, s_w); return; }
+  if (per == 8) { sort_scan_body<8>(nb, count, start, s_w); return; }
+  if (per == 16) { sort_scan_body<16>(nb, count, start, s_w); return; }
+  if (per == 32) { sort_scan_body<32>(nb, count, start, s_w); return; }
+  sort_scan_body<64>(nb, count, start, s_w);
 }
 
 __global__ void __launch_bounds__(256) k_sort_scatter(int P, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ctrl,

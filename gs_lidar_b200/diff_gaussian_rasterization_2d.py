@@ -586,7 +586,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     entry = None
                     break
 
-        split = inputs["shs_rest"].numel() != 0  # never together with the exchange (GaussianRasterizer.forward)
+        split = inputs["shs_rest"].numel() != 0  # SH as two parameter tensors (dc, rest)
         ex = _exchange if (_exchange is not None and P > 0 and
                            (_exchange.world_size() > 1 or getattr(_exchange, "force", False))) else None
         if ex is not None and M == 0:
@@ -743,6 +743,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 d_means3D, d_means2D, d_opacity = g["means3D"], g["means2D"], g["opacities"]
                 d_scales, d_rot, d_features, d_sh = g["scales"], g["rotations"], g["features"], g["shs"]
                 v = g
+            if ex is not None and split:
+                # the exchanges rebuild dL_dsh as ONE (P,M,4) tensor from the factors; the two parameter tensors receive views
+                d_sh, d_sh_rest = d_sh[:, :1], d_sh[:, 1:]
             if fold is not None:
                 # the exchanged rows carried dL/dvelocity, dL/dt, dL/dscaling_t of every rank's own timestamp behind the
                 # features; the glue's backward (renderer._ActivateSurfels) takes them from the record
@@ -825,8 +828,6 @@ class GaussianRasterizer(nn.Module):
         empty = lambda: torch.empty(0, dtype=torch.float32, device=dev)
         if shs_rest is not None and shs is None:
             raise Exception('shs_rest needs shs (the DC coefficient)')
-        if shs_rest is not None and _exchange is not None and (_exchange.world_size() > 1 or getattr(_exchange, "force", False)):
-            shs, shs_rest = torch.cat((shs, shs_rest), dim=1), None  # the factored exchange works on one (P,M,4) tensor
         if shs is None:
             shs = empty()
         if colors_precomp is None:

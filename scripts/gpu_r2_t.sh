@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# round 2, call t (N GPUs): the headline step and the dynamic step (c4, glue folded into the exchange) frame-parallel
+set -u
+mkdir -p gpurun_out
+N=${1:-2}
+run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@"; }
+if [ "$N" = "2" ]; then
+timeout 600 python -m pytest tests/test_peer_exchange_gpu.py -q -m gpu -k "two_processes" > gpurun_out/pytest_peer.log 2>&1
+echo "pytest peer exit $?"; tail -2 gpurun_out/pytest_peer.log
+fi
+run --steps ${STEPS:-50} --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "c3 n$N exit $?"; tail -2 gpurun_out/bench_n$N.err | cut -c1-200
+run --config c4 --steps 30 --warmup 5 > gpurun_out/bench_c4_n$N.json 2> gpurun_out/bench_c4_n$N.err; echo "c4 n$N exit $?"; tail -2 gpurun_out/bench_c4_n$N.err | cut -c1-300
+python - <<PY
+import json
+for f in ('bench_n$N', 'bench_c4_n$N'):
+    try:
+        d=json.load(open('gpurun_out/%s.json' % f))
+        print(f, round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), d.get('exchange_parity'), d.get('per_rank_ms_without_exchange'))
+        print('   ', {k: round(v['ms_per_launch'],4) for k,v in d.get('kernels',{}).items() if 'peer' in k or 'bwd' in k})
+    except Exception as ex:
+        print(f, 'no line', ex)
+PY
