@@ -28,15 +28,17 @@ def _side_streams(device, n):
 def render_frames(settings_list, means3D, opacities, means2D=None, streams="auto", consume=None, **surfels):
     """Renders one frame per element of `settings_list` (GaussianRasterizationSettings: one camera each).  `surfels` are the
     keyword arguments of GaussianRasterizer.forward shared by all frames (shs / colors_precomp, features, scales, rotations,
-    mask, shs_rest).  streams: how many alternating streams ("auto": 2 for large scenes, 1 for host-bound small ones).
+    mask, shs_rest).  streams: how many alternating streams ("auto": 1, see below).
     `consume(i, outputs)`, if given, is called on the frame's stream right after frame i was issued (to
     copy results out, accumulate metrics ...) and the outputs are not kept; otherwise the list of outputs is returned."""
     dev = means3D.device
     if streams == "auto":
         # small scenes are host-bound (a 100k-surfel frame is 0.2 ms of GPU work, about what issuing it costs): the stream
-        # switches then cost more than the overlap returns (measured: 0.37 vs 0.20 ms per frame at 100k surfels, 2.49 vs 3.02 ms
-        # at 4M surfels)
-        streams = 2 if means3D.shape[0] >= 500000 else 1
+        # switches then cost more than the overlap returns (measured: 0.37 vs 0.20 ms per frame at 100k surfels).  At 4M
+        # surfels two alternating streams used to win (2.49 vs 3.02 ms per frame) while the surfel sort left the GPU half
+        # idle; with the warp-per-bucket sort one stream measured faster (2.26 vs 2.43 ms per frame, 64 frames,
+        # profiles/r02_bench_c5_n1_64frames.json), so "auto" is one stream at every size now; streams=2 remains selectable
+        streams = 1
     if means2D is None:
         means2D = torch.zeros((means3D.shape[0], 4), dtype=means3D.dtype, device=dev)
     main = torch.cuda.current_stream(dev)
