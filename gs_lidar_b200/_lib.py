@@ -109,6 +109,7 @@ SYMBOLS = {
     "gsl_abi_version": (C.c_int, []),
     "gsl_last_error": (C.c_char_p, []),
     "gsl_workspace_sizes": (C.c_int, [C.POINTER(gsl_params), C.c_int64, C.POINTER(gsl_ws_sizes)]),
+    "gsl_bin_groups": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32]),
     "gsl_forward_preprocess": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs),
                                          C.POINTER(gsl_fwd_outputs), C.POINTER(gsl_workspace), vp]),
     "gsl_forward_render": (C.c_int, [C.POINTER(gsl_params), C.POINTER(gsl_fwd_inputs),

@@ -176,6 +176,14 @@ GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_
   return 0;
 }
 
+GSL_API int32_t gsl_bin_groups(int32_t W, int32_t H, int32_t* groups, int32_t capacity) {
+  if (W <= 0 || H <= 0 || W > 32767 || H > 32767 || capacity < 0 || (capacity > 0 && !groups)) {
+    set_error(GSL_EINVAL, "bin_groups: bad arguments");
+    return -1;
+  }
+  return bin_groups_describe(W, H, groups, capacity);
+}
+
 GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,
                            gsl_workspace* ws, void* stream) {
   int rc = validate(p);

@@ -450,6 +450,18 @@ static TileGroup tile_group(int gx, int gy, int g) {
   return tg;
 }
 
+// host-side view of the grouping for include/gsl_b200.h: gsl_bin_groups (CPU tests of the partition)
+int bin_groups_describe(int W, int H, int32_t* out, int capacity) {
+  const int gx = (W + GSL_BLOCK_X - 1) / GSL_BLOCK_X, gy = (H + GSL_BLOCK_Y - 1) / GSL_BLOCK_Y;
+  const int n = bin_group_count(gx, gy);
+  for (int g = 0; g < n && g < capacity; ++g) {
+    const TileGroup tg = tile_group(gx, gy, g);
+    int32_t* o = out + 6 * g;
+    o[0] = tg.t0; o[1] = tg.nt; o[2] = tg.y0; o[3] = tg.y1; o[4] = tg.x0; o[5] = tg.x1 < gx ? tg.x1 : gx;
+  }
+  return n;
+}
+
 // The surfels are already depth-sorted (launch_surfel_sort): one stable counting pass per tile group, then the block
 // lists.  Nothing here needs R on the host; r_host receives (R, overflow) asynchronously.
 int launch_binning(const gsl_params& p, const GeomView& g, const ImageView& im, const BinView& b,

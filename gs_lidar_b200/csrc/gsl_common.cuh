@@ -205,6 +205,7 @@ int launch_preprocess(const gsl_params& p, const gsl_fwd_inputs& in, gsl_fwd_out
 int launch_scan(const gsl_params& p, const GeomView& g, int32_t* r_host, cudaStream_t st);
 int launch_depth_keys(const gsl_params& p, const gsl_fwd_inputs& in, const GeomView& g, cudaStream_t st);
 int launch_surfel_sort(const gsl_params& p, const GeomView& g, cudaStream_t st);
+int bin_groups_describe(int W, int H, int32_t* out, int capacity);
 uint32_t sort_num_buckets_host(int P);
 bool is_sort_kernel(const void* func);        // kernels that run with the side stream's (high) priority
 bool is_depth_keys_kernel(const void* func);

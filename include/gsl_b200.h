@@ -148,6 +148,13 @@ GSL_API const char* gsl_last_error(void);
 /* Sizes of the scratch chunks for P surfels, r_capacity tile instances and W*H pixels. */
 GSL_API int gsl_workspace_sizes(const gsl_params* p, int64_t r_capacity, gsl_ws_sizes* out);
 
+/* How the binning walks the 16x16 tiles of a W x H image: groups of at most 1024 consecutive tile ids, whole tile rows
+ * or -- beyond 16384 pixels of width -- pieces of one row (the counting pass that replaces the reference's 64-bit key sort,
+ * rasterizer_impl.cu:338-344, holds a shared-memory bitmap per tile).  Returns the number of groups and writes up to
+ * `capacity` of them as (first tile id, tiles, first tile row, end row, first tile column, end column); -1 on bad
+ * arguments.  Informational: the forward pass does this itself. */
+GSL_API int32_t gsl_bin_groups(int32_t W, int32_t H, int32_t* groups, int32_t capacity);
+
 /* Stage 1 of the forward pass: per-surfel preprocess with the depth sort of the surfels on a side stream under
  * it.  Never blocks the host. */
 GSL_API int gsl_forward_preprocess(const gsl_params* p, const gsl_fwd_inputs* in, gsl_fwd_outputs* out,

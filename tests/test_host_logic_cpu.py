@@ -160,3 +160,62 @@ def test_peer_exchange_row_ranges_cover_the_surfels_on_tile_boundaries():
             assert r[0][0] == 0 and r[-1][1] == P and len(r) <= chunks
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))          # contiguous
             assert all(rb % 256 == 0 for rb, _ in r)                    # ranges start on a 256-surfel tile
+
+
+def test_peer_exchange_rows_carry_the_glue_gradients_behind_the_features():
+    """parallel.PeerExchange with render()'s glue folded in (gsl_peer_glue): the exchange moves
+    4 ceil(S/4) + 8 'feature' channels and split_glue() takes them apart again."""
+    import ctypes as C
+    from gs_lidar_b200 import parallel
+    from gs_lidar_b200 import _lib as L
+    lib = L.load()
+    ex = parallel.PeerExchange(sync=False)
+    assert [ex.rows_channels(S) for S in (0, 2, 4)] == [0, 2, 4]
+    P = 11
+    raw = [torch.zeros(P, w) for w in (3, 3, 1, 1, 1, 3, 4)]  # xyz, velocity, t, scaling_t, opacity, scaling, rotation
+    p = L.gsl_glue_params(P, 0.25, 0.05, 0.2, 1.0, 1)
+    ex.set_glue(dict(p=p, raw=raw, extras=None))
+    g = ex._glue[0]
+    assert (g.timestamp, g.time_shift, g.cycle, g.dynamic) == (0.25, C.c_float(0.05).value, C.c_float(0.2).value, 1)
+    assert g.xyz == raw[0].data_ptr() and g.velocity == raw[1].data_ptr() and g.opacity == raw[4].data_ptr()
+    for S in (0, 2, 4):
+        n = ex.rows_channels(S)
+        assert n == lib.gsl_peer_rows_channels(S, 1) == 4 * ((S + 3) // 4) + 8
+        assert lib.gsl_peer_row_width(n) == 24  # 96-byte rows: three geometry quads + features + two glue quads
+        f = torch.arange(P * n, dtype=torch.float32).view(P, n)
+        feats, extras = ex.split_glue(dict(features=f), S)
+        q = 4 * ((S + 3) // 4)
+        assert feats.shape == (P, S) and torch.equal(feats, f[:, :S])
+        assert torch.equal(extras["velocity"], f[:, q:q + 3]) and torch.equal(extras["t"], f[:, q + 3:q + 4])
+        assert torch.equal(extras["scaling_t"], f[:, q + 4:q + 5])
+    ex.set_glue(None)
+    assert ex.rows_channels(4) == 4 and ex.split_glue(dict(features=torch.zeros(P, 4)), 4)[1] is None
+    # the buffer grows with the row width only in the staging / result areas
+    assert lib.gsl_peer_buffer_bytes(100000, 12, 2) > lib.gsl_peer_buffer_bytes(100000, 4, 2)
+
+
+def test_binning_tile_groups_partition_the_tile_grid():
+    """gsl_bin_groups: the counting pass of the binning takes at most 1024 consecutive tile ids at a time (DESIGN.md 2.2);
+    the groups must cover every tile exactly once, in ascending tile-id order, as whole rows or pieces of one row."""
+    import ctypes as C
+    from gs_lidar_b200 import _lib as L
+    lib = L.load()
+    for W, H in ((1030, 66), (515, 66), (2048, 128), (1040, 272), (2040, 500), (16500, 24), (32767, 40), (17, 32767), (16, 16),
+                 (16384, 16), (16385, 33)):
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        n = lib.gsl_bin_groups(W, H, None, 0)
+        assert n >= 1
+        buf = (C.c_int32 * (6 * n))()
+        assert lib.gsl_bin_groups(W, H, buf, n) == n
+        groups = [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
+        nxt = 0
+        for t0, nt, y0, y1, x0, x1 in groups:
+            assert t0 == nxt and 1 <= nt <= 1024
+            assert 0 <= y0 < y1 <= gy and 0 <= x0 < x1 <= gx
+            assert nt == (y1 - y0) * (x1 - x0) and t0 == y0 * gx + x0
+            assert (x0 == 0 and x1 == gx) or y1 == y0 + 1  # whole rows, or a piece of ONE row
+            nxt = t0 + nt
+        assert nxt == gx * gy
+        if gx * gy <= 1024:
+            assert n == 1
+    assert lib.gsl_bin_groups(0, 66, None, 0) == -1 and b"bin_groups" in lib.gsl_last_error()
