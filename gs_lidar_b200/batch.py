@@ -1,9 +1,9 @@
 """Forward-only rendering of many LiDAR frames (cameras) of one surfel set -- the inference side of SURVEY.md 8(e):
-"frames sharded frame_id % G; no collective".  Frames are independent, so consecutive frames are issued on alternating CUDA
-streams with their own workspaces: the per-surfel stages of frame k+1 (HBM-bound) run under the compositing of frame k
-(issue-bound), and the one host wait a forward has (the instance count, polled after all of its launches) no longer leaves
-the GPU idle.  The reference renders frame by frame on the default stream with a blocking copy in the middle of every
-forward (rasterizer_impl.cu:314-315).
+"frames sharded frame_id % G; no collective".  Frames are independent: each is issued with its own workspace, without the
+blocking copy the reference has in the middle of every forward (rasterizer_impl.cu:314-315) -- the one host wait of a
+forward (the instance count) is polled after all of its launches.  With streams=2 consecutive frames alternate between two
+CUDA streams, so that the per-surfel stages of frame k+1 run under the compositing of frame k; whether that pays depends on
+how much of the GPU a single frame leaves idle (see the note at "auto" below).
 
     frames = render_frames(settings_list, means3D=..., opacities=..., shs=..., scales=..., rotations=..., features=...)
 

@@ -12,8 +12,8 @@
 //     rgb[i]      float4   SH colour (forward.cu:275-278); unused with colors_precomp
 //     rect[i]     ushort4  tile rect (min.x, min.y, max.x, max.y) of getRect (auxiliary.h:47-55)
 //     pixbox[i]   short4   conservative pixel box of the surfel's support (this design)
-//     tiles[i]    u32      tiles_touched;  offs[i] u32 inclusive scan (general binning path, state export) /
-//                          scratch of the surfel sort (fast path)
+//     tiles[i]    u32      tiles_touched;  offs[i] u32 inclusive scan (state export only) /
+//                          scratch of the surfel sort
 //     skey_a/b, sval_a/b u32  surfel depth sort: keys, bucket-scattered (key, id), ids in (depth, id) order
 //     clamped[i]  u8       bit c set when SH channel c was clamped (forward.cu:64-67)
 //     grad[i]     float[32] packed gradient accumulators, kept all-zero between steps:

@@ -530,7 +530,7 @@ __global__ void GSL_PFWD_BOUNDS k_preprocess_fwd(
   }
 }
 
-// Keys of the surfel depth sort (fast binning): bits of the view-space range r, computed with exactly the
+// Keys of the surfel depth sort: bits of the view-space range r, computed with exactly the
 // instruction sequence of k_preprocess_fwd (forward.cu:116-125) so that the order is the order of the stored
 // depths.  Culled surfels get a key too -- they emit no instances, so where they sort does not matter.  Kept
 // separate from k_preprocess_fwd so that the (latency-bound) sort of gsl_sort.cu can run on a side stream UNDER the
