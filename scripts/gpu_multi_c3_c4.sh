@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, call t (N GPUs): the headline step and the dynamic step (c4, glue folded into the exchange) frame-parallel
+# N GPUs (arg 1): the headline step and the dynamic step (c4, glue folded into the exchange) frame-parallel
 set -u
 mkdir -p gpurun_out
 N=${1:-2}

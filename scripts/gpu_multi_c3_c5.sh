@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, GPU call N (N GPUs): final multi-GPU lines -- c3 with the default exchange schedule (+ early-high at 8), c5 frame-sharded
+# N GPUs (arg 1): the headline step with the default exchange schedule (+ early-high at 8) and c5 frame-sharded
 set -u
 mkdir -p gpurun_out
 N=${1:-2}

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, GPU call J (N GPUs): schedules of the fused exchange step side by side (bench at N, one line per schedule)
+# N GPUs (arg 1): schedules of the fused exchange step side by side (bench at N, one line per schedule)
 set -u
 mkdir -p gpurun_out
 N=${1:-2}

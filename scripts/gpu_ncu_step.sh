@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, GPU call M: ncu evidence -- launch list of one bench-shaped run + full capture of every kernel of the step
+# ncu evidence -- launch list of one bench-shaped run + full capture of every kernel of the step
 set -u
 mkdir -p gpurun_out
 timeout 300 python scripts/one_step.py --impl ours --iters 3 > gpurun_out/plain_ours.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_ours.log; exit 1; }

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, call v: final single-GPU record -- GPU suite, the headline line with both CPU baselines, c4, c2, c5
+# one GPU: GPU suite, the headline line with both CPU baselines, c4, c5 (64 frames), c2
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1
